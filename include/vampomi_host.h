@@ -1,0 +1,80 @@
+/*
+ * vampomi_host.h — C entry points of the C++ host driver that sits ABOVE the kernel ABI (vampomi.h).
+ *
+ * The driver is the B200 counterpart of the reference's main_meth.exe (src/main_meth.cpp:9-270) and of
+ * `class vamp` (src/vamp.hpp:83-150): it owns the command line, the phenotype / vector / CSV files and the VAMP
+ * iteration logic, and reaches the GPU only through the functions declared in vampomi.h.
+ *
+ *   vampomi_main          the whole program: same flags, run modes and output files as main_meth.exe
+ *   vampomi_solver_*      the VAMP loop as a stepping object (one call = one VAMP iteration, src/vamp.cpp:148-428 or
+ *                         src/vamp_probit.cpp:68-463) for callers that hold their data in memory (bench, tests)
+ */
+#ifndef VAMPOMI_HOST_H
+#define VAMPOMI_HOST_H
+
+#include "vampomi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Runs main_meth's command line (argv[0] is ignored). Returns the process exit status (0 ok, 1 after a FATAL line).
+ * With --gpus G > 1 it drives G marker shards from G host threads of this process, one GPU each. */
+int vampomi_main(int argc, char** argv);
+
+#define VAMPOMI_MAX_MIX 32
+
+typedef struct vampomi_solver_config {
+    /* defaults in comments: src/options.hpp:63-104 / src/main_meth.cpp:51-66 */
+    int model;                 /* 0 = linear (src/vamp.cpp:110), 1 = bin_class / probit (src/vamp_probit.cpp:19) */
+    double gam1;               /* 1e-6 */
+    double gamw;               /* 1/(1-h2), h2 = 0.5 */
+    double rho;                /* 0.5 */
+    int CG_max_iter;           /* 500 */
+    double CG_err_tol;         /* 1e-5 */
+    int EM_max_iter;           /* 1 */
+    double EM_err_thr;         /* 1e-2 */
+    int learn_vars;            /* 1 */
+    int learn_prior_delay;     /* 1 */
+    double merge_vars_thr;     /* 0.5 */
+    int L;                     /* number of mixture components */
+    double probs[VAMPOMI_MAX_MIX];
+    double vars[VAMPOMI_MAX_MIX];     /* as given on the command line (NOT yet multiplied by N) */
+    unsigned long long seed;   /* Hutchinson probe / probit start */
+    int redundant_passes;      /* 1 = also recompute A^T y and A x2 where the reference does (src/vamp.cpp:303,826);
+                                  0 = reuse them (same results, 2 fewer matrix passes per iteration) */
+} vampomi_solver_config;
+
+typedef struct vampomi_iter_result {
+    int it;                    /* iteration number just completed (1-based) */
+    int n_params, n_metrics;   /* linear: 5 / 6, probit: 8 / 12 — the columns of _params.csv / _metrics.csv */
+    double params[8];
+    double metrics[12];
+    double nmse;               /* sqrt(|x1_prev - x1|^2 / |x1_prev|^2), src/vamp.cpp:413 */
+    double gam1_next;          /* gam1 the next iteration will use */
+    int cg_iters_lmmse;        /* k1 */
+    int cg_iters_onsager;      /* k2 */
+    int L;                     /* mixture components after this iteration's prior update */
+    double probs[VAMPOMI_MAX_MIX];
+    double vars[VAMPOMI_MAX_MIX];     /* internal (x N) variances */
+    long long matrix_passes;   /* full passes over the marker block this iteration */
+    double true_gam1, true_gam2;      /* diagnostics printed by the reference (src/vamp.cpp:270,359) */
+} vampomi_iter_result;
+
+typedef struct vampomi_solver vampomi_solver;
+
+void vampomi_solver_default_config(vampomi_solver_config* cfg);
+
+/* `ctx` must hold the matrix block with statistics computed. y_N: phenotype as the reference's data::get_phen()
+ * returns it (already scaled for the linear model). true_signal_M / x1hat_init_M may be NULL (zeros). */
+int vampomi_solver_create(vampomi_ctx* ctx, const vampomi_solver_config* cfg, const double* y_N,
+                          const double* true_signal_M, const double* x1hat_init_M, vampomi_solver** out);
+/* One VAMP iteration. If x1_scaled_M / r1_scaled_M are non-NULL they receive x1_hat/sqrt(N) and r1/sqrt(N) — the
+ * content of _it_{k}.bin and _r1_it_{k}.bin (src/vamp.cpp:235-249) — for this shard. */
+int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M);
+int vampomi_solver_destroy(vampomi_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAMPOMI_HOST_H */

@@ -1,0 +1,563 @@
+// extern "C" layer of libvampomi_cuda.so (declared in include/vampomi.h): context lifetime, HBM upload path,
+// NCCL plumbing, and thin wrappers that launch the kernels of kernels_matrix.cu / kernels_vector.cu / cg.cu.
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cmath>
+#include <new>
+#include "common.h"
+
+namespace vampomi {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int nccl_load(NcclApi** out) {
+    static NcclApi api;
+    static int state = 0;      // 0 untried, 1 ok, -1 failed
+    if (state == 0) {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) { state = -1; }
+        else {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+            api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+            state = (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString) ? 1 : -1;
+        }
+    }
+    if (state != 1) {
+        set_error("libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
+        return VAMPOMI_ERR_NCCL;
+    }
+    *out = &api;
+    return VAMPOMI_OK;
+}
+
+int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n) {
+    if (c->nranks == 1) return VAMPOMI_OK;
+    if (!c->comm) { set_error("nranks > 1 but vampomi_comm_init was not called"); return VAMPOMI_ERR_STATE; }
+    ncclResult_t r = c->nccl->AllReduce(dev, dev, n, ncclDouble, ncclSum, c->comm, c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllReduce: %s", c->nccl->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
+    c->counters[3]++;
+    return VAMPOMI_OK;
+}
+
+static int ensure_stage(vampomi_ctx* c, size_t elems) {
+    if (elems <= c->stage_elems) return VAMPOMI_OK;
+    if (c->stage) VO_CUDA(cudaFreeHost(c->stage));
+    c->stage = nullptr; c->stage_elems = 0;
+    VO_CUDA(cudaMallocHost(&c->stage, elems * sizeof(double)));
+    c->stage_elems = elems;
+    return VAMPOMI_OK;
+}
+
+// device sums -> pinned host -> caller, after the (optional) packed all-reduce; ONE sync
+static int fetch_sums(vampomi_ctx* c, int n, bool reduce, double* out) {
+    if (reduce) VO_CHECK(allreduce_inplace(c, c->sums, (size_t)n));
+    VO_CUDA(cudaMemcpyAsync(c->sums_host, c->sums, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++) out[i] = c->sums_host[i];
+    return VAMPOMI_OK;
+}
+
+static int h2d_vec(vampomi_ctx* c, double* dev, const double* host, long long n) {
+    VO_CHECK(ensure_stage(c, (size_t)n));
+    memcpy(c->stage, host, (size_t)n * sizeof(double));
+    VO_CUDA(cudaMemcpyAsync(dev, c->stage, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));      // the staging buffer is reused by the next call
+    return VAMPOMI_OK;
+}
+static int d2h_vec(vampomi_ctx* c, double* host, const double* dev, long long n) {
+    VO_CHECK(ensure_stage(c, (size_t)n));
+    VO_CUDA(cudaMemcpyAsync(c->stage, dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(host, c->stage, (size_t)n * sizeof(double));
+    return VAMPOMI_OK;
+}
+
+}  // namespace vampomi
+
+using namespace vampomi;
+
+extern "C" {
+
+const char* vampomi_last_error(void) { return g_err; }
+int vampomi_abi_version(void) { return VAMPOMI_ABI_VERSION; }
+
+int vampomi_device_count(int* count) {
+    VO_ARG(count != nullptr, "device_count: NULL argument");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess || *count == 0) {
+        *count = 0;
+        set_error("no CUDA device available (%s); libvampomi_cuda has no CPU fallback", cudaGetErrorString(e));
+        return VAMPOMI_ERR_CUDA;
+    }
+    return VAMPOMI_OK;
+}
+
+int vampomi_divide_work(long long Mt, int nranks, int rank, long long* M, long long* S) {
+    VO_ARG(Mt >= 1 && nranks >= 1 && rank >= 0 && rank < nranks && M && S, "divide_work: bad arguments");
+    const long long modu = Mt % nranks, size = Mt / nranks;           // src/utilities.cpp:214-225
+    *M = rank < modu ? size + 1 : size;
+    *S = rank * size + (rank < modu ? rank : modu);
+    return VAMPOMI_OK;
+}
+
+int vampomi_create(int device, int N, long long Mt, int nranks, int rank, vampomi_ctx** out) {
+    VO_ARG(out != nullptr, "create: out is NULL");
+    *out = nullptr;
+    VO_ARG(N >= 2 && Mt >= 1, "create: need N >= 2 and Mt >= 1 (got N=%d Mt=%lld)", N, Mt);
+    VO_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "create: bad rank %d of %d", rank, nranks);
+    VO_ARG(Mt >= nranks, "create: fewer markers (%lld) than shards (%d)", Mt, nranks);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s); libvampomi_cuda has no CPU fallback", cudaGetErrorString(e));
+        return VAMPOMI_ERR_CUDA;
+    }
+    VO_ARG(device >= 0 && device < ndev, "create: device %d out of range (%d devices)", device, ndev);
+    VO_CUDA(cudaSetDevice(device));
+    vampomi_ctx* c = new (std::nothrow) vampomi_ctx();
+    VO_ARG(c != nullptr, "create: out of host memory");
+    c->device = device; c->N = N; c->Mt = Mt; c->nranks = nranks; c->rank = rank;
+    vampomi_divide_work(Mt, nranks, rank, &c->M, &c->S);
+    c->ld = ((size_t)N + 15) / 16 * 16;
+    c->mpad = ((size_t)c->M + 15) / 16 * 16;
+    int rc = [&]() -> int {
+        cudaDeviceProp prop;
+        VO_CUDA(cudaGetDeviceProperties(&prop, device));
+        c->num_sms = prop.multiProcessorCount;
+        VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        VO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        const size_t a_bytes = (size_t)c->M * c->ld * sizeof(double);
+        cudaError_t ea = cudaMalloc(&c->A, a_bytes);
+        if (ea != cudaSuccess) {
+            set_error("cudaMalloc of the %.3f GB marker block failed: %s", a_bytes / 1e9, cudaGetErrorString(ea));
+            return VAMPOMI_ERR_CUDA;
+        }
+        if (c->ld != (size_t)N) VO_CUDA(cudaMemsetAsync(c->A, 0, a_bytes, c->stream));     // pad rows must be zero
+        VO_CUDA(cudaMalloc(&c->mave, c->mpad * sizeof(double)));
+        VO_CUDA(cudaMalloc(&c->msig, c->mpad * sizeof(double)));
+        for (int i = 0; i < VAMPOMI_V_NUM_M; i++) {
+            VO_CUDA(cudaMalloc(&c->mvec[i], c->mpad * sizeof(double)));
+            VO_CUDA(cudaMemsetAsync(c->mvec[i], 0, c->mpad * sizeof(double), c->stream));
+        }
+        for (int i = 0; i < VAMPOMI_V_NUM_N; i++) {
+            VO_CUDA(cudaMalloc(&c->nvec[i], c->ld * sizeof(double)));
+            VO_CUDA(cudaMemsetAsync(c->nvec[i], 0, c->ld * sizeof(double), c->stream));
+        }
+        VO_CUDA(cudaMalloc(&c->red_partials, (size_t)RED_BLOCKS * MAX_SUMS * sizeof(double)));
+        VO_CUDA(cudaMalloc(&c->red_tickets, MAX_DOTS * sizeof(unsigned int)));
+        VO_CUDA(cudaMemsetAsync(c->red_tickets, 0, MAX_DOTS * sizeof(unsigned int), c->stream));
+        VO_CUDA(cudaMalloc(&c->sums, MAX_SUMS * sizeof(double)));
+        VO_CUDA(cudaMemsetAsync(c->sums, 0, MAX_SUMS * sizeof(double), c->stream));
+        VO_CUDA(cudaMallocHost(&c->sums_host, MAX_SUMS * sizeof(double)));
+        VO_CUDA(cudaMalloc(&c->cg, sizeof(CgScalars)));
+        VO_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgScalars), c->stream));
+        VO_CUDA(cudaMallocHost(&c->cg_poll_host, 64 * sizeof(int)));
+        size_t st = (size_t)(3 * c->M > (long long)c->ld ? 3 * c->M : (long long)c->ld);
+        VO_CHECK(ensure_stage(c, st));
+        VO_CUDA(cudaStreamSynchronize(c->stream));
+        return VAMPOMI_OK;
+    }();
+    if (rc != VAMPOMI_OK) { vampomi_destroy(c); return rc; }
+    *out = c;
+    return VAMPOMI_OK;
+}
+
+int vampomi_destroy(vampomi_ctx* c) {
+    if (!c) return VAMPOMI_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
+    cudaFree(c->A); cudaFree(c->mave); cudaFree(c->msig);
+    for (auto p : c->mvec) cudaFree(p);
+    for (auto p : c->nvec) cudaFree(p);
+    cudaFree(c->ax_partial); cudaFree(c->red_partials); cudaFree(c->red_tickets); cudaFree(c->sums); cudaFree(c->cg);
+    if (c->sums_host) cudaFreeHost(c->sums_host);
+    if (c->cg_poll_host) cudaFreeHost(c->cg_poll_host);
+    if (c->stage) cudaFreeHost(c->stage);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return VAMPOMI_OK;
+}
+
+int vampomi_shard(const vampomi_ctx* c, long long* M, long long* S) {
+    VO_ARG(c && M && S, "shard: NULL argument");
+    *M = c->M; *S = c->S;
+    return VAMPOMI_OK;
+}
+
+int vampomi_dims(const vampomi_ctx* c, int* N, long long* Mt, int* nranks, int* rank) {
+    VO_ARG(c, "dims: NULL context");
+    if (N) *N = c->N;
+    if (Mt) *Mt = c->Mt;
+    if (nranks) *nranks = c->nranks;
+    if (rank) *rank = c->rank;
+    return VAMPOMI_OK;
+}
+
+int vampomi_comm_get_unique_id(void* id128) {
+    VO_ARG(id128 != nullptr, "comm_get_unique_id: NULL buffer");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    NcclApi* api = nullptr;
+    VO_CHECK(nccl_load(&api));
+    ncclUniqueId id;
+    ncclResult_t r = api->GetUniqueId(&id);
+    if (r != ncclSuccess) { set_error("ncclGetUniqueId: %s", api->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
+    memcpy(id128, &id, 128);
+    return VAMPOMI_OK;
+}
+
+int vampomi_comm_init(vampomi_ctx* c, const void* id128) {
+    VO_ARG(c && id128, "comm_init: NULL argument");
+    if (c->nranks == 1) return VAMPOMI_OK;
+    VO_CHECK(nccl_load(&c->nccl));
+    VO_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = c->nccl->CommInitRank(&c->comm, c->nranks, id, c->rank);
+    if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", c->nccl->GetErrorString(r)); c->comm = nullptr; return VAMPOMI_ERR_NCCL; }
+    return VAMPOMI_OK;
+}
+
+// ---- design matrix --------------------------------------------------------------------------------------------
+int vampomi_upload_columns(vampomi_ctx* c, long long j0, long long ncols, const double* host) {
+    VO_ARG(c && host && j0 >= 0 && ncols >= 0 && j0 + ncols <= c->M, "upload_columns: range [%lld,+%lld) outside the shard", j0, ncols);
+    VO_CUDA(cudaSetDevice(c->device));
+    if (ncols == 0) return VAMPOMI_OK;
+    VO_CUDA(cudaMemcpy2DAsync(c->A + (size_t)j0 * c->ld, c->ld * sizeof(double), host, (size_t)c->N * sizeof(double),
+                              (size_t)c->N * sizeof(double), (size_t)ncols, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_ready = false;
+    return VAMPOMI_OK;
+}
+
+int vampomi_download_columns(vampomi_ctx* c, long long j0, long long ncols, double* host) {
+    VO_ARG(c && host && j0 >= 0 && ncols >= 0 && j0 + ncols <= c->M, "download_columns: range outside the shard");
+    VO_CUDA(cudaSetDevice(c->device));
+    if (ncols == 0) return VAMPOMI_OK;
+    VO_CUDA(cudaMemcpy2DAsync(host, (size_t)c->N * sizeof(double), c->A + (size_t)j0 * c->ld, c->ld * sizeof(double),
+                              (size_t)c->N * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    return VAMPOMI_OK;
+}
+
+int vampomi_load_file(vampomi_ctx* c, const char* path) {
+    VO_ARG(c && path, "load_file: NULL argument");
+    VO_CUDA(cudaSetDevice(c->device));
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) { set_error("could not open methylation file %s", path); return VAMPOMI_ERR_IO; }
+    const size_t col_bytes = (size_t)c->N * sizeof(double);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size < (size_t)(c->S + c->M) * col_bytes) {
+        close(fd);
+        set_error("%s is too short for N=%d and markers [%lld,%lld)", path, c->N, c->S, c->S + c->M);
+        return VAMPOMI_ERR_IO;
+    }
+    // ring of pinned staging buffers: pread into slot k while the copies of slots k-1, k-2 are still in flight
+    constexpr int NSLOT = 3;
+    long long cols_per_slot = (long long)((64ull << 20) / col_bytes);
+    if (cols_per_slot < 1) cols_per_slot = 1;
+    if (cols_per_slot > c->M) cols_per_slot = c->M;
+    double* slot[NSLOT] = {};
+    cudaEvent_t ev[NSLOT] = {};
+    int rc = [&]() -> int {
+        for (int k = 0; k < NSLOT; k++) {
+            VO_CUDA(cudaMallocHost(&slot[k], (size_t)cols_per_slot * col_bytes));
+            VO_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+        }
+        int k = 0;
+        for (long long j = 0; j < c->M; j += cols_per_slot, k = (k + 1) % NSLOT) {
+            long long nc = c->M - j < cols_per_slot ? c->M - j : cols_per_slot;
+            VO_CUDA(cudaEventSynchronize(ev[k]));                     // slot free again?
+            size_t want = (size_t)nc * col_bytes, got = 0;
+            off_t off = (off_t)((size_t)(c->S + j) * col_bytes);      // byte offset S*N*8, src/data.cpp:134
+            while (got < want) {
+                ssize_t r = pread(fd, (char*)slot[k] + got, want - got, off + (off_t)got);
+                if (r <= 0) { set_error("short read from %s", path); return VAMPOMI_ERR_IO; }
+                got += (size_t)r;
+            }
+            VO_CUDA(cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), slot[k], col_bytes, col_bytes, (size_t)nc,
+                                      cudaMemcpyHostToDevice, c->copy_stream));
+            VO_CUDA(cudaEventRecord(ev[k], c->copy_stream));
+        }
+        VO_CUDA(cudaStreamSynchronize(c->copy_stream));
+        return VAMPOMI_OK;
+    }();
+    close(fd);
+    for (int k = 0; k < NSLOT; k++) { if (slot[k]) cudaFreeHost(slot[k]); if (ev[k]) cudaEventDestroy(ev[k]); }
+    c->stats_ready = false;
+    return rc;
+}
+
+int vampomi_generate_iid(vampomi_ctx* c, unsigned long long seed) {
+    VO_ARG(c, "generate_iid: NULL context");
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(launch_generate_iid(c, seed));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_ready = false;
+    return VAMPOMI_OK;
+}
+
+int vampomi_compute_stats(vampomi_ctx* c, double alpha_scale) {
+    VO_ARG(c, "compute_stats: NULL context");
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(launch_stats(c, alpha_scale));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats_ready = true;
+    return VAMPOMI_OK;
+}
+
+int vampomi_get_stats(vampomi_ctx* c, double* mave, double* msig) {
+    VO_ARG(c && mave && msig, "get_stats: NULL argument");
+    if (!c->stats_ready) { set_error("get_stats before compute_stats"); return VAMPOMI_ERR_STATE; }
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(d2h_vec(c, mave, c->mave, c->M));
+    VO_CHECK(d2h_vec(c, msig, c->msig, c->M));
+    return VAMPOMI_OK;
+}
+
+#define NEED_STATS(c, what) \
+    do { if (!(c)->stats_ready) { set_error(what " before compute_stats"); return VAMPOMI_ERR_STATE; } } while (0)
+
+int vampomi_atx(vampomi_ctx* c, const double* p_N, double* out_M) {
+    VO_ARG(c && p_N && out_M, "atx: NULL argument");
+    NEED_STATS(c, "atx");
+    VO_CUDA(cudaSetDevice(c->device));
+    double* p = c->nvec[VAMPOMI_V_TMP_N1 - 32];
+    double* o = c->mvec[VAMPOMI_V_TMP_M1];
+    VO_CHECK(h2d_vec(c, p, p_N, c->N));
+    VO_CHECK(launch_atx(c, p, o, nullptr));
+    VO_CHECK(d2h_vec(c, out_M, o, c->M));
+    return VAMPOMI_OK;
+}
+
+int vampomi_ax(vampomi_ctx* c, const double* x_M, double* out_N) {
+    VO_ARG(c && x_M && out_N, "ax: NULL argument");
+    NEED_STATS(c, "ax");
+    VO_CUDA(cudaSetDevice(c->device));
+    double* x = c->mvec[VAMPOMI_V_TMP_M1];
+    double* o = c->nvec[VAMPOMI_V_TMP_N1 - 32];
+    VO_CHECK(h2d_vec(c, x, x_M, c->M));
+    VO_CHECK(launch_ax(c, x, o, nullptr));
+    VO_CHECK(d2h_vec(c, out_N, o, c->N));
+    return VAMPOMI_OK;
+}
+
+// ---- vectors ----------------------------------------------------------------------------------------------------
+int vampomi_vec_len(const vampomi_ctx* c, int vec, long long* len) {
+    VO_ARG(c && len && vec_len(c, vec) >= 0, "vec_len: bad vector id %d", vec);
+    *len = vec_len(c, vec);
+    return VAMPOMI_OK;
+}
+int vampomi_vec_set(vampomi_ctx* c, int vec, const double* host) {
+    VO_ARG(c && host && vec_ptr(c, vec), "vec_set: bad vector id %d or NULL buffer", vec);
+    VO_CUDA(cudaSetDevice(c->device));
+    return h2d_vec(c, vec_ptr(c, vec), host, vec_len(c, vec));
+}
+int vampomi_vec_get(vampomi_ctx* c, int vec, double* host) {
+    VO_ARG(c && host && vec_ptr(c, vec), "vec_get: bad vector id %d or NULL buffer", vec);
+    VO_CUDA(cudaSetDevice(c->device));
+    return d2h_vec(c, host, vec_ptr(c, vec), vec_len(c, vec));
+}
+int vampomi_vec_get_scaled(vampomi_ctx* c, int vec, double divisor, double* host) {
+    VO_ARG(c && host && vec_ptr(c, vec), "vec_get_scaled: bad vector id %d or NULL buffer", vec);
+    VO_CUDA(cudaSetDevice(c->device));
+    const bool m = is_mvec(vec);
+    double* tmp = m ? c->mvec[VAMPOMI_V_TMP_M1] : c->nvec[VAMPOMI_V_TMP_N1 - 32];
+    VO_CHECK(launch_scale_div(c, tmp, vec_ptr(c, vec), divisor, vec_len(c, vec), nullptr));
+    return d2h_vec(c, host, tmp, vec_len(c, vec));
+}
+int vampomi_vec_fill(vampomi_ctx* c, int vec, double value) {
+    VO_ARG(c && vec_ptr(c, vec), "vec_fill: bad vector id %d", vec);
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_fill(c, vec_ptr(c, vec), vec_len(c, vec), value);
+}
+int vampomi_vec_copy(vampomi_ctx* c, int dst, int src) {
+    VO_ARG(c && vec_ptr(c, dst) && vec_ptr(c, src) && is_mvec(dst) == is_mvec(src), "vec_copy: bad vector ids %d <- %d", dst, src);
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CUDA(cudaMemcpyAsync(vec_ptr(c, dst), vec_ptr(c, src), (size_t)vec_len(c, dst) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return VAMPOMI_OK;
+}
+int vampomi_vec_lincomb(vampomi_ctx* c, int dst, double a, int x, double b, int y, double cdiv) {
+    VO_ARG(c && vec_ptr(c, dst) && vec_ptr(c, x) && vec_ptr(c, y) && is_mvec(dst) == is_mvec(x) && is_mvec(dst) == is_mvec(y),
+           "vec_lincomb: bad vector ids %d <- %d, %d", dst, x, y);
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_lincomb(c, vec_ptr(c, dst), a, vec_ptr(c, x), b, vec_ptr(c, y), cdiv, vec_len(c, dst));
+}
+
+int vampomi_dots(vampomi_ctx* c, int n, const int* kind, const int* a, const int* b, const double* scale, double* out) {
+    VO_ARG(c && kind && a && b && out && n >= 1 && n <= MAX_DOTS, "dots: need 1..%d items", MAX_DOTS);
+    VO_CUDA(cudaSetDevice(c->device));
+    const double* pa[MAX_DOTS]; const double* pb[MAX_DOTS]; long long len[MAX_DOTS];
+    bool any_m = false;
+    for (int i = 0; i < n; i++) {
+        VO_ARG(vec_ptr(c, a[i]) && vec_ptr(c, b[i]) && is_mvec(a[i]) == is_mvec(b[i]) && kind[i] >= 0 && kind[i] <= 2,
+               "dots: item %d is malformed", i);
+        pa[i] = vec_ptr(c, a[i]); pb[i] = vec_ptr(c, b[i]); len[i] = vec_len(c, a[i]);
+        any_m |= is_mvec(a[i]);
+    }
+    VO_CHECK(launch_dots(c, n, kind, pa, pb, len, scale, c->sums));
+    if (c->nranks > 1 && any_m) {
+        // N-vector items are replicated: divide them by nranks after the packed sum so that one all-reduce serves all
+        VO_CHECK(allreduce_inplace(c, c->sums, (size_t)n));
+    }
+    VO_CHECK(fetch_sums(c, n, false, out));
+    if (c->nranks > 1 && any_m)
+        for (int i = 0; i < n; i++) if (!is_mvec(a[i])) out[i] /= (double)c->nranks;
+    return VAMPOMI_OK;
+}
+
+int vampomi_draw_probe(vampomi_ctx* c, unsigned long long seed, int it) {
+    VO_ARG(c, "draw_probe: NULL context");
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_probe(c, seed, it);
+}
+
+int vampomi_ax_dev(vampomi_ctx* c, int x_vec, int out_vec) {
+    VO_ARG(c && is_mvec(x_vec) && vec_ptr(c, out_vec) && !is_mvec(out_vec), "ax_dev: need M-vector in, N-vector out");
+    NEED_STATS(c, "ax_dev");
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_ax(c, vec_ptr(c, x_vec), vec_ptr(c, out_vec), nullptr);
+}
+int vampomi_atx_dev(vampomi_ctx* c, int p_vec, int out_vec) {
+    VO_ARG(c && vec_ptr(c, p_vec) && !is_mvec(p_vec) && is_mvec(out_vec), "atx_dev: need N-vector in, M-vector out");
+    NEED_STATS(c, "atx_dev");
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_atx(c, vec_ptr(c, p_vec), vec_ptr(c, out_vec), nullptr);
+}
+
+// ---- denoiser / EM / probit ----------------------------------------------------------------------------------------
+static int fill_mix(MixParams& mp, const double* probs, const double* vars, int L) {
+    VO_ARG(probs && vars && L >= 1 && L <= MAX_MIX, "mixture: need 1..%d components (got %d)", MAX_MIX, L);
+    mp.L = L;
+    for (int i = 0; i < MAX_MIX; i++) { mp.probs[i] = i < L ? probs[i] : 0.0; mp.vars[i] = i < L ? vars[i] : 0.0; }
+    return VAMPOMI_OK;
+}
+
+int vampomi_denoise(vampomi_ctx* c, double gam1, const double* probs, const double* vars, int L, int damp, double rho,
+                    double* sum_g1d) {
+    VO_ARG(c && sum_g1d, "denoise: NULL argument");
+    VO_CUDA(cudaSetDevice(c->device));
+    MixParams mp;
+    VO_CHECK(fill_mix(mp, probs, vars, L));
+    VO_CHECK(launch_denoise(c, gam1, mp, damp, rho, c->sums));
+    return fetch_sums(c, 1, true, sum_g1d);                         // MPI_Allreduce of sum_d, src/vamp.cpp:222
+}
+
+int vampomi_em_sums(vampomi_ctx* c, double gam1, double lambda, const double* omegas, const double* vars, int L, double* sums) {
+    VO_ARG(c && sums, "em_sums: NULL argument");
+    VO_ARG(L >= 2, "em_sums: needs at least 2 mixture components");
+    VO_CUDA(cudaSetDevice(c->device));
+    MixParams mp;
+    VO_CHECK(fill_mix(mp, omegas, vars, L));
+    VO_CHECK(launch_em_sums(c, gam1, lambda, mp, c->sums));
+    return fetch_sums(c, 2 * L - 1, true, sums);                    // src/vamp.cpp:578,596,597 packed into one
+}
+
+int vampomi_probit_zdenoise(vampomi_ctx* c, double tau1, double* sum_g1d) {
+    VO_ARG(c && sum_g1d, "probit_zdenoise: NULL argument");
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(launch_probit_z(c, tau1, c->sums));
+    return fetch_sums(c, 1, false, sum_g1d);                        // N-vectors are replicated: no all-reduce
+}
+
+// ---- association tests ------------------------------------------------------------------------------------------
+int vampomi_pvals_se(vampomi_ctx* c, const double* r1_M, double gam1, double* pvals_M) {
+    VO_ARG(c && r1_M && pvals_M, "pvals_se: NULL argument");
+    VO_CUDA(cudaSetDevice(c->device));
+    double* r = c->mvec[VAMPOMI_V_TMP_M0];
+    double* o = c->mvec[VAMPOMI_V_TMP_M1];
+    VO_CHECK(h2d_vec(c, r, r1_M, c->M));
+    VO_CHECK(launch_pvals_se(c, r, sqrt(1.0 / (gam1 * (double)c->N)), o));
+    return d2h_vec(c, pvals_M, o, c->M);
+}
+
+int vampomi_loo_sums(vampomi_ctx* c, int w_vec, double* sums_3M) {
+    VO_ARG(c && sums_3M && vec_ptr(c, w_vec) && !is_mvec(w_vec), "loo_sums: need an N-vector id");
+    VO_CUDA(cudaSetDevice(c->device));
+    double* dsums = nullptr;
+    VO_CUDA(cudaMalloc(&dsums, (size_t)3 * c->M * sizeof(double)));
+    int rc = launch_loo_sums(c, vec_ptr(c, w_vec), dsums);
+    if (rc == VAMPOMI_OK) rc = d2h_vec(c, sums_3M, dsums, 3 * c->M);
+    cudaFree(dsums);
+    return rc;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------------------------
+int vampomi_counters(vampomi_ctx* c, long long out[4], int reset) {
+    VO_ARG(c && out, "counters: NULL argument");
+    for (int i = 0; i < 4; i++) { out[i] = c->counters[i]; if (reset) c->counters[i] = 0; }
+    return VAMPOMI_OK;
+}
+
+int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
+    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 3, "time_kernel: bad arguments");
+    if (which != 2) NEED_STATS(c, "time_kernel");
+    VO_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    VO_CUDA(cudaEventCreate(&e0));
+    VO_CUDA(cudaEventCreate(&e1));
+    double* dsums = nullptr;
+    if (which == 3) VO_CUDA(cudaMalloc(&dsums, (size_t)3 * c->M * sizeof(double)));
+    long long saved[4];
+    memcpy(saved, c->counters, sizeof(saved));
+    int rc = VAMPOMI_OK;
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    VO_CUDA(cudaEventRecord(e0, c->stream));
+    for (int r = 0; r < reps && rc == VAMPOMI_OK; r++) {
+        switch (which) {
+            case 0: rc = launch_ax(c, c->mvec[VAMPOMI_V_TMP_M1], c->nvec[VAMPOMI_V_TMP_N1 - 32], nullptr); break;
+            case 1: rc = launch_atx(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], c->mvec[VAMPOMI_V_TMP_M1], nullptr); break;
+            case 2: rc = launch_stats(c, 1.0); break;
+            default: rc = launch_loo_sums(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], dsums); break;
+        }
+    }
+    VO_CUDA(cudaEventRecord(e1, c->stream));
+    VO_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    VO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_avg = (double)ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (dsums) cudaFree(dsums);
+    memcpy(c->counters, saved, sizeof(saved));
+    return rc;
+}
+
+int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
+    VO_ARG(c && name, "set_tuning: NULL argument");
+    struct { const char* n; int* p; int lo, hi; } knobs[] = {
+        {"ax_rv", &c->tune.ax_rv, 1, 4},           {"ax_unroll", &c->tune.ax_unroll, 2, 8},
+        {"ax_ctas_per_sm", &c->tune.ax_ctas_per_sm, 0, 32}, {"atx_cols", &c->tune.atx_cols, 1, 4},
+        {"atx_unroll", &c->tune.atx_unroll, 2, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
+        {"cg_depth", &c->tune.cg_depth, 1, 32},
+    };
+    for (auto& k : knobs)
+        if (!strcmp(k.n, name)) {
+            VO_ARG(value >= k.lo && value <= k.hi, "set_tuning: %s must be in [%d,%d]", name, k.lo, k.hi);
+            *k.p = value;
+            return VAMPOMI_OK;
+        }
+    set_error("set_tuning: unknown knob %s", name);
+    return VAMPOMI_ERR_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,152 @@
+// Internal declarations of libvampomi_cuda.so (not part of the public ABI; see include/vampomi.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/vampomi.h"
+
+namespace vampomi {
+
+void set_error(const char* fmt, ...);
+
+#define VO_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            vampomi::set_error("CUDA error %s at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return VAMPOMI_ERR_CUDA;                                                                    \
+        }                                                                                               \
+    } while (0)
+
+#define VO_CHECK(expr)                 \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != VAMPOMI_OK) return rc__; \
+    } while (0)
+
+#define VO_ARG(cond, ...)                      \
+    do {                                       \
+        if (!(cond)) {                         \
+            vampomi::set_error(__VA_ARGS__);   \
+            return VAMPOMI_ERR_ARG;            \
+        }                                      \
+    } while (0)
+
+// NCCL is loaded lazily with dlopen("libnccl.so.2"): inside a torch process that resolves to the already-mapped
+// torch-bundled library, in the standalone host binary to the system one. Single-GPU use never touches it.
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+int nccl_load(NcclApi** api);
+
+constexpr int MAX_MIX = 32;          // mixture components the denoiser/EM kernels accept
+constexpr int RED_BLOCKS = 296;      // grid size of vector kernels (2 CTAs x 148 SMs)
+constexpr int RED_THREADS = 256;
+constexpr int MAX_DOTS = 16;         // reductions per vampomi_dots() call
+constexpr int MAX_SUMS = 64;         // doubles in the packed scalar all-reduce buffer
+
+struct MixParams {                   // passed by value to the denoiser / EM kernels
+    int L;
+    double probs[MAX_MIX];           // probs (denoiser) or omegas (EM)
+    double vars[MAX_MIX];
+};
+
+struct CgScalars {                   // device-resident CG scalars (src/vamp.cpp:694-751); slot = iteration parity
+    double rz[2];
+    double prev_onsager[2];
+    double vv;
+    double rel_err;
+    double vmu;
+    int done;                        // 0 running, 1 onsager test, 2 residual test, 3 max_iter
+    int iters;
+};
+
+struct Tuning {
+    int ax_rv = 2;                   // 256-bit vectors per thread per column in Ax (tile = 1024*rv rows)
+    int ax_unroll = 4;               // columns in flight per thread
+    int ax_ctas_per_sm = 0;              // 0 = one resident wave (occupancy query)
+    int atx_cols = 2;                // columns per warp pass in ATx
+    int atx_unroll = 4;
+    int atx_ctas_per_sm = 0;
+    int cg_depth = 2;                // CG iterations kept enqueued ahead of the completion poll
+};
+
+}  // namespace vampomi
+
+struct vampomi_ctx {
+    int device = 0, N = 0, nranks = 1, rank = 0, num_sms = 148;
+    long long Mt = 0, M = 0, S = 0;
+    size_t ld = 0;                   // column stride of A in doubles (N rounded up to 16)
+    size_t mpad = 0;                 // allocated length of M-vectors
+    bool stats_ready = false;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    double* A = nullptr;             // [M][ld] column-major block in HBM
+    double* mave = nullptr;
+    double* msig = nullptr;
+    double* mvec[VAMPOMI_V_NUM_M] = {};
+    double* nvec[VAMPOMI_V_NUM_N] = {};
+    double* ax_partial = nullptr;    // [ax_chunks][ld]
+    size_t ax_partial_elems = 0;
+    double* red_partials = nullptr;  // [MAX_DOTS][RED_BLOCKS][MAX_SUMS] scratch of the deterministic reductions
+    unsigned int* red_tickets = nullptr;
+    double* sums = nullptr;          // [MAX_SUMS] packed scalars (device), all-reduced in place
+    double* sums_host = nullptr;     // pinned mirror
+    vampomi::CgScalars* cg = nullptr;
+    int* cg_poll_host = nullptr;     // pinned ring of done flags
+    double* stage = nullptr;         // pinned staging for host<->device vector traffic (max(M,N,3M) doubles)
+    size_t stage_elems = 0;
+    ncclComm_t comm = nullptr;
+    vampomi::NcclApi* nccl = nullptr;
+    vampomi::Tuning tune;
+    long long counters[4] = {0, 0, 0, 0};
+};
+
+namespace vampomi {
+
+inline double* vec_ptr(const vampomi_ctx* c, int id) {
+    if (id >= 0 && id < VAMPOMI_V_NUM_M) return c->mvec[id];
+    if (id >= 32 && id < 32 + VAMPOMI_V_NUM_N) return c->nvec[id - 32];
+    return nullptr;
+}
+inline long long vec_len(const vampomi_ctx* c, int id) {
+    if (id >= 0 && id < VAMPOMI_V_NUM_M) return c->M;
+    if (id >= 32 && id < 32 + VAMPOMI_V_NUM_N) return c->N;
+    return -1;
+}
+inline bool is_mvec(int id) { return id >= 0 && id < VAMPOMI_V_NUM_M; }
+
+// ---- launchers (kernels_matrix.cu) ----
+int launch_generate_iid(vampomi_ctx* c, uint64_t seed);
+int launch_stats(vampomi_ctx* c, double alpha_scale);
+int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag);     // incl. all-reduce and 1/sqrt(N)
+int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
+int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev);
+// ---- launchers (kernels_vector.cu) ----
+int launch_fill(vampomi_ctx* c, double* dst, long long n, double v);
+int launch_lincomb(vampomi_ctx* c, double* dst, double a, const double* x, double b, const double* y, double cdiv, long long n);
+int launch_scale_div(vampomi_ctx* c, double* dst, const double* src, double divisor, long long n, const int* done_flag);
+int launch_dots(vampomi_ctx* c, int n, const int* kind, const double* const* a, const double* const* b, const long long* len,
+                const double* scale, double* sums_dev);
+int launch_probe(vampomi_ctx* c, uint64_t seed, int it);
+int launch_denoise(vampomi_ctx* c, double gam1, const MixParams& mp, int damp, double rho, double* sums_dev);
+int launch_em_sums(vampomi_ctx* c, double gam1, double lambda, const MixParams& mp, double* sums_dev);
+int launch_probit_z(vampomi_ctx* c, double tau1, double* sums_dev);
+int launch_pvals_se(vampomi_ctx* c, const double* r1_dev, double sd, double* out_dev);
+int launch_cg_init(vampomi_ctx* c, const double* v, double* mu, const double* atx_out, int warm, double tau, double gam2,
+                   double diag, double* sums_dev);
+int launch_cg_init_finish(vampomi_ctx* c, const double* sums_dev);
+int launch_cg_dp(vampomi_ctx* c, const double* atx_out, double tau, double gam2, double* sums_dev);
+int launch_cg_step(vampomi_ctx* c, const double* v, double* mu, double diag, int parity, const double* dp_dev, double* sums_dev);
+int launch_cg_finish(vampomi_ctx* c, int parity, double gam2, double tol, int max_iter, int onsager_mode, const double* sums_dev);
+// all-reduce `n` doubles in place on the context stream (no-op for nranks == 1)
+int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n);
+
+}  // namespace vampomi

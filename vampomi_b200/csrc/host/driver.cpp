@@ -1,0 +1,313 @@
+// main_meth's program logic (reference: src/main_meth.cpp:9-270) over the kernel ABI. One "rank" = one marker shard on
+// one GPU; with --gpus G the G ranks run as threads of this process and meet in NCCL collectives, where the reference
+// runs G MPI processes. Output files, their byte layout, stdout landmarks and exit codes follow the reference.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+#include <vector>
+#include "../../../include/vampomi_host.h"
+#include "io.h"
+#include "options.h"
+#include "vamp.h"
+
+namespace vampomi_host {
+namespace {
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct Rank {
+    const Options& opt;
+    int rank, nranks;
+    const void* nccl_id;
+    vampomi_ctx* ctx = nullptr;
+    long long M = 0, S = 0;
+    bool root() const { return rank == 0; }
+};
+
+int fatal(const Rank& r, const std::string& msg) {
+    if (r.root() || r.nranks > 1) std::cout << "FATAL: " << msg << std::endl;
+    return 1;
+}
+int fatal_abi(const Rank& r, const char* what) {
+    std::cout << "FATAL: " << what << " failed on rank " << r.rank << ": " << vampomi_last_error() << std::endl;
+    return 1;
+}
+
+// `class data` constructor (src/data.cpp:24-47): phenotype, marker block into HBM, marker statistics.
+int load_dataset(Rank& r, const std::string& phenfp, const std::string& methfp, int N, std::vector<double>* y) {
+    if (!read_phen(phenfp, r.opt.model != "bin_class", y)) return 1;                  // src/data.cpp:40-43
+    if ((int)y->size() != N) {
+        std::cout << "FATAL: phenotype file " << phenfp << " has " << y->size() << " rows but --N is " << N << std::endl;
+        return 1;                                                                      // assert(nas + nonas == N), :85
+    }
+    int ndev = 0;
+    if (vampomi_device_count(&ndev) != VAMPOMI_OK) return fatal_abi(r, "device query");
+    if (r.nranks > ndev) return fatal(r, "--gpus " + std::to_string(r.nranks) + " exceeds the " + std::to_string(ndev) + " visible CUDA devices");
+    if (vampomi_create(r.rank, N, (long long)r.opt.Mt, r.nranks, r.rank, &r.ctx) != VAMPOMI_OK) return fatal_abi(r, "vampomi_create");
+    if (r.nranks > 1 && vampomi_comm_init(r.ctx, r.nccl_id) != VAMPOMI_OK) return fatal_abi(r, "vampomi_comm_init");
+    if (r.root()) std::cout << "meth file name = " << methfp << std::endl;            // :123
+    printf("INFO  : rank %d has allocated %zu bytes (%.3f GB) for raw data.\n", r.rank, (size_t)r.M * (size_t)N * 8,
+           double((size_t)r.M * (size_t)N * 8) / 1.0E9);                               // :131
+    double ts = now_s();
+    if (vampomi_load_file(r.ctx, methfp.c_str()) != VAMPOMI_OK) return fatal_abi(r, "loading the methylation data");
+    double te = now_s();
+    if (r.root()) std::cout << "reading methylation data took " << te - ts << " seconds." << std::endl;   // :151
+    if (vampomi_compute_stats(r.ctx, r.opt.alpha_scale) != VAMPOMI_OK) return fatal_abi(r, "marker statistics");
+    if (r.root()) std::cout << "rank = " << r.rank << ": statistics took " << now_s() - te << " seconds to run." << std::endl;   // :281
+    return 0;
+}
+
+// src/utilities.cpp:104-122 — whitespace-separated text estimates, entries [S, S+M)
+std::vector<double> read_text_vec(const std::string& path, long long M, long long S) {
+    std::vector<double> v;
+    std::ifstream in(path);
+    double value;
+    long long it = 0;
+    while (in >> value) {
+        if (it >= S && it < S + M) v.push_back(value);
+        else if (it >= S + M) break;
+        it++;
+    }
+    v.resize((size_t)M, 0.0);
+    return v;
+}
+
+int run_infere(Rank& r) {
+    const Options& o = r.opt;
+    const int N = (int)o.N;
+    std::vector<double> y;
+    if (int rc = load_dataset(r, o.phen_file, o.meth_file, N, &y)) return rc;
+
+    std::vector<double> true_signal((size_t)r.M, 0.0), x1hat_init((size_t)r.M, 0.0);
+    if (!o.true_signal_file.empty()) true_signal = read_vec(o.true_signal_file, r.M, r.S);     // src/main_meth.cpp:69-73
+    if (!o.estimate_file.empty()) x1hat_init = read_vec(o.estimate_file, r.M, r.S);            // :75-80
+
+    vampomi_solver_config cfg;
+    vampomi_solver_default_config(&cfg);
+    if (o.model == "linear") cfg.model = 0;
+    else if (o.model == "bin_class") cfg.model = 1;
+    else throw std::runtime_error("Invalid model specification!");                             // src/vamp.cpp:104
+    cfg.gam1 = o.gam1;
+    cfg.gamw = 1.0 / (1.0 - o.h2);                                                             // src/main_meth.cpp:52
+    cfg.rho = o.rho;
+    cfg.CG_max_iter = (int)o.CG_max_iter; cfg.CG_err_tol = o.CG_err_tol;
+    cfg.EM_max_iter = (int)o.EM_max_iter; cfg.EM_err_thr = o.EM_err_thr;
+    cfg.learn_vars = (int)o.learn_vars; cfg.learn_prior_delay = (int)o.learn_prior_delay;
+    cfg.merge_vars_thr = o.merge_vars_thr;
+    if (o.probs.size() != o.vars.size() || o.probs.empty() || o.probs.size() > VAMPOMI_MAX_MIX)
+        return fatal(r, "--probs and --vars must have the same length, between 1 and " + std::to_string(VAMPOMI_MAX_MIX));
+    cfg.L = (int)o.probs.size();
+    for (int i = 0; i < cfg.L; i++) { cfg.probs[i] = o.probs[i]; cfg.vars[i] = o.vars[i]; }
+    cfg.seed = o.seed;
+    cfg.redundant_passes = 0;
+
+    Vamp vamp(r.ctx, cfg);
+    vamp.verbose = r.root();
+    vamp.verbosity = o.verbosity;
+    if (vamp.init(y.data(), true_signal.data(), x1hat_init.data()) != VAMPOMI_OK) return fatal_abi(r, "solver initialisation");
+
+    // setup_io (src/vamp.cpp:854-882): rank 0 owns the three CSVs
+    const std::string base = o.out_dir + "/" + o.out_name;
+    CsvFile csv_metrics, csv_params, csv_prior;
+    if (r.root()) {
+        if (!csv_metrics.open(base + "_metrics.csv") || !csv_params.open(base + "_params.csv") || !csv_prior.open(base + "_prior.csv")) {
+            fprintf(stderr, "*FATAL*: could not create the CSV files under %s\n", o.out_dir.c_str());   // check_mpi abort
+            return 1;
+        }
+        if (cfg.model == 0) {                                                                  // headers only in infere_linear, src/vamp.cpp:115-123
+            csv_metrics.header({"iteration", "R2 denoising", "x1 correlation denoising", "R2 LMMSE", "x2 correlation LMMSE",
+                                "z1 correlation denoising", "z2 correlation LMMSE"});
+            csv_params.header({"iteration", "alpha1", "gam1", "alpha2", "gam2", "gamw"});
+            std::vector<std::string> ph{"iteration", "number of components"};
+            for (size_t i = 0; i < o.probs.size(); i++) ph.push_back("prob" + std::to_string(i));
+            for (size_t i = 0; i < o.vars.size(); i++) ph.push_back("var" + std::to_string(i));
+            csv_prior.header(ph);
+        }
+    }
+
+    std::vector<double> x1s((size_t)r.M), r1s((size_t)r.M);
+    double total_time = 0;
+    const int max_iter = (int)o.iterations;
+    for (int it = 1; it <= max_iter; it++) {
+        if (r.root())
+            std::cout << std::endl << "********************" << std::endl << "iteration = " << it << std::endl
+                      << "********************" << std::endl;
+        const double t0 = now_s();
+        vampomi_iter_result res;
+        if (vamp.step(&res, x1s.data(), r1s.data()) != VAMPOMI_OK) return fatal_abi(r, "VAMP iteration");
+        const double t1 = now_s();
+        const std::string f_x1 = base + "_it_" + std::to_string(it) + ".bin";                  // src/vamp.cpp:235-249
+        const std::string f_r1 = base + "_r1_it_" + std::to_string(it) + ".bin";
+        if (!store_vec(f_x1, x1s.data(), r.M, r.S) || !store_vec(f_r1, r1s.data(), r.M, r.S))
+            return fatal(r, "could not write " + f_x1);
+        if (r.root()) {
+            std::cout << "x1_hat filepath_out is " << f_x1 << std::endl << "r1_hat filepath_out is " << f_r1 << std::endl;
+            std::cout << "[CG] LMMSE solve: " << res.cg_iters_lmmse << " iterations, onsager solve: " << res.cg_iters_onsager
+                      << " iterations, matrix passes: " << res.matrix_passes << std::endl;
+            std::cout << "...storing parameters to CSV files" << std::endl;
+            csv_params.row(it, std::vector<double>(res.params, res.params + res.n_params));    // :390-391
+            csv_metrics.row(it, std::vector<double>(res.metrics, res.metrics + res.n_metrics));
+            if (cfg.model == 1) {                                                              // src/vamp_probit.cpp:423-434
+                std::vector<double> prior{(double)res.L};
+                prior.insert(prior.end(), res.probs, res.probs + res.L);
+                prior.insert(prior.end(), res.vars, res.vars + res.L);
+                csv_prior.row(it, prior);
+            }
+            total_time += t1 - t0;
+            std::cout << "Total iteration time = " << t1 - t0 << std::endl;                    // src/vamp.cpp:400-401
+            std::cout << "Total computation time so far = " << total_time << std::endl;
+            std::cout << "...stopping criteria assessment" << std::endl;
+            std::cout << "x1_hat NMSE = " << res.nmse << std::endl;                            // :415-417
+            std::cout << "stop_criteria_thr = " << o.stop_criteria_thr << std::endl;
+        }
+        if (it > 1 && res.nmse < o.stop_criteria_thr) {                                        // :419-423
+            if (r.root()) std::cout << "...stopping criteria fulfilled" << std::endl;
+            break;
+        }
+        if (it == max_iter && r.root())
+            std::cout << "...maximal number of iterations was achieved. The algorithm might not converge!" << std::endl;
+    }
+    return 0;
+}
+
+int run_test(Rank& r) {                                                                        // src/main_meth.cpp:112-205
+    const Options& o = r.opt;
+    const int N_test = (int)o.N_test;
+    std::vector<double> y;
+    if (int rc = load_dataset(r, o.phen_file_test, o.meth_file_test, N_test, &y)) return rc;
+    CsvFile csv;
+    if (r.root()) {
+        if (!csv.open(o.out_dir + "/" + o.out_name + "_test.csv")) { fprintf(stderr, "*FATAL*: could not create _test.csv\n"); return 1; }
+        csv.header({"iteration", "R2 test", "z correlation test"});
+    }
+    const std::string est = o.estimate_file;
+    const size_t pos_dot = est.find(".");                                                      // :151 (first dot, sic)
+    const std::string ext = pos_dot == std::string::npos ? est : est.substr(pos_dot + 1);
+    const size_t pos_it = est.rfind("it");
+    if (r.root()) std::cout << "est_file_name = " << est << std::endl
+                            << "iter range = [" << o.test_iter_range[0] << ", " << o.test_iter_range[1] << "]" << std::endl;
+    std::vector<double> z((size_t)N_test);
+    for (int it = o.test_iter_range[0]; it <= o.test_iter_range[1]; it++) {
+        const std::string f = est.substr(0, pos_it) + "it_" + std::to_string(it) + "." + ext;  // :166
+        std::vector<double> x = ext == "bin" ? read_vec(f, r.M, r.S) : read_text_vec(f, r.M, r.S);
+        for (double& v : x) v *= std::sqrt((double)N_test);                                    // :174-175
+        if (vampomi_ax(r.ctx, x.data(), z.data()) != VAMPOMI_OK) return fatal_abi(r, "Ax");    // :178
+        double l2 = 0, zy = 0, zz = 0, yy = 0;
+        for (int i = 0; i < N_test; i++) {
+            l2 += (y[i] - z[i]) * (y[i] - z[i]);
+            zy += z[i] * y[i]; zz += z[i] * z[i]; yy += y[i] * y[i];
+        }
+        const double sd = calc_stdev(y);
+        const double r2 = 1 - l2 / (sd * sd * y.size());                                       // :187-188
+        const double corr_y = (zy * r.nranks) / std::sqrt((zz * r.nranks) * (yy * r.nranks));  // :191 (sync=1 on replicated vectors)
+        if (r.root()) {
+            std::cout << r2 << ", ";
+            csv.row(it, {r2, corr_y * corr_y});
+        }
+    }
+    return 0;
+}
+
+int run_association(Rank& r) {                                                                 // src/main_meth.cpp:206-265
+    const Options& o = r.opt;
+    const int N = (int)o.N;
+    std::vector<double> y;
+    if (int rc = load_dataset(r, o.phen_file, o.meth_file, N, &y)) return rc;
+    auto iter_tag = [](const std::string& name, std::string* tag) -> bool {                    // :223-226
+        size_t p1 = name.rfind("it_"), p2 = name.rfind(".bin");
+        if (p1 == std::string::npos || p2 == std::string::npos || p2 < p1 + 3) return false;
+        *tag = name.substr(p1 + 3, p2 - (p1 + 3));
+        try { (void)std::stoi(*tag); } catch (...) { return false; }
+        return true;
+    };
+    std::vector<double> pvals((size_t)r.M, 0.0);
+    std::string out, tag;
+    if (o.pval_method == "se") {
+        if (!iter_tag(o.r1_file, &tag)) return fatal(r, "cannot parse the iteration number from --r1-file " + o.r1_file);
+        if (r.root()) std::cout << o.r1_file << std::endl;
+        std::vector<double> r1 = read_vec(o.r1_file, r.M, r.S);
+        if (vampomi_pvals_se(r.ctx, r1.data(), o.gam1, pvals.data()) != VAMPOMI_OK) return fatal_abi(r, "se p-values");
+        out = o.out_dir + "/" + o.out_name + "_it_" + tag + "_pval_se.bin";
+    } else if (o.pval_method == "loo") {
+        if (!iter_tag(o.estimate_file, &tag)) return fatal(r, "cannot parse the iteration number from --estimate-file " + o.estimate_file);
+        std::vector<double> x1 = read_vec(o.estimate_file, r.M, r.S);
+        const double sqrtN = std::sqrt((double)N);
+        for (double& v : x1) v *= sqrtN;                                                       // :254-255
+        // y_mod = y - A x1_hat (src/data.cpp:390-391), then one streaming pass for the per-marker sums
+        if (vampomi_vec_set(r.ctx, VAMPOMI_V_Y, y.data()) != VAMPOMI_OK || vampomi_vec_set(r.ctx, VAMPOMI_V_X1, x1.data()) != VAMPOMI_OK ||
+            vampomi_ax_dev(r.ctx, VAMPOMI_V_X1, VAMPOMI_V_Z1) != VAMPOMI_OK ||
+            vampomi_vec_lincomb(r.ctx, VAMPOMI_V_USER_N1, 1.0, VAMPOMI_V_Y, -1.0, VAMPOMI_V_Z1, 1.0) != VAMPOMI_OK)
+            return fatal_abi(r, "loo residual");
+        std::vector<double> w((size_t)N), sums((size_t)3 * r.M);
+        if (vampomi_vec_get(r.ctx, VAMPOMI_V_USER_N1, w.data()) != VAMPOMI_OK || vampomi_loo_sums(r.ctx, VAMPOMI_V_USER_N1, sums.data()) != VAMPOMI_OK)
+            return fatal_abi(r, "loo sums");
+        double sw = 0, sww = 0;
+        for (double v : w) { sw += v; sww += v * v; }
+        for (long long j = 0; j < r.M; j++) {
+            // y_mark = y_mod + x * c, c = x1_hat[j]/sqrt(N) (src/data.cpp:404-405): its sums follow from those of x and y_mod
+            const double c = x1[j] / sqrtN, sx = sums[3 * j], sxx = sums[3 * j + 1], sxw = sums[3 * j + 2];
+            const double sumy = sw + c * sx, sumxy = sxw + c * sxx, sumsqy = sww + 2 * c * sxw + c * c * sxx;
+            pvals[j] = linear_reg1d_pvals(sx, sxx, sumxy, sumy, sumsqy, N);                    // :414
+        }
+        out = o.out_dir + "/" + o.out_name + "_it_" + tag + "_pval_loo.bin";
+    } else {
+        return 0;                                                                              // the reference silently does nothing
+    }
+    if (r.root()) std::cout << "Storing p-values to file " + out << std::endl;
+    if (!store_vec(out, pvals.data(), r.M, r.S)) return fatal(r, "could not write " + out);
+    return 0;
+}
+
+int run_rank(const Options& opt, int rank, int nranks, const void* nccl_id) {
+    Rank r{opt, rank, nranks, nccl_id};
+    if (vampomi_divide_work((long long)opt.Mt, nranks, rank, &r.M, &r.S) != VAMPOMI_OK) return fatal_abi(r, "divide_work");
+    const long long Mm = opt.Mt % nranks != 0 ? opt.Mt / nranks + 1 : opt.Mt / nranks;
+    printf("INFO   : rank %4d has %lld markers over tot Mt = %u, max Mm = %lld, starting at S = %lld\n", rank, r.M, opt.Mt, Mm, r.S);   // src/utilities.cpp:231
+    int rc = 0;
+    try {
+        if (opt.run_mode == "infere") rc = run_infere(r);
+        else if (opt.run_mode == "test") rc = run_test(r);
+        else if (opt.run_mode == "association_test") rc = run_association(r);
+    } catch (const std::exception& e) {
+        std::cout << "FATAL: " << e.what() << std::endl;     // the reference throws string literals and terminates
+        rc = 1;
+    }
+    if (r.ctx) vampomi_destroy(r.ctx);
+    return rc;
+}
+
+}  // namespace
+}  // namespace vampomi_host
+
+extern "C" int vampomi_main(int argc, char** argv) {
+    using namespace vampomi_host;
+    Options opt;
+    std::string echo;
+    if (!opt.parse(argc, argv, &echo)) return 1;
+    std::cout << echo << std::endl;                                                            // rank 0 echo, src/options.cpp:288-289
+    if (opt.Mt == 0 || (opt.run_mode == "test" ? opt.N_test == 0 : opt.N == 0)) {
+        std::cout << "FATAL  : --Mt and --N (or --N-test in test mode) have to be given" << std::endl;
+        return 1;
+    }
+    const int G = opt.gpus;
+    if (G == 1) return run_rank(opt, 0, 1, nullptr);
+    char id[128];
+    if (vampomi_comm_get_unique_id(id) != VAMPOMI_OK) {
+        std::cout << "FATAL: NCCL bootstrap failed: " << vampomi_last_error() << std::endl;
+        return 1;
+    }
+    std::vector<int> rcs((size_t)G, 0);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++) th.emplace_back([&, g]() { rcs[g] = run_rank(opt, g, G, id); });
+    for (auto& t : th) t.join();
+    for (int rc : rcs) if (rc) return rc;
+    return 0;
+}

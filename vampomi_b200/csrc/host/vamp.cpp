@@ -1,0 +1,417 @@
+#include "vamp.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+#include "io.h"
+
+namespace vampomi_host {
+
+namespace {
+constexpr double kGammaMin = 1e-11, kGammaMax = 1e11;      // src/vamp.hpp:33-34
+inline double clampg(double g) { return std::min(std::max(g, kGammaMin), kGammaMax); }
+}  // namespace
+
+#define VH(call)                          \
+    do {                                  \
+        int rc__ = (call);                \
+        if (rc__ != VAMPOMI_OK) return rc__; \
+    } while (0)
+
+void merge_components(std::vector<double>& probs, std::vector<double>& vars, double thr) {
+    for (size_t j = 0; j < vars.size(); j++) {
+        for (size_t k = j + 1; k < vars.size(); k++) {
+            double denom = vars[j] != 0 ? std::min(vars[j], vars[k]) : 1e-7;
+            if (std::fabs(vars[j] - vars[k]) / denom < thr) {
+                double s = probs[j] + probs[k];
+                vars.erase(vars.begin() + k);
+                probs.erase(probs.begin() + k);
+                probs[j] = s;
+                k--;
+            }
+        }
+    }
+}
+
+Vamp::Vamp(vampomi_ctx* ctx, const vampomi_solver_config& cfg) : ctx_(ctx), cfg_(cfg) {
+    gam1_ = cfg.gam1;
+    gamw_ = cfg.gamw;
+}
+
+int Vamp::init(const double* y, const double* true_signal, const double* x1hat_init) {
+    VH(vampomi_dims(ctx_, &N_, &Mt_, nullptr, nullptr));
+    VH(vampomi_shard(ctx_, &M_, &S_));
+    if (cfg_.L < 1 || cfg_.L > VAMPOMI_MAX_MIX) return VAMPOMI_ERR_ARG;
+    probs_.assign(cfg_.probs, cfg_.probs + cfg_.L);
+    vars_.assign(cfg_.vars, cfg_.vars + cfg_.L);
+    for (double& v : vars_) v *= N_;                                            // src/vamp.cpp:87-88
+    y_host_.assign(y, y + N_);
+    zbuf_.assign((size_t)N_, 0.0);
+    VH(vampomi_vec_set(ctx_, VAMPOMI_V_Y, y));
+    std::vector<double> tmp((size_t)M_, 0.0);
+    if (true_signal) VH(vampomi_vec_set(ctx_, VAMPOMI_V_TRUE, true_signal));
+    else VH(vampomi_vec_set(ctx_, VAMPOMI_V_TRUE, tmp.data()));
+    if (x1hat_init) {                                                           // src/vamp.cpp:71-72,78-79 (with patch P1)
+        const double sq = std::sqrt((double)N_);
+        for (long long i = 0; i < M_; i++) tmp[i] = x1hat_init[i] / sq;
+    }
+    VH(vampomi_vec_set(ctx_, VAMPOMI_V_X1, tmp.data()));
+    VH(vampomi_vec_set(ctx_, VAMPOMI_V_R1, tmp.data()));
+    VH(vampomi_vec_fill(ctx_, VAMPOMI_V_X2, 0.0));
+    VH(vampomi_vec_fill(ctx_, VAMPOMI_V_R2, 0.0));
+    it_ = 0;
+    aty_ready_ = false;
+    if (cfg_.model == 1) {                                                      // src/vamp_probit.cpp:35-61
+        tau1_ = gam1_;
+        std::vector<double> p1 = probit_p1(cfg_.seed, N_);
+        VH(vampomi_vec_set(ctx_, VAMPOMI_V_P1, p1.data()));
+        VH(vampomi_vec_fill(ctx_, VAMPOMI_V_R1, 0.0));
+        VH(vampomi_vec_fill(ctx_, VAMPOMI_V_R2, 0.0));
+        alpha1_ = 0;
+        if (cfg_.redundant_passes) {                                            // true_g = A * true_signal_scaled (:46), unused
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, std::sqrt((double)N_), VAMPOMI_V_TRUE, 0.0, VAMPOMI_V_TRUE, 1.0));
+            VH(vampomi_ax_dev(ctx_, VAMPOMI_V_USER_M0, VAMPOMI_V_USER_N0));
+        }
+    }
+    return VAMPOMI_OK;
+}
+
+void Vamp::fill_prior(vampomi_iter_result* res) const {
+    res->L = (int)probs_.size();
+    for (int i = 0; i < VAMPOMI_MAX_MIX; i++) {
+        res->probs[i] = i < res->L ? probs_[i] : 0.0;
+        res->vars[i] = i < res->L ? vars_[i] : 0.0;
+    }
+}
+
+int Vamp::dump(double* x1_scaled, double* r1_scaled) {
+    const double sq = std::sqrt((double)N_);
+    if (x1_scaled) VH(vampomi_vec_get_scaled(ctx_, VAMPOMI_V_X1, sq, x1_scaled));   // src/vamp.cpp:237-239
+    if (r1_scaled) VH(vampomi_vec_get_scaled(ctx_, VAMPOMI_V_R1, sq, r1_scaled));   // :246-249
+    return VAMPOMI_OK;
+}
+
+// src/vamp.cpp:531-643 — the per-marker sums come from the device, everything else is L-length host arithmetic
+int Vamp::update_prior() {
+    double lambda = 1 - probs_[0];
+    std::vector<double> omegas = probs_;
+    for (size_t j = 1; j < omegas.size(); j++) omegas[j] /= lambda;
+    int em_it = 0;
+    for (em_it = 0; em_it < cfg_.EM_max_iter; em_it++) {
+        const int L = (int)probs_.size();
+        std::vector<double> probs_prev = probs_, vars_prev = vars_;
+        std::vector<double> sums((size_t)(2 * L - 1), 0.0);
+        VH(vampomi_em_sums(ctx_, gam1_, lambda, omegas.data(), vars_.data(), L, sums.data()));
+        const double lambda_total = sums[0];
+        lambda = lambda_total / (double)Mt_;                                    // :579
+        const double sum_of_pin = lambda_total;                                 // :587
+        for (int j = 0; j < L - 1; j++) {
+            const double res_total = sums[1 + j], res_gammas_total = sums[L + j];
+            if (cfg_.learn_vars == 1) vars_[j + 1] = res_gammas_total / res_total;   // :598-599
+            omegas[j + 1] = res_total / sum_of_pin;
+            probs_[j + 1] = lambda * omegas[j + 1];
+        }
+        probs_[0] = 1 - lambda;
+        double dp = 0, np = 0, dv = 0, nv = 0;
+        for (int j = 0; j < L; j++) {
+            dp += (probs_[j] - probs_prev[j]) * (probs_[j] - probs_prev[j]);
+            np += probs_[j] * probs_[j];
+            dv += (vars_[j] - vars_prev[j]) * (vars_[j] - vars_prev[j]);
+            nv += vars_[j] * vars_[j];
+        }
+        const double dist_probs = std::sqrt(dp / np), dist_vars = std::sqrt(dv / nv);
+        if (verbose && verbosity == 1)
+            std::cout << "it = " << em_it << ": dist_probs = " << dist_probs << " & dist_vars = " << dist_vars << std::endl;
+        if (dist_probs < cfg_.EM_err_thr && dist_vars < cfg_.EM_err_thr) break;
+    }
+    if (verbose && verbosity == 1)
+        std::cout << "Final number of prior EM iterations = " << std::min(em_it + 1, cfg_.EM_max_iter) << " / "
+                  << cfg_.EM_max_iter << std::endl;
+    merge_components(probs_, vars_, cfg_.merge_vars_thr);
+    return VAMPOMI_OK;
+}
+
+int Vamp::step(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
+    if (!res) return VAMPOMI_ERR_ARG;
+    if (Mt_ == 0) return VAMPOMI_ERR_STATE;
+    long long c0[4], c1[4];
+    VH(vampomi_counters(ctx_, c0, 0));
+    std::memset(res, 0, sizeof(*res));
+    it_++;
+    res->it = it_;
+    int rc = cfg_.model == 0 ? step_linear(res, x1_scaled, r1_scaled) : step_probit(res, x1_scaled, r1_scaled);
+    if (rc != VAMPOMI_OK) return rc;
+    VH(vampomi_counters(ctx_, c1, 0));
+    res->matrix_passes = c1[1] - c0[1];
+    res->gam1_next = gam1_;
+    fill_prior(res);
+    return VAMPOMI_OK;
+}
+
+// One iteration of src/vamp.cpp:148-428.
+int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
+    const int it = it_;
+    const double sqrtN = std::sqrt((double)N_), rho = cfg_.rho;
+    if (verbose) std::cout << "->DENOISING" << std::endl;
+    if (it > cfg_.learn_prior_delay) VH(update_prior());                        // :186-187
+    if (verbose) {
+        std::cout << "Prior variances = ";
+        for (double v : vars_) std::cout << v / (double)N_ << ' ';
+        std::cout << std::endl << "Prior probabilities = ";
+        for (double p : probs_) std::cout << p << ' ';
+        std::cout << std::endl;
+    }
+    double sum_d = 0;
+    VH(vampomi_denoise(ctx_, gam1_, probs_.data(), vars_.data(), (int)probs_.size(), it > 1, rho, &sum_d));   // :203-219
+    alpha1_ = sum_d / (double)Mt_;                                              // :221-223
+    eta1_ = gam1_ / alpha1_;
+    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X1, VAMPOMI_V_Z1));                       // :232
+    VH(dump(x1_scaled, r1_scaled));                                             // :235-249
+    gam2_ = clampg(eta1_ - gam1_);                                              // :255-256
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R2, eta1_, VAMPOMI_V_X1, -gam1_, VAMPOMI_V_R1, gam2_));   // :259-261
+
+    // err_measures(1) (:760-852), true-gam2 diagnostic (:264-270) and the NMSE sums (:409-413) in one reduction launch
+    {
+        const int kind[10] = {VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DIFF2, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT,
+                              VAMPOMI_SQDEV, VAMPOMI_DIFF2, VAMPOMI_DOT};
+        const int a[10] = {VAMPOMI_V_X1, VAMPOMI_V_X1, VAMPOMI_V_TRUE, VAMPOMI_V_Y, VAMPOMI_V_Y, VAMPOMI_V_Z1, VAMPOMI_V_Z1,
+                           VAMPOMI_V_R2, VAMPOMI_V_X1_PREV, VAMPOMI_V_X1_PREV};
+        const int b[10] = {VAMPOMI_V_TRUE, VAMPOMI_V_X1, VAMPOMI_V_TRUE, VAMPOMI_V_Z1, VAMPOMI_V_Y, VAMPOMI_V_Y, VAMPOMI_V_Z1,
+                           VAMPOMI_V_TRUE, VAMPOMI_V_X1, VAMPOMI_V_X1_PREV};
+        double scale[10] = {1, 1, 1, 1, 1, 1, 1, sqrtN, 1, 1}, d[10];
+        VH(vampomi_dots(ctx_, 10, kind, a, b, scale, d));
+        const double corr = d[0] / std::sqrt(d[1] * d[2]);                      // :767
+        const double l2_pred_err = std::sqrt(d[3] / d[4]);                      // :832
+        const double R2 = 1 - l2_pred_err * l2_pred_err;
+        const double corr_y = d[5] / std::sqrt(d[6] * d[4]);                    // :835
+        res->metrics[1] = corr; res->metrics[0] = R2; res->metrics[4] = corr_y * corr_y;
+        res->true_gam2 = (double)Mt_ / d[7];
+        res->nmse = std::sqrt(d[8] / d[9]);
+        if (verbose) {
+            std::cout << "Corr(x1_hat, x0) = " << corr << std::endl;
+            std::cout << "Corr(y_hat, y)^2 = " << corr_y * corr_y << std::endl << "R2 = " << R2 << std::endl
+                      << "L2(y_hat, y) = " << l2_pred_err << std::endl;
+        }
+    }
+    res->params[0] = alpha1_; res->params[1] = gam1_;                           // :275-276
+    if (verbose)
+        std::cout << "alpha1 = " << alpha1_ << std::endl << "gam1 = " << gam1_ << std::endl << "gam2 = " << gam2_ << std::endl
+                  << "true gam2 = " << res->true_gam2 << std::endl << "______________________" << std::endl << "->LMMSE" << std::endl;
+
+    VH(vampomi_draw_probe(ctx_, cfg_.seed, it));                                // :295-296
+    if (cfg_.redundant_passes || !aty_ready_) {                                 // v = gamw * A^T y + gam2 * r2, :303-306
+        VH(vampomi_atx_dev(ctx_, VAMPOMI_V_Y, VAMPOMI_V_ATY));
+        aty_ready_ = true;
+    }
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_V, gamw_, VAMPOMI_V_ATY, gam2_, VAMPOMI_V_R2, 1.0));
+    int k1 = 0, k2 = 0;
+    double rel = 0, vmu = 0;
+    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, it > 1, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel,
+                        nullptr));                                              // :308-311
+    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2,
+                        &rel, &vmu));                                           // g2d_onsager, :494-501
+    alpha2_ = gam2_ * vmu;
+    res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
+    eta2_ = gam2_ / alpha2_;                                                    // :341
+    const double gam1_prev = gam1_;
+    gam1_ = clampg(eta2_ - gam2_);
+    gam1_ = rho * gam1_ + (1 - rho) * gam1_prev;                                // :346
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R1, eta2_, VAMPOMI_V_X2, -gam2_, VAMPOMI_V_R2, gam1_));   // :348-350
+
+    // updateNoisePrec (:504-529) + err_measures(2) share A x2_hat; the reference computes it twice (:508, :826)
+    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));           // :518
+    VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));            // :519
+    if (cfg_.redundant_passes) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    {
+        const int kind[9] = {VAMPOMI_DIFF2, VAMPOMI_DOT, VAMPOMI_SQDEV, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT,
+                             VAMPOMI_DOT, VAMPOMI_DOT};
+        const int a[9] = {VAMPOMI_V_Z2, VAMPOMI_V_BERN, VAMPOMI_V_R1, VAMPOMI_V_X2, VAMPOMI_V_X2, VAMPOMI_V_TRUE, VAMPOMI_V_Y,
+                          VAMPOMI_V_Z2, VAMPOMI_V_Z2};
+        const int b[9] = {VAMPOMI_V_Y, VAMPOMI_V_USER_M0, VAMPOMI_V_TRUE, VAMPOMI_V_TRUE, VAMPOMI_V_X2, VAMPOMI_V_TRUE, VAMPOMI_V_Y,
+                          VAMPOMI_V_Y, VAMPOMI_V_Z2};
+        double scale[9] = {1, 1, sqrtN, 1, 1, 1, 1, 1, 1}, d[9];
+        VH(vampomi_dots(ctx_, 9, kind, a, b, scale, d));
+        const double temp_norm2 = d[0];
+        const double trace_corr = d[1] * (double)Mt_;                           // :521
+        if (verbose)
+            std::cout << "l2_norm2(temp) / N = " << temp_norm2 / N_ << std::endl << "trace_correction / N = " << trace_corr / N_ << std::endl;
+        gamw_ = (double)N_ / (temp_norm2 + trace_corr);                         // :528
+        res->true_gam1 = (double)Mt_ / d[2];
+        const double corr2 = d[3] / std::sqrt(d[4] * d[5]);
+        const double l2_pred_err = std::sqrt(d[0] / d[6]);
+        const double R2 = 1 - l2_pred_err * l2_pred_err;
+        const double corr_y = d[7] / std::sqrt(d[8] * d[6]);
+        res->metrics[3] = corr2; res->metrics[2] = R2; res->metrics[5] = corr_y * corr_y;
+        if (verbose)
+            std::cout << "Corr(x2_hat, x0)= " << corr2 << std::endl << "Corr(y_hat, y)^2 = " << corr_y * corr_y << std::endl
+                      << "R2 = " << R2 << std::endl << "L2(y_hat, y) = " << l2_pred_err << std::endl;
+    }
+    res->params[2] = alpha2_; res->params[3] = gam2_; res->params[4] = gamw_;   // :368-370
+    res->n_params = 5; res->n_metrics = 6;
+    if (verbose)
+        std::cout << "alpha2 = " << alpha2_ << std::endl << "gam2 = " << gam2_ << std::endl << "gam1 = " << gam1_ << std::endl
+                  << "true gam1 = " << res->true_gam1 << std::endl << "gamw = " << gamw_ << std::endl;
+    return VAMPOMI_OK;
+}
+
+// One iteration of src/vamp_probit.cpp:68-463.
+int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
+    const int it = it_;
+    const double sqrtN = std::sqrt((double)N_), rho = cfg_.rho;
+    if (verbose) std::cout << "...calculating covariate effects" << std::endl << "->DENOISING" << std::endl;
+    const double alpha1_prev = alpha1_;
+    double sum_d = 0;
+    // g1 / g1d with the CURRENT prior, no damping yet (:112-130)
+    VH(vampomi_denoise(ctx_, gam1_, probs_.data(), vars_.data(), (int)probs_.size(), 0, rho, &sum_d));
+    alpha1_ = sum_d / (double)Mt_;
+    eta1_ = gam1_ / alpha1_;
+    if (it > 1) {
+        VH(update_prior());                                                     // :139
+        // damping of x1_hat and alpha1 (:160-165): x1 = rho*x1 + (1-rho)*x1_prev
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_X1, rho, VAMPOMI_V_X1, 1 - rho, VAMPOMI_V_X1_PREV, 1.0));
+        alpha1_ = rho * alpha1_ + (1 - rho) * alpha1_prev;
+    }
+    if (verbose) {
+        std::cout << "Prior variances = ";
+        for (double v : vars_) std::cout << v / (double)N_ << ' ';
+        std::cout << std::endl << "Prior probabilities = ";
+        for (double p : probs_) std::cout << p << ' ';
+        std::cout << std::endl;
+    }
+    VH(dump(x1_scaled, r1_scaled));                                             // :167-186
+    gam2_ = clampg(eta1_ - gam1_);                                              // :194
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R2, eta1_, VAMPOMI_V_X1, -gam1_, VAMPOMI_V_R1, gam2_));   // :197-198
+    double x1_corr;
+    {
+        const int kind[5] = {VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DIFF2, VAMPOMI_DOT};
+        const int a[5] = {VAMPOMI_V_X1, VAMPOMI_V_X1, VAMPOMI_V_TRUE, VAMPOMI_V_X1_PREV, VAMPOMI_V_X1_PREV};
+        const int b[5] = {VAMPOMI_V_TRUE, VAMPOMI_V_X1, VAMPOMI_V_TRUE, VAMPOMI_V_X1, VAMPOMI_V_X1_PREV};
+        double d[5];
+        VH(vampomi_dots(ctx_, 5, kind, a, b, nullptr, d));
+        // Corr(x1_hat, sqrt(N)*true_signal) (:189): the sqrt(N) factors written out as the reference multiplies them in
+        x1_corr = (d[0] * sqrtN) / std::sqrt(d[1] * (d[2] * sqrtN * sqrtN));
+        res->nmse = std::sqrt(d[3] / d[4]);
+    }
+    // z channel (:213-253)
+    double beta1 = 0;
+    VH(vampomi_probit_zdenoise(ctx_, tau1_, &beta1));
+    if (beta1 >= N_) beta1 = N_ - 1.0;                                          // :234-235
+    beta1 /= N_;
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_P2, 1.0, VAMPOMI_V_Z1HAT, -beta1, VAMPOMI_V_P1, 1 - beta1));   // :250-251
+    const double tau2 = tau1_ * (1 - beta1) / beta1;                            // :253
+    res->params[0] = alpha1_; res->params[1] = beta1; res->params[2] = gam1_; res->params[3] = tau1_;
+    if (verbose)
+        std::cout << "alpha1 = " << alpha1_ << std::endl << "beta1 = " << beta1 << std::endl << "tau1 = " << tau1_ << std::endl;
+
+    auto confusion = [&](int xvec, double* out6, double corr) -> int {          // :271-282 / :403-415
+        // A (x/sqrt(N)) then probit prediction at threshold 0.5 and the confusion matrix, on the host (N values)
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, xvec, 0.0, xvec, sqrtN));
+        VH(vampomi_ax_dev(ctx_, VAMPOMI_V_USER_M0, VAMPOMI_V_USER_N0));
+        VH(vampomi_vec_get(ctx_, VAMPOMI_V_USER_N0, zbuf_.data()));
+        int TP = 0, TN = 0, FP = 0, FN = 0;
+        for (int i = 0; i < N_; i++) {
+            const double yhat = normal_cdf(zbuf_[i]) >= 0.5 ? 1.0 : 0.0;       // predict_probit, :619-629
+            const double yi = y_host_[i];
+            if (yi == 1 && yhat == 1) TP++;
+            else if (yi == 0 && yhat == 0) TN++;
+            else if (yi == 1 && yhat == 0) FN++;
+            else if (yi == 0 && yhat == 1) FP++;
+        }
+        out6[0] = TP; out6[1] = TN; out6[2] = FP; out6[3] = FN;
+        out6[4] = (double)(TP + TN) / (double)(TP + TN + FP + FN);
+        out6[5] = corr;
+        return VAMPOMI_OK;
+    };
+    VH(confusion(VAMPOMI_V_X1, res->metrics, x1_corr));
+    if (verbose) std::cout << "Corr(x1_hat,x0) = " << x1_corr << std::endl << "Accuracy1 = " << res->metrics[4] << std::endl
+                           << std::endl << "->LMMSE" << std::endl;
+
+    // LMMSE for x (:296-349)
+    VH(vampomi_draw_probe(ctx_, cfg_.seed, it));
+    VH(vampomi_atx_dev(ctx_, VAMPOMI_V_P2, VAMPOMI_V_USER_M0));                 // :300
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_V, tau2, VAMPOMI_V_USER_M0, gam2_, VAMPOMI_V_R2, 1.0));   // :302-303
+    int k1 = 0, k2 = 0;
+    double rel = 0, vmu = 0;
+    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel, nullptr));   // :307
+    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2, &rel, &vmu));
+    const double alpha2 = gam2_ * vmu;                                          // :311
+    res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
+    double x2_corr;
+    {
+        const int kind[3] = {VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT};
+        const int a[3] = {VAMPOMI_V_X2, VAMPOMI_V_X2, VAMPOMI_V_TRUE};
+        const int b[3] = {VAMPOMI_V_TRUE, VAMPOMI_V_X2, VAMPOMI_V_TRUE};
+        double d[3];
+        VH(vampomi_dots(ctx_, 3, kind, a, b, nullptr, d));
+        x2_corr = (d[0] * sqrtN) / std::sqrt(d[1] * (d[2] * sqrtN * sqrtN));    // :324
+    }
+    eta2_ = gam2_ / alpha2;
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R1, 1.0, VAMPOMI_V_X2, -alpha2, VAMPOMI_V_R2, 1 - alpha2));   // :337-338
+    gam1_ = clampg(gam2_ * (1 - alpha2) / alpha2);                              // :345-346
+    // LMMSE for z (:352-376)
+    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    const double beta2 = (double)Mt_ / N_ * (1 - alpha2);
+    VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_P1, 1.0, VAMPOMI_V_Z2, -beta2, VAMPOMI_V_P2, 1 - beta2));     // :367-368
+    tau1_ = clampg(tau2 * (1 - beta2) / beta2);                                 // :375-376
+    res->params[4] = alpha2; res->params[5] = beta2; res->params[6] = gam2_; res->params[7] = tau2;
+    if (verbose)
+        std::cout << "alpha2 = " << alpha2 << std::endl << "beta2 = " << beta2 << std::endl << "gam1 = " << gam1_ << std::endl
+                  << "gam2 = " << gam2_ << std::endl << "tau2 = " << tau2 << std::endl;
+    VH(confusion(VAMPOMI_V_X2, res->metrics + 6, x2_corr));
+    if (verbose) std::cout << "Corr(x2_hat, x0) = " << x2_corr << std::endl << "Accuracy2 = " << res->metrics[10] << std::endl;
+    res->n_params = 8; res->n_metrics = 12;
+    alpha2_ = alpha2;
+    return VAMPOMI_OK;
+}
+
+}  // namespace vampomi_host
+
+// ------------------------------------------------------------------------------------------------------------------
+// C entry points (include/vampomi_host.h)
+// ------------------------------------------------------------------------------------------------------------------
+struct vampomi_solver {
+    vampomi_host::Vamp* impl;
+};
+
+extern "C" {
+
+int vampomi_solver_create(vampomi_ctx* ctx, const vampomi_solver_config* cfg, const double* y_N, const double* true_signal_M,
+                          const double* x1hat_init_M, vampomi_solver** out) {
+    if (!ctx || !cfg || !y_N || !out) return VAMPOMI_ERR_ARG;
+    *out = nullptr;
+    vampomi_host::Vamp* v = new vampomi_host::Vamp(ctx, *cfg);
+    int rc = v->init(y_N, true_signal_M, x1hat_init_M);
+    if (rc != VAMPOMI_OK) { delete v; return rc; }
+    *out = new vampomi_solver{v};
+    return VAMPOMI_OK;
+}
+
+int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M) {
+    if (!s || !s->impl) return VAMPOMI_ERR_ARG;
+    return s->impl->step(res, x1_scaled_M, r1_scaled_M);
+}
+
+int vampomi_solver_destroy(vampomi_solver* s) {
+    if (s) { delete s->impl; delete s; }
+    return VAMPOMI_OK;
+}
+
+void vampomi_solver_default_config(vampomi_solver_config* cfg) {
+    if (!cfg) return;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->model = 0;
+    cfg->gam1 = 1e-6; cfg->gamw = 2.0; cfg->rho = 0.5;
+    cfg->CG_max_iter = 500; cfg->CG_err_tol = 1e-5;
+    cfg->EM_max_iter = 1; cfg->EM_err_thr = 1e-2;
+    cfg->learn_vars = 1; cfg->learn_prior_delay = 1; cfg->merge_vars_thr = 0.5;
+    const double vars[10] = {0, 1e-06, 6e-06, 3e-05, 2e-04, 1e-03, 6e-03, 3e-02, 2e-01, 1e+00};
+    const double probs[10] = {9.90000e-01, 5.00000e-03, 2.50000e-03, 1.25000e-03, 6.25000e-04,
+                              3.12500e-04, 1.56250e-04, 7.81250e-05, 3.90625e-05, 3.90625e-05};
+    cfg->L = 10;
+    for (int i = 0; i < 10; i++) { cfg->vars[i] = vars[i]; cfg->probs[i] = probs[i]; }
+    cfg->seed = 0;
+    cfg->redundant_passes = 0;
+}
+
+}  // extern "C"

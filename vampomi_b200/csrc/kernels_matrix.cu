@@ -1,0 +1,438 @@
+// Streaming kernels over the marker-major FP64 design-matrix block held in HBM (sm_100a).
+//
+//   A is [M][ld] doubles, column (marker) j contiguous at A + j*ld, ld = N rounded up to 16 (128-byte columns),
+//   pad rows are zero. All four kernels are HBM-bandwidth bound: 8 bytes of A per 2-3 FP64 operations, so they
+//   are written as pure streaming code — 256-bit non-allocating loads (LDG.E.256, L1 bypass) with several
+//   independent loads in flight per thread, on-the-fly standardisation (a - mave_j) * msig_j, warp-shuffle
+//   reductions, a deterministic two-stage reduction for Ax — and never touch tensor cores.
+//
+//   reference            kernel here
+//   data::compute_markers_statistics (src/data.cpp:233-283)  k_stats
+//   data::ATx / dot_product          (src/data.cpp:294-333)  k_atx
+//   data::Ax                         (src/data.cpp:340-373)  k_ax_partial + k_ax_reduce (+ all-reduce + k_scale_div)
+//   data::pvals_loo inner sums       (src/data.cpp:396-413)  k_loo_sums
+#include "common.h"
+#include "rng.h"
+
+namespace vampomi {
+
+struct __align__(32) d4 { double x, y, z, w; };
+
+// 256-bit streaming load: read-only path, no L1 allocation (A is touched once per pass).
+__device__ __forceinline__ d4 ld_stream(const double* p) {
+    d4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+// 256-bit cached load for the small vector every column reuses (p in ATx): allocate in L1.
+__device__ __forceinline__ d4 ld_cached(const double* p) {
+    d4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+        : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(double* p, const d4& v) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// synthetic block: A[j][i] = N(0,1) from hash(seed, global marker S+j, sample i); pad rows zero
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate_iid(double* __restrict__ A, size_t ld, int N, long long M, long long S,
+                                                      uint64_t seed) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((size_t)i >= ld) return;
+    for (long long j = blockIdx.y; j < M; j += gridDim.y) {
+        double v = 0.0;
+        if (i < N) v = normal_from_hash(hash3(seed, STREAM_MATRIX, (uint64_t)(S + j), (uint64_t)i));
+        A[(size_t)j * ld + i] = v;
+    }
+}
+
+int launch_generate_iid(vampomi_ctx* c, uint64_t seed) {
+    dim3 grid((unsigned)((c->ld + 255) / 256), (unsigned)(c->M < 16384 ? c->M : 16384));
+    k_generate_iid<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->N, c->M, c->S, seed);
+    c->counters[0]++;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// marker statistics: one warp per column, two passes (the second one is served by L2)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stats(const double* __restrict__ A, size_t ld, int N, long long M, double alpha_scale,
+                                               double* __restrict__ mave, double* __restrict__ msig) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = N >> 2;
+    for (long long j = warp; j < M; j += nwarps) {
+        const double* col = A + (size_t)j * ld;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int v = lane; v < nvec; v += 32) {
+            d4 a = ld_cached(col + 4 * (size_t)v);
+            s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+        }
+        for (int i = (nvec << 2) + lane; i < N; i += 32) s0 += col[i];
+        double mean = warp_sum((s0 + s1) + (s2 + s3)) / (double)N;               // suma / nonas, src/data.cpp:258
+        s0 = s1 = s2 = s3 = 0;
+        for (int v = lane; v < nvec; v += 32) {
+            d4 a = ld_cached(col + 4 * (size_t)v);
+            double d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+            s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+        }
+        for (int i = (nvec << 2) + lane; i < N; i += 32) { double d = col[i] - mean; s0 = fma(d, d, s0); }
+        double sumsqr = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) {
+            double sig = 1.0;                                                     // constant column, src/data.cpp:275-276
+            if (sumsqr != 0.0) {
+                double sd = sqrt(sumsqr / ((double)N - 1.0));
+                sig = (alpha_scale == 1.0) ? 1.0 / sd : 1.0 / pow(sd, alpha_scale);   // src/data.cpp:271-274
+            }
+            mave[j] = mean;
+            msig[j] = sig;
+        }
+    }
+}
+
+int launch_stats(vampomi_ctx* c, double alpha_scale) {
+    int blocks = c->num_sms * 8;
+    k_stats<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->N, c->M, alpha_scale, c->mave, c->msig);
+    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ax: out[i] = sum_j (A[i,j] - mave[j]) * (msig[j] * x[j])
+// stage 1: CTA (tile, chunk) owns `tile_rows` rows x `cols_per_chunk` columns; every thread keeps RV 256-bit
+//          accumulators (4*RV rows) in registers and streams down the columns with U columns in flight.
+// stage 2: k_ax_reduce sums the chunk partials in fixed order (bitwise reproducible, no FP64 atomics).
+// ---------------------------------------------------------------------------------------------------------------
+template <int RV, int U>
+__global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                    const double* __restrict__ msig, const double* __restrict__ x,
+                                                    int tile_rows, int cols_per_chunk, long long M,
+                                                    double* __restrict__ partial, const int* __restrict__ done) {
+    if (done != nullptr && *done != 0) return;
+    const int tid = threadIdx.x;
+    const size_t rbase = (size_t)blockIdx.x * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+
+    d4 acc[RV];
+    const double* ap[RV];
+    bool valid[RV];
+#pragma unroll
+    for (int k = 0; k < RV; k++) {
+        acc[k] = d4{0.0, 0.0, 0.0, 0.0};
+        int off = (k * 256 + tid) * 4;
+        valid[k] = off < tile_rows && rbase + off < ld;
+        ap[k] = A + rbase + (valid[k] ? off : 0);
+    }
+
+    long long j = c0;
+    for (; j + U <= c1; j += U) {
+        d4 a[U][RV];
+        double m[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int k = 0; k < RV; k++)
+                if (valid[k]) a[u][k] = ld_stream(ap[k] + (size_t)(j + u) * ld);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            m[u] = __ldg(mave + j + u);
+            w[u] = __ldg(msig + j + u) * __ldg(x + j + u);      // sig_phen_i, src/data.cpp:354
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+#pragma unroll
+            for (int k = 0; k < RV; k++) {
+                if (valid[k]) {
+                    acc[k].x = fma(a[u][k].x - m[u], w[u], acc[k].x);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
+                    acc[k].y = fma(a[u][k].y - m[u], w[u], acc[k].y);
+                    acc[k].z = fma(a[u][k].z - m[u], w[u], acc[k].z);
+                    acc[k].w = fma(a[u][k].w - m[u], w[u], acc[k].w);
+                }
+            }
+        }
+    }
+    for (; j < c1; j++) {
+        double m = __ldg(mave + j), w = __ldg(msig + j) * __ldg(x + j);
+#pragma unroll
+        for (int k = 0; k < RV; k++) {
+            if (valid[k]) {
+                d4 a = ld_stream(ap[k] + (size_t)j * ld);
+                acc[k].x = fma(a.x - m, w, acc[k].x);
+                acc[k].y = fma(a.y - m, w, acc[k].y);
+                acc[k].z = fma(a.z - m, w, acc[k].z);
+                acc[k].w = fma(a.w - m, w, acc[k].w);
+            }
+        }
+    }
+    double* prow = partial + (size_t)blockIdx.y * ld + rbase;
+#pragma unroll
+    for (int k = 0; k < RV; k++)
+        if (valid[k]) st256(prow + (k * 256 + tid) * 4, acc[k]);
+}
+
+// out[i] = (sum_c partial[c][i]) / divisor for i < N. Thread (i, s) sums chunks s, s+SL, ...; slices combine in smem
+// in fixed order, so the result does not depend on scheduling.
+template <int SL>
+__global__ void __launch_bounds__(256) k_ax_reduce(const double* __restrict__ partial, size_t ld, int nchunks, int N,
+                                                   double divisor, double* __restrict__ out, const int* __restrict__ done) {
+    if (done != nullptr && *done != 0) return;
+    __shared__ double sm[SL][256 / SL];
+    constexpr int ROWS = 256 / SL;
+    const int r = threadIdx.x % ROWS, s = threadIdx.x / ROWS;
+    const int i = blockIdx.x * ROWS + r;
+    double acc = 0.0;
+    if (i < N)
+        for (int cidx = s; cidx < nchunks; cidx += SL) acc += __ldcg(partial + (size_t)cidx * ld + i);
+    sm[s][r] = acc;
+    __syncthreads();
+    if (s == 0 && i < N) {
+        double t = sm[0][r];
+#pragma unroll
+        for (int q = 1; q < SL; q++) t += sm[q][r];
+        out[i] = t / divisor;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_scale_div(double* __restrict__ dst, const double* __restrict__ src, double divisor,
+                                                   long long n, const int* __restrict__ done) {
+    if (done != nullptr && *done != 0) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i] / divisor;
+}
+
+int launch_scale_div(vampomi_ctx* c, double* dst, const double* src, double divisor, long long n, const int* done_flag) {
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    k_scale_div<<<blocks, 256, 0, c->stream>>>(dst, src, divisor, n, done_flag);
+    c->counters[0]++;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
+struct AxPlan { int rv, U, ntiles, tile_rows, nchunks, cols_per_chunk; };
+
+typedef void (*ax_kernel_t)(const double*, size_t, const double*, const double*, const double*, int, int, long long, double*,
+                            const int*);
+
+static ax_kernel_t ax_kernel(int rv, int U) {
+    switch (rv * 10 + U) {
+        case 12: return k_ax_partial<1, 2>; case 14: return k_ax_partial<1, 4>; case 18: return k_ax_partial<1, 8>;
+        case 22: return k_ax_partial<2, 2>; case 24: return k_ax_partial<2, 4>; case 28: return k_ax_partial<2, 8>;
+        case 42: return k_ax_partial<4, 2>; case 44: return k_ax_partial<4, 4>;
+        default: return nullptr;
+    }
+}
+
+// CTAs of `kernel` that fit on one SM (registers / shared memory) — grids are sized to exactly one resident wave so
+// that the static work split has no tail.
+static int resident_ctas(const void* kernel, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+
+static AxPlan plan_ax(const vampomi_ctx* c) {
+    AxPlan p;
+    p.rv = c->tune.ax_rv;
+    p.U = c->tune.ax_unroll;
+    if (ax_kernel(p.rv, p.U) == nullptr) { p.rv = 2; p.U = 4; }
+    while (p.rv > 1 && (size_t)(1024 * (p.rv / 2)) >= c->ld) p.rv /= 2;      // do not leave most lanes idle on small N
+    if (ax_kernel(p.rv, p.U) == nullptr) p.U = 4;
+    int cap = 1024 * p.rv;
+    p.ntiles = (int)((c->ld + cap - 1) / cap);
+    size_t tr = (c->ld + p.ntiles - 1) / p.ntiles;
+    p.tile_rows = (int)((tr + 15) / 16 * 16);                                // 128-byte aligned tile starts
+    int per_sm = c->tune.ax_ctas_per_sm > 0 ? c->tune.ax_ctas_per_sm
+                                            : resident_ctas((const void*)ax_kernel(p.rv, p.U), 256, 0);
+    long long slots = (long long)c->num_sms * per_sm;
+    long long nch = slots / p.ntiles;
+    if (nch < 1) nch = 1;
+    if (nch > c->M) nch = c->M;
+    p.cols_per_chunk = (int)((c->M + nch - 1) / nch);
+    p.nchunks = (int)((c->M + p.cols_per_chunk - 1) / p.cols_per_chunk);
+    return p;
+}
+
+int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag) {
+    AxPlan p = plan_ax(c);
+    size_t need = (size_t)p.nchunks * c->ld;
+    if (need > c->ax_partial_elems) {
+        VO_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->ax_partial) VO_CUDA(cudaFree(c->ax_partial));
+        c->ax_partial = nullptr;
+        VO_CUDA(cudaMalloc(&c->ax_partial, need * sizeof(double)));
+        c->ax_partial_elems = need;
+    }
+    dim3 grid(p.ntiles, p.nchunks);
+    ax_kernel(p.rv, p.U)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
+                                                      c->ax_partial, done_flag);
+    VO_CUDA(cudaGetLastError());
+    const double sqrtN = sqrt((double)c->N);
+    constexpr int SL = 8;
+    int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
+    // single shard: divide by sqrt(N) right here (src/data.cpp:369-370); sharded: the division follows the all-reduce
+    k_ax_reduce<SL><<<rblocks, 256, 0, c->stream>>>(c->ax_partial, c->ld, p.nchunks, c->N, c->nranks == 1 ? sqrtN : 1.0,
+                                                    out_dev, done_flag);
+    VO_CUDA(cudaGetLastError());
+    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    if (c->nranks > 1) {
+        VO_CHECK(allreduce_inplace(c, out_dev, (size_t)c->N));                // MPI_Allreduce, src/data.cpp:367
+        VO_CHECK(launch_scale_div(c, out_dev, out_dev, sqrtN, c->N, done_flag));
+    }
+    return VAMPOMI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ATx: out[j] = msig[j] * (sum_i (A[i,j] - mave[j]) * p[i]) * (1/sqrt(N)); one warp owns C columns at a time, reads
+// each 256-bit slice of p once (L1-resident) for all C columns, keeps C*U 256-bit loads of A in flight per lane.
+// No block-level synchronisation at all; reduction by warp shuffles in a fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, int U>
+__global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                             const double* __restrict__ msig, const double* __restrict__ p, long long M,
+                                             double scale, double* __restrict__ out, const int* __restrict__ done) {
+    if (done != nullptr && *done != 0) return;
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = (int)(ld >> 2);                       // pad rows of A and p are zero: they add (0 - m) * 0
+    const long long ngroups = (M + C - 1) / C;
+    const long long per = (ngroups + nwarps - 1) / nwarps;
+    long long g0 = warp * per, g1 = g0 + per;
+    if (g1 > ngroups) g1 = ngroups;
+    for (long long g = g0; g < g1; g++) {
+        const long long j0 = g * C;
+        const double* col[C];
+        double m[C], acc[C][4];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            long long j = j0 + cc < M ? j0 + cc : M - 1;
+            col[cc] = A + (size_t)j * ld;
+            m[cc] = __ldg(mave + j);
+            acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0;
+        }
+        int v = lane;
+        for (; v + 32 * (U - 1) < nvec; v += 32 * U) {
+            d4 pv[U], a[U][C];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) a[u][cc] = ld_stream(col[cc] + 4 * (size_t)(v + 32 * u));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) pv[u] = ld_cached(p + 4 * (size_t)(v + 32 * u));
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) {
+                    acc[cc][0] = fma(a[u][cc].x - m[cc], pv[u].x, acc[cc][0]);   // (meth[i] - mu) * phen[i], src/data.cpp:304
+                    acc[cc][1] = fma(a[u][cc].y - m[cc], pv[u].y, acc[cc][1]);
+                    acc[cc][2] = fma(a[u][cc].z - m[cc], pv[u].z, acc[cc][2]);
+                    acc[cc][3] = fma(a[u][cc].w - m[cc], pv[u].w, acc[cc][3]);
+                }
+            }
+        }
+        for (; v < nvec; v += 32) {
+            d4 pv = ld_cached(p + 4 * (size_t)v);
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                d4 a = ld_stream(col[cc] + 4 * (size_t)v);
+                acc[cc][0] = fma(a.x - m[cc], pv.x, acc[cc][0]);
+                acc[cc][1] = fma(a.y - m[cc], pv.y, acc[cc][1]);
+                acc[cc][2] = fma(a.z - m[cc], pv.z, acc[cc][2]);
+                acc[cc][3] = fma(a.w - m[cc], pv.w, acc[cc][3]);
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            double s = warp_sum((acc[cc][0] + acc[cc][1]) + (acc[cc][2] + acc[cc][3]));
+            if (lane == 0 && j0 + cc < M) out[j0 + cc] = (__ldg(msig + j0 + cc) * s) * scale;   // sigma_inv * dpa (:306), then * scale (:330)
+        }
+    }
+}
+
+typedef void (*atx_kernel_t)(const double*, size_t, const double*, const double*, const double*, long long, double, double*,
+                             const int*);
+
+static atx_kernel_t atx_kernel(int C, int U) {
+    switch (C * 10 + U) {
+        case 12: return k_atx<1, 2>; case 14: return k_atx<1, 4>; case 18: return k_atx<1, 8>;
+        case 22: return k_atx<2, 2>; case 24: return k_atx<2, 4>; case 28: return k_atx<2, 8>;
+        case 42: return k_atx<4, 2>; case 44: return k_atx<4, 4>;
+        default: return nullptr;
+    }
+}
+
+int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag) {
+    int C = c->tune.atx_cols, U = c->tune.atx_unroll;
+    if (atx_kernel(C, U) == nullptr) { C = 2; U = 4; }
+    int per_sm = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)atx_kernel(C, U), 256, 0);
+    int blocks = c->num_sms * per_sm;
+    long long maxb = (c->M + 8 * C - 1) / (8 * C);
+    if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
+    const double scale = 1.0 / sqrt((double)c->N);                              // src/data.cpp:326-327
+    atx_kernel(C, U)<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
+    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// loo: per RAW column sums  sum x, sum x^2, sum x*w  (w = y - z1) — the only per-marker quantities pvals_loo needs
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_loo_sums(const double* __restrict__ A, size_t ld, const double* __restrict__ w,
+                                                  long long M, double* __restrict__ sums) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const int nvec = (int)(ld >> 2);
+    for (long long j = warp; j < M; j += nwarps) {
+        const double* col = A + (size_t)j * ld;
+        double sx = 0, sxx = 0, sxw = 0, tx = 0, txx = 0, txw = 0;
+        int v = lane;
+        for (; v + 32 < nvec; v += 64) {
+            d4 a = ld_stream(col + 4 * (size_t)v), b = ld_stream(col + 4 * (size_t)(v + 32));
+            d4 wa = ld_cached(w + 4 * (size_t)v), wb = ld_cached(w + 4 * (size_t)(v + 32));
+            sx += (a.x + a.y) + (a.z + a.w);
+            tx += (b.x + b.y) + (b.z + b.w);
+            sxx = fma(a.x, a.x, sxx); sxx = fma(a.y, a.y, sxx); sxx = fma(a.z, a.z, sxx); sxx = fma(a.w, a.w, sxx);
+            txx = fma(b.x, b.x, txx); txx = fma(b.y, b.y, txx); txx = fma(b.z, b.z, txx); txx = fma(b.w, b.w, txx);
+            sxw = fma(a.x, wa.x, sxw); sxw = fma(a.y, wa.y, sxw); sxw = fma(a.z, wa.z, sxw); sxw = fma(a.w, wa.w, sxw);
+            txw = fma(b.x, wb.x, txw); txw = fma(b.y, wb.y, txw); txw = fma(b.z, wb.z, txw); txw = fma(b.w, wb.w, txw);
+        }
+        for (; v < nvec; v += 32) {
+            d4 a = ld_stream(col + 4 * (size_t)v);
+            d4 wa = ld_cached(w + 4 * (size_t)v);
+            sx += (a.x + a.y) + (a.z + a.w);
+            sxx = fma(a.x, a.x, sxx); sxx = fma(a.y, a.y, sxx); sxx = fma(a.z, a.z, sxx); sxx = fma(a.w, a.w, sxx);
+            sxw = fma(a.x, wa.x, sxw); sxw = fma(a.y, wa.y, sxw); sxw = fma(a.z, wa.z, sxw); sxw = fma(a.w, wa.w, sxw);
+        }
+        sx = warp_sum(sx + tx); sxx = warp_sum(sxx + txx); sxw = warp_sum(sxw + txw);
+        if (lane == 0) { sums[3 * j] = sx; sums[3 * j + 1] = sxx; sums[3 * j + 2] = sxw; }
+    }
+}
+
+int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev) {
+    k_loo_sums<<<c->num_sms * 8, 256, 0, c->stream>>>(c->A, c->ld, w_dev, c->M, sums_dev);
+    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
+}  // namespace vampomi

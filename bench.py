@@ -1,0 +1,316 @@
+#!/usr/bin/env python3
+"""Benchmark of the VAMP inference hot path (BASELINE.json: VAMP iterations/s at N=20k, M=850k FP64 on 1/2/4/8 B200).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one rank per GPU; torchrun for N > 1)
+  python bench.py --impl reference ...                     the reference's own CPU implementation (oracle/_ref) beside it
+
+A "step" is ONE full VAMP iteration (Gaussian-mixture denoiser + EM prior update + LMMSE conjugate-gradient solve +
+Onsager solve + noise-precision update + metrics) on the synthetic i.i.d. design of the headline configuration, markers
+sharded over the N GPUs (total problem fixed: strong scaling). Two timed legs over the SAME iterations (W+1 .. W+K of
+two identically initialised solvers):
+  value  device-resident: matrix, phenotype and all vectors already in HBM; only the ~20 CSV scalars leave the device
+  e2e    the same iterations through the host-buffer C ABI a main_meth run uses: every step re-uploads the phenotype
+         (H2D) and brings x1_hat/sqrt(N) and r1/sqrt(N) — the content of _it_k.bin / _r1_it_k.bin — back to host memory
+Timing: CUDA events on the library's own stream, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vamp_iterations_per_s"
+UNIT = "it/s"
+H2 = 0.5            # CLI default --h2 (src/options.hpp:98) -> gamw = 2
+LAM = 0.01          # sparsity of the simulated effects
+DATA_SEED = 2026
+PROBE_SEED = 17
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--N", type=int, default=20000)
+    ap.add_argument("--Mt", type=int, default=850000)
+    ap.add_argument("--cpu-sample-M", type=int, default=4000, help="markers of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(N, Mt):
+    return (f"linear VAMP inference, synthetic i.i.d. FP64 design N={N} Mt={Mt} ({N * Mt * 8 / 1e9:.0f} GB), CLI defaults "
+            f"(10 mixture components, rho 0.5, gam1 1e-6, CG tol 1e-5, EM 1 it), lam={LAM}, h2={H2}")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, windows):
+        sm, smax, reasons = [], 0.0, set()
+        for t, c in self.rows:
+            if not any(a <= t <= b for a, b in windows) or len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax = max(smax, float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference on the host cores (oracle/_ref), on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference_sample(N, Mt, sample_M, iterations, threads):
+    """Runs the patched reference binary on N x sample_M markers of the same synthetic model for `iterations` VAMP
+    iterations and returns (per-iteration seconds list, description). Its own 'Total iteration time' lines are used
+    (src/vamp.cpp:400), load time excluded, exactly as for the GPU arm."""
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "main_meth_ref")
+    if not os.path.isfile(ref_bin):
+        return None, "oracle/_ref/main_meth_ref missing"
+    from vampomi_b200 import sim
+    with tempfile.TemporaryDirectory() as d:
+        sim.write_dataset(d, "s", N, sample_M, lam=max(LAM, 2.0 / sample_M), h2=H2, seed=DATA_SEED)
+        os.makedirs(os.path.join(d, "out"))
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), VAMPOMI_SEED=str(PROBE_SEED))
+        cmd = [ref_bin, "--meth-file", f"{d}/s.bin", "--phen-file", f"{d}/s.phen", "--N", str(N), "--Mt", str(sample_M), "--out-dir",
+               f"{d}/out", "--out-name", "s", "--iterations", str(iterations), "--stop-criteria-thr", "0", "--true-signal-file",
+               f"{d}/s_ts.bin"]
+        res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            return None, "reference binary failed: " + res.stdout[-300:].replace("\n", " ")
+        times = [float(x) for x in re.findall(r"Total iteration time = ([0-9.eE+-]+)", res.stdout)]
+    desc = (f"oracle/_ref (patched reference, g++ -Ofast -fopenmp, 1 rank x {threads} OpenMP threads) on N={N} x {sample_M} of the "
+            f"{Mt} markers; its own per-iteration timer; it/s scaled by {sample_M}/{Mt} (cost is linear in M)")
+    return times, desc
+
+
+def cpu_baseline(N, Mt, sample_M, warmup, steps):
+    threads = os.cpu_count() or 1
+    times, desc = run_reference_sample(N, Mt, sample_M, warmup + steps, threads)
+    if not times or len(times) < warmup + steps:
+        return None, desc
+    t = float(np.mean(times[warmup:warmup + steps]))
+    value = (1.0 / t) * (sample_M / Mt)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": desc,
+            "sample_s_per_iteration": t}, desc
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    # bounded: W+K iterations of a sample whose iteration takes ~2-4 s on the host cores
+    cb, desc = cpu_baseline(args.N, args.Mt, args.cpu_sample_M, args.warmup, args.steps)
+    if cb is None:
+        print(json.dumps({"impl": "reference", "unavailable": desc}))
+        return 0
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(args.N, args.Mt), "sample": desc},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vampomi_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    N, Mt = args.N, args.Mt
+    t_setup = time.time()
+    sh = capi.Shard(N, Mt, device=local, nranks=world, rank=rank, nccl_id=nccl_id)
+    sh.generate_iid(DATA_SEED)
+    sh.compute_stats()
+    # phenotype of the simulated model y = A beta + noise (simulation/data_sim.py:37-47), built with the device operator
+    rng = np.random.default_rng(DATA_SEED)
+    CM = max(int(Mt * LAM), 1)
+    idx = rng.choice(Mt, size=CM, replace=False)
+    beta = np.zeros(Mt)
+    beta[idx] = rng.normal(0.0, math.sqrt(H2 / CM), CM)
+    noise = rng.normal(0.0, math.sqrt(1.0 - H2), N)
+    beta_sh = beta[sh.S:sh.S + sh.M]
+    g = sh.Ax(beta_sh * math.sqrt(N))
+    y = g + noise
+    y = y * math.sqrt((N - 1) / float(((y - y.mean()) ** 2).sum()))         # data::read_phen scaling, src/data.cpp:97-99
+    setup_s = time.time() - t_setup
+
+    stream = torch.cuda.ExternalStream(sh.stream(), device=torch.device("cuda", local))
+    y_pinned = torch.from_numpy(y.copy()).pin_memory()
+    x1_host = torch.empty(sh.M, dtype=torch.float64).pin_memory()
+    r1_host = torch.empty(sh.M, dtype=torch.float64).pin_memory()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    windows = []
+
+    def leg(e2e):
+        sol = capi.Solver(sh, y, model="linear", true_signal=beta_sh, gamw=1.0 / (1.0 - H2), seed=PROBE_SEED)
+        hist = []
+        for _ in range(args.warmup):
+            hist.append(sol.step(want_vectors=False))
+        barrier()
+        sh.counters(reset=True)
+        sh.profile(True)
+        sh.profile_read(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            if e2e:
+                sh.set(capi.V_Y, y_pinned.numpy())                        # H2D of the step's input
+                hist.append(sol.step(want_vectors=True, out_x1=x1_host.numpy(), out_r1=r1_host.numpy()))   # D2H of its result
+            else:
+                hist.append(sol.step(want_vectors=False))
+        e1.record(stream)
+        barrier()
+        w1 = time.time()
+        windows.append((w0, w1))
+        ms = e0.elapsed_time(e1)
+        prof = sh.profile_read(reset=True)
+        sh.profile(False)
+        cnt = sh.counters()
+        sol.close()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            k = torch.tensor([float(cnt["kernels"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(k)
+            cnt["kernels"] = int(k.item())
+        return ms, hist[args.warmup:], prof, cnt
+
+    ms_dev, hist_dev, prof_dev, cnt_dev = leg(e2e=False)
+    ms_e2e, hist_e2e, prof_e2e, cnt_e2e = leg(e2e=True)
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        sh.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = args.steps / (ms_dev / 1e3)
+    e2e_value = args.steps / (ms_e2e / 1e3)
+    peak, peak_src = measured_peak()
+    # dominant kernel: the matrix pass with the larger total device time in the timed region (rank 0's shard)
+    dom = max(("ax_partial", "atx"), key=lambda k: prof_dev[k]["ms"])
+    pd = prof_dev[dom]
+    bytes_per_launch = pd["bytes"] / max(pd["launches"], 1)
+    avg_ms = pd["ms"] / max(pd["launches"], 1)
+    achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    passes = sum(h["matrix_passes"] for h in hist_dev)
+    iter_bytes = passes * float(N) * float(Mt) * 8.0                       # whole job: P * N * Mt * 8 over the timed region
+    iter_gbs_per_gpu = iter_bytes / (ms_dev * 1e-3) / 1e9 / world
+    matrix_ms = sum(prof_dev[k]["ms"] for k in prof_dev)
+    roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                "launches_timed": pd["launches"],
+                "other_kernel": {k: (prof_dev[k]["bytes"] / max(prof_dev[k]["ms"], 1e-9) / 1e6) for k in ("ax_partial", "atx")},
+                "matrix_kernel_share_of_step": matrix_ms / ms_dev,
+                "whole_iteration": {"passes": passes, "gbs_per_gpu": iter_gbs_per_gpu, "frac_of_peak": iter_gbs_per_gpu / peak,
+                                    "frac_of_8TBs_spec": iter_gbs_per_gpu / 8000.0}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(N, Mt), "N": N, "Mt": Mt, "markers_per_gpu": sh.M, "parallelism": f"marker-shard x{world}",
+                       "l2_note": f"inputs larger than L2: every matrix pass streams {sh.M * N * 8 / 1e9:.1f} GB per GPU",
+                       "cg_iters_per_step": [[h["k1"], h["k2"]] for h in hist_dev], "setup_s": round(setup_s, 2)},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(N * 8 + 2 * 32 * 8), "d2h_bytes_per_step": int(2 * sh.M * 8 * world + 64 * 8 * 12),
+                    "note": "vampomi_solver_step through the host-buffer C ABI; per step: phenotype H2D, x1_hat and r1 D2H"},
+            "gpu_launches": int(cnt_dev["kernels"]),
+            "clocks": sampler.summary(windows)}
+    if not args.no_cpu_baseline and world == 1:
+        cb, _ = cpu_baseline(N, Mt, args.cpu_sample_M, 1, 2)
+        if cb:
+            line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    sh.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

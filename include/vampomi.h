@@ -181,6 +181,13 @@ int vampomi_counters(vampomi_ctx* ctx, long long out[4], int reset);
 /* Times `reps` back-to-back launches of one matrix kernel with CUDA events on the context's stream.
  * which: 0 = Ax (partial + reduce), 1 = ATx, 2 = stats, 3 = loo sums. Returns average milliseconds per launch. */
 int vampomi_time_kernel(vampomi_ctx* ctx, int which, int reps, double* ms_avg);
+/* Per-kernel device timing of the matrix passes (CUDA events on the context stream around every launch while enabled).
+ * read(): out[3k] = launches, out[3k+1] = total ms, out[3k+2] = bytes of A streamed, for k = 0 (k_ax_partial),
+ * 1 (k_ax_reduce + all-reduce + scaling) and 2 (k_atx); synchronises the stream; `reset` clears the accumulators. */
+int vampomi_profile_enable(vampomi_ctx* ctx, int on);
+int vampomi_profile_read(vampomi_ctx* ctx, double out[9], int reset);
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on — for callers that time with their own events. */
+int vampomi_stream(vampomi_ctx* ctx, void** stream);
 /* Tuning knobs (kernel variants); see DESIGN.md. Unknown names fail with VAMPOMI_ERR_ARG. */
 int vampomi_set_tuning(vampomi_ctx* ctx, const char* name, int value);
 

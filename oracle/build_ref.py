@@ -25,6 +25,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("VAMPOMI_REFERENCE_SRC", "/root/reference/src")
 OUT_DIR = os.path.join(HERE, "_ref")
 OUT_BIN = os.path.join(OUT_DIR, "main_meth_ref")
+OUT_BIN_STRICT = os.path.join(OUT_DIR, "main_meth_ref_O2")      # IEEE-strict build (-O2, no fast-math), see DESIGN.md "parity floor"
 
 PATCHES = {
     "vamp.cpp": [
@@ -48,10 +49,11 @@ def available():
     return os.path.isdir(REF_SRC) and all(os.path.isfile(os.path.join(REF_SRC, u)) for u in UNITS)
 
 
-def up_to_date():
-    if not os.path.isfile(OUT_BIN):
+def up_to_date(out_bin=None):
+    out_bin = out_bin or OUT_BIN
+    if not os.path.isfile(out_bin):
         return False
-    t = os.path.getmtime(OUT_BIN)
+    t = os.path.getmtime(out_bin)
     deps = [os.path.abspath(__file__)]
     for root, _, files in os.walk(os.path.join(HERE, "ref_shims")):
         deps += [os.path.join(root, f) for f in files]
@@ -60,12 +62,14 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, strict=False):
+    out_bin = OUT_BIN_STRICT if strict else OUT_BIN
+    opt = ["-O2"] if strict else ["-Ofast"]
     if not available():
         if verbose:
             print(f"[oracle/_ref] reference sources not present at {REF_SRC}; keeping prebuilt binary (if any)")
-        return os.path.isfile(OUT_BIN)
-    if not force and up_to_date():
+        return os.path.isfile(out_bin)
+    if not force and up_to_date(out_bin):
         return True
     os.makedirs(OUT_DIR, exist_ok=True)
     tmp = tempfile.mkdtemp(prefix="vampomi_ref_")
@@ -81,14 +85,14 @@ def build(force=False, verbose=True):
                 with open(os.path.join(tmp, f), "w") as fh:
                     fh.write(text)
         shims = os.path.join(HERE, "ref_shims")
-        cmd = ["g++", "-std=c++17", "-Ofast", "-march=x86-64-v3", "-fopenmp", "-w",
+        cmd = ["g++", "-std=c++17"] + opt + ["-march=x86-64-v3", "-fopenmp", "-w",
                "-I", shims, "-include", os.path.join(shims, "oracle_hooks.h")]
         cmd += [os.path.join(tmp, u) for u in UNITS]
-        cmd += ["-o", OUT_BIN + ".tmp"]
+        cmd += ["-o", out_bin + ".tmp"]
         if verbose:
             print("[oracle/_ref] " + " ".join(cmd))
         subprocess.run(cmd, check=True)
-        os.replace(OUT_BIN + ".tmp", OUT_BIN)
+        os.replace(out_bin + ".tmp", out_bin)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     return True
@@ -96,5 +100,7 @@ def build(force=False, verbose=True):
 
 if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
+    if "--strict" in sys.argv:
+        ok = build(force="--force" in sys.argv, strict=True) and ok
     print(OUT_BIN if ok else "unavailable")
     sys.exit(0 if ok else 1)

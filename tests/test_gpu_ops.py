@@ -1,0 +1,265 @@
+"""Parity of every kernel-level entry point of the C ABI against the numpy oracle, on seeded inputs, through ctypes.
+Shapes include ragged ones (N not a multiple of 4/16/32, a single marker, fewer markers than CTAs, a constant column)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import vamp_oracle as vo
+from vampomi_b200 import capi
+from vampomi_b200.capi import (DIFF2, DOT, SQDEV, V_ATY, V_BERN, V_P1, V_QINV_BERN, V_R1, V_R2, V_TRUE, V_USER_M0,
+                               V_USER_N0, V_USER_N1, V_V, V_X1, V_X1_PREV, V_X2, V_Y, V_Z1, V_Z1HAT)
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(300, 800), (333, 517), (1000, 64), (64, 1), (2050, 300), (4100, 129), (17, 40)]
+
+
+def make(N, M, seed=0, offset=0.0, scale=1.0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((M, N)) * scale + offset
+    y = rng.standard_normal(N)
+    sh = capi.Shard(N, M)
+    sh.upload(A)
+    sh.compute_stats()
+    return sh, A, y, rng
+
+
+@pytest.mark.parametrize("N,M", SHAPES)
+def test_upload_download_stats_ax_atx(N, M):
+    sh, A, y, rng = make(N, M, seed=N + M, offset=0.5, scale=0.1)      # methylation-like: mean 0.5, small spread
+    assert np.array_equal(sh.download(), A)
+    d = vo.Data(A, y)
+    mave, msig = sh.stats()
+    assert np.allclose(mave, d.mave, rtol=1e-13, atol=1e-15) and np.allclose(msig, d.msig, rtol=1e-12)
+    p, x = rng.standard_normal(N), rng.standard_normal(M)
+    assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
+    assert rel_l2(sh.Ax(x), d.Ax(x)) < 1e-12
+    # run-to-run bitwise reproducibility (fixed-order reductions, no atomics on data)
+    assert np.array_equal(sh.Ax(x), sh.Ax(x)) and np.array_equal(sh.ATx(p), sh.ATx(p))
+    sh.close()
+
+
+def test_constant_column_and_alpha_scale():
+    N, M = 200, 50
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((M, N))
+    A[7] = 0.25                                   # constant marker -> msig = 1 (src/data.cpp:275-276)
+    sh = capi.Shard(N, M)
+    sh.upload(A)
+    sh.compute_stats(1.0)
+    assert sh.stats()[1][7] == 1.0
+    sh.compute_stats(0.5)                         # src/data.cpp:273-274
+    want = vo.marker_stats(A, 0.5)[1]
+    assert np.allclose(sh.stats()[1], want, rtol=1e-12)
+    sh.close()
+
+
+@pytest.mark.parametrize("knobs", [dict(ax_rv=1, ax_unroll=2), dict(ax_rv=1, ax_unroll=8), dict(ax_rv=2, ax_unroll=2),
+                                   dict(ax_rv=2, ax_unroll=8), dict(ax_rv=4, ax_unroll=2), dict(ax_rv=4, ax_unroll=4),
+                                   dict(ax_ctas_per_sm=1), dict(ax_ctas_per_sm=7),
+                                   dict(atx_cols=1, atx_unroll=2), dict(atx_cols=1, atx_unroll=8), dict(atx_cols=2, atx_unroll=2),
+                                   dict(atx_cols=2, atx_unroll=8), dict(atx_cols=4, atx_unroll=2), dict(atx_cols=4, atx_unroll=4),
+                                   dict(atx_ctas_per_sm=1), dict(atx_ctas_per_sm=9)])
+def test_kernel_variants_agree(knobs):
+    N, M = 4100, 1033
+    sh, A, y, rng = make(N, M, seed=5)
+    d = vo.Data(A, y)
+    p, x = rng.standard_normal(N), rng.standard_normal(M)
+    for k, v in knobs.items():
+        sh.set_tuning(k, v)
+    assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
+    assert rel_l2(sh.Ax(x), d.Ax(x)) < 1e-12
+    sh.close()
+
+
+def test_generate_iid_is_sharding_invariant_and_matches_restatement():
+    N, Mt = 257, 91
+    full = capi.Shard(N, Mt)
+    full.generate_iid(42)
+    A = full.download()
+    assert np.allclose(A, vo.generate_iid_block(42, 0, Mt, N), rtol=0, atol=1e-13)
+    assert abs(A.mean()) < 0.02 and abs(A.std() - 1) < 0.02
+    for rank in range(3):
+        part = capi.Shard(N, Mt, nranks=3, rank=rank, nccl_id=False)
+        part.generate_iid(42)
+        assert np.array_equal(part.download(), A[part.S:part.S + part.M])     # identical bits for any shard count
+        part.close()
+    full.close()
+
+
+def test_load_file_reads_the_shard_block(tmp_path):
+    N, Mt = 123, 77
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((Mt, N))
+    A.tofile(tmp_path / "a.bin")
+    for rank in range(2):
+        sh = capi.Shard(N, Mt, nranks=2, rank=rank, nccl_id=False)
+        sh.load_file(str(tmp_path / "a.bin"))
+        assert np.array_equal(sh.download(), A[sh.S:sh.S + sh.M])            # byte offset S*N*8, src/data.cpp:134
+        sh.close()
+    sh = capi.Shard(N, Mt + 1)
+    with pytest.raises(capi.VampomiError, match="too short"):
+        sh.load_file(str(tmp_path / "a.bin"))
+    with pytest.raises(capi.VampomiError, match="could not open"):
+        sh.load_file(str(tmp_path / "missing.bin"))
+    sh.close()
+
+
+def test_two_shards_sum_to_the_full_product():
+    N, Mt = 500, 301
+    rng = np.random.default_rng(9)
+    A, x = rng.standard_normal((Mt, N)), rng.standard_normal(Mt)
+    full = capi.Shard(N, Mt)
+    full.upload(A)
+    full.compute_stats()
+    total = np.zeros(N)
+    for r in range(2):
+        M, S = capi.divide_work(Mt, 2, r)
+        part = capi.Shard(N, M)                       # an independent single-rank context over the shard's columns
+        part.upload(A[S:S + M])
+        part.compute_stats()
+        total += part.Ax(x[S:S + M])
+        part.close()
+    assert rel_l2(total, full.Ax(x)) < 1e-13
+    full.close()
+
+
+def test_vector_ops_and_dots():
+    N, M = 300, 1000
+    sh, A, y, rng = make(N, M, seed=2)
+    a, b = rng.standard_normal(M), rng.standard_normal(M)
+    sh.set(V_X1, a)
+    sh.set(V_R1, b)
+    sh.set(V_Y, y)
+    sh.lincomb(V_R2, 1.7, V_X1, -0.3, V_R1, 2.5)
+    assert np.allclose(sh.get(V_R2), (1.7 * a - 0.3 * b) / 2.5, rtol=1e-15)
+    assert np.allclose(sh.get(V_X1, divisor=math.sqrt(N)), a / math.sqrt(N), rtol=1e-15)
+    sh.copy(V_X2, V_X1)
+    assert np.array_equal(sh.get(V_X2), a)
+    sh.fill(V_V, 3.0)
+    got = sh.dots([(DOT, V_X1, V_R1), (DIFF2, V_X1, V_R1), (SQDEV, V_X1, V_R1, 2.0), (DOT, V_Y, V_Y), (DOT, V_V, V_V)])
+    want = [a @ b, ((a - b) ** 2).sum(), ((a - 2 * b) ** 2).sum(), y @ y, 9.0 * M]
+    assert np.allclose(got, want, rtol=1e-13)
+    sh.close()
+
+
+def test_probe_matches_counter_hash():
+    sh = capi.Shard(100, 997, nranks=3, rank=1, nccl_id=False)
+    sh.draw_probe(12345, 4)
+    want = vo.probe_signs(12345, 4, sh.S, sh.M) / math.sqrt(997)
+    assert np.array_equal(sh.get(V_BERN), want)
+    sh.close()
+
+
+@pytest.mark.parametrize("gam1", [1e-6, 0.37, 25.0, 1e12])
+def test_denoiser_matches_oracle(gam1):
+    N, M = 200, 5000
+    sh, A, y, rng = make(N, M, seed=4)
+    probs = np.array(vo.DEFAULT_PROBS)
+    vars_int = np.array(vo.DEFAULT_VARS) * N
+    r1 = rng.standard_normal(M) * 3
+    r1[:5] = [0.0, 1e-300, -40.0, 40.0, 1e3]
+    prev = rng.standard_normal(M)
+    o = vo.Vamp(vo.Data(A, y), vars=vo.DEFAULT_VARS, probs=vo.DEFAULT_PROBS)
+    for damp in (False, True):
+        sh.set(V_R1, r1)
+        sh.set(V_X1, prev)
+        s = sh.denoise(gam1, probs, vars_int, damp=damp, rho=0.3)
+        g, gd = o.g1(r1, gam1), o.g1d(r1, gam1)
+        want = 0.3 * g + 0.7 * prev if damp else g
+        assert rel_l2(sh.get(V_X1), want) < 1e-12
+        assert np.array_equal(sh.get(V_X1_PREV), prev)
+        assert abs(s - gd.sum()) <= 1e-9 * max(abs(gd).sum(), 1.0)      # gd cancels to ~1e-8 per term when gam1 is tiny
+    sh.close()
+
+
+def test_em_sums_match_oracle():
+    N, M = 150, 4000
+    sh, A, y, rng = make(N, M, seed=6)
+    r1 = rng.standard_normal(M) * 2
+    sh.set(V_R1, r1)
+    o = vo.Vamp(vo.Data(A, y))
+    probs, vars_int = list(o.probs), list(o.vars)
+    lam = 1 - probs[0]
+    omegas = [probs[0]] + [p / lam for p in probs[1:]]
+    s_pin, s_beta, s_gam = o.em_sums(r1, 0.8, lam, omegas, vars_int)
+    got = sh.em_sums(0.8, lam, omegas, vars_int)
+    L = len(probs)
+    assert np.allclose(got[0], s_pin, rtol=1e-12)
+    assert np.allclose(got[1:L], s_beta, rtol=1e-11, atol=1e-300)
+    assert np.allclose(got[L:], s_gam, rtol=1e-11, atol=1e-300)
+    sh.close()
+
+
+def test_probit_z_channel_matches_oracle():
+    N, M = 3000, 40
+    sh, A, y, rng = make(N, M, seed=7)
+    yb = (rng.random(N) > 0.5).astype(float)
+    p1 = rng.standard_normal(N) * 4
+    p1[:4] = [0.0, 30.0, -30.0, 12.0]             # hits both erfcx clamps of src/utilities.cpp:295-298
+    sh.set(V_Y, yb)
+    sh.set(V_P1, p1)
+    for tau1 in (1e-2, 1.3, 50.0):
+        s = sh.probit_zdenoise(tau1)
+        want_z = vo.g1_bin_class(p1, tau1, yb)
+        want_d = vo.g1d_bin_class(p1, tau1, yb)
+        got_z = sh.get(V_Z1HAT)
+        fin = np.isfinite(want_z)
+        assert np.array_equal(np.isfinite(got_z), fin)
+        assert np.allclose(got_z[fin], want_z[fin], rtol=1e-12, atol=1e-300)
+        if np.isfinite(want_d.sum()):
+            assert abs(s - want_d.sum()) <= 1e-11 * abs(want_d).sum()
+    sh.close()
+
+
+@pytest.mark.parametrize("onsager", [False, True])
+def test_cg_matches_oracle(onsager):
+    N, M = 400, 1000
+    sh, A, y, rng = make(N, M, seed=8)
+    d = vo.Data(A, y)
+    o = vo.Vamp(d, CG_err_tol=1e-7)
+    o.gam2 = 1.9
+    tau = 2.3
+    v = rng.standard_normal(M)
+    mu0 = rng.standard_normal(M) * 0.1
+    sh.set(V_V, v)
+    # cold start
+    mu = o.precondCG_solver(v, None, tau, 0 if onsager else 1)
+    it, rel, vmu = sh.cg_solve(V_V, V_X2, tau, 1.9, warm_start=False, tol=1e-7, max_iter=500, onsager_mode=onsager)
+    assert it == o.cg_iters[-1][2]
+    assert rel_l2(sh.get(V_X2), mu) < 1e-11
+    assert abs(vmu - v @ mu) < 1e-11 * abs(v @ mu)
+    # warm start (src/vamp.cpp:311): same fixed point, fewer iterations
+    mu_w = o.precondCG_solver(v, mu0, tau, 1)
+    sh.set(V_X2, mu0)
+    it_w, rel_w, _ = sh.cg_solve(V_V, V_X2, tau, 1.9, warm_start=True, tol=1e-7, max_iter=500)
+    assert it_w == o.cg_iters[-1][2] and rel_l2(sh.get(V_X2), mu_w) < 1e-11
+    # iteration cap (CG_max_iter) and different look-ahead depths give the same answer
+    it_c, _, _ = sh.cg_solve(V_V, V_X2, tau, 1.9, tol=1e-30, max_iter=3)
+    assert it_c == 3
+    for depth in (1, 4):
+        sh.set_tuning("cg_depth", depth)
+        it_d, _, _ = sh.cg_solve(V_V, V_QINV_BERN, tau, 1.9, tol=1e-7, max_iter=500, onsager_mode=onsager)
+        assert it_d == it and rel_l2(sh.get(V_QINV_BERN), mu) < 1e-11
+    sh.close()
+
+
+def test_association_pvalues_match_oracle():
+    N, M = 300, 700
+    sh, A, y, rng = make(N, M, seed=10, offset=0.4, scale=0.2)
+    d = vo.Data(A, y)
+    r1 = rng.standard_normal(M) * 0.2
+    r1[:3] = [0.0, -5.0, 5.0]
+    got = sh.pvals_se(r1, 3.3)
+    assert np.allclose(got, vo.pvals_se(r1, 3.3, N), rtol=1e-12, atol=1e-300)
+    # loo: device sums over the RAW columns, host algebra of src/data.cpp:404-414
+    x1 = rng.standard_normal(M) * 0.3
+    z1 = d.Ax(x1)
+    w = y - z1
+    sh.set(V_USER_N1, w)
+    sums = sh.loo_sums(V_USER_N1)
+    assert np.allclose(sums[:, 0], A.sum(1), rtol=1e-12) and np.allclose(sums[:, 1], (A * A).sum(1), rtol=1e-12)
+    assert np.allclose(sums[:, 2], A @ w, rtol=1e-10, atol=1e-10)
+    sh.close()

@@ -1,0 +1,116 @@
+#!/usr/bin/env python3
+"""Regenerates tests/golden/*.npz from the reference itself (oracle/_ref/main_meth_ref, built by oracle/build_ref.py
+from /root/reference with the four scripted patches). Runs only in the build container (the GPU box has no
+/root/reference); the fixtures are committed. Inputs are NOT stored: tests rebuild them from the seeds recorded in
+each fixture with vampomi_b200.sim.simulate and verify the recorded SHA-256 first.
+"""
+import hashlib
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import build_ref  # noqa: E402
+from oracle import vamp_oracle as vo  # noqa: E402
+from vampomi_b200 import sim  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    "linear_small": dict(N=300, M=800, lam=0.05, h2=0.6, data_seed=11, probe_seed=3, iterations=6, model="linear", extra=[]),
+    "linear_readme": dict(N=1000, M=2000, lam=0.1, h2=0.8, data_seed=1234, probe_seed=7, iterations=10, model="linear", extra=[]),
+    "linear_ragged": dict(N=333, M=517, lam=0.05, h2=0.5, data_seed=5, probe_seed=9, iterations=5, model="linear",
+                          extra=["--EM-max-iter", "3", "--learn-prior-delay", "2", "--rho", "0.7"]),
+    "linear_wellcond": dict(N=300, M=800, lam=0.05, h2=0.6, data_seed=11, probe_seed=3, iterations=6, model="linear",
+                            extra=["--gam1", "1e-2"]),
+    "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
+                         extra=["--gam1", "1e-2"]),
+}
+
+
+def run_ref(args, seed, threads=4, binary=None):
+    env = dict(os.environ, VAMPOMI_SEED=str(seed), OMP_NUM_THREADS=str(threads))
+    res = subprocess.run([binary or build_ref.OUT_BIN] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(res.stdout[-3000:])
+    return res.stdout
+
+
+def cg_counts(log):
+    """Per VAMP iteration (k1, k2) from the --verbosity 1 log: '[CG] it = i' lines; the onsager solve prints one line
+    less than it iterates when its own test stops it (src/vamp.cpp:718-719 breaks before :747-748)."""
+    out = []
+    for block in log.split("iteration = ")[1:]:
+        lm, ons = block.split("CG took")[0], block.split("CG took")[1].split("onsager took")[0]
+        k1 = len(re.findall(r"\[CG\] it = ", lm))
+        n_cg = len(re.findall(r"\[CG\] it = ", ons))
+        n_on = len(re.findall(r"\[CG onsager\] it = ", ons))
+        last_rel = re.findall(r"\|\|r_it\|\| / \|\|RHS\|\| = ([0-9.e+-]+)", ons)
+        # iterations executed = residual lines + 1 if the onsager test ended the solve
+        k2 = n_cg + (0 if n_on == n_cg and last_rel and float(last_rel[-1]) < 1e-5 else 1)
+        out.append((k1, k2))
+    return np.array(out, dtype=np.int64)
+
+
+def make_case(name, c):
+    with tempfile.TemporaryDirectory() as d:
+        X, y, beta = sim.write_dataset(d, "ex", c["N"], c["M"], c["lam"], c["h2"], c["data_seed"], binary=c["model"] == "bin_class")
+        os.makedirs(os.path.join(d, "out"))
+        args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", str(c["N"]), "--Mt", str(c["M"]),
+                "--out-dir", f"{d}/out", "--out-name", "g", "--iterations", str(c["iterations"]), "--true-signal-file",
+                f"{d}/ex_ts.bin", "--model", c["model"], "--stop-criteria-thr", "0", "--verbosity", "1"] + c["extra"]
+        log = run_ref(args, c["probe_seed"])
+        x1 = np.stack([np.fromfile(f"{d}/out/g_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+        r1 = np.stack([np.fromfile(f"{d}/out/g_r1_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+        blob = {k: np.frombuffer(open(f"{d}/out/g_{k}.csv", "rb").read(), dtype=np.uint8) for k in ("params", "metrics", "prior")}
+        fix = dict(x1=x1, r1=r1, csv_params=blob["params"], csv_metrics=blob["metrics"], csv_prior=blob["prior"],
+                   N=c["N"], M=c["M"], lam=c["lam"], h2=c["h2"], data_seed=c["data_seed"], probe_seed=c["probe_seed"],
+                   iterations=c["iterations"], model=c["model"], extra=np.array(c["extra"], dtype="U32"),
+                   sha256_A=hashlib.sha256(X.tobytes()).hexdigest(), sha256_phen=hashlib.sha256(open(f"{d}/ex.phen", "rb").read()).hexdigest())
+        if c["model"] == "linear":
+            fix["cg_iters"] = cg_counts(log)
+        if name == "linear_small":
+            # the same run by an IEEE-strict (-O2) build of the same patched sources: how far the reference is from
+            # ITSELF when only compiler flags change — the floor any independent implementation can be held to
+            os.makedirs(os.path.join(d, "out2"))
+            args2 = [a.replace(f"{d}/out", f"{d}/out2") for a in args]
+            run_ref(args2, c["probe_seed"], binary=build_ref.OUT_BIN_STRICT)
+            fix["x1_O2"] = np.stack([np.fromfile(f"{d}/out2/g_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+            fix["r1_O2"] = np.stack([np.fromfile(f"{d}/out2/g_r1_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+            # association tests and out-of-sample test mode from this run's saved files (src/main_meth.cpp:112-265)
+            params = vo.read_csv_rows(f"{d}/out/g_params.csv")
+            last = c["iterations"]
+            gam1_last = params[last][1]
+            run_ref(["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", str(c["N"]), "--Mt", str(c["M"]),
+                     "--out-dir", f"{d}/out", "--out-name", "g", "--run-mode", "association_test", "--pval-method", "se",
+                     "--r1-file", f"{d}/out/g_r1_it_{last}.bin", "--gam1", repr(gam1_last)], c["probe_seed"])
+            run_ref(["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", str(c["N"]), "--Mt", str(c["M"]),
+                     "--out-dir", f"{d}/out", "--out-name", "g", "--run-mode", "association_test", "--pval-method", "loo",
+                     "--estimate-file", f"{d}/out/g_it_{last}.bin"], c["probe_seed"])
+            fix["se_gam1"] = gam1_last
+            fix["pval_se"] = np.fromfile(f"{d}/out/g_it_{last}_pval_se.bin")
+            fix["pval_loo"] = np.fromfile(f"{d}/out/g_it_{last}_pval_loo.bin")
+            Nt = 200
+            sim.write_dataset(d, "tst", Nt, c["M"], c["lam"], c["h2"], c["data_seed"] + 1000)
+            run_ref(["--meth-file-test", f"{d}/tst.bin", "--phen-file-test", f"{d}/tst.phen", "--N-test", str(Nt), "--Mt", str(c["M"]),
+                     "--out-dir", f"{d}/out", "--out-name", "g", "--run-mode", "test", "--estimate-file", f"{d}/out/g_it_1.bin",
+                     "--test-iter-range", f"1,{last}"], c["probe_seed"])
+            fix["N_test"] = Nt
+            fix["csv_test"] = np.frombuffer(open(f"{d}/out/g_test.csv", "rb").read(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **fix)
+        print(name, "ok:", {k: (v.shape if hasattr(v, "shape") else v) for k, v in fix.items() if k in ("x1", "cg_iters", "csv_params")})
+
+
+if __name__ == "__main__":
+    if not build_ref.build() or not build_ref.build(strict=True):
+        sys.exit("oracle/_ref is not available (no /root/reference here?)")
+    os.makedirs(GOLDEN, exist_ok=True)
+    for n, c in CASES.items():
+        if len(sys.argv) > 1 and n not in sys.argv[1:]:
+            continue
+        make_case(n, c)

@@ -57,6 +57,39 @@ int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n) {
     return VAMPOMI_OK;
 }
 
+int prof_begin(vampomi_ctx* c, int kind, double bytes) {
+    if (!c->profile) return -1;
+    vampomi_ctx::ProfSpan sp;
+    sp.kind = kind; sp.bytes = bytes;
+    for (cudaEvent_t* e : {&sp.e0, &sp.e1}) {
+        if (!c->prof_free.empty()) { *e = c->prof_free.back(); c->prof_free.pop_back(); }
+        else if (cudaEventCreate(e) != cudaSuccess) return -1;
+    }
+    cudaEventRecord(sp.e0, c->stream);
+    c->prof_pending.push_back(sp);
+    return (int)c->prof_pending.size() - 1;
+}
+void prof_end(vampomi_ctx* c, int idx) {
+    if (idx < 0 || idx >= (int)c->prof_pending.size()) return;
+    cudaEventRecord(c->prof_pending[idx].e1, c->stream);
+}
+int prof_resolve(vampomi_ctx* c) {
+    if (c->prof_pending.empty()) return VAMPOMI_OK;
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& sp : c->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) {
+            c->prof_acc[3 * sp.kind] += 1.0;
+            c->prof_acc[3 * sp.kind + 1] += (double)ms;
+            c->prof_acc[3 * sp.kind + 2] += sp.bytes;
+        }
+        c->prof_free.push_back(sp.e0);
+        c->prof_free.push_back(sp.e1);
+    }
+    c->prof_pending.clear();
+    return VAMPOMI_OK;
+}
+
 static int ensure_stage(vampomi_ctx* c, size_t elems) {
     if (elems <= c->stage_elems) return VAMPOMI_OK;
     if (c->stage) VO_CUDA(cudaFreeHost(c->stage));
@@ -185,6 +218,8 @@ int vampomi_destroy(vampomi_ctx* c) {
     if (!c) return VAMPOMI_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& sp : c->prof_pending) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
+    for (auto e : c->prof_free) cudaEventDestroy(e);
     if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
     cudaFree(c->A); cudaFree(c->mave); cudaFree(c->msig);
     for (auto p : c->mvec) cudaFree(p);
@@ -540,6 +575,28 @@ int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
     if (dsums) cudaFree(dsums);
     memcpy(c->counters, saved, sizeof(saved));
     return rc;
+}
+
+int vampomi_profile_enable(vampomi_ctx* c, int on) {
+    VO_ARG(c, "profile_enable: NULL context");
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(prof_resolve(c));
+    c->profile = on != 0;
+    return VAMPOMI_OK;
+}
+
+int vampomi_profile_read(vampomi_ctx* c, double out[9], int reset) {
+    VO_ARG(c && out, "profile_read: NULL argument");
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(prof_resolve(c));
+    for (int i = 0; i < 9; i++) { out[i] = c->prof_acc[i]; if (reset) c->prof_acc[i] = 0; }
+    return VAMPOMI_OK;
+}
+
+int vampomi_stream(vampomi_ctx* c, void** stream) {
+    VO_ARG(c && stream, "stream: NULL argument");
+    *stream = (void*)c->stream;
+    return VAMPOMI_OK;
 }
 
 int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {

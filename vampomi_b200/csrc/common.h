@@ -107,6 +107,12 @@ struct vampomi_ctx {
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;
     long long counters[4] = {0, 0, 0, 0};
+    // optional per-launch device timing (vampomi_profile_*)
+    bool profile = false;
+    struct ProfSpan { int kind; cudaEvent_t e0, e1; double bytes; };
+    std::vector<ProfSpan> prof_pending;
+    std::vector<cudaEvent_t> prof_free;
+    double prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace vampomi {
@@ -148,5 +154,9 @@ int launch_cg_step(vampomi_ctx* c, const double* v, double* mu, double diag, int
 int launch_cg_finish(vampomi_ctx* c, int parity, double gam2, double tol, int max_iter, int onsager_mode, const double* sums_dev);
 // all-reduce `n` doubles in place on the context stream (no-op for nranks == 1)
 int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n);
+// profiling spans: begin returns an index (or -1 when profiling is off), end closes it
+int prof_begin(vampomi_ctx* c, int kind, double bytes);
+void prof_end(vampomi_ctx* c, int idx);
+int prof_resolve(vampomi_ctx* c);
 
 }  // namespace vampomi

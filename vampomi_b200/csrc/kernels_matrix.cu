@@ -280,9 +280,14 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
         c->ax_partial_elems = need;
     }
     dim3 grid(p.ntiles, p.nchunks);
+    const double a_bytes = (double)c->M * c->N * 8.0;
+    if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
+    int sp = prof_begin(c, 0, a_bytes);
     ax_kernel(p.rv, p.U)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
                                                       c->ax_partial, done_flag);
+    prof_end(c, sp);
     VO_CUDA(cudaGetLastError());
+    sp = prof_begin(c, 1, 0.0);
     const double sqrtN = sqrt((double)c->N);
     constexpr int SL = 8;
     int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
@@ -295,6 +300,7 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
         VO_CHECK(allreduce_inplace(c, out_dev, (size_t)c->N));                // MPI_Allreduce, src/data.cpp:367
         VO_CHECK(launch_scale_div(c, out_dev, out_dev, sqrtN, c->N, done_flag));
     }
+    prof_end(c, sp);
     return VAMPOMI_OK;
 }
 
@@ -387,7 +393,9 @@ int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* 
     long long maxb = (c->M + 8 * C - 1) / (8 * C);
     if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
     const double scale = 1.0 / sqrt((double)c->N);                              // src/data.cpp:326-327
+    int sp = prof_begin(c, 2, (double)c->M * c->N * 8.0);
     atx_kernel(C, U)<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
+    prof_end(c, sp);
     c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;

@@ -1,0 +1,36 @@
+"""Marker sharding over several GPUs of one node (NCCL all-reduce of the N-length A x partial sums and of the packed
+scalar sums): results must not depend on the number of shards. Skipped on single-GPU boxes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from vampomi_b200 import build, capi
+from helpers import assert_rows_close, csv_rows, golden_inputs, load_golden, rel_l2, tolerances
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,gpus", [("linear_wellcond", 2), ("probit_small", 2), ("linear_ragged", 3), ("linear_wellcond", 4)])
+def test_main_meth_is_shard_invariant(name, gpus, tmp_path):
+    if capi.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    g = load_golden(name)
+    rel_vec, rel_csv = tolerances(g)
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    its = int(g["iterations"])
+    args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out",
+            "--out-name", "g", "--iterations", its, "--true-signal-file", f"{d}/ex_ts.bin", "--model", g["model"],
+            "--stop-criteria-thr", "0", "--seed", g["probe_seed"], "--gpus", gpus] + list(g["extra"])
+    res = subprocess.run([build.MAIN_METH] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:]
+    for k in range(1, its + 1):
+        x1 = np.fromfile(f"{d}/out/g_it_{k}.bin")
+        assert x1.size == int(g["M"])
+        assert rel_l2(x1, g["x1"][k - 1]) < rel_vec
+        assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < rel_vec
+    for kind in ("params", "metrics"):
+        assert_rows_close(csv_rows(open(f"{d}/out/g_{kind}.csv", "rb").read()), csv_rows(g[f"csv_{kind}"]), rel_csv, kind)

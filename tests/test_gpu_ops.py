@@ -38,6 +38,12 @@ def test_upload_download_stats_ax_atx(N, M):
     assert rel_l2(sh.Ax(x), d.Ax(x)) < 1e-12
     # run-to-run bitwise reproducibility (fixed-order reductions, no atomics on data)
     assert np.array_equal(sh.Ax(x), sh.Ax(x)) and np.array_equal(sh.ATx(p), sh.ATx(p))
+    # the bulk-copy (cp.async.bulk + mbarrier) pipelines on the same ragged shapes
+    sh.set_tuning("ax_impl", 1)
+    sh.set_tuning("atx_impl", 1)
+    assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
+    assert rel_l2(sh.Ax(x), d.Ax(x)) < 1e-12
+    assert np.array_equal(sh.Ax(x), sh.Ax(x)) and np.array_equal(sh.ATx(p), sh.ATx(p))
     sh.close()
 
 
@@ -61,7 +67,8 @@ def test_constant_column_and_alpha_scale():
                                    dict(ax_ctas_per_sm=1), dict(ax_ctas_per_sm=7),
                                    dict(atx_cols=1, atx_unroll=2), dict(atx_cols=1, atx_unroll=8), dict(atx_cols=2, atx_unroll=2),
                                    dict(atx_cols=2, atx_unroll=8), dict(atx_cols=4, atx_unroll=2), dict(atx_cols=4, atx_unroll=4),
-                                   dict(atx_ctas_per_sm=1), dict(atx_ctas_per_sm=9)])
+                                   dict(atx_ctas_per_sm=1), dict(atx_ctas_per_sm=9),
+                                   dict(ax_impl=1), dict(atx_impl=1), dict(ax_impl=1, ax_ctas_per_sm=1), dict(atx_impl=1, atx_ctas_per_sm=1)])
 def test_kernel_variants_agree(knobs):
     N, M = 4100, 1033
     sh, A, y, rng = make(N, M, seed=5)
@@ -169,7 +176,10 @@ def test_denoiser_matches_oracle(gam1):
         s = sh.denoise(gam1, probs, vars_int, damp=damp, rho=0.3)
         g, gd = o.g1(r1, gam1), o.g1d(r1, gam1)
         want = 0.3 * g + 0.7 * prev if damp else g
-        assert rel_l2(sh.get(V_X1), want) < 1e-12
+        # g1 = y + sigma*pkd/pk cancels against y when gam1 is tiny (|g1| ~ 1e-7 |y| at gam1 = 1e-6): the error budget
+        # is a few ulps of the INPUT magnitude, not of the output
+        err = np.linalg.norm(sh.get(V_X1) - want)
+        assert err <= 1e-12 * np.linalg.norm(want) + 2e-15 * np.linalg.norm(r1[np.abs(r1) < 100]), (err, np.linalg.norm(want))
         assert np.array_equal(sh.get(V_X1_PREV), prev)
         assert abs(s - gd.sum()) <= 1e-9 * max(abs(gd).sum(), 1.0)      # gd cancels to ~1e-8 per term when gam1 is tiny
     sh.close()

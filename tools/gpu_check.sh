@@ -13,7 +13,7 @@ nvidia-smi > $OUT/nvidia-smi.txt 2>&1
 ( nproc; lscpu | grep -E "Model name|Socket|Core|Thread|^CPU\(s\)"; free -g | head -2 ) > $OUT/host.txt 2>&1
 
 step smoke timeout 600 python -c "import __graft_entry__ as g; g.smoke()"
-step pytest_gpu timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600
+step pytest_gpu timeout 1500 python -m pytest tests -m gpu -q --timeout 600
 if [ "${SKIP_SWEEP:-0}" != "1" ]; then
   step sweep timeout 900 python tools/sweep.py --reps 10
 fi

@@ -46,6 +46,11 @@ for (rv, u), o in itertools.product(ax_variants, occ):
     t(0, "ax", ax_rv=rv, ax_unroll=u, ax_ctas_per_sm=o)
 for (c, u), o in itertools.product(atx_variants, occ):
     t(1, "atx", atx_cols=c, atx_unroll=u, atx_ctas_per_sm=o)
+for o in ([0] if a.quick else [0, 1, 2, 3]):
+    t(0, "ax", ax_impl=1, ax_ctas_per_sm=o)
+    t(1, "atx", atx_impl=1, atx_ctas_per_sm=o)
+sh.set_tuning("ax_impl", 0)
+sh.set_tuning("atx_impl", 0)
 t(2, "stats")
 t(3, "loo")
 best = {k: max((r for r in results if r["kernel"] == k), key=lambda r: r["gbs"]) for k in ("ax", "atx")}

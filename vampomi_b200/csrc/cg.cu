@@ -11,6 +11,7 @@
 // every later launch returns at its first instruction. The host never waits for a dot product: it keeps
 // `cg_depth` iterations enqueued ahead and only polls the done flag of an iteration that has already finished.
 #include <string.h>
+#include <vector>
 #include "common.h"
 
 extern "C" int vampomi_cg_solve(vampomi_ctx* c, int rhs_vec, int sol_vec, int warm_start, double tau, double gam2,
@@ -46,12 +47,20 @@ extern "C" int vampomi_cg_solve(vampomi_ctx* c, int rhs_vec, int sol_vec, int wa
     cudaEvent_t ev[32];
     for (int k = 0; k < depth; k++) VO_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
     int rc = VAMPOMI_OK;
+    // bookkeeping of what was enqueued per CG iteration, so that look-ahead launches that turn out to be no-ops (the
+    // done flag was already set when they ran) are not reported as matrix passes / streamed bytes / timed launches
+    int launched = 0;
+    std::vector<size_t> span_mark;
+    if (c->prof_pending.size() > 2048) VO_CHECK(prof_resolve(c));
+    const long long pass_bytes = (long long)c->M * c->N * 8;
     for (int i = 0; i < max_iter; i++) {
         const int parity = i & 1, slot = i % depth;
         if (i >= depth) {                                   // poll the flag of iteration i - depth (already retired or close to)
             if (cudaEventSynchronize(ev[slot]) != cudaSuccess) { set_error("cg_solve: event sync failed"); rc = VAMPOMI_ERR_CUDA; break; }
             if (c->cg_poll_host[slot] != 0) break;
         }
+        span_mark.push_back(c->prof_pending.size());
+        launched = i + 1;
         if ((rc = launch_ax(c, p, tmpN, done)) != VAMPOMI_OK) break;
         if ((rc = launch_atx(c, tmpN, atx_out, done)) != VAMPOMI_OK) break;
         if ((rc = launch_cg_dp(c, atx_out, tau, gam2, c->sums)) != VAMPOMI_OK) break;
@@ -74,6 +83,19 @@ extern "C" int vampomi_cg_solve(vampomi_ctx* c, int rhs_vec, int sol_vec, int wa
             rc = VAMPOMI_ERR_CUDA;
         } else {
             memcpy(&fin, c->sums_host, sizeof(CgScalars));
+            if (fin.iters < launched) {
+                const int idle = launched - fin.iters;
+                c->counters[1] -= 2LL * idle;
+                c->counters[2] -= 2LL * idle * pass_bytes;
+                if (c->profile && (size_t)fin.iters < span_mark.size() && span_mark[fin.iters] <= c->prof_pending.size()) {
+                    // drop the spans of the idle iterations
+                    for (size_t k = span_mark[fin.iters]; k < c->prof_pending.size(); k++) {
+                        c->prof_free.push_back(c->prof_pending[k].e0);
+                        c->prof_free.push_back(c->prof_pending[k].e1);
+                    }
+                    c->prof_pending.resize(span_mark[fin.iters]);
+                }
+            }
             if (iters) *iters = fin.iters;
             if (rel_err) *rel_err = fin.rel_err;
             if (rhs_dot_sol) *rhs_dot_sol = fin.vmu;

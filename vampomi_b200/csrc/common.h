@@ -77,6 +77,8 @@ struct Tuning {
     int atx_unroll = 4;
     int atx_ctas_per_sm = 0;
     int cg_depth = 2;                // CG iterations kept enqueued ahead of the completion poll
+    int ax_impl = 0;                 // 0 = per-thread 256-bit LDG streaming, 1 = bulk-copy (cp.async.bulk + mbarrier) pipeline
+    int atx_impl = 0;
 };
 
 }  // namespace vampomi
@@ -107,6 +109,7 @@ struct vampomi_ctx {
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;
     long long counters[4] = {0, 0, 0, 0};
+    bool bulk_attr_ax = false, bulk_attr_atx = false;   // opt-in shared-memory size set for the bulk kernels on this device
     // optional per-launch device timing (vampomi_profile_*)
     bool profile = false;
     struct ProfSpan { int kind; cudaEvent_t e0, e1; double bytes; };
@@ -135,6 +138,9 @@ int launch_stats(vampomi_ctx* c, double alpha_scale);
 int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag);     // incl. all-reduce and 1/sqrt(N)
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
 int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev);
+// ---- launchers (kernels_bulk.cu) ----
+int launch_atx_bulk(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
+int launch_ax_bulk(vampomi_ctx* c, const double* x_dev, const int* done_flag, int* nchunks_out);
 // ---- launchers (kernels_vector.cu) ----
 int launch_fill(vampomi_ctx* c, double* dst, long long n, double v);
 int launch_lincomb(vampomi_ctx* c, double* dst, double a, const double* x, double b, const double* y, double cdiv, long long n);

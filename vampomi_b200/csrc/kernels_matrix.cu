@@ -271,22 +271,30 @@ static AxPlan plan_ax(const vampomi_ctx* c) {
 
 int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag) {
     AxPlan p = plan_ax(c);
-    size_t need = (size_t)p.nchunks * c->ld;
-    if (need > c->ax_partial_elems) {
-        VO_CUDA(cudaStreamSynchronize(c->stream));
-        if (c->ax_partial) VO_CUDA(cudaFree(c->ax_partial));
-        c->ax_partial = nullptr;
-        VO_CUDA(cudaMalloc(&c->ax_partial, need * sizeof(double)));
-        c->ax_partial_elems = need;
-    }
-    dim3 grid(p.ntiles, p.nchunks);
     const double a_bytes = (double)c->M * c->N * 8.0;
     if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
-    int sp = prof_begin(c, 0, a_bytes);
-    ax_kernel(p.rv, p.U)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
-                                                      c->ax_partial, done_flag);
-    prof_end(c, sp);
-    VO_CUDA(cudaGetLastError());
+    int sp;
+    if (c->tune.ax_impl == 1) {
+        sp = prof_begin(c, 0, a_bytes);
+        int rc = launch_ax_bulk(c, x_dev, done_flag, &p.nchunks);
+        prof_end(c, sp);
+        VO_CHECK(rc);
+    } else {
+        size_t need = (size_t)p.nchunks * c->ld;
+        if (need > c->ax_partial_elems) {
+            VO_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->ax_partial) VO_CUDA(cudaFree(c->ax_partial));
+            c->ax_partial = nullptr;
+            VO_CUDA(cudaMalloc(&c->ax_partial, need * sizeof(double)));
+            c->ax_partial_elems = need;
+        }
+        dim3 grid(p.ntiles, p.nchunks);
+        sp = prof_begin(c, 0, a_bytes);
+        ax_kernel(p.rv, p.U)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
+                                                          c->ax_partial, done_flag);
+        prof_end(c, sp);
+        VO_CUDA(cudaGetLastError());
+    }
     sp = prof_begin(c, 1, 0.0);
     const double sqrtN = sqrt((double)c->N);
     constexpr int SL = 8;
@@ -394,6 +402,12 @@ int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* 
     if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
     const double scale = 1.0 / sqrt((double)c->N);                              // src/data.cpp:326-327
     int sp = prof_begin(c, 2, (double)c->M * c->N * 8.0);
+    if (c->tune.atx_impl == 1) {
+        int rc = launch_atx_bulk(c, p_dev, out_dev, done_flag);
+        prof_end(c, sp);
+        c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+        return rc;
+    }
     atx_kernel(C, U)<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
     prof_end(c, sp);
     c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;

@@ -17,6 +17,8 @@ ap.add_argument("--N", type=int, default=20000)
 ap.add_argument("--M", type=int, default=106250)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--sustained", type=int, default=0, help="also time a short list of variants with this many back-to-back reps "
+                "(seconds-long, i.e. under the power cap) instead of a burst")
 a = ap.parse_args()
 
 sh = vb.Shard(a.N, a.M)
@@ -29,15 +31,34 @@ gb = a.N * a.M * 8 / 1e9
 results = []
 
 
-def t(which, label, **knobs):
+def t(which, label, reps=None, **knobs):
     for k, v in knobs.items():
         sh.set_tuning(k, v)
     sh.time_kernel(which, 2)
-    ms = sh.time_kernel(which, a.reps)
-    rec = dict(kernel=label, ms=ms, gbs=gb / (ms * 1e-3), **knobs)
+    ms = sh.time_kernel(which, reps or a.reps)
+    rec = dict(kernel=label, ms=ms, gbs=gb / (ms * 1e-3), reps=reps or a.reps, **knobs)
     results.append(rec)
     print(json.dumps(rec), flush=True)
 
+
+if a.sustained:
+    base = dict(ax_impl=0, atx_impl=0, center_split=0, ax_ctas_per_sm=0, atx_ctas_per_sm=0)
+    for split in (0,):
+        for rv, u in ((2, 4), (4, 2)):
+            t(0, "ax_sustained", a.sustained, **dict(base, ax_rv=rv, ax_unroll=u, center_split=split))
+        for c_, u in ((2, 4), (1, 2)):
+            t(1, "atx_sustained", a.sustained, **dict(base, atx_cols=c_, atx_unroll=u, center_split=split))
+    for c_, u in ((1, 2), (1, 4), (1, 8), (2, 2), (2, 4), (2, 8), (4, 2), (4, 4)):
+        for o in (0, 4, 8):
+            t(1, "atx_cta_sustained", a.sustained, **dict(base, atx_impl=2, atx_cols=c_, atx_unroll=u, atx_ctas_per_sm=o))
+    t(0, "ax_sustained", a.sustained, **dict(base, ax_impl=1))
+    t(1, "atx_sustained", a.sustained, **dict(base, atx_impl=1))
+    t(3, "loo_sustained", a.sustained)
+    for k, v in base.items():
+        sh.set_tuning(k, v)
+    sh.set_tuning("ax_rv", 2); sh.set_tuning("ax_unroll", 4); sh.set_tuning("atx_cols", 2); sh.set_tuning("atx_unroll", 4)
+    if a.quick:
+        sys.exit(0)
 
 ax_variants = [(1, 2), (1, 4), (1, 8), (2, 2), (2, 4), (2, 8), (4, 2), (4, 4)]
 atx_variants = [(1, 2), (1, 4), (1, 8), (2, 2), (2, 4), (2, 8), (4, 2), (4, 4)]

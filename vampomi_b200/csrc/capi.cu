@@ -201,6 +201,7 @@ int vampomi_create(int device, int N, long long Mt, int nranks, int rank, vampom
         VO_CUDA(cudaMalloc(&c->sums, MAX_SUMS * sizeof(double)));
         VO_CUDA(cudaMemsetAsync(c->sums, 0, MAX_SUMS * sizeof(double), c->stream));
         VO_CUDA(cudaMallocHost(&c->sums_host, MAX_SUMS * sizeof(double)));
+        VO_CUDA(cudaMalloc(&c->psum, sizeof(double)));
         VO_CUDA(cudaMalloc(&c->cg, sizeof(CgScalars)));
         VO_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgScalars), c->stream));
         VO_CUDA(cudaMallocHost(&c->cg_poll_host, 64 * sizeof(int)));
@@ -224,6 +225,7 @@ int vampomi_destroy(vampomi_ctx* c) {
     cudaFree(c->A); cudaFree(c->mave); cudaFree(c->msig);
     for (auto p : c->mvec) cudaFree(p);
     for (auto p : c->nvec) cudaFree(p);
+    cudaFree(c->psum);
     cudaFree(c->ax_partial); cudaFree(c->red_partials); cudaFree(c->red_tickets); cudaFree(c->sums); cudaFree(c->cg);
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->cg_poll_host) cudaFreeHost(c->cg_poll_host);
@@ -603,10 +605,10 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
     VO_ARG(c && name, "set_tuning: NULL argument");
     struct { const char* n; int* p; int lo, hi; } knobs[] = {
         {"ax_rv", &c->tune.ax_rv, 1, 4},           {"ax_unroll", &c->tune.ax_unroll, 2, 8},
-        {"ax_ctas_per_sm", &c->tune.ax_ctas_per_sm, 0, 32}, {"atx_cols", &c->tune.atx_cols, 1, 4},
-        {"atx_unroll", &c->tune.atx_unroll, 2, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
+        {"ax_ctas_per_sm", &c->tune.ax_ctas_per_sm, 0, 32}, {"atx_cols", &c->tune.atx_cols, 0, 4},
+        {"atx_unroll", &c->tune.atx_unroll, 0, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
         {"cg_depth", &c->tune.cg_depth, 1, 32},     {"ax_impl", &c->tune.ax_impl, 0, 1},
-        {"atx_impl", &c->tune.atx_impl, 0, 1},
+        {"atx_impl", &c->tune.atx_impl, 0, 3},       {"center_split", &c->tune.center_split, 0, 1},
     };
     for (auto& k : knobs)
         if (!strcmp(k.n, name)) {

@@ -73,12 +73,13 @@ struct Tuning {
     int ax_rv = 2;                   // 256-bit vectors per thread per column in Ax (tile = 1024*rv rows)
     int ax_unroll = 4;               // columns in flight per thread
     int ax_ctas_per_sm = 0;              // 0 = one resident wave (occupancy query)
-    int atx_cols = 2;                // columns per warp pass in ATx
-    int atx_unroll = 4;
+    int atx_cols = 0;                // columns per pass in ATx (0 = default of the chosen implementation)
+    int atx_unroll = 0;
     int atx_ctas_per_sm = 0;
     int cg_depth = 2;                // CG iterations kept enqueued ahead of the completion poll
     int ax_impl = 0;                 // 0 = per-thread 256-bit LDG streaming, 1 = bulk-copy (cp.async.bulk + mbarrier) pipeline
-    int atx_impl = 0;
+    int atx_impl = 3;                // 0 = warp per column group, 1 = bulk-copy pipeline, 2 = CTA per column group, 3 = auto (2 when N >= 4096, else 0)
+    int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 
 }  // namespace vampomi
@@ -100,6 +101,7 @@ struct vampomi_ctx {
     double* red_partials = nullptr;  // [MAX_DOTS][RED_BLOCKS][MAX_SUMS] scratch of the deterministic reductions
     unsigned int* red_tickets = nullptr;
     double* sums = nullptr;          // [MAX_SUMS] packed scalars (device), all-reduced in place
+    double* psum = nullptr;          // sum of the N-vector fed to A^T (center_split form)
     double* sums_host = nullptr;     // pinned mirror
     vampomi::CgScalars* cg = nullptr;
     int* cg_poll_host = nullptr;     // pinned ring of done flags

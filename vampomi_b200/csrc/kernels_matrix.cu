@@ -115,7 +115,10 @@ int launch_stats(vampomi_ctx* c, double alpha_scale) {
 //          accumulators (4*RV rows) in registers and streams down the columns with U columns in flight.
 // stage 2: k_ax_reduce sums the chunk partials in fixed order (bitwise reproducible, no FP64 atomics).
 // ---------------------------------------------------------------------------------------------------------------
-template <int RV, int U>
+// SPLIT = false: (a - mave_j) * w_j per element, exactly the reference's expression (src/data.cpp:360).
+// SPLIT = true : a * w_j per element and one subtraction of sum_j mave_j * w_j per row at the end — one FP64 instruction
+//                less per element (less power under the 1 kW cap); same value up to summation order.
+template <int RV, int U, bool SPLIT>
 __global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                     const double* __restrict__ msig, const double* __restrict__ x,
                                                     int tile_rows, int cols_per_chunk, long long M,
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A
     d4 acc[RV];
     const double* ap[RV];
     bool valid[RV];
+    double corr = 0.0;
 #pragma unroll
     for (int k = 0; k < RV; k++) {
         acc[k] = d4{0.0, 0.0, 0.0, 0.0};
@@ -158,16 +162,25 @@ __global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A
 #pragma unroll
             for (int k = 0; k < RV; k++) {
                 if (valid[k]) {
-                    acc[k].x = fma(a[u][k].x - m[u], w[u], acc[k].x);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
-                    acc[k].y = fma(a[u][k].y - m[u], w[u], acc[k].y);
-                    acc[k].z = fma(a[u][k].z - m[u], w[u], acc[k].z);
-                    acc[k].w = fma(a[u][k].w - m[u], w[u], acc[k].w);
+                    if (SPLIT) {
+                        acc[k].x = fma(a[u][k].x, w[u], acc[k].x);
+                        acc[k].y = fma(a[u][k].y, w[u], acc[k].y);
+                        acc[k].z = fma(a[u][k].z, w[u], acc[k].z);
+                        acc[k].w = fma(a[u][k].w, w[u], acc[k].w);
+                    } else {
+                        acc[k].x = fma(a[u][k].x - m[u], w[u], acc[k].x);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
+                        acc[k].y = fma(a[u][k].y - m[u], w[u], acc[k].y);
+                        acc[k].z = fma(a[u][k].z - m[u], w[u], acc[k].z);
+                        acc[k].w = fma(a[u][k].w - m[u], w[u], acc[k].w);
+                    }
                 }
             }
+            if (SPLIT) corr = fma(m[u], w[u], corr);
         }
     }
     for (; j < c1; j++) {
         double m = __ldg(mave + j), w = __ldg(msig + j) * __ldg(x + j);
+        if (SPLIT) { corr = fma(m, w, corr); m = 0.0; }
 #pragma unroll
         for (int k = 0; k < RV; k++) {
             if (valid[k]) {
@@ -178,6 +191,10 @@ __global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A
                 acc[k].w = fma(a.w - m, w, acc[k].w);
             }
         }
+    }
+    if (SPLIT) {
+#pragma unroll
+        for (int k = 0; k < RV; k++) { acc[k].x -= corr; acc[k].y -= corr; acc[k].z -= corr; acc[k].w -= corr; }
     }
     double* prow = partial + (size_t)blockIdx.y * ld + rbase;
 #pragma unroll
@@ -230,11 +247,17 @@ struct AxPlan { int rv, U, ntiles, tile_rows, nchunks, cols_per_chunk; };
 typedef void (*ax_kernel_t)(const double*, size_t, const double*, const double*, const double*, int, int, long long, double*,
                             const int*);
 
-static ax_kernel_t ax_kernel(int rv, int U) {
+static ax_kernel_t ax_kernel(int rv, int U, bool split = false) {
+    if (split) switch (rv * 10 + U) {
+        case 12: return k_ax_partial<1, 2, true>; case 14: return k_ax_partial<1, 4, true>; case 18: return k_ax_partial<1, 8, true>;
+        case 22: return k_ax_partial<2, 2, true>; case 24: return k_ax_partial<2, 4, true>; case 28: return k_ax_partial<2, 8, true>;
+        case 42: return k_ax_partial<4, 2, true>; case 44: return k_ax_partial<4, 4, true>;
+        default: return nullptr;
+    }
     switch (rv * 10 + U) {
-        case 12: return k_ax_partial<1, 2>; case 14: return k_ax_partial<1, 4>; case 18: return k_ax_partial<1, 8>;
-        case 22: return k_ax_partial<2, 2>; case 24: return k_ax_partial<2, 4>; case 28: return k_ax_partial<2, 8>;
-        case 42: return k_ax_partial<4, 2>; case 44: return k_ax_partial<4, 4>;
+        case 12: return k_ax_partial<1, 2, false>; case 14: return k_ax_partial<1, 4, false>; case 18: return k_ax_partial<1, 8, false>;
+        case 22: return k_ax_partial<2, 2, false>; case 24: return k_ax_partial<2, 4, false>; case 28: return k_ax_partial<2, 8, false>;
+        case 42: return k_ax_partial<4, 2, false>; case 44: return k_ax_partial<4, 4, false>;
         default: return nullptr;
     }
 }
@@ -259,7 +282,7 @@ static AxPlan plan_ax(const vampomi_ctx* c) {
     size_t tr = (c->ld + p.ntiles - 1) / p.ntiles;
     p.tile_rows = (int)((tr + 15) / 16 * 16);                                // 128-byte aligned tile starts
     int per_sm = c->tune.ax_ctas_per_sm > 0 ? c->tune.ax_ctas_per_sm
-                                            : resident_ctas((const void*)ax_kernel(p.rv, p.U), 256, 0);
+                                            : resident_ctas((const void*)ax_kernel(p.rv, p.U, c->tune.center_split != 0), 256, 0);
     long long slots = (long long)c->num_sms * per_sm;
     long long nch = slots / p.ntiles;
     if (nch < 1) nch = 1;
@@ -290,7 +313,7 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
         }
         dim3 grid(p.ntiles, p.nchunks);
         sp = prof_begin(c, 0, a_bytes);
-        ax_kernel(p.rv, p.U)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
+        ax_kernel(p.rv, p.U, c->tune.center_split != 0)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
                                                           c->ax_partial, done_flag);
         prof_end(c, sp);
         VO_CUDA(cudaGetLastError());
@@ -317,10 +340,12 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
 // each 256-bit slice of p once (L1-resident) for all C columns, keeps C*U 256-bit loads of A in flight per lane.
 // No block-level synchronisation at all; reduction by warp shuffles in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C, int U>
+// SPLIT as in k_ax_partial: sum_i a_i p_i - mave_j * (sum_i p_i), with sum_i p_i precomputed once per launch (psum).
+template <int C, int U, bool SPLIT>
 __global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                              const double* __restrict__ msig, const double* __restrict__ p, long long M,
-                                             double scale, double* __restrict__ out, const int* __restrict__ done) {
+                                             double scale, double* __restrict__ out, const int* __restrict__ done,
+                                             const double* __restrict__ psum) {
     if (done != nullptr && *done != 0) return;
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -338,7 +363,7 @@ __global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_
         for (int cc = 0; cc < C; cc++) {
             long long j = j0 + cc < M ? j0 + cc : M - 1;
             col[cc] = A + (size_t)j * ld;
-            m[cc] = __ldg(mave + j);
+            m[cc] = SPLIT ? 0.0 : __ldg(mave + j);
             acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0;
         }
         int v = lane;
@@ -355,10 +380,17 @@ __global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_
             for (int u = 0; u < U; u++) {
 #pragma unroll
                 for (int cc = 0; cc < C; cc++) {
-                    acc[cc][0] = fma(a[u][cc].x - m[cc], pv[u].x, acc[cc][0]);   // (meth[i] - mu) * phen[i], src/data.cpp:304
-                    acc[cc][1] = fma(a[u][cc].y - m[cc], pv[u].y, acc[cc][1]);
-                    acc[cc][2] = fma(a[u][cc].z - m[cc], pv[u].z, acc[cc][2]);
-                    acc[cc][3] = fma(a[u][cc].w - m[cc], pv[u].w, acc[cc][3]);
+                    if (SPLIT) {
+                        acc[cc][0] = fma(a[u][cc].x, pv[u].x, acc[cc][0]);
+                        acc[cc][1] = fma(a[u][cc].y, pv[u].y, acc[cc][1]);
+                        acc[cc][2] = fma(a[u][cc].z, pv[u].z, acc[cc][2]);
+                        acc[cc][3] = fma(a[u][cc].w, pv[u].w, acc[cc][3]);
+                    } else {
+                        acc[cc][0] = fma(a[u][cc].x - m[cc], pv[u].x, acc[cc][0]);   // (meth[i] - mu) * phen[i], src/data.cpp:304
+                        acc[cc][1] = fma(a[u][cc].y - m[cc], pv[u].y, acc[cc][1]);
+                        acc[cc][2] = fma(a[u][cc].z - m[cc], pv[u].z, acc[cc][2]);
+                        acc[cc][3] = fma(a[u][cc].w - m[cc], pv[u].w, acc[cc][3]);
+                    }
                 }
             }
         }
@@ -376,41 +408,168 @@ __global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
             double s = warp_sum((acc[cc][0] + acc[cc][1]) + (acc[cc][2] + acc[cc][3]));
-            if (lane == 0 && j0 + cc < M) out[j0 + cc] = (__ldg(msig + j0 + cc) * s) * scale;   // sigma_inv * dpa (:306), then * scale (:330)
+            if (lane == 0 && j0 + cc < M) {
+                if (SPLIT) s -= __ldg(mave + j0 + cc) * __ldg(psum);
+                out[j0 + cc] = (__ldg(msig + j0 + cc) * s) * scale;                             // sigma_inv * dpa (:306), then * scale (:330)
+            }
         }
     }
 }
 
-typedef void (*atx_kernel_t)(const double*, size_t, const double*, const double*, const double*, long long, double, double*,
-                             const int*);
+// CTA-cooperative form of A^T p (atx_impl = 2): the 8 warps of a CTA walk the SAME C columns together, 8 KB of each
+// column per step (U steps in flight), so the chip streams ~900 long sequential runs instead of ~3500 per-warp ones;
+// one block barrier per column group (partials double-buffered in shared memory), fixed reduction order.
+template <int C, int U>
+__global__ void __launch_bounds__(256) k_atx_cta(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                 const double* __restrict__ msig, const double* __restrict__ p, long long M,
+                                                 double scale, double* __restrict__ out, const int* __restrict__ done) {
+    if (done != nullptr && *done != 0) return;
+    __shared__ double red[2][8][C];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nvec = (int)(ld >> 2);
+    const long long ngroups = (M + C - 1) / C;
+    const long long per = (ngroups + gridDim.x - 1) / gridDim.x;
+    long long g0 = (long long)blockIdx.x * per, g1 = g0 + per;
+    if (g1 > ngroups) g1 = ngroups;
+    int par = 0;
+    for (long long g = g0; g < g1; g++) {
+        const long long j0 = g * C;
+        const double* col[C];
+        double m[C], acc[C][4];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            long long j = j0 + cc < M ? j0 + cc : M - 1;
+            col[cc] = A + (size_t)j * ld;
+            m[cc] = __ldg(mave + j);
+            acc[cc][0] = acc[cc][1] = acc[cc][2] = acc[cc][3] = 0.0;
+        }
+        int v = tid;
+        for (; v + 256 * (U - 1) < nvec; v += 256 * U) {
+            d4 pv[U], a[U][C];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) a[u][cc] = ld_stream(col[cc] + 4 * (size_t)(v + 256 * u));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) pv[u] = ld_cached(p + 4 * (size_t)(v + 256 * u));
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) {
+                    acc[cc][0] = fma(a[u][cc].x - m[cc], pv[u].x, acc[cc][0]);   // (meth[i] - mu) * phen[i], src/data.cpp:304
+                    acc[cc][1] = fma(a[u][cc].y - m[cc], pv[u].y, acc[cc][1]);
+                    acc[cc][2] = fma(a[u][cc].z - m[cc], pv[u].z, acc[cc][2]);
+                    acc[cc][3] = fma(a[u][cc].w - m[cc], pv[u].w, acc[cc][3]);
+                }
+            }
+        }
+        for (; v < nvec; v += 256) {
+            d4 pv = ld_cached(p + 4 * (size_t)v);
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                d4 a = ld_stream(col[cc] + 4 * (size_t)v);
+                acc[cc][0] = fma(a.x - m[cc], pv.x, acc[cc][0]);
+                acc[cc][1] = fma(a.y - m[cc], pv.y, acc[cc][1]);
+                acc[cc][2] = fma(a.z - m[cc], pv.z, acc[cc][2]);
+                acc[cc][3] = fma(a.w - m[cc], pv.w, acc[cc][3]);
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            double sw = warp_sum((acc[cc][0] + acc[cc][1]) + (acc[cc][2] + acc[cc][3]));
+            if (lane == 0) red[par][wid][cc] = sw;
+        }
+        __syncthreads();
+        if (tid < C && j0 + tid < M) {
+            double t = red[par][0][tid];
+#pragma unroll
+            for (int w = 1; w < 8; w++) t += red[par][w][tid];
+            out[j0 + tid] = (__ldg(msig + j0 + tid) * t) * scale;               // sigma_inv * dpa (:306), then * scale (:330)
+        }
+        par ^= 1;
+    }
+}
 
-static atx_kernel_t atx_kernel(int C, int U) {
+typedef void (*atx_cta_kernel_t)(const double*, size_t, const double*, const double*, const double*, long long, double, double*,
+                                 const int*);
+static atx_cta_kernel_t atx_cta_kernel(int C, int U) {
     switch (C * 10 + U) {
-        case 12: return k_atx<1, 2>; case 14: return k_atx<1, 4>; case 18: return k_atx<1, 8>;
-        case 22: return k_atx<2, 2>; case 24: return k_atx<2, 4>; case 28: return k_atx<2, 8>;
-        case 42: return k_atx<4, 2>; case 44: return k_atx<4, 4>;
+        case 12: return k_atx_cta<1, 2>; case 14: return k_atx_cta<1, 4>; case 18: return k_atx_cta<1, 8>;
+        case 22: return k_atx_cta<2, 2>; case 24: return k_atx_cta<2, 4>; case 28: return k_atx_cta<2, 8>;
+        case 42: return k_atx_cta<4, 2>; case 44: return k_atx_cta<4, 4>;
         default: return nullptr;
     }
 }
 
+typedef void (*atx_kernel_t)(const double*, size_t, const double*, const double*, const double*, long long, double, double*,
+                             const int*, const double*);
+
+static atx_kernel_t atx_kernel(int C, int U, bool split = false) {
+    if (split) switch (C * 10 + U) {
+        case 12: return k_atx<1, 2, true>; case 14: return k_atx<1, 4, true>; case 18: return k_atx<1, 8, true>;
+        case 22: return k_atx<2, 2, true>; case 24: return k_atx<2, 4, true>; case 28: return k_atx<2, 8, true>;
+        case 42: return k_atx<4, 2, true>; case 44: return k_atx<4, 4, true>;
+        default: return nullptr;
+    }
+    switch (C * 10 + U) {
+        case 12: return k_atx<1, 2, false>; case 14: return k_atx<1, 4, false>; case 18: return k_atx<1, 8, false>;
+        case 22: return k_atx<2, 2, false>; case 24: return k_atx<2, 4, false>; case 28: return k_atx<2, 8, false>;
+        case 42: return k_atx<4, 2, false>; case 44: return k_atx<4, 4, false>;
+        default: return nullptr;
+    }
+}
+
+// psum = sum_i p[i] in a fixed order (one CTA), for the SPLIT form of A^T p
+__global__ void __launch_bounds__(1024) k_sum_vec(const double* __restrict__ p, int n, double* __restrict__ out, const int* __restrict__ done) {
+    if (done != nullptr && *done != 0) return;
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 1024) s += p[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = warp_sum(sm[threadIdx.x]);
+        if (threadIdx.x == 0) *out = t;
+    }
+}
+
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag) {
-    int C = c->tune.atx_cols, U = c->tune.atx_unroll;
-    if (atx_kernel(C, U) == nullptr) { C = 2; U = 4; }
-    int per_sm = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)atx_kernel(C, U), 256, 0);
-    int blocks = c->num_sms * per_sm;
-    long long maxb = (c->M + 8 * C - 1) / (8 * C);
-    if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
+    int impl = c->tune.atx_impl;
+    if (impl == 3) impl = c->ld >= 4096 ? 2 : 0;          // short columns leave most of a CTA idle: keep one warp per column group
+    // measured defaults (profiles/r01_sweep_*): CTA form C=2,U=2; warp form C=1,U=2
+    int C = c->tune.atx_cols > 0 ? c->tune.atx_cols : (impl == 2 ? 2 : 1);
+    int U = c->tune.atx_unroll > 0 ? c->tune.atx_unroll : 2;
     const double scale = 1.0 / sqrt((double)c->N);                              // src/data.cpp:326-327
     int sp = prof_begin(c, 2, (double)c->M * c->N * 8.0);
-    if (c->tune.atx_impl == 1) {
-        int rc = launch_atx_bulk(c, p_dev, out_dev, done_flag);
-        prof_end(c, sp);
-        c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
-        return rc;
+    int rc = VAMPOMI_OK;
+    if (impl == 1) {
+        rc = launch_atx_bulk(c, p_dev, out_dev, done_flag);
+    } else if (impl == 2) {
+        if (atx_cta_kernel(C, U) == nullptr) { C = 2; U = 2; }
+        atx_cta_kernel_t k = atx_cta_kernel(C, U);
+        int occ = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)k, 256, 0);
+        long long nb = (long long)c->num_sms * occ, ng = (c->M + C - 1) / C;
+        if (nb > ng) nb = ng;
+        k<<<(unsigned)nb, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
+    } else {
+        if (atx_kernel(C, U) == nullptr) { C = 1; U = 2; }
+        const bool split = c->tune.center_split != 0;
+        int per_sm = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)atx_kernel(C, U, split), 256, 0);
+        int blocks = c->num_sms * per_sm;
+        long long maxb = (c->M + 8 * C - 1) / (8 * C);
+        if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
+        if (split) {
+            k_sum_vec<<<1, 1024, 0, c->stream>>>(p_dev, c->N, c->psum, done_flag);
+            c->counters[0]++;
+        }
+        atx_kernel(C, U, split)<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag,
+                                                               c->psum);
     }
-    atx_kernel(C, U)<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
     prof_end(c, sp);
     c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    VO_CHECK(rc);
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }

@@ -38,9 +38,11 @@ def test_upload_download_stats_ax_atx(N, M):
     assert rel_l2(sh.Ax(x), d.Ax(x)) < 1e-12
     # run-to-run bitwise reproducibility (fixed-order reductions, no atomics on data)
     assert np.array_equal(sh.Ax(x), sh.Ax(x)) and np.array_equal(sh.ATx(p), sh.ATx(p))
-    # the CTA-cooperative A^T p and the bulk-copy (cp.async.bulk + mbarrier) pipelines on the same ragged shapes
-    sh.set_tuning("atx_impl", 2)
-    assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
+    # every A^T p implementation (warp, CTA-cooperative) and the bulk-copy (cp.async.bulk + mbarrier) pipelines on the
+    # same ragged shapes
+    for impl in (0, 2):
+        sh.set_tuning("atx_impl", impl)
+        assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
     sh.set_tuning("ax_impl", 1)
     sh.set_tuning("atx_impl", 1)
     assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
@@ -67,10 +69,11 @@ def test_constant_column_and_alpha_scale():
 @pytest.mark.parametrize("knobs", [dict(ax_rv=1, ax_unroll=2), dict(ax_rv=1, ax_unroll=8), dict(ax_rv=2, ax_unroll=2),
                                    dict(ax_rv=2, ax_unroll=8), dict(ax_rv=4, ax_unroll=2), dict(ax_rv=4, ax_unroll=4),
                                    dict(ax_ctas_per_sm=1), dict(ax_ctas_per_sm=7),
-                                   dict(atx_cols=1, atx_unroll=2), dict(atx_cols=1, atx_unroll=8), dict(atx_cols=2, atx_unroll=2),
-                                   dict(atx_cols=2, atx_unroll=8), dict(atx_cols=4, atx_unroll=2), dict(atx_cols=4, atx_unroll=4),
-                                   dict(atx_ctas_per_sm=1), dict(atx_ctas_per_sm=9),
-                                   dict(center_split=1), dict(center_split=1, ax_rv=1, ax_unroll=8, atx_cols=1, atx_unroll=2),
+                                   dict(atx_impl=0, atx_cols=1, atx_unroll=2), dict(atx_impl=0, atx_cols=1, atx_unroll=8),
+                                   dict(atx_impl=0, atx_cols=2, atx_unroll=2), dict(atx_impl=0, atx_cols=2, atx_unroll=8),
+                                   dict(atx_impl=0, atx_cols=4, atx_unroll=2), dict(atx_impl=0, atx_cols=4, atx_unroll=4),
+                                   dict(atx_impl=0, atx_ctas_per_sm=1), dict(atx_impl=0, atx_ctas_per_sm=9), dict(atx_ctas_per_sm=9),
+                                   dict(center_split=1, atx_impl=0), dict(center_split=1, ax_rv=1, ax_unroll=8, atx_impl=0, atx_cols=1, atx_unroll=2),
                                    dict(atx_impl=2), dict(atx_impl=2, atx_cols=1, atx_unroll=8), dict(atx_impl=2, atx_cols=4, atx_unroll=2),
                                    dict(atx_impl=2, atx_cols=2, atx_unroll=2, atx_ctas_per_sm=5),
                                    dict(ax_impl=1), dict(atx_impl=1), dict(ax_impl=1, ax_ctas_per_sm=1), dict(atx_impl=1, atx_ctas_per_sm=1)])

@@ -155,8 +155,8 @@ def test_full_size_properties():
     Ax, ATp = sh.Ax(x), sh.ATx(p)
     assert abs(Ax @ p - x @ ATp) <= 1e-11 * math.sqrt((Ax @ Ax) * (p @ p))
     assert rel_l2(sh.Ax(0.5 * x - 2 * x2), 0.5 * Ax - 2 * sh.Ax(x2)) < 1e-12
-    for knobs in (dict(ax_rv=1, ax_unroll=8), dict(ax_rv=4, ax_unroll=4), dict(atx_cols=1, atx_unroll=8), dict(atx_cols=4, atx_unroll=4),
-                  dict(ax_impl=1, atx_impl=1)):
+    for knobs in (dict(ax_rv=1, ax_unroll=8), dict(ax_rv=4, ax_unroll=4), dict(atx_impl=0, atx_cols=1, atx_unroll=8), dict(atx_impl=0, atx_cols=4, atx_unroll=4),
+                  dict(atx_impl=2, atx_cols=2, atx_unroll=4), dict(ax_impl=1, atx_impl=1)):
         for k, v in knobs.items():
             sh.set_tuning(k, v)
         assert rel_l2(sh.Ax(x), Ax) < 1e-13 and rel_l2(sh.ATx(p), ATp) < 1e-13

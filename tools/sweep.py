@@ -43,6 +43,8 @@ def t(which, label, reps=None, **knobs):
 
 if a.sustained:
     base = dict(ax_impl=0, atx_impl=0, center_split=0, ax_ctas_per_sm=0, atx_ctas_per_sm=0)
+    t(0, "ax_default", a.sustained)
+    t(1, "atx_default", a.sustained)
     for split in (0,):
         for rv, u in ((2, 4), (4, 2)):
             t(0, "ax_sustained", a.sustained, **dict(base, ax_rv=rv, ax_unroll=u, center_split=split))
@@ -56,7 +58,8 @@ if a.sustained:
     t(3, "loo_sustained", a.sustained)
     for k, v in base.items():
         sh.set_tuning(k, v)
-    sh.set_tuning("ax_rv", 2); sh.set_tuning("ax_unroll", 4); sh.set_tuning("atx_cols", 2); sh.set_tuning("atx_unroll", 4)
+    sh.set_tuning("ax_rv", 2); sh.set_tuning("ax_unroll", 4); sh.set_tuning("atx_cols", 0); sh.set_tuning("atx_unroll", 0)
+    sh.set_tuning("atx_impl", 3)
     if a.quick:
         sys.exit(0)
 
@@ -66,7 +69,7 @@ occ = [0] if a.quick else [0, 1, 2, 3, 4, 6, 8]
 for (rv, u), o in itertools.product(ax_variants, occ):
     t(0, "ax", ax_rv=rv, ax_unroll=u, ax_ctas_per_sm=o)
 for (c, u), o in itertools.product(atx_variants, occ):
-    t(1, "atx", atx_cols=c, atx_unroll=u, atx_ctas_per_sm=o)
+    t(1, "atx", atx_impl=0, atx_cols=c, atx_unroll=u, atx_ctas_per_sm=o)
 for o in ([0] if a.quick else [0, 1, 2, 3]):
     t(0, "ax", ax_impl=1, ax_ctas_per_sm=o)
     t(1, "atx", atx_impl=1, atx_ctas_per_sm=o)

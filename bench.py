@@ -300,7 +300,12 @@ def main_ours(args):
                 "frac_of_8TBs_spec": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "launches_timed": pd["launches"],
                 "other_kernel": {k: (prof_dev[k]["bytes"] / max(prof_dev[k]["ms"], 1e-9) / 1e6) for k in ("ax_partial", "atx")},
-                "matrix_kernel_share_of_step": matrix_ms / ms_dev,
+                "matrix_kernel_share_of_step": (prof_dev["ax_partial"]["ms"] + prof_dev["atx"]["ms"]) / ms_dev,
+                "phase_ms_per_step": {"k_ax_partial": prof_dev["ax_partial"]["ms"] / args.steps,
+                                      "k_ax_reduce+allreduce+scale": prof_dev["ax_reduce"]["ms"] / args.steps,
+                                      "k_atx": prof_dev["atx"]["ms"] / args.steps,
+                                      "everything_else": (ms_dev - matrix_ms) / args.steps,
+                                      "ax_reduce_avg_us": 1e3 * prof_dev["ax_reduce"]["ms"] / max(prof_dev["ax_reduce"]["launches"], 1)},
                 "whole_iteration": {"passes": passes, "gbs_per_gpu": iter_gbs_per_gpu, "frac_of_peak": iter_gbs_per_gpu / peak,
                                     "frac_of_8TBs_spec": iter_gbs_per_gpu / 8000.0}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

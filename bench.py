@@ -313,7 +313,8 @@ def main_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(N, Mt), "N": N, "Mt": Mt, "markers_per_gpu": sh.M, "parallelism": f"marker-shard x{world}",
                        "l2_note": f"inputs larger than L2: every matrix pass streams {sh.M * N * 8 / 1e9:.1f} GB per GPU",
-                       "cg_iters_per_step": [[h["k1"], h["k2"]] for h in hist_dev], "setup_s": round(setup_s, 2)},
+                       "cg_iters_per_step": [[h["k1"], h["k2"]] for h in hist_dev], "setup_s": round(setup_s, 2),
+                       "cross_gpu_sums": {0: "none (1 GPU)", 1: "NCCL all-reduce", 2: "fused NVLink peer-memory all-reduce"}[sh.comm_mode()]},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(N * 8 + 2 * 32 * 8), "d2h_bytes_per_step": int(2 * sh.M * 8 * world + 64 * 8 * 12),

@@ -99,6 +99,11 @@ int vampomi_divide_work(long long Mt, int nranks, int rank, long long* M, long l
  * file, a thread-shared buffer); then every rank calls comm_init. Not needed when nranks == 1. */
 int vampomi_comm_get_unique_id(void* id128);
 int vampomi_comm_init(vampomi_ctx* ctx, const void* id128);
+/* How cross-GPU sums are carried out: 0 = single shard (none), 1 = NCCL all-reduce after the producing kernel,
+ * 2 = one-shot all-reduce over NVLink peer memory fused into the producing kernels (A x partial reduce and the CG
+ * scalar reductions; csrc/xchg.cuh). Mode 2 is chosen at comm_init when every rank could map every peer (CUDA IPC
+ * between processes, peer access between threads); the environment variable VAMPOMI_XCHG=0 forces mode 1. */
+int vampomi_comm_mode(const vampomi_ctx* ctx, int* mode);
 
 /* ---- design matrix: data::read_methylation_data, src/data.cpp:116-153 -------------------------------------- */
 /* Copies `ncols` columns (each N doubles, contiguous) starting at local column j0 from host memory to HBM. */

@@ -34,3 +34,32 @@ def test_main_meth_is_shard_invariant(name, gpus, tmp_path):
         assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < rel_vec
     for kind in ("params", "metrics"):
         assert_rows_close(csv_rows(open(f"{d}/out/g_{kind}.csv", "rb").read()), csv_rows(g[f"csv_{kind}"]), rel_csv, kind)
+
+
+@pytest.mark.parametrize("gpus", [2, 4, 8])
+def test_peer_exchange_equals_nccl(gpus, tmp_path):
+    """The fused peer-memory all-reduce (mode 2) and the NCCL path (VAMPOMI_XCHG=0) must give the same iterates: both add
+    the same shard contributions, only the order of the G additions may differ."""
+    if capi.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    g = load_golden("linear_wellcond")
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    its = 4
+    outs = {}
+    for mode in ("1", "0"):
+        os.makedirs(tmp_path / f"out{mode}")
+        args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out{mode}",
+                "--out-name", "g", "--iterations", its, "--true-signal-file", f"{d}/ex_ts.bin", "--stop-criteria-thr", "0", "--seed",
+                g["probe_seed"], "--gpus", gpus] + list(g["extra"])
+        res = subprocess.run([build.MAIN_METH] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                             timeout=600, env=dict(os.environ, VAMPOMI_XCHG=mode))
+        assert res.returncode == 0, res.stdout[-3000:]
+        assert ("NVLink peer memory" in res.stdout) == (mode == "1"), res.stdout[:2000]
+        outs[mode] = res.stdout
+    for k in range(1, its + 1):
+        a, b = np.fromfile(f"{d}/out1/g_it_{k}.bin"), np.fromfile(f"{d}/out0/g_it_{k}.bin")
+        assert rel_l2(a, b) < 1e-12
+        assert rel_l2(a, g["x1"][k - 1]) < 1e-9
+    cg = lambda s: [l for l in s.splitlines() if l.startswith("[CG] LMMSE solve")]
+    assert cg(outs["1"]) == cg(outs["0"])

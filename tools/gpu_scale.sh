@@ -1,5 +1,6 @@
 #!/bin/bash
-# Multi-GPU visit (gpurun --gpus G): shard-invariance tests through main_meth --gpus, then bench.py at 1..G ranks.
+# Multi-GPU visit (gpurun --gpus G): shard-invariance tests through main_meth --gpus, then bench.py at the rank counts
+# in SCALE_LIST, each with the fused peer-memory all-reduce (default) and, if AB=1, again with NCCL collectives.
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out
@@ -7,13 +8,24 @@ mkdir -p $OUT
 G=${1:-2}
 nvidia-smi topo -m > $OUT/topo_$G.txt 2>&1
 timeout 1200 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 600 > $OUT/pytest_multi_$G.log 2>&1; echo "pytest_multi rc=$?" | tee $OUT/status_scale_$G.txt
-for n in ${SCALE_LIST:-1 $G}; do
+tail -5 $OUT/pytest_multi_$G.log
+run_bench() {  # n tag env
+  local n=$1 tag=$2
   if [ "$n" = "1" ]; then
-    timeout 1200 python bench.py --gpus 1 --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} --no-cpu-baseline > $OUT/bench_g1_of$G.log 2>&1
+    timeout 1200 python bench.py --gpus 1 --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} --no-cpu-baseline > $OUT/bench_g${n}_of${G}${tag}.log 2>&1
   else
     NCCL_DEBUG=${NCCL_DEBUG:-WARN} timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
-      bench.py --gpus $n --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} > $OUT/bench_g${n}_of$G.log 2>&1
+      bench.py --gpus $n --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} > $OUT/bench_g${n}_of${G}${tag}.log 2>&1
   fi
-  echo "bench n=$n rc=$?" | tee -a $OUT/status_scale_$G.txt
-  grep -h '^{' $OUT/bench_g${n}_of$G.log | tail -1 | cut -c1-400
+  echo "bench n=$n$tag rc=$?" | tee -a $OUT/status_scale_$G.txt
+  grep -h '^{' $OUT/bench_g${n}_of${G}${tag}.log | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+r = d['roofline']
+print(d['n_gpus'], 'it/s', round(d['value'], 3), 'ms', round(d['ms_per_step'], 2), d['config'].get('cross_gpu_sums'), {k: round(v, 3) for k, v in r['phase_ms_per_step'].items()})
+" || tail -20 $OUT/bench_g${n}_of${G}${tag}.log
+}
+for n in ${SCALE_LIST:-1 $G}; do
+  run_bench $n ""
+  if [ "${AB:-0}" = "1" ] && [ "$n" != "1" ]; then VAMPOMI_XCHG=0 run_bench $n "_nccl"; fi
 done

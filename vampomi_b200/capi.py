@@ -52,6 +52,7 @@ _SIGNATURES = {
     "vampomi_divide_work": (C.c_int, [C.c_longlong, C.c_int, C.c_int, c_ll_p, c_ll_p]),
     "vampomi_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "vampomi_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vampomi_comm_mode": (C.c_int, [C.c_void_p, c_int_p]),
     "vampomi_upload_columns": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     "vampomi_download_columns": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     "vampomi_load_file": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -194,6 +195,12 @@ class Shard:
 
     def __exit__(self, *a):
         self.close()
+
+    def comm_mode(self):
+        """0 single shard, 1 NCCL all-reduce, 2 fused peer-memory all-reduce (include/vampomi.h)."""
+        m = C.c_int()
+        _check(self.lib.vampomi_comm_mode(self.h, C.byref(m)), "comm_mode")
+        return m.value
 
     # ---- matrix ----
     def upload(self, A, j0=0):

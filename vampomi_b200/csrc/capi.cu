@@ -7,6 +7,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <cmath>
+#include <vector>
 #include <new>
 #include "common.h"
 
@@ -36,8 +37,9 @@ int nccl_load(NcclApi** out) {
             api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
             api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
             api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
+            api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
             api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-            state = (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString) ? 1 : -1;
+            state = (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString) ? 1 : -1;
         }
     }
     if (state != 1) {
@@ -87,6 +89,91 @@ int prof_resolve(vampomi_ctx* c) {
         c->prof_free.push_back(sp.e1);
     }
     c->prof_pending.clear();
+    return VAMPOMI_OK;
+}
+
+// ---- peer-memory exchange set-up (xchg.cuh) -----------------------------------------------------------------------
+struct XchgInfo {            // what every rank tells the others about its exchange region
+    long long pid;
+    int device, ok;
+    unsigned long long ptr;
+    cudaIpcMemHandle_t handle;
+};
+
+static void xchg_teardown(vampomi_ctx* c) {
+    for (int g = 0; g < XCHG_MAX_RANKS; g++)
+        if (c->xchg_ipc_opened[g]) { cudaIpcCloseMemHandle(c->xchg_ipc_opened[g]); c->xchg_ipc_opened[g] = nullptr; }
+    if (c->xchg_region) cudaFree(c->xchg_region);
+    if (c->xchg_local) cudaFree(c->xchg_local);
+    c->xchg_region = nullptr; c->xchg_local = nullptr;
+    c->xchg_ready = false; c->xchg.enabled = 0;
+}
+
+// Maps every rank's exchange region into this rank's address space: CUDA IPC between processes (torchrun, one rank
+// per process), plain peer access between the rank threads of one process (main_meth --gpus G). Collective: all ranks
+// call it right after ncclCommInitRank; the exchange is enabled only if it could be set up on EVERY rank.
+static int xchg_setup(vampomi_ctx* c) {
+    auto align = [](size_t v) { return (v + 255) / 256 * 256; };
+    int ok = c->nranks <= XCHG_MAX_RANKS ? 1 : 0;
+    const char* env = getenv("VAMPOMI_XCHG");
+    if (env && env[0] == '0') c->tune.xchg = 0;
+    Xchg& x = c->xchg;
+    x = Xchg{};
+    x.G = c->nranks; x.rank = c->rank; x.ld = c->ld;
+    x.maxb = (int)((c->ld + 31) / 32);
+    size_t off = 0;
+    x.off_flag_vec = off; off = align(off + (size_t)x.G * x.maxb * sizeof(unsigned int));
+    x.off_flag_sc = off;  off = align(off + (size_t)x.G * 32 * sizeof(unsigned int));
+    x.off_recv_vec = off; off = align(off + (size_t)2 * x.G * c->ld * sizeof(double));
+    x.off_recv_sc = off;  off = align(off + (size_t)2 * x.G * XCHG_SCALARS * sizeof(double));
+    const size_t region_bytes = off;
+    XchgInfo mine{};
+    mine.pid = (long long)getpid(); mine.device = c->device;
+    if (ok && (cudaMalloc(&c->xchg_region, region_bytes) != cudaSuccess || cudaMemset(c->xchg_region, 0, region_bytes) != cudaSuccess ||
+               cudaMalloc(&c->xchg_local, 4 * sizeof(unsigned int)) != cudaSuccess ||
+               cudaMemset(c->xchg_local, 0, 4 * sizeof(unsigned int)) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.handle, c->xchg_region) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess))
+        ok = 0;
+    cudaGetLastError();
+    mine.ok = ok; mine.ptr = (unsigned long long)(uintptr_t)c->xchg_region;
+    // all-gather the descriptors through NCCL itself (device staging), so no second bootstrap channel is needed
+    std::vector<XchgInfo> all((size_t)c->nranks);
+    XchgInfo *d_send = nullptr, *d_recv = nullptr;
+    VO_CUDA(cudaMalloc(&d_send, sizeof(XchgInfo)));
+    VO_CUDA(cudaMalloc(&d_recv, sizeof(XchgInfo) * c->nranks));
+    VO_CUDA(cudaMemcpyAsync(d_send, &mine, sizeof(XchgInfo), cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t r = c->nccl->AllGather(d_send, d_recv, sizeof(XchgInfo), ncclChar, c->comm, c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllGather: %s", c->nccl->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
+    VO_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(XchgInfo) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < c->nranks && ok; g++) {
+        if (!all[g].ok) { ok = 0; break; }
+        if (g == c->rank) { x.peer[g] = c->xchg_region; continue; }
+        if (all[g].pid == mine.pid) {                         // a rank thread of this process: direct peer access
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[g].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+            cudaGetLastError();
+            x.peer[g] = (unsigned char*)(uintptr_t)all[g].ptr;
+        } else {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[g].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            else { c->xchg_ipc_opened[g] = p; x.peer[g] = (unsigned char*)p; }
+        }
+    }
+    // enable only if EVERY rank succeeded (a mixed job would deadlock): min-reduce the flag; doubles as the barrier that
+    // guarantees every region is zeroed before the first push
+    int* d_ok = reinterpret_cast<int*>(d_send);
+    VO_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    r = c->nccl->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllReduce: %s", c->nccl->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
+    int all_ok = 0;
+    VO_CUDA(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_send); cudaFree(d_recv);
+    if (!all_ok) { xchg_teardown(c); return VAMPOMI_OK; }     // stay on the NCCL collectives
+    x.seq = c->xchg_local; x.ticket = c->xchg_local + 2;
+    c->xchg_ready = true;
+    x.enabled = c->tune.xchg ? 1 : 0;
     return VAMPOMI_OK;
 }
 
@@ -221,6 +308,7 @@ int vampomi_destroy(vampomi_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& sp : c->prof_pending) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : c->prof_free) cudaEventDestroy(e);
+    xchg_teardown(c);
     if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
     cudaFree(c->A); cudaFree(c->mave); cudaFree(c->msig);
     for (auto p : c->mvec) cudaFree(p);
@@ -272,6 +360,12 @@ int vampomi_comm_init(vampomi_ctx* c, const void* id128) {
     memcpy(&id, id128, 128);
     ncclResult_t r = c->nccl->CommInitRank(&c->comm, c->nranks, id, c->rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", c->nccl->GetErrorString(r)); c->comm = nullptr; return VAMPOMI_ERR_NCCL; }
+    return xchg_setup(c);
+}
+
+int vampomi_comm_mode(const vampomi_ctx* c, int* mode) {
+    VO_ARG(c && mode, "comm_mode: NULL argument");
+    *mode = c->nranks == 1 ? 0 : (c->xchg.enabled ? 2 : 1);
     return VAMPOMI_OK;
 }
 
@@ -608,12 +702,13 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"ax_ctas_per_sm", &c->tune.ax_ctas_per_sm, 0, 32}, {"atx_cols", &c->tune.atx_cols, 0, 4},
         {"atx_unroll", &c->tune.atx_unroll, 0, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
         {"cg_depth", &c->tune.cg_depth, 1, 32},     {"ax_impl", &c->tune.ax_impl, 0, 1},
-        {"atx_impl", &c->tune.atx_impl, 0, 3},       {"center_split", &c->tune.center_split, 0, 1},
+        {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
     };
     for (auto& k : knobs)
         if (!strcmp(k.n, name)) {
             VO_ARG(value >= k.lo && value <= k.hi, "set_tuning: %s must be in [%d,%d]", name, k.lo, k.hi);
             *k.p = value;
+            c->xchg.enabled = (c->xchg_ready && c->tune.xchg) ? 1 : 0;
             return VAMPOMI_OK;
         }
     set_error("set_tuning: unknown knob %s", name);

@@ -38,7 +38,8 @@ extern "C" int vampomi_cg_solve(vampomi_ctx* c, int rhs_vec, int sol_vec, int wa
         VO_CHECK(launch_atx(c, tmpN, atx_out, nullptr));
     }
     VO_CHECK(launch_cg_init(c, v, mu, atx_out, warm_start ? 1 : 0, tau, gam2, diag, c->sums));
-    VO_CHECK(allreduce_inplace(c, c->sums, 2));
+    const bool nccl_scalars = !c->xchg.enabled;          // with the peer-memory exchange the kernels' last block already summed over GPUs
+    if (nccl_scalars) VO_CHECK(allreduce_inplace(c, c->sums, 2));
     VO_CHECK(launch_cg_init_finish(c, c->sums));
 
     int depth = c->tune.cg_depth;
@@ -64,9 +65,9 @@ extern "C" int vampomi_cg_solve(vampomi_ctx* c, int rhs_vec, int sol_vec, int wa
         if ((rc = launch_ax(c, p, tmpN, done)) != VAMPOMI_OK) break;
         if ((rc = launch_atx(c, tmpN, atx_out, done)) != VAMPOMI_OK) break;
         if ((rc = launch_cg_dp(c, atx_out, tau, gam2, c->sums)) != VAMPOMI_OK) break;
-        if ((rc = allreduce_inplace(c, c->sums, 1)) != VAMPOMI_OK) break;
+        if (nccl_scalars && (rc = allreduce_inplace(c, c->sums, 1)) != VAMPOMI_OK) break;
         if ((rc = launch_cg_step(c, v, mu, diag, parity, c->sums, c->sums + 1)) != VAMPOMI_OK) break;
-        if ((rc = allreduce_inplace(c, c->sums + 1, 3)) != VAMPOMI_OK) break;
+        if (nccl_scalars && (rc = allreduce_inplace(c, c->sums + 1, 3)) != VAMPOMI_OK) break;
         if ((rc = launch_cg_finish(c, parity, gam2, tol, max_iter, onsager_mode, c->sums)) != VAMPOMI_OK) break;
         if (cudaMemcpyAsync(&c->cg_poll_host[slot], done, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaEventRecord(ev[slot], c->stream) != cudaSuccess) {

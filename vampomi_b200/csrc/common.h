@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include "../../include/vampomi.h"
+#include "xchg.cuh"
 
 namespace vampomi {
 
@@ -43,6 +44,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 int nccl_load(NcclApi** api);
@@ -79,6 +81,7 @@ struct Tuning {
     int cg_depth = 2;                // CG iterations kept enqueued ahead of the completion poll
     int ax_impl = 0;                 // 0 = per-thread 256-bit LDG streaming, 1 = bulk-copy (cp.async.bulk + mbarrier) pipeline
     int atx_impl = 3;                // 0 = warp per column group, 1 = bulk-copy pipeline, 2 = CTA per column group, 3 = auto (2 when N >= 4096, else 0)
+    int xchg = 1;                    // 1 = fused peer-memory all-reduce (xchg.cuh) when it could be set up, 0 = NCCL collectives
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 
@@ -107,6 +110,11 @@ struct vampomi_ctx {
     int* cg_poll_host = nullptr;     // pinned ring of done flags
     double* stage = nullptr;         // pinned staging for host<->device vector traffic (max(M,N,3M) doubles)
     size_t stage_elems = 0;
+    vampomi::Xchg xchg = {};         // peer-memory exchange descriptor (enabled == 0 -> NCCL path)
+    bool xchg_ready = false;         // set up successfully at comm_init
+    unsigned char* xchg_region = nullptr;
+    unsigned int* xchg_local = nullptr;
+    void* xchg_ipc_opened[vampomi::XCHG_MAX_RANKS] = {};
     ncclComm_t comm = nullptr;
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;

@@ -53,6 +53,12 @@ int load_dataset(Rank& r, const std::string& phenfp, const std::string& methfp, 
     if (r.nranks > ndev) return fatal(r, "--gpus " + std::to_string(r.nranks) + " exceeds the " + std::to_string(ndev) + " visible CUDA devices");
     if (vampomi_create(r.rank, N, (long long)r.opt.Mt, r.nranks, r.rank, &r.ctx) != VAMPOMI_OK) return fatal_abi(r, "vampomi_create");
     if (r.nranks > 1 && vampomi_comm_init(r.ctx, r.nccl_id) != VAMPOMI_OK) return fatal_abi(r, "vampomi_comm_init");
+    if (r.nranks > 1 && r.root()) {
+        int mode = 0;
+        vampomi_comm_mode(r.ctx, &mode);
+        std::cout << "INFO  : cross-GPU sums over " << (mode == 2 ? "NVLink peer memory (fused one-shot all-reduce)" : "NCCL all-reduce")
+                  << " on " << r.nranks << " GPUs" << std::endl;
+    }
     if (r.root()) std::cout << "meth file name = " << methfp << std::endl;            // :123
     printf("INFO  : rank %d has allocated %zu bytes (%.3f GB) for raw data.\n", r.rank, (size_t)r.M * (size_t)N * 8,
            double((size_t)r.M * (size_t)N * 8) / 1.0E9);                               // :131

@@ -225,6 +225,53 @@ __global__ void __launch_bounds__(256) k_ax_reduce(const double* __restrict__ pa
     }
 }
 
+// k_ax_reduce fused with the cross-GPU sum (xchg.cuh): every CTA reduces the chunk partials of its 256/SL rows, pushes
+// them to all ranks, waits for the same rows of all ranks, adds them in rank order and divides by sqrt(N) — the reference's
+// MPI_Allreduce + scaling of src/data.cpp:367-370 — in ONE launch instead of kernel + ncclAllReduce + kernel.
+template <int SL>
+__global__ void __launch_bounds__(256) k_ax_reduce_xchg(const double* __restrict__ partial, size_t ld, int nchunks, int N,
+                                                        double divisor, double* __restrict__ out, const int* __restrict__ done,
+                                                        Xchg x) {
+    if (done != nullptr && *done != 0) return;
+    __shared__ double sm[SL][256 / SL];
+    __shared__ unsigned int s_seq;
+    constexpr int ROWS = 256 / SL;
+    static_assert(ROWS == 32, "the exchange below is written for one warp owning the CTA's rows");
+    const int r = threadIdx.x % ROWS, s = threadIdx.x / ROWS;
+    const int i = blockIdx.x * ROWS + r;
+    if (threadIdx.x == 0) s_seq = ld_volatile_u32(x.seq) + 1u;
+    double acc = 0.0;
+    if (i < N)
+        for (int cidx = s; cidx < nchunks; cidx += SL) acc += __ldcg(partial + (size_t)cidx * ld + i);
+    sm[s][r] = acc;
+    __syncthreads();
+    if (s == 0) {                                              // warp 0: lane r owns row i
+        const unsigned int seq = s_seq, slot = seq & 1u;
+        double t = sm[0][r];
+#pragma unroll
+        for (int q = 1; q < SL; q++) t += sm[q][r];
+        if (i < N)
+            for (int g = 0; g < x.G; g++) xchg_recv_vec(x, g, slot, x.rank)[i] = t;
+        __threadfence_system();
+        __syncwarp();
+        if (r < x.G) {
+            st_release_sys(xchg_flag_vec(x, r, x.rank, blockIdx.x), seq);
+            xchg_wait_flag(xchg_flag_vec(x, x.rank, r, blockIdx.x), seq);
+        }
+        __syncwarp();
+        if (i < N) {
+            double tot = 0.0;
+            for (int g = 0; g < x.G; g++) tot += __ldcg(xchg_recv_vec(x, x.rank, slot, g) + i);
+            out[i] = tot / divisor;
+        }
+        __syncwarp();
+        if (r == 0) {                                          // the last CTA to finish publishes the new sequence number
+            __threadfence();
+            if (atomicAdd(x.ticket, 1u) == gridDim.x - 1) { x.seq[0] = seq; *x.ticket = 0u; }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_scale_div(double* __restrict__ dst, const double* __restrict__ src, double divisor,
                                                    long long n, const int* __restrict__ done) {
     if (done != nullptr && *done != 0) return;
@@ -322,11 +369,18 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
     const double sqrtN = sqrt((double)c->N);
     constexpr int SL = 8;
     int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
-    // single shard: divide by sqrt(N) right here (src/data.cpp:369-370); sharded: the division follows the all-reduce
+    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    if (c->nranks > 1 && c->xchg.enabled) {
+        // reduce + cross-GPU sum over peer memory + scaling in one kernel
+        k_ax_reduce_xchg<SL><<<rblocks, 256, 0, c->stream>>>(c->ax_partial, c->ld, p.nchunks, c->N, sqrtN, out_dev, done_flag, c->xchg);
+        VO_CUDA(cudaGetLastError());
+        prof_end(c, sp);
+        return VAMPOMI_OK;
+    }
+    // single shard: divide by sqrt(N) right here (src/data.cpp:369-370); sharded over NCCL: the division follows the all-reduce
     k_ax_reduce<SL><<<rblocks, 256, 0, c->stream>>>(c->ax_partial, c->ld, p.nchunks, c->N, c->nranks == 1 ? sqrtN : 1.0,
                                                     out_dev, done_flag);
     VO_CUDA(cudaGetLastError());
-    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
     if (c->nranks > 1) {
         VO_CHECK(allreduce_inplace(c, out_dev, (size_t)c->N));                // MPI_Allreduce, src/data.cpp:367
         VO_CHECK(launch_scale_div(c, out_dev, out_dev, sqrtN, c->N, done_flag));

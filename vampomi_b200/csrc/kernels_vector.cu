@@ -7,6 +7,7 @@
 #include <math_constants.h>
 #include "common.h"
 #include "rng.h"
+#include "xchg.cuh"
 
 namespace vampomi {
 
@@ -17,9 +18,12 @@ __device__ __forceinline__ double warp_sum_v(double v) {
 }
 
 // Sums K per-thread values over the whole grid. `partials` is [gridDim.x][K], `ticket` a zero-initialised counter
-// that this routine leaves at zero again. Result lands in out[0..K) (written by the last block only).
-__device__ void grid_reduce(const double* v, int K, double* __restrict__ partials, unsigned int* ticket, double* out) {
+// that this routine leaves at zero again. Result lands in out[0..K) (written by the last block only). With `x` enabled
+// the last block also sums over the GPUs of the job through peer memory (xchg.cuh) before writing out[].
+__device__ void grid_reduce(const double* v, int K, double* __restrict__ partials, unsigned int* ticket, double* out,
+                            const Xchg* x = nullptr) {
     __shared__ double sm[RED_THREADS / 32][MAX_SUMS];
+    __shared__ double fin[MAX_SUMS];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int k = 0; k < K; k++) {
@@ -50,9 +54,12 @@ __device__ void grid_reduce(const double* v, int K, double* __restrict__ partial
             double r = sm[0][0];
 #pragma unroll
             for (int w = 1; w < RED_THREADS / 32; w++) r += sm[w][0];
-            out[k] = r;
+            fin[k] = r;
         }
     }
+    __syncthreads();
+    if (x != nullptr && x->enabled) xchg_allreduce_scalars(*x, fin, K, out);
+    else if (tid < K) out[tid] = fin[tid];
     if (tid == 0) *ticket = 0u;
 }
 
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_init(const double* __restric
                                                          const double* __restrict__ atx_out, double* __restrict__ r,
                                                          double* __restrict__ z, double* __restrict__ p, long long M, int warm,
                                                          double tau, double gam2, double diag, double* __restrict__ partials,
-                                                         unsigned int* ticket, double* __restrict__ out) {
+                                                         unsigned int* ticket, double* __restrict__ out, Xchg xc) {
     double acc[2] = {0.0, 0.0};
     GRID_STRIDE(i, M) {
         const double vi = v[i];
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_init(const double* __restric
         acc[0] = fma(ri, zi, acc[0]);
         acc[1] = fma(vi, vi, acc[1]);
     }
-    grid_reduce(acc, 2, partials, ticket, out);
+    grid_reduce(acc, 2, partials, ticket, out, &xc);
 }
 
 __global__ void k_cg_init_finish(CgScalars* cg, const double* __restrict__ sums) {
@@ -340,7 +347,7 @@ __global__ void k_cg_init_finish(CgScalars* cg, const double* __restrict__ sums)
 __global__ void __launch_bounds__(RED_THREADS) k_cg_dp(const double* __restrict__ atx_out, const double* __restrict__ p,
                                                        double* __restrict__ d, long long M, double tau, double gam2,
                                                        const CgScalars* __restrict__ cg, double* __restrict__ partials,
-                                                       unsigned int* ticket, double* __restrict__ out) {
+                                                       unsigned int* ticket, double* __restrict__ out, Xchg xc) {
     if (cg->done) return;
     double acc = 0.0;
     GRID_STRIDE(i, M) {
@@ -350,7 +357,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_dp(const double* __restrict_
         d[i] = di;
         acc = fma(di, pi, acc);
     }
-    grid_reduce(&acc, 1, partials, ticket, out);
+    grid_reduce(&acc, 1, partials, ticket, out, &xc);
 }
 
 // alpha = <r,z>/<d,p>; mu += alpha p; r -= alpha d; z = r/diag; sums[1..3] = <v,mu>, <r,z>, <r,r>   (:701-706, :728-734)
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_step(const double* __restric
                                                          const double* __restrict__ d, long long M, double diag, int parity,
                                                          const CgScalars* __restrict__ cg, const double* __restrict__ dp,
                                                          double* __restrict__ partials, unsigned int* ticket,
-                                                         double* __restrict__ out) {
+                                                         double* __restrict__ out, Xchg xc) {
     if (cg->done) return;
     const double alpha = cg->rz[parity] / dp[0];
     double acc[3] = {0.0, 0.0, 0.0};
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_step(const double* __restric
         acc[1] = fma(ri, zi, acc[1]);
         acc[2] = fma(ri, ri, acc[2]);
     }
-    grid_reduce(acc, 3, partials, ticket, out);
+    grid_reduce(acc, 3, partials, ticket, out, &xc);
 }
 
 // scalar logic of one CG iteration (:708-726 onsager test, :731-751 beta and residual test) + p = z + beta p (:738-739).
@@ -417,7 +424,7 @@ int launch_cg_init(vampomi_ctx* c, const double* v, double* mu, const double* at
                    double diag, double* sums_dev) {
     k_cg_init<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(v, mu, atx_out, c->mvec[VAMPOMI_V_CG_R], c->mvec[VAMPOMI_V_CG_Z],
                                                               c->mvec[VAMPOMI_V_CG_P], c->M, warm, tau, gam2, diag,
-                                                              c->red_partials, c->red_tickets, sums_dev);
+                                                              c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
@@ -430,7 +437,7 @@ int launch_cg_init_finish(vampomi_ctx* c, const double* sums_dev) {
 }
 int launch_cg_dp(vampomi_ctx* c, const double* atx_out, double tau, double gam2, double* sums_dev) {
     k_cg_dp<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(atx_out, c->mvec[VAMPOMI_V_CG_P], c->mvec[VAMPOMI_V_CG_D], c->M, tau, gam2,
-                                                            c->cg, c->red_partials, c->red_tickets, sums_dev);
+                                                            c->cg, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
@@ -438,7 +445,7 @@ int launch_cg_dp(vampomi_ctx* c, const double* atx_out, double tau, double gam2,
 int launch_cg_step(vampomi_ctx* c, const double* v, double* mu, double diag, int parity, const double* dp_dev, double* sums_dev) {
     k_cg_step<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(v, mu, c->mvec[VAMPOMI_V_CG_R], c->mvec[VAMPOMI_V_CG_Z],
                                                               c->mvec[VAMPOMI_V_CG_P], c->mvec[VAMPOMI_V_CG_D], c->M, diag, parity,
-                                                              c->cg, dp_dev, c->red_partials, c->red_tickets, sums_dev);
+                                                              c->cg, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;

@@ -1,0 +1,98 @@
+// One-shot all-reduce over NVLink peer memory, fused into the kernels that produce the values to be summed.
+//
+// The reference sums its rank-local partial results with MPI_Allreduce: N doubles after every data::Ax
+// (src/data.cpp:367) and single doubles after every inner product of the CG loop (src/utilities.cpp:151). At N = 20 000
+// the vector is 160 kB and the scalars are 8-24 bytes: pure latency. Instead of a library collective after the kernel,
+// the producing kernel itself exchanges the values:
+//
+//   push   every rank stores its contribution into slot [seq & 1][my_rank] of EVERY rank's receive area (peer-mapped
+//          pointers, plain st.global over NVLink), fences at system scope and then raises a per-rank flag to `seq`
+//   wait   it polls its own, LOCAL flags until all ranks have reached `seq` (ld.acquire.sys)
+//   sum    it adds the G contributions from its local receive area in rank order 0..G-1 — every rank adds the same
+//          values in the same order, so results are bitwise identical on all GPUs and independent of timing
+//
+// Slot reuse is safe with two slots: a rank can only start exchange s+2 after it has passed the wait of s+1, and a peer
+// raises its flag for s+1 only after it has finished reading slot (s & 1) of exchange s (stream order on that GPU).
+// `seq` lives in device memory and advances only when an exchange really ran, so launches that return early at the CG
+// done flag (identical on all ranks) do not desynchronise it. A peer that never arrives traps instead of hanging.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vampomi {
+
+constexpr int XCHG_MAX_RANKS = 8;
+constexpr int XCHG_SCALARS = 64;        // doubles per scalar exchange (>= MAX_SUMS)
+
+struct Xchg {                           // passed by value to kernels; all offsets identical on every rank
+    int enabled;
+    int G, rank;
+    int maxb;                           // CTA slots per rank in the vector flag array
+    unsigned long long ld;              // length of one vector contribution (doubles)
+    unsigned long long off_flag_vec, off_flag_sc, off_recv_vec, off_recv_sc;   // byte offsets inside a region
+    unsigned char* peer[XCHG_MAX_RANKS];   // base of every rank's region as mapped into THIS rank's address space
+    unsigned int* seq;                  // local: [0] vector exchanges done, [1] scalar exchanges done
+    unsigned int* ticket;               // local: CTA completion counter of the vector exchange kernel
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void xchg_wait_flag(const unsigned int* flag, unsigned int seq) {
+    unsigned long long spins = 0;
+    // sequence numbers are monotonic; (int) difference tolerates 32-bit wrap
+    while ((int)(ld_acquire_sys(flag) - seq) < 0)
+        if (++spins > (1ull << 28)) __trap();        // ~ tens of seconds: a rank is gone — fault instead of hanging
+}
+
+__device__ __forceinline__ double* xchg_recv_vec(const Xchg& x, int on_rank, unsigned slot, int from_rank) {
+    return reinterpret_cast<double*>(x.peer[on_rank] + x.off_recv_vec) + ((size_t)slot * x.G + from_rank) * x.ld;
+}
+__device__ __forceinline__ unsigned int* xchg_flag_vec(const Xchg& x, int on_rank, int from_rank, int cta) {
+    return reinterpret_cast<unsigned int*>(x.peer[on_rank] + x.off_flag_vec) + (size_t)from_rank * x.maxb + cta;
+}
+__device__ __forceinline__ double* xchg_recv_sc(const Xchg& x, int on_rank, unsigned slot, int from_rank) {
+    return reinterpret_cast<double*>(x.peer[on_rank] + x.off_recv_sc) + ((size_t)slot * x.G + from_rank) * XCHG_SCALARS;
+}
+__device__ __forceinline__ unsigned int* xchg_flag_sc(const Xchg& x, int on_rank, int from_rank) {
+    return reinterpret_cast<unsigned int*>(x.peer[on_rank] + x.off_flag_sc) + (size_t)from_rank * 32;   // one 128-byte line each
+}
+
+// Scalar all-reduce executed by ONE thread block (the block that finished a grid reduction last). `vals` holds K <= 64
+// local sums in shared memory; on return out[k] = sum over ranks, identical on every rank. All threads of the block call.
+__device__ inline void xchg_allreduce_scalars(const Xchg& x, const double* vals, int K, double* out) {
+    const int tid = threadIdx.x;
+    __shared__ unsigned int s_seq;
+    if (tid == 0) s_seq = ld_volatile_u32(x.seq + 1) + 1u;
+    __syncthreads();
+    const unsigned int seq = s_seq, slot = seq & 1u;
+    if (tid < K) {
+        const double v = vals[tid];
+        for (int g = 0; g < x.G; g++) xchg_recv_sc(x, g, slot, x.rank)[tid] = v;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid < x.G) {
+        st_release_sys(xchg_flag_sc(x, tid, x.rank), seq);                  // tell rank `tid` that my K values have landed
+        xchg_wait_flag(xchg_flag_sc(x, x.rank, tid), seq);                  // and wait for rank `tid`'s values here
+    }
+    __syncthreads();
+    if (tid < K) {
+        double t = 0.0;
+        for (int g = 0; g < x.G; g++) t += __ldcg(xchg_recv_sc(x, x.rank, slot, g) + tid);
+        out[tid] = t;
+    }
+    if (tid == 0) x.seq[1] = seq;
+}
+
+}  // namespace vampomi

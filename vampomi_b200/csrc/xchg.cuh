@@ -52,7 +52,7 @@ __device__ __forceinline__ void xchg_wait_flag(const unsigned int* flag, unsigne
     unsigned long long spins = 0;
     // sequence numbers are monotonic; (int) difference tolerates 32-bit wrap
     while ((int)(ld_acquire_sys(flag) - seq) < 0)
-        if (++spins > (1ull << 28)) __trap();        // ~ tens of seconds: a rank is gone — fault instead of hanging
+        if (++spins > (1ull << 26)) __trap();        // ~ tens of seconds: a rank is gone — fault instead of hanging
 }
 
 __device__ __forceinline__ double* xchg_recv_vec(const Xchg& x, int on_rank, unsigned slot, int from_rank) {

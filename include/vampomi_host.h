@@ -74,6 +74,22 @@ int vampomi_solver_create(vampomi_ctx* ctx, const vampomi_solver_config* cfg, co
 int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M);
 int vampomi_solver_destroy(vampomi_solver* s);
 
+/* ---- host-only pieces of the reference's driver, exported so that they can be checked without a GPU -------------- */
+/* One CSV row exactly as write_ofile_csv formats it (src/utilities.cpp:366-385): "%5d" then ", %20.15f" per value and
+ * a newline; returns the row length (the reference places the row at byte offset it * length) or -1 if it does not fit. */
+int vampomi_host_csv_row(unsigned it, const double* values, int n, char* buf, int buflen);
+/* data::read_phen (src/data.cpp:58-110): third whitespace token per line, scaled by sqrt((n-1)/sum((y-mean)^2)) when
+ * `standardize`, never centred. Writes up to `cap` values, returns the number of rows, -1 if the file cannot be opened,
+ * -2 on an NA value ("NAN in data!"). */
+long long vampomi_host_read_phen(const char* path, int standardize, double* out, long long cap);
+/* linear_reg1d_pvals (src/utilities.cpp:269-282) with boost's Student-t complement restated by a continued fraction. */
+double vampomi_host_linear_reg1d_pvals(double sumx, double sumsqx, double sumxy, double sumy, double sumsqy, int n);
+/* The counter-hash stand-ins for std::random_device (oracle patches P2/P3): probe sign (+1/-1) and probit start p1. */
+double vampomi_host_probe_sign(unsigned long long seed, int it, unsigned long long global_marker);
+void vampomi_host_probit_p1(unsigned long long seed, int N, double* out);
+/* vamp::updatePrior's component merge (src/vamp.cpp:627-642), in place; returns the new number of components. */
+int vampomi_host_merge_components(double* probs, double* vars, int L, double thr);
+
 #ifdef __cplusplus
 }
 #endif

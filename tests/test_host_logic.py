@@ -1,0 +1,99 @@
+"""Host-side logic of the C++ driver, checked without a GPU against the oracle (which is pinned to the reference
+binary's outputs): CSV row formatting incl. non-finite values, phenotype reader, Student-t p-values, the counter hash
+that replaces std::random_device, and the mixture-component merge."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+from scipy import stats as spstats
+
+from oracle import vamp_oracle as vo
+from vampomi_b200 import capi
+
+c_double_p = C.POINTER(C.c_double)
+
+
+def arr(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_double_p)
+
+
+@pytest.mark.parametrize("values", [[0.0] * 5, [1.5, -2.25e-7, 123456.789, 1e11, 1e-11, 3.0], [float("nan"), -float("nan"), float("inf"), -float("inf")],
+                                    [1e22, -1e22, 0.1], []])
+def test_csv_row_bytes_match_reference_format(lib, values):
+    buf = C.create_string_buffer(4096)
+    a, pa = arr(values) if values else (None, None)
+    for it in (1, 7, 12345, 123456):
+        n = lib.vampomi_host_csv_row(it, pa, len(values), buf, 4096)
+        got = buf.raw[:n].decode()
+        assert got == vo.csv_row(it, values)          # the oracle's formatter is held to the reference's CSV bytes
+        assert n == len(got)
+    # 0.0/0.0 as x86 produces it (sign bit set) prints "-nan", as in row 1 of the reference's _metrics.csv
+    with np.errstate(all="ignore"):
+        neg_nan = np.float64(0.0) / np.float64(0.0)
+    a, pa = arr([neg_nan])
+    n = lib.vampomi_host_csv_row(1, pa, 1, buf, 4096)
+    assert buf.raw[:n].decode() == vo.csv_row(1, [neg_nan])
+
+
+def test_read_phen_matches_oracle(lib, tmp_path):
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(257) * 3 + 1
+    p = tmp_path / "a.phen"
+    with open(p, "w") as f:
+        for i, v in enumerate(y):
+            sep = "\t" if i % 3 == 0 else "  "
+            f.write(f"{i}{sep}{i} {v:0.10f}\n")
+    out, po = arr(np.zeros(300))
+    for std in (1, 0):
+        n = lib.vampomi_host_read_phen(str(p).encode(), std, po, 300)
+        assert n == 257
+        want = vo.read_phen(str(p), standardize=bool(std))
+        assert np.allclose(out[:n], want, rtol=1e-15, atol=0)
+    if True:   # scaled, not centred (src/data.cpp:97-99)
+        lib.vampomi_host_read_phen(str(p).encode(), 1, po, 300)
+        assert abs(out[:257].std(ddof=1) - 1) < 1e-12 and abs(out[:257].mean()) > 0.1
+    assert lib.vampomi_host_read_phen(b"/nonexistent/file.phen", 1, po, 300) == -1
+    with open(p, "a") as f:
+        f.write("9 9 NA\n")
+    assert lib.vampomi_host_read_phen(str(p).encode(), 1, po, 300) == -2
+
+
+def test_students_t_pvalues_match_scipy(lib):
+    rng = np.random.default_rng(1)
+    for n in (10, 300, 20000):
+        x = rng.standard_normal(n)
+        for slope in (0.0, 0.05, 0.5, 5.0):
+            yv = slope * x + rng.standard_normal(n)
+            got = lib.vampomi_host_linear_reg1d_pvals(x.sum(), (x * x).sum(), (x * yv).sum(), yv.sum(), (yv * yv).sum(), n)
+            want = vo.linear_reg1d_pvals(x.sum(), (x * x).sum(), (x * yv).sum(), yv.sum(), (yv * yv).sum(), n)
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-300)
+            assert got == pytest.approx(spstats.linregress(x, yv).pvalue, rel=1e-7, abs=1e-300)
+
+
+def test_counter_hash_matches_oracle_and_reference_hooks(lib):
+    for seed in (0, 7, 2 ** 63 + 5):
+        for it in (1, 2, 50):
+            want = vo.probe_signs(seed, it, 1000, 64)
+            got = np.array([lib.vampomi_host_probe_sign(seed, it, 1000 + j) for j in range(64)])
+            assert np.array_equal(got, want)
+        out, po = arr(np.zeros(500))
+        lib.vampomi_host_probit_p1(seed, 500, po)
+        assert np.allclose(out, vo.probit_p1(seed, 500), rtol=0, atol=1e-14)
+    s = vo.probe_signs(3, 1, 0, 100000)
+    assert abs(s.mean()) < 0.02 and set(np.unique(s)) == {-1.0, 1.0}
+
+
+@pytest.mark.parametrize("vars_,probs,thr", [([0, 1e-6, 1.4e-6, 1e-3, 1.2e-3, 1.0], [0.9, 0.02, 0.02, 0.02, 0.02, 0.02], 0.5),
+                                             ([0, 1e-8, 1e-3], [0.5, 0.25, 0.25], 0.5), ([0, 1, 2, 4, 8], [0.2] * 5, 1.01),
+                                             ([1.0, 1.0, 1.0], [0.2, 0.3, 0.5], 0.5), ([0, 5e-8, 1.0], [0.5, 0.2, 0.3], 0.9)])
+def test_merge_components_matches_oracle(lib, vars_, probs, thr):
+    p_want, v_want = list(probs), list(vars_)
+    vo.merge_components(p_want, v_want, thr)
+    p, pp = arr(probs)
+    v, pv = arr(vars_)
+    L = lib.vampomi_host_merge_components(pp, pv, len(probs), thr)
+    assert L == len(p_want)
+    assert np.allclose(p[:L], p_want, rtol=1e-15) and np.allclose(v[:L], v_want, rtol=1e-15)
+    assert math.isclose(sum(p[:L]), sum(probs), rel_tol=1e-14)

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <iostream>
 #include "io.h"
+#include "../rng.h"
 
 namespace vampomi_host {
 
@@ -395,6 +396,45 @@ int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_
 int vampomi_solver_destroy(vampomi_solver* s) {
     if (s) { delete s->impl; delete s; }
     return VAMPOMI_OK;
+}
+
+int vampomi_host_csv_row(unsigned it, const double* values, int n, char* buf, int buflen) {
+    if (!buf || n < 0 || (n > 0 && !values)) return -1;
+    std::string row = vampomi_host::CsvFile::format_row(it, std::vector<double>(values, values + n));
+    if ((int)row.size() + 1 > buflen) return -1;
+    std::memcpy(buf, row.c_str(), row.size() + 1);
+    return (int)row.size();
+}
+
+long long vampomi_host_read_phen(const char* path, int standardize, double* out, long long cap) {
+    std::vector<double> y;
+    try {
+        if (!path || !vampomi_host::read_phen(path, standardize != 0, &y)) return -1;
+    } catch (const std::exception&) {
+        return -2;
+    }
+    for (long long i = 0; i < (long long)y.size() && i < cap; i++) out[i] = y[i];
+    return (long long)y.size();
+}
+
+double vampomi_host_linear_reg1d_pvals(double sumx, double sumsqx, double sumxy, double sumy, double sumsqy, int n) {
+    return vampomi_host::linear_reg1d_pvals(sumx, sumsqx, sumxy, sumy, sumsqy, n);
+}
+
+double vampomi_host_probe_sign(unsigned long long seed, int it, unsigned long long global_marker) {
+    return vampomi::probe_sign(seed, it, global_marker);
+}
+
+void vampomi_host_probit_p1(unsigned long long seed, int N, double* out) {
+    std::vector<double> p = vampomi_host::probit_p1(seed, N);
+    for (int i = 0; i < N; i++) out[i] = p[i];
+}
+
+int vampomi_host_merge_components(double* probs, double* vars, int L, double thr) {
+    std::vector<double> p(probs, probs + L), v(vars, vars + L);
+    vampomi_host::merge_components(p, v, thr);
+    for (size_t i = 0; i < p.size(); i++) { probs[i] = p[i]; vars[i] = v[i]; }
+    return (int)p.size();
 }
 
 void vampomi_solver_default_config(vampomi_solver_config* cfg) {

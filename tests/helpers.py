@@ -56,8 +56,11 @@ def extra_kwargs(g):
     """Maps the extra command-line flags recorded in a fixture to oracle/solver keyword arguments."""
     ex = list(g["extra"]) if len(g["extra"]) else []
     kw = {}
+    flist = lambda t: [float(x) for x in str(t).split(",")]
     names = {"--EM-max-iter": ("EM_max_iter", int), "--learn-prior-delay": ("learn_prior_delay", int), "--rho": ("rho", float),
-             "--gam1": ("gam1", float), "--CG-err-tol": ("CG_err_tol", float), "--EM-err-thr": ("EM_err_thr", float)}
+             "--gam1": ("gam1", float), "--CG-err-tol": ("CG_err_tol", float), "--EM-err-thr": ("EM_err_thr", float),
+             "--vars": ("vars", flist), "--probs": ("probs", flist), "--learn-vars": ("learn_vars", int),
+             "--merge-vars-thr": ("merge_vars_thr", float), "--alpha-scale": ("alpha_scale", float)}
     for k, v in zip(ex[::2], ex[1::2]):
         n, f = names[str(k)]
         kw[n] = f(v)
@@ -97,12 +100,15 @@ def assert_rows_close(got, want, rel, what):
                 assert abs(a - b) <= rel * abs(b) + 2e-15, f"{what} it {it} col {j}: {a} vs {b}"
 
 
-def oracle_run(g, A, y_txt, beta, out_dir=None, comm=None, S=0, Mt=None):
+def oracle_run(g, A, y_txt, beta, out_dir=None, comm=None, S=0, Mt=None, max_iter=None):
     model = g["model"]
     y = standardize_phen(y_txt) if model == "linear" else y_txt
-    d = vo.Data(A, y, Mt=Mt, S=S, comm=comm)
     kw = extra_kwargs(g)
-    v = vo.Vamp(d, gamw=1.0 / (1.0 - 0.5), max_iter=int(g["iterations"]), true_signal=beta, out_dir=out_dir, out_name="o",
-                model=model, seed=int(g["probe_seed"]), stop_criteria_thr=0.0, **kw)
+    d = vo.Data(A, y, Mt=Mt, S=S, comm=comm, alpha_scale=kw.pop("alpha_scale", 1.0))
+    init = g.get("x1hat_init")
+    if init is not None:
+        init = np.asarray(init)[S:S + A.shape[0]]
+    v = vo.Vamp(d, gamw=1.0 / (1.0 - 0.5), max_iter=int(max_iter or g["iterations"]), true_signal=beta, out_dir=out_dir, out_name="o",
+                model=model, seed=int(g["probe_seed"]), stop_criteria_thr=float(g.get("stop_thr", 0.0)), x1hat_init=init, **kw)
     v.infere()
     return v

@@ -16,19 +16,20 @@ from helpers import (assert_rows_close, csv_rows, extra_kwargs, golden_inputs, l
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "probit_small"]
+CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+         "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged"]
 
 
 def solver_for(g, A, y_txt, beta, **over):
     model = g["model"]
     y = standardize_phen(y_txt) if model == "linear" else y_txt
-    sh = capi.Shard(int(g["N"]), int(g["M"]))
-    sh.upload(A)
-    sh.compute_stats()
     kw = dict(gamw=2.0, seed=int(g["probe_seed"]))
     kw.update(extra_kwargs(g))
     kw.update(over)
-    return sh, capi.Solver(sh, y, model=model, true_signal=beta, **kw)
+    sh = capi.Shard(int(g["N"]), int(g["M"]))
+    sh.upload(A)
+    sh.compute_stats(kw.pop("alpha_scale", 1.0))
+    return sh, capi.Solver(sh, y, model=model, true_signal=beta, x1hat_init=g.get("x1hat_init"), **kw)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -55,6 +56,8 @@ def test_solver_matches_reference_fixture(name, redundant):
                 assert r["matrix_passes"] == base + (5 if k == 1 else 6)
     assert_rows_close(got_params, want_params, rel_csv, "params")
     assert_rows_close(got_metrics, want_metrics, rel_csv, "metrics")
+    if float(g.get("stop_thr", 0)) > 0:          # the reference stopped here on its own NMSE test (src/vamp.cpp:419-423)
+        assert r["nmse"] < float(g["stop_thr"])
     sol.close()
     sh.close()
 
@@ -81,7 +84,8 @@ def run_cli(args, **kw):
     return res.stdout
 
 
-@pytest.mark.parametrize("name", ["linear_small", "probit_small"])
+@pytest.mark.parametrize("name", ["linear_small", "probit_small", "linear_stops_early", "linear_warm_start", "linear_alpha_scale",
+                                  "linear_two_comp"])
 def test_main_meth_command_line_outputs(name, tmp_path):
     g = load_golden(name)
     rel_vec, rel_csv = tolerances(g)
@@ -89,11 +93,17 @@ def test_main_meth_command_line_outputs(name, tmp_path):
     golden_inputs(g, d)
     os.makedirs(tmp_path / "out")
     its = int(g["iterations"])
+    early = float(g.get("stop_thr", 0)) > 0
     args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out",
-            "--out-name", "g", "--iterations", its, "--true-signal-file", f"{d}/ex_ts.bin", "--model", g["model"],
-            "--stop-criteria-thr", "0", "--seed", g["probe_seed"], "--run-mode", "inference"] + list(g["extra"])
+            "--out-name", "g", "--iterations", 40 if early else its, "--true-signal-file", f"{d}/ex_ts.bin", "--model", g["model"],
+            "--stop-criteria-thr", g.get("stop_thr", 0), "--seed", g["probe_seed"], "--run-mode", "inference"] + list(g["extra"])
+    if "x1hat_init" in g:
+        g["x1hat_init"].tofile(f"{d}/init_it_3.bin")
+        args += ["--estimate-file", f"{d}/init_it_3.bin"]
     out = run_cli(args)
     assert "iteration = 1" in out and "x1_hat NMSE" in out
+    if early:
+        assert "...stopping criteria fulfilled" in out and not os.path.exists(f"{d}/out/g_it_{its + 1}.bin")
     for k in range(1, its + 1):
         assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), g["x1"][k - 1]) < rel_vec
         assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < rel_vec

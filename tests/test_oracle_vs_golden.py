@@ -11,12 +11,18 @@ from helpers import (REL_CSV, REL_VEC, assert_rows_close, csv_rows, golden_input
                      standardize_phen, tolerances, REL_VEC_ILLCOND)
 
 
-@pytest.mark.parametrize("name", ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "probit_small"])
+ALL_CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+             "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged"]
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_oracle_matches_reference_run(name, tmp_path):
     g = load_golden(name)
     REL_VEC, REL_CSV = tolerances(g)
     A, y_txt, beta = golden_inputs(g)
-    v = oracle_run(g, A, y_txt, beta, out_dir=str(tmp_path))
+    # ask for more iterations than the reference ran when it stopped on its own NMSE criterion (src/vamp.cpp:419-423)
+    v = oracle_run(g, A, y_txt, beta, out_dir=str(tmp_path), max_iter=40 if float(g.get("stop_thr", 0)) > 0 else None)
+    assert len(v.history) == int(g["iterations"]), "number of VAMP iterations run"
     for k in range(1, int(g["iterations"]) + 1):
         x1 = np.fromfile(tmp_path / f"o_it_{k}.bin")
         r1 = np.fromfile(tmp_path / f"o_r1_it_{k}.bin")

@@ -28,6 +28,16 @@ CASES = {
                           extra=["--EM-max-iter", "3", "--learn-prior-delay", "2", "--rho", "0.7"]),
     "linear_wellcond": dict(N=300, M=800, lam=0.05, h2=0.6, data_seed=11, probe_seed=3, iterations=6, model="linear",
                             extra=["--gam1", "1e-2"]),
+    "linear_two_comp": dict(N=200, M=300, lam=0.1, h2=0.7, data_seed=31, probe_seed=2, iterations=5, model="linear",
+                            extra=["--vars", "0,0.001", "--probs", "0.9,0.1", "--learn-vars", "0", "--gam1", "1e-2"]),
+    "linear_alpha_scale": dict(N=250, M=400, lam=0.1, h2=0.7, data_seed=32, probe_seed=4, iterations=4, model="linear",
+                               extra=["--alpha-scale", "0.5", "--gam1", "1e-2", "--merge-vars-thr", "0.9"]),
+    "linear_stops_early": dict(N=300, M=200, lam=0.1, h2=0.8, data_seed=33, probe_seed=6, iterations=40, model="linear",
+                               extra=["--gam1", "1e-2"], stop_thr="0.01"),
+    "linear_warm_start": dict(N=200, M=300, lam=0.1, h2=0.7, data_seed=34, probe_seed=8, iterations=3, model="linear",
+                              extra=["--gam1", "1e-2"], warm_from=3),
+    "probit_ragged": dict(N=333, M=217, lam=0.1, h2=0.5, data_seed=35, probe_seed=10, iterations=5, model="bin_class",
+                          extra=["--gam1", "1e-2", "--rho", "0.8"]),
     "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
                          extra=["--gam1", "1e-2"]),
 }
@@ -63,8 +73,18 @@ def make_case(name, c):
         os.makedirs(os.path.join(d, "out"))
         args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", str(c["N"]), "--Mt", str(c["M"]),
                 "--out-dir", f"{d}/out", "--out-name", "g", "--iterations", str(c["iterations"]), "--true-signal-file",
-                f"{d}/ex_ts.bin", "--model", c["model"], "--stop-criteria-thr", "0", "--verbosity", "1"] + c["extra"]
+                f"{d}/ex_ts.bin", "--model", c["model"], "--stop-criteria-thr", c.get("stop_thr", "0"), "--verbosity", "1"] + c["extra"]
+        init = None
+        if c.get("warm_from"):
+            # --estimate-file start (src/main_meth.cpp:75-80, src/vamp.cpp:71-79 with patch P1): first produce an estimate
+            os.makedirs(os.path.join(d, "pre"))
+            pre = [a_.replace(f"{d}/out", f"{d}/pre") for a_ in args]
+            run_ref(pre, c["probe_seed"])
+            init = np.fromfile(f"{d}/pre/g_it_{c['warm_from']}.bin")
+            args += ["--estimate-file", f"{d}/pre/g_it_{c['warm_from']}.bin"]
         log = run_ref(args, c["probe_seed"])
+        ran = len([f for f in os.listdir(f"{d}/out") if f.startswith("g_it_")])
+        c = dict(c, iterations=ran)          # early stop: fewer iterations than asked for
         x1 = np.stack([np.fromfile(f"{d}/out/g_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
         r1 = np.stack([np.fromfile(f"{d}/out/g_r1_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
         blob = {k: np.frombuffer(open(f"{d}/out/g_{k}.csv", "rb").read(), dtype=np.uint8) for k in ("params", "metrics", "prior")}
@@ -72,6 +92,9 @@ def make_case(name, c):
                    N=c["N"], M=c["M"], lam=c["lam"], h2=c["h2"], data_seed=c["data_seed"], probe_seed=c["probe_seed"],
                    iterations=c["iterations"], model=c["model"], extra=np.array(c["extra"], dtype="U32"),
                    sha256_A=hashlib.sha256(X.tobytes()).hexdigest(), sha256_phen=hashlib.sha256(open(f"{d}/ex.phen", "rb").read()).hexdigest())
+        fix["stop_thr"] = float(c.get("stop_thr", "0"))
+        if init is not None:
+            fix["x1hat_init"] = init
         if c["model"] == "linear":
             fix["cg_iters"] = cg_counts(log)
         if name == "linear_small":

@@ -114,6 +114,13 @@ def test_load_file_reads_the_shard_block(tmp_path):
         sh.load_file(str(tmp_path / "a.bin"))
         assert np.array_equal(sh.download(), A[sh.S:sh.S + sh.M])            # byte offset S*N*8, src/data.cpp:134
         sh.close()
+    # single reader, many readers and more readers than 32 MB column groups give the same block
+    sh = capi.Shard(N, Mt)
+    for threads in (1, 3, 16):
+        sh.set_tuning("load_threads", threads)
+        sh.load_file(str(tmp_path / "a.bin"))
+        assert np.array_equal(sh.download(), A)
+    sh.close()
     sh = capi.Shard(N, Mt + 1)
     with pytest.raises(capi.VampomiError, match="too short"):
         sh.load_file(str(tmp_path / "a.bin"))

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <vector>
 #include <new>
+#include <string>
+#include <thread>
 #include "common.h"
 
 namespace vampomi {
@@ -403,40 +405,60 @@ int vampomi_load_file(vampomi_ctx* c, const char* path) {
         set_error("%s is too short for N=%d and markers [%lld,%lld)", path, c->N, c->S, c->S + c->M);
         return VAMPOMI_ERR_IO;
     }
-    // ring of pinned staging buffers: pread into slot k while the copies of slots k-1, k-2 are still in flight
-    constexpr int NSLOT = 3;
-    long long cols_per_slot = (long long)((64ull << 20) / col_bytes);
+    // T reader threads, each with two pinned staging buffers and its own copy stream: pread of one 32 MB column group
+    // overlaps the host-to-device copy of the previous one, and T of these pipelines run side by side (a single pread
+    // stream tops out at a few GB/s; PCIe gen5 takes ~50 GB/s). Column groups are dealt round-robin.
+    long long cols_per_slot = (long long)((32ull << 20) / col_bytes);
     if (cols_per_slot < 1) cols_per_slot = 1;
     if (cols_per_slot > c->M) cols_per_slot = c->M;
-    double* slot[NSLOT] = {};
-    cudaEvent_t ev[NSLOT] = {};
-    int rc = [&]() -> int {
-        for (int k = 0; k < NSLOT; k++) {
-            VO_CUDA(cudaMallocHost(&slot[k], (size_t)cols_per_slot * col_bytes));
-            VO_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
-        }
+    const long long nitems = (c->M + cols_per_slot - 1) / cols_per_slot;
+    int T = c->tune.load_threads;
+    if (T < 1) T = 1;
+    if (T > 16) T = 16;
+    if ((long long)T > nitems) T = (int)nitems;
+    std::vector<int> rcs((size_t)T, VAMPOMI_OK);
+    std::vector<std::string> errs((size_t)T);
+    auto worker = [&](int t) {
+        auto fail = [&](int code, const std::string& msg) { rcs[t] = code; errs[t] = msg; };
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(VAMPOMI_ERR_CUDA, "cudaSetDevice failed in a loader thread");
+        double* slot[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t st = nullptr;
+        bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; k++)
+            ok = cudaMallocHost(&slot[k], (size_t)cols_per_slot * col_bytes) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) fail(VAMPOMI_ERR_CUDA, "could not allocate pinned staging buffers");
         int k = 0;
-        for (long long j = 0; j < c->M; j += cols_per_slot, k = (k + 1) % NSLOT) {
-            long long nc = c->M - j < cols_per_slot ? c->M - j : cols_per_slot;
-            VO_CUDA(cudaEventSynchronize(ev[k]));                     // slot free again?
+        for (long long item = t; item < nitems && ok; item += T, k ^= 1) {
+            const long long j = item * cols_per_slot;
+            const long long nc = c->M - j < cols_per_slot ? c->M - j : cols_per_slot;
+            if (cudaEventSynchronize(ev[k]) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "event sync failed"); break; }   // slot free again?
             size_t want = (size_t)nc * col_bytes, got = 0;
-            off_t off = (off_t)((size_t)(c->S + j) * col_bytes);      // byte offset S*N*8, src/data.cpp:134
+            const off_t off = (off_t)((size_t)(c->S + j) * col_bytes);     // byte offset S*N*8, src/data.cpp:134
             while (got < want) {
                 ssize_t r = pread(fd, (char*)slot[k] + got, want - got, off + (off_t)got);
-                if (r <= 0) { set_error("short read from %s", path); return VAMPOMI_ERR_IO; }
+                if (r <= 0) { fail(VAMPOMI_ERR_IO, std::string("short read from ") + path); ok = false; break; }
                 got += (size_t)r;
             }
-            VO_CUDA(cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), slot[k], col_bytes, col_bytes, (size_t)nc,
-                                      cudaMemcpyHostToDevice, c->copy_stream));
-            VO_CUDA(cudaEventRecord(ev[k], c->copy_stream));
+            if (!ok) break;
+            if (cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), slot[k], col_bytes, col_bytes, (size_t)nc,
+                                  cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                cudaEventRecord(ev[k], st) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "host-to-device copy failed"); break; }
         }
-        VO_CUDA(cudaStreamSynchronize(c->copy_stream));
-        return VAMPOMI_OK;
-    }();
+        if (st) cudaStreamSynchronize(st);
+        for (int q = 0; q < 2; q++) { if (slot[q]) cudaFreeHost(slot[q]); if (ev[q]) cudaEventDestroy(ev[q]); }
+        if (st) cudaStreamDestroy(st);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& x : th) x.join();
     close(fd);
-    for (int k = 0; k < NSLOT; k++) { if (slot[k]) cudaFreeHost(slot[k]); if (ev[k]) cudaEventDestroy(ev[k]); }
     c->stats_ready = false;
-    return rc;
+    for (int t = 0; t < T; t++)
+        if (rcs[t] != VAMPOMI_OK) { set_error("%s", errs[t].c_str()); return rcs[t]; }
+    return VAMPOMI_OK;
 }
 
 int vampomi_generate_iid(vampomi_ctx* c, unsigned long long seed) {
@@ -702,7 +724,8 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"ax_ctas_per_sm", &c->tune.ax_ctas_per_sm, 0, 32}, {"atx_cols", &c->tune.atx_cols, 0, 4},
         {"atx_unroll", &c->tune.atx_unroll, 0, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
         {"cg_depth", &c->tune.cg_depth, 1, 32},     {"ax_impl", &c->tune.ax_impl, 0, 1},
-        {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
+        {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},
+        {"load_threads", &c->tune.load_threads, 1, 16},       {"center_split", &c->tune.center_split, 0, 1},
     };
     for (auto& k : knobs)
         if (!strcmp(k.n, name)) {

@@ -82,6 +82,7 @@ struct Tuning {
     int ax_impl = 0;                 // 0 = per-thread 256-bit LDG streaming, 1 = bulk-copy (cp.async.bulk + mbarrier) pipeline
     int atx_impl = 3;                // 0 = warp per column group, 1 = bulk-copy pipeline, 2 = CTA per column group, 3 = auto (2 when N >= 4096, else 0)
     int xchg = 1;                    // 1 = fused peer-memory all-reduce (xchg.cuh) when it could be set up, 0 = NCCL collectives
+    int load_threads = 4;            // parallel pread -> pinned -> HBM pipelines of vampomi_load_file
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 

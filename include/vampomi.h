@@ -86,6 +86,15 @@ int vampomi_device_count(int* count);
  * (src/utilities.cpp:214-225): first Mt % nranks shards get floor(Mt/nranks)+1 markers. Allocates the M x N block
  * in HBM (column stride padded to a multiple of 16 doubles) and all work vectors. */
 int vampomi_create(int device, int N, long long Mt, int nranks, int rank, vampomi_ctx** out);
+/* Same, with a choice of how the marker block is HELD in HBM: VAMPOMI_STORE_F64 (the reference's layout, what
+ * vampomi_create uses) or VAMPOMI_STORE_F32 — every value is rounded to FP32 when it is uploaded / loaded / generated and
+ * widened back to FP64 inside the kernels, so all arithmetic and every interface stay FP64 while each matrix pass streams
+ * half the bytes. This is an opt-in mode outside the reference's contract: results equal those of the reference run on
+ * the ROUNDED matrix (to the usual 1e-9), not on the original one. */
+#define VAMPOMI_STORE_F64 0
+#define VAMPOMI_STORE_F32 1
+int vampomi_create_ex(int device, int N, long long Mt, int nranks, int rank, int storage, vampomi_ctx** out);
+int vampomi_storage(const vampomi_ctx* ctx, int* storage);
 int vampomi_destroy(vampomi_ctx* ctx);
 /* M (markers of this shard) and S (global index of its first marker) — divide_work's MS[0], MS[1]. */
 int vampomi_shard(const vampomi_ctx* ctx, long long* M, long long* S);

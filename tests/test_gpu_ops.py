@@ -288,3 +288,49 @@ def test_association_pvalues_match_oracle():
     assert np.allclose(sums[:, 0], A.sum(1), rtol=1e-12) and np.allclose(sums[:, 1], (A * A).sum(1), rtol=1e-12)
     assert np.allclose(sums[:, 2], A @ w, rtol=1e-10, atol=1e-10)
     sh.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# opt-in FP32 storage of the marker block (vampomi_create_ex): every value is rounded once, arithmetic stays FP64, so the
+# results must equal the oracle's on the ROUNDED matrix
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M", [(300, 800), (333, 517), (4100, 1033), (64, 1)])
+def test_f32_storage_matches_oracle_on_rounded_matrix(N, M, tmp_path):
+    rng = np.random.default_rng(N * 7 + M)
+    A = rng.standard_normal((M, N)) * 0.1 + 0.5
+    A32 = A.astype(np.float32).astype(np.float64)
+    y = rng.standard_normal(N)
+    sh = capi.Shard(N, M, storage="f32")
+    sh.upload(A)
+    assert np.array_equal(sh.download(), A32)
+    sh.compute_stats()
+    d = vo.Data(A32, y)
+    mave, msig = sh.stats()
+    assert np.allclose(mave, d.mave, rtol=1e-13, atol=1e-15) and np.allclose(msig, d.msig, rtol=1e-12)
+    p, x = rng.standard_normal(N), rng.standard_normal(M)
+    for knobs in (dict(), dict(atx_impl=0), dict(atx_impl=2, atx_cols=4, atx_unroll=2), dict(ax_rv=1, ax_unroll=8), dict(ax_rv=4, ax_unroll=2),
+                  dict(ax_impl=1, atx_impl=1)):          # the bulk knobs fall back to the LDG kernels for FP32 storage
+        for k, v in knobs.items():
+            sh.set_tuning(k, v)
+        assert rel_l2(sh.ATx(p), d.ATx(p)) < 1e-12
+        assert rel_l2(sh.Ax(x), d.Ax(x)) < 1e-12
+    w = rng.standard_normal(N)
+    sh.set(V_USER_N1, w)
+    sums = sh.loo_sums(V_USER_N1)
+    assert np.allclose(sums[:, 0], A32.sum(1), rtol=1e-12) and np.allclose(sums[:, 2], A32 @ w, rtol=1e-10, atol=1e-10)
+    # file ingest rounds the same way
+    A.tofile(tmp_path / "a.bin")
+    sh.load_file(str(tmp_path / "a.bin"))
+    assert np.array_equal(sh.download(), A32)
+    sh.close()
+
+
+def test_f32_storage_generator_is_the_rounded_f64_generator():
+    N, M = 257, 91
+    a = capi.Shard(N, M)
+    b = capi.Shard(N, M, storage="f32")
+    a.generate_iid(42)
+    b.generate_iid(42)
+    assert np.array_equal(b.download(), a.download().astype(np.float32).astype(np.float64))
+    a.close()
+    b.close()

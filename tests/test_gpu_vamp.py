@@ -180,3 +180,35 @@ def test_full_size_properties():
     assert 1 < it < 200 and np.linalg.norm(res) / np.linalg.norm(v) < 2e-8
     assert abs(np.linalg.norm(res) / np.linalg.norm(v) - rel) < 1e-9
     sh.close()
+
+
+@pytest.mark.parametrize("name", ["linear_wellcond", "probit_small"])
+def test_f32_storage_vamp_matches_oracle_on_rounded_matrix(name, tmp_path):
+    """--storage f32 (opt-in, outside the reference's contract): the whole VAMP run equals the oracle's run on the matrix
+    rounded to FP32, to the same 1e-9 — the mode changes the data that is held, not the arithmetic."""
+    g = load_golden(name)
+    A, y_txt, beta = golden_inputs(g)
+    A32 = A.astype(np.float32).astype(np.float64)
+    v = oracle_run(g, A32, y_txt, beta)
+    model = g["model"]
+    y = standardize_phen(y_txt) if model == "linear" else y_txt
+    sh = capi.Shard(int(g["N"]), int(g["M"]), storage="f32")
+    sh.upload(A)
+    sh.compute_stats()
+    kw = dict(gamw=2.0, seed=int(g["probe_seed"]))
+    kw.update(extra_kwargs(g))
+    sol = capi.Solver(sh, y, model=model, true_signal=beta, **kw)
+    for k in range(1, int(g["iterations"]) + 1):
+        r = sol.step()
+        assert rel_l2(r["x1"], v.dump[k][0]) < 1e-9 and rel_l2(r["r1"], v.dump[k][1]) < 1e-9
+    sol.close()
+    sh.close()
+    # and through the command line
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    run_cli(["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
+             "--iterations", 3, "--true-signal-file", f"{d}/ex_ts.bin", "--model", model, "--stop-criteria-thr", "0", "--seed", g["probe_seed"],
+             "--storage", "f32"] + list(g["extra"]))
+    for k in range(1, 4):
+        assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), v.dump[k][0]) < 1e-9

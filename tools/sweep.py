@@ -17,17 +17,18 @@ ap.add_argument("--N", type=int, default=20000)
 ap.add_argument("--M", type=int, default=106250)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--quick", action="store_true")
+ap.add_argument("--storage", default="f64", choices=["f64", "f32"])
 ap.add_argument("--sustained", type=int, default=0, help="also time a short list of variants with this many back-to-back reps "
                 "(seconds-long, i.e. under the power cap) instead of a burst")
 a = ap.parse_args()
 
-sh = vb.Shard(a.N, a.M)
+sh = vb.Shard(a.N, a.M, storage=a.storage)
 sh.generate_iid(1)
 sh.compute_stats()
 rng = np.random.default_rng(0)
 sh.Ax(rng.standard_normal(a.M))
 sh.ATx(rng.standard_normal(a.N))
-gb = a.N * a.M * 8 / 1e9
+gb = a.N * a.M * (8 if a.storage == "f64" else 4) / 1e9
 results = []
 
 

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "vampomi_abi_version": (C.c_int, []),
     "vampomi_device_count": (C.c_int, [c_int_p]),
     "vampomi_create": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vampomi_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vampomi_storage": (C.c_int, [C.c_void_p, c_int_p]),
     "vampomi_destroy": (C.c_int, [C.c_void_p]),
     "vampomi_shard": (C.c_int, [C.c_void_p, c_ll_p, c_ll_p]),
     "vampomi_dims": (C.c_int, [C.c_void_p, c_int_p, c_ll_p, c_int_p, c_int_p]),
@@ -171,10 +173,12 @@ def comm_unique_id():
 class Shard:
     """One marker shard on one GPU: the `class data` of the reference (src/data.hpp:47-90) plus the device vectors."""
 
-    def __init__(self, N, Mt, device=0, nranks=1, rank=0, nccl_id=None):
+    def __init__(self, N, Mt, device=0, nranks=1, rank=0, nccl_id=None, storage="f64"):
+        """storage: "f64" (the reference's layout) or "f32" (opt-in: the block is rounded to FP32 in HBM, arithmetic stays FP64)."""
         self.lib = load_library()
         h = C.c_void_p()
-        _check(self.lib.vampomi_create(device, N, Mt, nranks, rank, C.byref(h)), "vampomi_create")
+        self.storage = storage
+        _check(self.lib.vampomi_create_ex(device, N, Mt, nranks, rank, {"f64": 0, "f32": 1}[storage], C.byref(h)), "vampomi_create")
         self.h = h
         self.N, self.Mt, self.nranks, self.rank = int(N), int(Mt), nranks, rank
         M, S = C.c_longlong(), C.c_longlong()

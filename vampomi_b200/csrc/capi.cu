@@ -242,8 +242,19 @@ int vampomi_divide_work(long long Mt, int nranks, int rank, long long* M, long l
 }
 
 int vampomi_create(int device, int N, long long Mt, int nranks, int rank, vampomi_ctx** out) {
+    return vampomi_create_ex(device, N, Mt, nranks, rank, VAMPOMI_STORE_F64, out);
+}
+
+int vampomi_storage(const vampomi_ctx* c, int* storage) {
+    VO_ARG(c && storage, "storage: NULL argument");
+    *storage = c->storage;
+    return VAMPOMI_OK;
+}
+
+int vampomi_create_ex(int device, int N, long long Mt, int nranks, int rank, int storage, vampomi_ctx** out) {
     VO_ARG(out != nullptr, "create: out is NULL");
     *out = nullptr;
+    VO_ARG(storage == VAMPOMI_STORE_F64 || storage == VAMPOMI_STORE_F32, "create: unknown storage %d", storage);
     VO_ARG(N >= 2 && Mt >= 1, "create: need N >= 2 and Mt >= 1 (got N=%d Mt=%lld)", N, Mt);
     VO_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "create: bad rank %d of %d", rank, nranks);
     VO_ARG(Mt >= nranks, "create: fewer markers (%lld) than shards (%d)", Mt, nranks);
@@ -258,6 +269,7 @@ int vampomi_create(int device, int N, long long Mt, int nranks, int rank, vampom
     vampomi_ctx* c = new (std::nothrow) vampomi_ctx();
     VO_ARG(c != nullptr, "create: out of host memory");
     c->device = device; c->N = N; c->Mt = Mt; c->nranks = nranks; c->rank = rank;
+    c->storage = storage; c->elem_bytes = storage == VAMPOMI_STORE_F32 ? 4 : 8;
     vampomi_divide_work(Mt, nranks, rank, &c->M, &c->S);
     c->ld = ((size_t)N + 15) / 16 * 16;
     c->mpad = ((size_t)c->M + 15) / 16 * 16;
@@ -267,13 +279,15 @@ int vampomi_create(int device, int N, long long Mt, int nranks, int rank, vampom
         c->num_sms = prop.multiProcessorCount;
         VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         VO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        const size_t a_bytes = (size_t)c->M * c->ld * sizeof(double);
-        cudaError_t ea = cudaMalloc(&c->A, a_bytes);
+        const size_t a_bytes = (size_t)c->M * c->ld * (size_t)c->elem_bytes;
+        void* a_ptr = nullptr;
+        cudaError_t ea = cudaMalloc(&a_ptr, a_bytes);
         if (ea != cudaSuccess) {
             set_error("cudaMalloc of the %.3f GB marker block failed: %s", a_bytes / 1e9, cudaGetErrorString(ea));
             return VAMPOMI_ERR_CUDA;
         }
-        if (c->ld != (size_t)N) VO_CUDA(cudaMemsetAsync(c->A, 0, a_bytes, c->stream));     // pad rows must be zero
+        if (c->storage == VAMPOMI_STORE_F32) c->A32 = (float*)a_ptr; else c->A = (double*)a_ptr;
+        if (c->ld != (size_t)N) VO_CUDA(cudaMemsetAsync(a_ptr, 0, a_bytes, c->stream));    // pad rows must be zero
         VO_CUDA(cudaMalloc(&c->mave, c->mpad * sizeof(double)));
         VO_CUDA(cudaMalloc(&c->msig, c->mpad * sizeof(double)));
         for (int i = 0; i < VAMPOMI_V_NUM_M; i++) {
@@ -312,7 +326,7 @@ int vampomi_destroy(vampomi_ctx* c) {
     for (auto e : c->prof_free) cudaEventDestroy(e);
     xchg_teardown(c);
     if (c->comm && c->nccl) c->nccl->CommDestroy(c->comm);
-    cudaFree(c->A); cudaFree(c->mave); cudaFree(c->msig);
+    cudaFree(c->A); cudaFree(c->A32); cudaFree(c->mave); cudaFree(c->msig);
     for (auto p : c->mvec) cudaFree(p);
     for (auto p : c->nvec) cudaFree(p);
     cudaFree(c->psum);
@@ -376,10 +390,27 @@ int vampomi_upload_columns(vampomi_ctx* c, long long j0, long long ncols, const 
     VO_ARG(c && host && j0 >= 0 && ncols >= 0 && j0 + ncols <= c->M, "upload_columns: range [%lld,+%lld) outside the shard", j0, ncols);
     VO_CUDA(cudaSetDevice(c->device));
     if (ncols == 0) return VAMPOMI_OK;
+    c->stats_ready = false;
+    if (c->storage == VAMPOMI_STORE_F32) {                 // FP64 columns -> dense device staging -> rounded into place
+        long long chunk = (long long)((64ull << 20) / ((size_t)c->N * sizeof(double)));
+        if (chunk < 1) chunk = 1;
+        double* tmp = nullptr;
+        VO_CUDA(cudaMalloc(&tmp, (size_t)(chunk < ncols ? chunk : ncols) * c->N * sizeof(double)));
+        int rc = VAMPOMI_OK;
+        for (long long j = 0; j < ncols && rc == VAMPOMI_OK; j += chunk) {
+            const long long nc = ncols - j < chunk ? ncols - j : chunk;
+            if (cudaMemcpyAsync(tmp, host + (size_t)j * c->N, (size_t)nc * c->N * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+                set_error("upload_columns: host-to-device copy failed"); rc = VAMPOMI_ERR_CUDA; break;
+            }
+            rc = launch_f64_to_f32(c, c->A32 + (size_t)(j0 + j) * c->ld, tmp, nc, c->stream);
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("upload_columns: sync failed"); rc = VAMPOMI_ERR_CUDA; }
+        }
+        cudaFree(tmp);
+        return rc;
+    }
     VO_CUDA(cudaMemcpy2DAsync(c->A + (size_t)j0 * c->ld, c->ld * sizeof(double), host, (size_t)c->N * sizeof(double),
                               (size_t)c->N * sizeof(double), (size_t)ncols, cudaMemcpyHostToDevice, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
-    c->stats_ready = false;
     return VAMPOMI_OK;
 }
 
@@ -387,6 +418,23 @@ int vampomi_download_columns(vampomi_ctx* c, long long j0, long long ncols, doub
     VO_ARG(c && host && j0 >= 0 && ncols >= 0 && j0 + ncols <= c->M, "download_columns: range outside the shard");
     VO_CUDA(cudaSetDevice(c->device));
     if (ncols == 0) return VAMPOMI_OK;
+    if (c->storage == VAMPOMI_STORE_F32) {                 // the rounded values, widened back to FP64
+        long long chunk = (long long)((64ull << 20) / ((size_t)c->N * sizeof(double)));
+        if (chunk < 1) chunk = 1;
+        double* tmp = nullptr;
+        VO_CUDA(cudaMalloc(&tmp, (size_t)(chunk < ncols ? chunk : ncols) * c->N * sizeof(double)));
+        int rc = VAMPOMI_OK;
+        for (long long j = 0; j < ncols && rc == VAMPOMI_OK; j += chunk) {
+            const long long nc = ncols - j < chunk ? ncols - j : chunk;
+            rc = launch_f32_to_f64(c, tmp, c->A32 + (size_t)(j0 + j) * c->ld, nc, c->stream);
+            if (rc == VAMPOMI_OK && (cudaMemcpyAsync(host + (size_t)j * c->N, tmp, (size_t)nc * c->N * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                                     cudaStreamSynchronize(c->stream) != cudaSuccess)) {
+                set_error("download_columns: device-to-host copy failed"); rc = VAMPOMI_ERR_CUDA;
+            }
+        }
+        cudaFree(tmp);
+        return rc;
+    }
     VO_CUDA(cudaMemcpy2DAsync(host, (size_t)c->N * sizeof(double), c->A + (size_t)j0 * c->ld, c->ld * sizeof(double),
                               (size_t)c->N * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
@@ -422,12 +470,15 @@ int vampomi_load_file(vampomi_ctx* c, const char* path) {
         auto fail = [&](int code, const std::string& msg) { rcs[t] = code; errs[t] = msg; };
         if (cudaSetDevice(c->device) != cudaSuccess) return fail(VAMPOMI_ERR_CUDA, "cudaSetDevice failed in a loader thread");
         double* slot[2] = {nullptr, nullptr};
+        double* dslot[2] = {nullptr, nullptr};              // FP32 storage: dense FP64 staging on the device, rounded into place
         cudaEvent_t ev[2] = {nullptr, nullptr};
         cudaStream_t st = nullptr;
         bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
-        for (int k = 0; k < 2 && ok; k++)
+        for (int k = 0; k < 2 && ok; k++) {
             ok = cudaMallocHost(&slot[k], (size_t)cols_per_slot * col_bytes) == cudaSuccess &&
                  cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) == cudaSuccess;
+            if (ok && c->storage == VAMPOMI_STORE_F32) ok = cudaMalloc(&dslot[k], (size_t)cols_per_slot * col_bytes) == cudaSuccess;
+        }
         if (!ok) fail(VAMPOMI_ERR_CUDA, "could not allocate pinned staging buffers");
         int k = 0;
         for (long long item = t; item < nitems && ok; item += T, k ^= 1) {
@@ -442,12 +493,17 @@ int vampomi_load_file(vampomi_ctx* c, const char* path) {
                 got += (size_t)r;
             }
             if (!ok) break;
-            if (cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), slot[k], col_bytes, col_bytes, (size_t)nc,
-                                  cudaMemcpyHostToDevice, st) != cudaSuccess ||
-                cudaEventRecord(ev[k], st) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "host-to-device copy failed"); break; }
+            bool copied;
+            if (c->storage == VAMPOMI_STORE_F32)
+                copied = cudaMemcpyAsync(dslot[k], slot[k], want, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                         launch_f64_to_f32(c, c->A32 + (size_t)j * c->ld, dslot[k], nc, st) == VAMPOMI_OK;
+            else
+                copied = cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), slot[k], col_bytes, col_bytes, (size_t)nc,
+                                           cudaMemcpyHostToDevice, st) == cudaSuccess;
+            if (!copied || cudaEventRecord(ev[k], st) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "host-to-device copy failed"); break; }
         }
         if (st) cudaStreamSynchronize(st);
-        for (int q = 0; q < 2; q++) { if (slot[q]) cudaFreeHost(slot[q]); if (ev[q]) cudaEventDestroy(ev[q]); }
+        for (int q = 0; q < 2; q++) { if (slot[q]) cudaFreeHost(slot[q]); if (dslot[q]) cudaFree(dslot[q]); if (ev[q]) cudaEventDestroy(ev[q]); }
         if (st) cudaStreamDestroy(st);
     };
     std::vector<std::thread> th;

@@ -95,7 +95,10 @@ struct vampomi_ctx {
     size_t mpad = 0;                 // allocated length of M-vectors
     bool stats_ready = false;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    double* A = nullptr;             // [M][ld] column-major block in HBM
+    int storage = 0;                 // 0: A held as FP64 (reference layout), 1: A rounded to FP32 in HBM (opt-in; arithmetic stays FP64)
+    int elem_bytes = 8;
+    double* A = nullptr;             // [M][ld] column-major block in HBM (storage 0)
+    float* A32 = nullptr;            // same layout in FP32 (storage 1)
     double* mave = nullptr;
     double* msig = nullptr;
     double* mvec[VAMPOMI_V_NUM_M] = {};
@@ -149,6 +152,8 @@ int launch_stats(vampomi_ctx* c, double alpha_scale);
 int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag);     // incl. all-reduce and 1/sqrt(N)
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
 int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev);
+int launch_f64_to_f32(vampomi_ctx* c, float* dst, const double* src_dense, long long ncols, cudaStream_t st);
+int launch_f32_to_f64(vampomi_ctx* c, double* dst_dense, const float* src, long long ncols, cudaStream_t st);
 // ---- launchers (kernels_bulk.cu) ----
 int launch_atx_bulk(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
 int launch_ax_bulk(vampomi_ctx* c, const double* x_dev, const int* done_flag, int* nchunks_out);

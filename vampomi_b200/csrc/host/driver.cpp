@@ -51,7 +51,10 @@ int load_dataset(Rank& r, const std::string& phenfp, const std::string& methfp, 
     int ndev = 0;
     if (vampomi_device_count(&ndev) != VAMPOMI_OK) return fatal_abi(r, "device query");
     if (r.nranks > ndev) return fatal(r, "--gpus " + std::to_string(r.nranks) + " exceeds the " + std::to_string(ndev) + " visible CUDA devices");
-    if (vampomi_create(r.rank, N, (long long)r.opt.Mt, r.nranks, r.rank, &r.ctx) != VAMPOMI_OK) return fatal_abi(r, "vampomi_create");
+    const int storage = r.opt.storage == "f32" ? VAMPOMI_STORE_F32 : VAMPOMI_STORE_F64;
+    if (vampomi_create_ex(r.rank, N, (long long)r.opt.Mt, r.nranks, r.rank, storage, &r.ctx) != VAMPOMI_OK) return fatal_abi(r, "vampomi_create");
+    if (storage == VAMPOMI_STORE_F32 && r.root())
+        std::cout << "INFO  : --storage f32: the marker block is rounded to FP32 in GPU memory (all arithmetic stays FP64)" << std::endl;
     if (r.nranks > 1 && vampomi_comm_init(r.ctx, r.nccl_id) != VAMPOMI_OK) return fatal_abi(r, "vampomi_comm_init");
     if (r.nranks > 1 && r.root()) {
         int mode = 0;
@@ -60,8 +63,8 @@ int load_dataset(Rank& r, const std::string& phenfp, const std::string& methfp, 
                   << " on " << r.nranks << " GPUs" << std::endl;
     }
     if (r.root()) std::cout << "meth file name = " << methfp << std::endl;            // :123
-    printf("INFO  : rank %d has allocated %zu bytes (%.3f GB) for raw data.\n", r.rank, (size_t)r.M * (size_t)N * 8,
-           double((size_t)r.M * (size_t)N * 8) / 1.0E9);                               // :131
+    const size_t raw_bytes = (size_t)r.M * (size_t)N * (storage == VAMPOMI_STORE_F32 ? 4 : 8);
+    printf("INFO  : rank %d has allocated %zu bytes (%.3f GB) for raw data.\n", r.rank, raw_bytes, double(raw_bytes) / 1.0E9);   // :131
     double ts = now_s();
     if (vampomi_load_file(r.ctx, methfp.c_str()) != VAMPOMI_OK) return fatal_abi(r, "loading the methylation data");
     double te = now_s();

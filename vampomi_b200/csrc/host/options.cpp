@@ -106,6 +106,14 @@ bool Options::parse(int argc, char** argv, std::string* echo) {
             if (!need_value()) return false;
             seed = strtoull(argv[++i], nullptr, 10);
             ss << "--seed " << seed << "\n";
+        } else if (!strcmp(a, "--storage")) {
+            if (!need_value()) return false;
+            storage = argv[++i];
+            if (storage != "f64" && storage != "f32") {
+                std::cout << "FATAL  : option --storage has to be f64 or f32! (" << storage << " was passed)" << std::endl;
+                return false;
+            }
+            ss << "--storage " << storage << "\n";
         } else if (!strcmp(a, "--gpus")) {
             if (!need_value()) return false;
             gpus = atoi(argv[++i]);

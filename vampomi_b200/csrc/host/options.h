@@ -27,6 +27,7 @@ struct Options {
     // additions
     unsigned long long seed = 0;
     int gpus = 1;
+    std::string storage = "f64";     // "f32": hold the marker block rounded to FP32 in HBM (arithmetic stays FP64)
 
     // Parses argv. On error prints the reference's FATAL line to stdout and returns false (caller exits 1).
     // `echo` receives the "ardyh command line options" block the reference prints from rank 0.

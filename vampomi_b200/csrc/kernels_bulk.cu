@@ -275,6 +275,7 @@ static int bulk_resident(const void* kernel, size_t smem) {
 }
 
 int launch_atx_bulk(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag) {
+    if (c->storage != VAMPOMI_STORE_F64) { set_error("the bulk-copy kernels exist for FP64 storage only"); return VAMPOMI_ERR_STATE; }
     auto kern = k_atx_bulk<ATX_C, ATX_SEG, ATX_STAGES>;
     const size_t smem = (size_t)ATX_STAGES * (ATX_C + 1) * ATX_SEG * sizeof(double);
     if (!c->bulk_attr_atx) {                                                // per device: the context owns the flag
@@ -293,6 +294,7 @@ int launch_atx_bulk(vampomi_ctx* c, const double* p_dev, double* out_dev, const 
 
 // plans the (tile, chunk) grid for the bulk Ax kernel and launches it; returns the number of chunks written
 int launch_ax_bulk(vampomi_ctx* c, const double* x_dev, const int* done_flag, int* nchunks_out) {
+    if (c->storage != VAMPOMI_STORE_F64) { set_error("the bulk-copy kernels exist for FP64 storage only"); return VAMPOMI_ERR_STATE; }
     auto kern = k_ax_bulk<AX_TR, AX_G, AX_STAGES>;
     const size_t smem = (size_t)AX_STAGES * AX_G * AX_TR * sizeof(double);
     if (!c->bulk_attr_ax) {

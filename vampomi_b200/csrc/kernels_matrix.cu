@@ -32,6 +32,18 @@ __device__ __forceinline__ d4 ld_cached(const double* p) {
         : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
     return r;
 }
+// FP32 storage (opt-in, vampomi_create_ex): four markers' worth of a column as one 128-bit load, widened to FP64 at once —
+// all arithmetic stays FP64, only the bytes streamed from HBM halve.
+__device__ __forceinline__ d4 ld_stream(const float* p) {
+    float x, y, z, w;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(p));
+    return d4{(double)x, (double)y, (double)z, (double)w};
+}
+__device__ __forceinline__ d4 ld_cached(const float* p) {
+    float x, y, z, w;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(p));
+    return d4{(double)x, (double)y, (double)z, (double)w};
+}
 __device__ __forceinline__ void st256(double* p, const d4& v) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
@@ -44,21 +56,47 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------------------------
 // synthetic block: A[j][i] = N(0,1) from hash(seed, global marker S+j, sample i); pad rows zero
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_generate_iid(double* __restrict__ A, size_t ld, int N, long long M, long long S,
+template <typename T>
+__global__ void __launch_bounds__(256) k_generate_iid(T* __restrict__ A, size_t ld, int N, long long M, long long S,
                                                       uint64_t seed) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if ((size_t)i >= ld) return;
     for (long long j = blockIdx.y; j < M; j += gridDim.y) {
         double v = 0.0;
         if (i < N) v = normal_from_hash(hash3(seed, STREAM_MATRIX, (uint64_t)(S + j), (uint64_t)i));
-        A[(size_t)j * ld + i] = v;
+        A[(size_t)j * ld + i] = (T)v;
     }
 }
 
 int launch_generate_iid(vampomi_ctx* c, uint64_t seed) {
     dim3 grid((unsigned)((c->ld + 255) / 256), (unsigned)(c->M < 16384 ? c->M : 16384));
-    k_generate_iid<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->N, c->M, c->S, seed);
+    if (c->storage == 1) k_generate_iid<float><<<grid, 256, 0, c->stream>>>(c->A32, c->ld, c->N, c->M, c->S, seed);
+    else k_generate_iid<double><<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->N, c->M, c->S, seed);
     c->counters[0]++;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
+// FP32 storage: rounding of uploaded FP64 columns (dst pitch ld floats, src pitch N doubles) and the way back
+__global__ void __launch_bounds__(256) k_f64_to_f32(float* __restrict__ dst, size_t ld, const double* __restrict__ src, int N, long long ncols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (long long j = blockIdx.y; j < ncols; j += gridDim.y) dst[(size_t)j * ld + i] = (float)src[(size_t)j * N + i];
+}
+__global__ void __launch_bounds__(256) k_f32_to_f64(double* __restrict__ dst, const float* __restrict__ src, size_t ld, int N, long long ncols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (long long j = blockIdx.y; j < ncols; j += gridDim.y) dst[(size_t)j * N + i] = (double)src[(size_t)j * ld + i];
+}
+int launch_f64_to_f32(vampomi_ctx* c, float* dst, const double* src_dense, long long ncols, cudaStream_t st) {
+    dim3 grid((unsigned)((c->N + 255) / 256), (unsigned)(ncols < 16384 ? (ncols < 1 ? 1 : ncols) : 16384));
+    k_f64_to_f32<<<grid, 256, 0, st>>>(dst, c->ld, src_dense, c->N, ncols);
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+int launch_f32_to_f64(vampomi_ctx* c, double* dst_dense, const float* src, long long ncols, cudaStream_t st) {
+    dim3 grid((unsigned)((c->N + 255) / 256), (unsigned)(ncols < 16384 ? (ncols < 1 ? 1 : ncols) : 16384));
+    k_f32_to_f64<<<grid, 256, 0, st>>>(dst_dense, src, c->ld, c->N, ncols);
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
@@ -66,20 +104,21 @@ int launch_generate_iid(vampomi_ctx* c, uint64_t seed) {
 // ---------------------------------------------------------------------------------------------------------------
 // marker statistics: one warp per column, two passes (the second one is served by L2)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_stats(const double* __restrict__ A, size_t ld, int N, long long M, double alpha_scale,
+template <typename T>
+__global__ void __launch_bounds__(256) k_stats(const T* __restrict__ A, size_t ld, int N, long long M, double alpha_scale,
                                                double* __restrict__ mave, double* __restrict__ msig) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int nvec = N >> 2;
     for (long long j = warp; j < M; j += nwarps) {
-        const double* col = A + (size_t)j * ld;
+        const T* col = A + (size_t)j * ld;
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         for (int v = lane; v < nvec; v += 32) {
             d4 a = ld_cached(col + 4 * (size_t)v);
             s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
         }
-        for (int i = (nvec << 2) + lane; i < N; i += 32) s0 += col[i];
+        for (int i = (nvec << 2) + lane; i < N; i += 32) s0 += (double)col[i];
         double mean = warp_sum((s0 + s1) + (s2 + s3)) / (double)N;               // suma / nonas, src/data.cpp:258
         s0 = s1 = s2 = s3 = 0;
         for (int v = lane; v < nvec; v += 32) {
@@ -87,7 +126,7 @@ __global__ void __launch_bounds__(256) k_stats(const double* __restrict__ A, siz
             double d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
             s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
         }
-        for (int i = (nvec << 2) + lane; i < N; i += 32) { double d = col[i] - mean; s0 = fma(d, d, s0); }
+        for (int i = (nvec << 2) + lane; i < N; i += 32) { double d = (double)col[i] - mean; s0 = fma(d, d, s0); }
         double sumsqr = warp_sum((s0 + s1) + (s2 + s3));
         if (lane == 0) {
             double sig = 1.0;                                                     // constant column, src/data.cpp:275-276
@@ -103,8 +142,9 @@ __global__ void __launch_bounds__(256) k_stats(const double* __restrict__ A, siz
 
 int launch_stats(vampomi_ctx* c, double alpha_scale) {
     int blocks = c->num_sms * 8;
-    k_stats<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->N, c->M, alpha_scale, c->mave, c->msig);
-    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    if (c->storage == 1) k_stats<float><<<blocks, 256, 0, c->stream>>>(c->A32, c->ld, c->N, c->M, alpha_scale, c->mave, c->msig);
+    else k_stats<double><<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->N, c->M, alpha_scale, c->mave, c->msig);
+    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
@@ -118,8 +158,8 @@ int launch_stats(vampomi_ctx* c, double alpha_scale) {
 // SPLIT = false: (a - mave_j) * w_j per element, exactly the reference's expression (src/data.cpp:360).
 // SPLIT = true : a * w_j per element and one subtraction of sum_j mave_j * w_j per row at the end — one FP64 instruction
 //                less per element (less power under the 1 kW cap); same value up to summation order.
-template <int RV, int U, bool SPLIT>
-__global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+template <typename T, int RV, int U, bool SPLIT>
+__global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                     const double* __restrict__ msig, const double* __restrict__ x,
                                                     int tile_rows, int cols_per_chunk, long long M,
                                                     double* __restrict__ partial, const int* __restrict__ done) {
@@ -131,7 +171,7 @@ __global__ void __launch_bounds__(256) k_ax_partial(const double* __restrict__ A
     if (c1 > M) c1 = M;
 
     d4 acc[RV];
-    const double* ap[RV];
+    const T* ap[RV];
     bool valid[RV];
     double corr = 0.0;
 #pragma unroll
@@ -291,22 +331,26 @@ int launch_scale_div(vampomi_ctx* c, double* dst, const double* src, double divi
 
 struct AxPlan { int rv, U, ntiles, tile_rows, nchunks, cols_per_chunk; };
 
-typedef void (*ax_kernel_t)(const double*, size_t, const double*, const double*, const double*, int, int, long long, double*,
-                            const int*);
+template <typename T>
+using ax_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, int, int, long long, double*, const int*);
 
-static ax_kernel_t ax_kernel(int rv, int U, bool split = false) {
+template <typename T>
+static ax_kernel_t<T> ax_kernel(int rv, int U, bool split = false) {
     if (split) switch (rv * 10 + U) {
-        case 12: return k_ax_partial<1, 2, true>; case 14: return k_ax_partial<1, 4, true>; case 18: return k_ax_partial<1, 8, true>;
-        case 22: return k_ax_partial<2, 2, true>; case 24: return k_ax_partial<2, 4, true>; case 28: return k_ax_partial<2, 8, true>;
-        case 42: return k_ax_partial<4, 2, true>; case 44: return k_ax_partial<4, 4, true>;
+        case 12: return k_ax_partial<T, 1, 2, true>; case 14: return k_ax_partial<T, 1, 4, true>; case 18: return k_ax_partial<T, 1, 8, true>;
+        case 22: return k_ax_partial<T, 2, 2, true>; case 24: return k_ax_partial<T, 2, 4, true>; case 28: return k_ax_partial<T, 2, 8, true>;
+        case 42: return k_ax_partial<T, 4, 2, true>; case 44: return k_ax_partial<T, 4, 4, true>;
         default: return nullptr;
     }
     switch (rv * 10 + U) {
-        case 12: return k_ax_partial<1, 2, false>; case 14: return k_ax_partial<1, 4, false>; case 18: return k_ax_partial<1, 8, false>;
-        case 22: return k_ax_partial<2, 2, false>; case 24: return k_ax_partial<2, 4, false>; case 28: return k_ax_partial<2, 8, false>;
-        case 42: return k_ax_partial<4, 2, false>; case 44: return k_ax_partial<4, 4, false>;
+        case 12: return k_ax_partial<T, 1, 2, false>; case 14: return k_ax_partial<T, 1, 4, false>; case 18: return k_ax_partial<T, 1, 8, false>;
+        case 22: return k_ax_partial<T, 2, 2, false>; case 24: return k_ax_partial<T, 2, 4, false>; case 28: return k_ax_partial<T, 2, 8, false>;
+        case 42: return k_ax_partial<T, 4, 2, false>; case 44: return k_ax_partial<T, 4, 4, false>;
         default: return nullptr;
     }
+}
+static const void* ax_kernel_any(const vampomi_ctx* c, int rv, int U, bool split) {
+    return c->storage == 1 ? (const void*)ax_kernel<float>(rv, U, split) : (const void*)ax_kernel<double>(rv, U, split);
 }
 
 // CTAs of `kernel` that fit on one SM (registers / shared memory) — grids are sized to exactly one resident wave so
@@ -321,15 +365,15 @@ static AxPlan plan_ax(const vampomi_ctx* c) {
     AxPlan p;
     p.rv = c->tune.ax_rv;
     p.U = c->tune.ax_unroll;
-    if (ax_kernel(p.rv, p.U) == nullptr) { p.rv = 2; p.U = 4; }
+    if (ax_kernel<double>(p.rv, p.U) == nullptr) { p.rv = 2; p.U = 4; }
     while (p.rv > 1 && (size_t)(1024 * (p.rv / 2)) >= c->ld) p.rv /= 2;      // do not leave most lanes idle on small N
-    if (ax_kernel(p.rv, p.U) == nullptr) p.U = 4;
+    if (ax_kernel<double>(p.rv, p.U) == nullptr) p.U = 4;
     int cap = 1024 * p.rv;
     p.ntiles = (int)((c->ld + cap - 1) / cap);
     size_t tr = (c->ld + p.ntiles - 1) / p.ntiles;
     p.tile_rows = (int)((tr + 15) / 16 * 16);                                // 128-byte aligned tile starts
     int per_sm = c->tune.ax_ctas_per_sm > 0 ? c->tune.ax_ctas_per_sm
-                                            : resident_ctas((const void*)ax_kernel(p.rv, p.U, c->tune.center_split != 0), 256, 0);
+                                            : resident_ctas(ax_kernel_any(c, p.rv, p.U, c->tune.center_split != 0), 256, 0);
     long long slots = (long long)c->num_sms * per_sm;
     long long nch = slots / p.ntiles;
     if (nch < 1) nch = 1;
@@ -341,10 +385,10 @@ static AxPlan plan_ax(const vampomi_ctx* c) {
 
 int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag) {
     AxPlan p = plan_ax(c);
-    const double a_bytes = (double)c->M * c->N * 8.0;
+    const double a_bytes = (double)c->M * c->N * (double)c->elem_bytes;
     if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
     int sp;
-    if (c->tune.ax_impl == 1) {
+    if (c->tune.ax_impl == 1 && c->storage == 0) {
         sp = prof_begin(c, 0, a_bytes);
         int rc = launch_ax_bulk(c, x_dev, done_flag, &p.nchunks);
         prof_end(c, sp);
@@ -360,8 +404,12 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
         }
         dim3 grid(p.ntiles, p.nchunks);
         sp = prof_begin(c, 0, a_bytes);
-        ax_kernel(p.rv, p.U, c->tune.center_split != 0)<<<grid, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M,
-                                                          c->ax_partial, done_flag);
+        if (c->storage == 1)
+            ax_kernel<float>(p.rv, p.U, c->tune.center_split != 0)<<<grid, 256, 0, c->stream>>>(
+                c->A32, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag);
+        else
+            ax_kernel<double>(p.rv, p.U, c->tune.center_split != 0)<<<grid, 256, 0, c->stream>>>(
+                c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag);
         prof_end(c, sp);
         VO_CUDA(cudaGetLastError());
     }
@@ -369,7 +417,7 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
     const double sqrtN = sqrt((double)c->N);
     constexpr int SL = 8;
     int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
-    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
     if (c->nranks > 1 && c->xchg.enabled) {
         // reduce + cross-GPU sum over peer memory + scaling in one kernel
         k_ax_reduce_xchg<SL><<<rblocks, 256, 0, c->stream>>>(c->ax_partial, c->ld, p.nchunks, c->N, sqrtN, out_dev, done_flag, c->xchg);
@@ -395,8 +443,8 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
 // No block-level synchronisation at all; reduction by warp shuffles in a fixed order.
 // ---------------------------------------------------------------------------------------------------------------
 // SPLIT as in k_ax_partial: sum_i a_i p_i - mave_j * (sum_i p_i), with sum_i p_i precomputed once per launch (psum).
-template <int C, int U, bool SPLIT>
-__global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+template <typename T, int C, int U, bool SPLIT>
+__global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                              const double* __restrict__ msig, const double* __restrict__ p, long long M,
                                              double scale, double* __restrict__ out, const int* __restrict__ done,
                                              const double* __restrict__ psum) {
@@ -411,7 +459,7 @@ __global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_
     if (g1 > ngroups) g1 = ngroups;
     for (long long g = g0; g < g1; g++) {
         const long long j0 = g * C;
-        const double* col[C];
+        const T* col[C];
         double m[C], acc[C][4];
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
@@ -473,8 +521,8 @@ __global__ void __launch_bounds__(256) k_atx(const double* __restrict__ A, size_
 // CTA-cooperative form of A^T p (atx_impl = 2): the 8 warps of a CTA walk the SAME C columns together, 8 KB of each
 // column per step (U steps in flight), so the chip streams ~900 long sequential runs instead of ~3500 per-warp ones;
 // one block barrier per column group (partials double-buffered in shared memory), fixed reduction order.
-template <int C, int U>
-__global__ void __launch_bounds__(256) k_atx_cta(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+template <typename T, int C, int U>
+__global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                  const double* __restrict__ msig, const double* __restrict__ p, long long M,
                                                  double scale, double* __restrict__ out, const int* __restrict__ done) {
     if (done != nullptr && *done != 0) return;
@@ -488,7 +536,7 @@ __global__ void __launch_bounds__(256) k_atx_cta(const double* __restrict__ A, s
     int par = 0;
     for (long long g = g0; g < g1; g++) {
         const long long j0 = g * C;
-        const double* col[C];
+        const T* col[C];
         double m[C], acc[C][4];
 #pragma unroll
         for (int cc = 0; cc < C; cc++) {
@@ -545,31 +593,33 @@ __global__ void __launch_bounds__(256) k_atx_cta(const double* __restrict__ A, s
     }
 }
 
-typedef void (*atx_cta_kernel_t)(const double*, size_t, const double*, const double*, const double*, long long, double, double*,
-                                 const int*);
-static atx_cta_kernel_t atx_cta_kernel(int C, int U) {
+template <typename T>
+using atx_cta_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, long long, double, double*, const int*);
+template <typename T>
+static atx_cta_kernel_t<T> atx_cta_kernel(int C, int U) {
     switch (C * 10 + U) {
-        case 12: return k_atx_cta<1, 2>; case 14: return k_atx_cta<1, 4>; case 18: return k_atx_cta<1, 8>;
-        case 22: return k_atx_cta<2, 2>; case 24: return k_atx_cta<2, 4>; case 28: return k_atx_cta<2, 8>;
-        case 42: return k_atx_cta<4, 2>; case 44: return k_atx_cta<4, 4>;
+        case 12: return k_atx_cta<T, 1, 2>; case 14: return k_atx_cta<T, 1, 4>; case 18: return k_atx_cta<T, 1, 8>;
+        case 22: return k_atx_cta<T, 2, 2>; case 24: return k_atx_cta<T, 2, 4>; case 28: return k_atx_cta<T, 2, 8>;
+        case 42: return k_atx_cta<T, 4, 2>; case 44: return k_atx_cta<T, 4, 4>;
         default: return nullptr;
     }
 }
 
-typedef void (*atx_kernel_t)(const double*, size_t, const double*, const double*, const double*, long long, double, double*,
-                             const int*, const double*);
-
-static atx_kernel_t atx_kernel(int C, int U, bool split = false) {
+template <typename T>
+using atx_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, long long, double, double*, const int*,
+                              const double*);
+template <typename T>
+static atx_kernel_t<T> atx_kernel(int C, int U, bool split = false) {
     if (split) switch (C * 10 + U) {
-        case 12: return k_atx<1, 2, true>; case 14: return k_atx<1, 4, true>; case 18: return k_atx<1, 8, true>;
-        case 22: return k_atx<2, 2, true>; case 24: return k_atx<2, 4, true>; case 28: return k_atx<2, 8, true>;
-        case 42: return k_atx<4, 2, true>; case 44: return k_atx<4, 4, true>;
+        case 12: return k_atx<T, 1, 2, true>; case 14: return k_atx<T, 1, 4, true>; case 18: return k_atx<T, 1, 8, true>;
+        case 22: return k_atx<T, 2, 2, true>; case 24: return k_atx<T, 2, 4, true>; case 28: return k_atx<T, 2, 8, true>;
+        case 42: return k_atx<T, 4, 2, true>; case 44: return k_atx<T, 4, 4, true>;
         default: return nullptr;
     }
     switch (C * 10 + U) {
-        case 12: return k_atx<1, 2, false>; case 14: return k_atx<1, 4, false>; case 18: return k_atx<1, 8, false>;
-        case 22: return k_atx<2, 2, false>; case 24: return k_atx<2, 4, false>; case 28: return k_atx<2, 8, false>;
-        case 42: return k_atx<4, 2, false>; case 44: return k_atx<4, 4, false>;
+        case 12: return k_atx<T, 1, 2, false>; case 14: return k_atx<T, 1, 4, false>; case 18: return k_atx<T, 1, 8, false>;
+        case 22: return k_atx<T, 2, 2, false>; case 24: return k_atx<T, 2, 4, false>; case 28: return k_atx<T, 2, 8, false>;
+        case 42: return k_atx<T, 4, 2, false>; case 44: return k_atx<T, 4, 4, false>;
         default: return nullptr;
     }
 }
@@ -589,40 +639,47 @@ __global__ void __launch_bounds__(1024) k_sum_vec(const double* __restrict__ p, 
     }
 }
 
+template <typename T>
+static int launch_atx_t(vampomi_ctx* c, const T* A, int impl, int C, int U, const double* p_dev, double* out_dev, const int* done_flag,
+                        double scale) {
+    if (impl == 2) {
+        if (atx_cta_kernel<T>(C, U) == nullptr) { C = 2; U = 2; }
+        atx_cta_kernel_t<T> k = atx_cta_kernel<T>(C, U);
+        int occ = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)k, 256, 0);
+        long long nb = (long long)c->num_sms * occ, ng = (c->M + C - 1) / C;
+        if (nb > ng) nb = ng;
+        k<<<(unsigned)nb, 256, 0, c->stream>>>(A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
+        return VAMPOMI_OK;
+    }
+    if (atx_kernel<T>(C, U) == nullptr) { C = 1; U = 2; }
+    const bool split = c->tune.center_split != 0;
+    int per_sm = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)atx_kernel<T>(C, U, split), 256, 0);
+    int blocks = c->num_sms * per_sm;
+    long long maxb = (c->M + 8 * C - 1) / (8 * C);
+    if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
+    if (split) {
+        k_sum_vec<<<1, 1024, 0, c->stream>>>(p_dev, c->N, c->psum, done_flag);
+        c->counters[0]++;
+    }
+    atx_kernel<T>(C, U, split)<<<blocks, 256, 0, c->stream>>>(A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag, c->psum);
+    return VAMPOMI_OK;
+}
+
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag) {
     int impl = c->tune.atx_impl;
     if (impl == 3) impl = c->ld >= 4096 ? 2 : 0;          // short columns leave most of a CTA idle: keep one warp per column group
+    if (impl == 1 && c->storage == 1) impl = 2;           // the bulk-copy pipeline exists for FP64 storage only
     // measured defaults (profiles/r01_sweep_*): CTA form C=2,U=2; warp form C=1,U=2
     int C = c->tune.atx_cols > 0 ? c->tune.atx_cols : (impl == 2 ? 2 : 1);
     int U = c->tune.atx_unroll > 0 ? c->tune.atx_unroll : 2;
     const double scale = 1.0 / sqrt((double)c->N);                              // src/data.cpp:326-327
-    int sp = prof_begin(c, 2, (double)c->M * c->N * 8.0);
+    int sp = prof_begin(c, 2, (double)c->M * c->N * (double)c->elem_bytes);
     int rc = VAMPOMI_OK;
-    if (impl == 1) {
-        rc = launch_atx_bulk(c, p_dev, out_dev, done_flag);
-    } else if (impl == 2) {
-        if (atx_cta_kernel(C, U) == nullptr) { C = 2; U = 2; }
-        atx_cta_kernel_t k = atx_cta_kernel(C, U);
-        int occ = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)k, 256, 0);
-        long long nb = (long long)c->num_sms * occ, ng = (c->M + C - 1) / C;
-        if (nb > ng) nb = ng;
-        k<<<(unsigned)nb, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
-    } else {
-        if (atx_kernel(C, U) == nullptr) { C = 1; U = 2; }
-        const bool split = c->tune.center_split != 0;
-        int per_sm = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)atx_kernel(C, U, split), 256, 0);
-        int blocks = c->num_sms * per_sm;
-        long long maxb = (c->M + 8 * C - 1) / (8 * C);
-        if (blocks > maxb) blocks = (int)(maxb < 1 ? 1 : maxb);
-        if (split) {
-            k_sum_vec<<<1, 1024, 0, c->stream>>>(p_dev, c->N, c->psum, done_flag);
-            c->counters[0]++;
-        }
-        atx_kernel(C, U, split)<<<blocks, 256, 0, c->stream>>>(c->A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag,
-                                                               c->psum);
-    }
+    if (impl == 1) rc = launch_atx_bulk(c, p_dev, out_dev, done_flag);
+    else if (c->storage == 1) rc = launch_atx_t<float>(c, c->A32, impl, C, U, p_dev, out_dev, done_flag, scale);
+    else rc = launch_atx_t<double>(c, c->A, impl, C, U, p_dev, out_dev, done_flag, scale);
     prof_end(c, sp);
-    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
     VO_CHECK(rc);
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
@@ -631,14 +688,15 @@ int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* 
 // ---------------------------------------------------------------------------------------------------------------
 // loo: per RAW column sums  sum x, sum x^2, sum x*w  (w = y - z1) — the only per-marker quantities pvals_loo needs
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_loo_sums(const double* __restrict__ A, size_t ld, const double* __restrict__ w,
+template <typename T>
+__global__ void __launch_bounds__(256) k_loo_sums(const T* __restrict__ A, size_t ld, const double* __restrict__ w,
                                                   long long M, double* __restrict__ sums) {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
     const int nvec = (int)(ld >> 2);
     for (long long j = warp; j < M; j += nwarps) {
-        const double* col = A + (size_t)j * ld;
+        const T* col = A + (size_t)j * ld;
         double sx = 0, sxx = 0, sxw = 0, tx = 0, txx = 0, txw = 0;
         int v = lane;
         for (; v + 32 < nvec; v += 64) {
@@ -664,8 +722,9 @@ __global__ void __launch_bounds__(256) k_loo_sums(const double* __restrict__ A, 
 }
 
 int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev) {
-    k_loo_sums<<<c->num_sms * 8, 256, 0, c->stream>>>(c->A, c->ld, w_dev, c->M, sums_dev);
-    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * 8;
+    if (c->storage == 1) k_loo_sums<float><<<c->num_sms * 8, 256, 0, c->stream>>>(c->A32, c->ld, w_dev, c->M, sums_dev);
+    else k_loo_sums<double><<<c->num_sms * 8, 256, 0, c->stream>>>(c->A, c->ld, w_dev, c->M, sums_dev);
+    c->counters[0]++; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }

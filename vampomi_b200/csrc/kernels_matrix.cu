@@ -18,32 +18,60 @@ namespace vampomi {
 
 struct __align__(32) d4 { double x, y, z, w; };
 
-// 256-bit streaming load: read-only path, no L1 allocation (A is touched once per pass).
-__device__ __forceinline__ d4 ld_stream(const double* p) {
-    d4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-        : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
-// 256-bit cached load for the small vector every column reuses (p in ATx): allocate in L1.
-__device__ __forceinline__ d4 ld_cached(const double* p) {
-    d4 r;
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-        : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
-    return r;
-}
-// FP32 storage (opt-in, vampomi_create_ex): four markers' worth of a column as one 128-bit load, widened to FP64 at once —
-// all arithmetic stays FP64, only the bytes streamed from HBM halve.
-__device__ __forceinline__ d4 ld_stream(const float* p) {
-    float x, y, z, w;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(p));
-    return d4{(double)x, (double)y, (double)z, (double)w};
-}
-__device__ __forceinline__ d4 ld_cached(const float* p) {
-    float x, y, z, w;
-    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "l"(p));
-    return d4{(double)x, (double)y, (double)z, (double)w};
-}
+// One 32-byte piece of a column of A, widened to FP64: 4 markers' values in FP64 storage, 8 in FP32 storage (opt-in,
+// vampomi_create_ex). Every thread keeps the same number of BYTES in flight in both modes; arithmetic is FP64 in both.
+//   stream(): LDG.E.256 on the read-only path without L1 allocation (A is touched once per pass)
+//   cached(): same but allocating in L1 (statistics read every column twice)
+template <typename T> struct V32;
+template <> struct V32<double> {
+    static constexpr int VE = 4;
+    double v[4];
+    static __device__ __forceinline__ V32 stream(const double* p) {
+        V32 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ V32 cached(const double* p) {
+        V32 r;
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+        return r;
+    }
+};
+template <> struct V32<float> {
+    static constexpr int VE = 8;
+    double v[8];
+    static __device__ __forceinline__ V32 widen(const float (&f)[8]) {
+        V32 r;
+#pragma unroll
+        for (int e = 0; e < 8; e++) r.v[e] = (double)f[e];
+        return r;
+    }
+    static __device__ __forceinline__ V32 stream(const float* p) {
+        float f[8];
+        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+        return widen(f);
+    }
+    static __device__ __forceinline__ V32 cached(const float* p) {
+        float f[8];
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+        return widen(f);
+    }
+};
+// VE consecutive doubles of a small, reused N-vector (p in A^T p, w in the loo sums): L1-allocating 256-bit loads.
+template <int VE> struct PV {
+    double v[VE];
+    static __device__ __forceinline__ PV load(const double* p) {
+        PV r;
+#pragma unroll
+        for (int q = 0; q < VE / 4; q++)
+            asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(r.v[4 * q]), "=d"(r.v[4 * q + 1]), "=d"(r.v[4 * q + 2]), "=d"(r.v[4 * q + 3]) : "l"(p + 4 * q));
+        return r;
+    }
+};
 __device__ __forceinline__ void st256(double* p, const d4& v) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
@@ -107,27 +135,29 @@ int launch_f32_to_f64(vampomi_ctx* c, double* dst_dense, const float* src, long 
 template <typename T>
 __global__ void __launch_bounds__(256) k_stats(const T* __restrict__ A, size_t ld, int N, long long M, double alpha_scale,
                                                double* __restrict__ mave, double* __restrict__ msig) {
+    constexpr int VE = V32<T>::VE;
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const int nvec = N >> 2;
+    const int nvec = N / VE;
     for (long long j = warp; j < M; j += nwarps) {
         const T* col = A + (size_t)j * ld;
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        double s[4] = {0, 0, 0, 0};
         for (int v = lane; v < nvec; v += 32) {
-            d4 a = ld_cached(col + 4 * (size_t)v);
-            s0 += a.x; s1 += a.y; s2 += a.z; s3 += a.w;
+            V32<T> a = V32<T>::cached(col + (size_t)VE * v);
+#pragma unroll
+            for (int e = 0; e < VE; e++) s[e & 3] += a.v[e];
         }
-        for (int i = (nvec << 2) + lane; i < N; i += 32) s0 += (double)col[i];
-        double mean = warp_sum((s0 + s1) + (s2 + s3)) / (double)N;               // suma / nonas, src/data.cpp:258
-        s0 = s1 = s2 = s3 = 0;
+        for (int i = nvec * VE + lane; i < N; i += 32) s[0] += (double)col[i];
+        double mean = warp_sum((s[0] + s[1]) + (s[2] + s[3])) / (double)N;       // suma / nonas, src/data.cpp:258
+        s[0] = s[1] = s[2] = s[3] = 0;
         for (int v = lane; v < nvec; v += 32) {
-            d4 a = ld_cached(col + 4 * (size_t)v);
-            double d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-            s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            V32<T> a = V32<T>::cached(col + (size_t)VE * v);
+#pragma unroll
+            for (int e = 0; e < VE; e++) { double d = a.v[e] - mean; s[e & 3] = fma(d, d, s[e & 3]); }
         }
-        for (int i = (nvec << 2) + lane; i < N; i += 32) { double d = (double)col[i] - mean; s0 = fma(d, d, s0); }
-        double sumsqr = warp_sum((s0 + s1) + (s2 + s3));
+        for (int i = nvec * VE + lane; i < N; i += 32) { double d = (double)col[i] - mean; s[0] = fma(d, d, s[0]); }
+        double sumsqr = warp_sum((s[0] + s[1]) + (s[2] + s[3]));
         if (lane == 0) {
             double sig = 1.0;                                                     // constant column, src/data.cpp:275-276
             if (sumsqr != 0.0) {
@@ -164,33 +194,35 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
                                                     int tile_rows, int cols_per_chunk, long long M,
                                                     double* __restrict__ partial, const int* __restrict__ done) {
     if (done != nullptr && *done != 0) return;
+    constexpr int VE = V32<T>::VE;
     const int tid = threadIdx.x;
     const size_t rbase = (size_t)blockIdx.x * tile_rows;
     const long long c0 = (long long)blockIdx.y * cols_per_chunk;
     long long c1 = c0 + cols_per_chunk;
     if (c1 > M) c1 = M;
 
-    d4 acc[RV];
+    double acc[RV][VE];
     const T* ap[RV];
     bool valid[RV];
     double corr = 0.0;
 #pragma unroll
     for (int k = 0; k < RV; k++) {
-        acc[k] = d4{0.0, 0.0, 0.0, 0.0};
-        int off = (k * 256 + tid) * 4;
+#pragma unroll
+        for (int e = 0; e < VE; e++) acc[k][e] = 0.0;
+        int off = (k * 256 + tid) * VE;
         valid[k] = off < tile_rows && rbase + off < ld;
         ap[k] = A + rbase + (valid[k] ? off : 0);
     }
 
     long long j = c0;
     for (; j + U <= c1; j += U) {
-        d4 a[U][RV];
+        V32<T> a[U][RV];
         double m[U], w[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
 #pragma unroll
             for (int k = 0; k < RV; k++)
-                if (valid[k]) a[u][k] = ld_stream(ap[k] + (size_t)(j + u) * ld);
+                if (valid[k]) a[u][k] = V32<T>::stream(ap[k] + (size_t)(j + u) * ld);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -202,16 +234,10 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
 #pragma unroll
             for (int k = 0; k < RV; k++) {
                 if (valid[k]) {
-                    if (SPLIT) {
-                        acc[k].x = fma(a[u][k].x, w[u], acc[k].x);
-                        acc[k].y = fma(a[u][k].y, w[u], acc[k].y);
-                        acc[k].z = fma(a[u][k].z, w[u], acc[k].z);
-                        acc[k].w = fma(a[u][k].w, w[u], acc[k].w);
-                    } else {
-                        acc[k].x = fma(a[u][k].x - m[u], w[u], acc[k].x);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
-                        acc[k].y = fma(a[u][k].y - m[u], w[u], acc[k].y);
-                        acc[k].z = fma(a[u][k].z - m[u], w[u], acc[k].z);
-                        acc[k].w = fma(a[u][k].w - m[u], w[u], acc[k].w);
+#pragma unroll
+                    for (int e = 0; e < VE; e++) {
+                        if (SPLIT) acc[k][e] = fma(a[u][k].v[e], w[u], acc[k][e]);
+                        else acc[k][e] = fma(a[u][k].v[e] - m[u], w[u], acc[k][e]);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
                     }
                 }
             }
@@ -224,22 +250,23 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
 #pragma unroll
         for (int k = 0; k < RV; k++) {
             if (valid[k]) {
-                d4 a = ld_stream(ap[k] + (size_t)j * ld);
-                acc[k].x = fma(a.x - m, w, acc[k].x);
-                acc[k].y = fma(a.y - m, w, acc[k].y);
-                acc[k].z = fma(a.z - m, w, acc[k].z);
-                acc[k].w = fma(a.w - m, w, acc[k].w);
+                V32<T> a = V32<T>::stream(ap[k] + (size_t)j * ld);
+#pragma unroll
+                for (int e = 0; e < VE; e++) acc[k][e] = fma(a.v[e] - m, w, acc[k][e]);
             }
         }
     }
-    if (SPLIT) {
-#pragma unroll
-        for (int k = 0; k < RV; k++) { acc[k].x -= corr; acc[k].y -= corr; acc[k].z -= corr; acc[k].w -= corr; }
-    }
     double* prow = partial + (size_t)blockIdx.y * ld + rbase;
 #pragma unroll
-    for (int k = 0; k < RV; k++)
-        if (valid[k]) st256(prow + (k * 256 + tid) * 4, acc[k]);
+    for (int k = 0; k < RV; k++) {
+        if (valid[k]) {
+#pragma unroll
+            for (int q = 0; q < VE / 4; q++) {
+                d4 o{acc[k][4 * q] - corr, acc[k][4 * q + 1] - corr, acc[k][4 * q + 2] - corr, acc[k][4 * q + 3] - corr};   // corr == 0 unless SPLIT
+                st256(prow + (k * 256 + tid) * VE + 4 * q, o);
+            }
+        }
+    }
 }
 
 // out[i] = (sum_c partial[c][i]) / divisor for i < N. Thread (i, s) sums chunks s, s+SL, ...; slices combine in smem
@@ -366,9 +393,10 @@ static AxPlan plan_ax(const vampomi_ctx* c) {
     p.rv = c->tune.ax_rv;
     p.U = c->tune.ax_unroll;
     if (ax_kernel<double>(p.rv, p.U) == nullptr) { p.rv = 2; p.U = 4; }
-    while (p.rv > 1 && (size_t)(1024 * (p.rv / 2)) >= c->ld) p.rv /= 2;      // do not leave most lanes idle on small N
+    const int ve = c->storage == 1 ? 8 : 4;                                  // elements per 32-byte vector
+    while (p.rv > 1 && (size_t)(256 * ve * (p.rv / 2)) >= c->ld) p.rv /= 2;  // do not leave most lanes idle on small N
     if (ax_kernel<double>(p.rv, p.U) == nullptr) p.U = 4;
-    int cap = 1024 * p.rv;
+    int cap = 256 * ve * p.rv;
     p.ntiles = (int)((c->ld + cap - 1) / cap);
     size_t tr = (c->ld + p.ntiles - 1) / p.ntiles;
     p.tile_rows = (int)((tr + 15) / 16 * 16);                                // 128-byte aligned tile starts
@@ -449,10 +477,11 @@ __global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld,
                                              double scale, double* __restrict__ out, const int* __restrict__ done,
                                              const double* __restrict__ psum) {
     if (done != nullptr && *done != 0) return;
+    constexpr int VE = V32<T>::VE;
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const int nvec = (int)(ld >> 2);                       // pad rows of A and p are zero: they add (0 - m) * 0
+    const int nvec = (int)(ld / VE);                       // pad rows of A and p are zero: they add (0 - m) * 0
     const long long ngroups = (M + C - 1) / C;
     const long long per = (ngroups + nwarps - 1) / nwarps;
     long long g0 = warp * per, g1 = g0 + per;
@@ -470,41 +499,32 @@ __global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld,
         }
         int v = lane;
         for (; v + 32 * (U - 1) < nvec; v += 32 * U) {
-            d4 pv[U], a[U][C];
+            PV<VE> pv[U];
+            V32<T> a[U][C];
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
-                for (int cc = 0; cc < C; cc++) a[u][cc] = ld_stream(col[cc] + 4 * (size_t)(v + 32 * u));
+                for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::stream(col[cc] + (size_t)VE * (v + 32 * u));
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) pv[u] = ld_cached(p + 4 * (size_t)(v + 32 * u));
+            for (int u = 0; u < U; u++) pv[u] = PV<VE>::load(p + (size_t)VE * (v + 32 * u));
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
                 for (int cc = 0; cc < C; cc++) {
-                    if (SPLIT) {
-                        acc[cc][0] = fma(a[u][cc].x, pv[u].x, acc[cc][0]);
-                        acc[cc][1] = fma(a[u][cc].y, pv[u].y, acc[cc][1]);
-                        acc[cc][2] = fma(a[u][cc].z, pv[u].z, acc[cc][2]);
-                        acc[cc][3] = fma(a[u][cc].w, pv[u].w, acc[cc][3]);
-                    } else {
-                        acc[cc][0] = fma(a[u][cc].x - m[cc], pv[u].x, acc[cc][0]);   // (meth[i] - mu) * phen[i], src/data.cpp:304
-                        acc[cc][1] = fma(a[u][cc].y - m[cc], pv[u].y, acc[cc][1]);
-                        acc[cc][2] = fma(a[u][cc].z - m[cc], pv[u].z, acc[cc][2]);
-                        acc[cc][3] = fma(a[u][cc].w - m[cc], pv[u].w, acc[cc][3]);
-                    }
+#pragma unroll
+                    for (int e = 0; e < VE; e++)        // (meth[i] - mu) * phen[i], src/data.cpp:304
+                        acc[cc][e & 3] = fma(a[u][cc].v[e] - m[cc], pv[u].v[e], acc[cc][e & 3]);
                 }
             }
         }
         for (; v < nvec; v += 32) {
-            d4 pv = ld_cached(p + 4 * (size_t)v);
+            PV<VE> pv = PV<VE>::load(p + (size_t)VE * v);
 #pragma unroll
             for (int cc = 0; cc < C; cc++) {
-                d4 a = ld_stream(col[cc] + 4 * (size_t)v);
-                acc[cc][0] = fma(a.x - m[cc], pv.x, acc[cc][0]);
-                acc[cc][1] = fma(a.y - m[cc], pv.y, acc[cc][1]);
-                acc[cc][2] = fma(a.z - m[cc], pv.z, acc[cc][2]);
-                acc[cc][3] = fma(a.w - m[cc], pv.w, acc[cc][3]);
+                V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
+#pragma unroll
+                for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.v[e] - m[cc], pv.v[e], acc[cc][e & 3]);
             }
         }
 #pragma unroll
@@ -526,9 +546,10 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
                                                  const double* __restrict__ msig, const double* __restrict__ p, long long M,
                                                  double scale, double* __restrict__ out, const int* __restrict__ done) {
     if (done != nullptr && *done != 0) return;
+    constexpr int VE = V32<T>::VE;
     __shared__ double red[2][8][C];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nvec = (int)(ld >> 2);
+    const int nvec = (int)(ld / VE);
     const long long ngroups = (M + C - 1) / C;
     const long long per = (ngroups + gridDim.x - 1) / gridDim.x;
     long long g0 = (long long)blockIdx.x * per, g1 = g0 + per;
@@ -547,34 +568,32 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
         }
         int v = tid;
         for (; v + 256 * (U - 1) < nvec; v += 256 * U) {
-            d4 pv[U], a[U][C];
+            PV<VE> pv[U];
+            V32<T> a[U][C];
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
-                for (int cc = 0; cc < C; cc++) a[u][cc] = ld_stream(col[cc] + 4 * (size_t)(v + 256 * u));
+                for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::stream(col[cc] + (size_t)VE * (v + 256 * u));
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) pv[u] = ld_cached(p + 4 * (size_t)(v + 256 * u));
+            for (int u = 0; u < U; u++) pv[u] = PV<VE>::load(p + (size_t)VE * (v + 256 * u));
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
                 for (int cc = 0; cc < C; cc++) {
-                    acc[cc][0] = fma(a[u][cc].x - m[cc], pv[u].x, acc[cc][0]);   // (meth[i] - mu) * phen[i], src/data.cpp:304
-                    acc[cc][1] = fma(a[u][cc].y - m[cc], pv[u].y, acc[cc][1]);
-                    acc[cc][2] = fma(a[u][cc].z - m[cc], pv[u].z, acc[cc][2]);
-                    acc[cc][3] = fma(a[u][cc].w - m[cc], pv[u].w, acc[cc][3]);
+#pragma unroll
+                    for (int e = 0; e < VE; e++)        // (meth[i] - mu) * phen[i], src/data.cpp:304
+                        acc[cc][e & 3] = fma(a[u][cc].v[e] - m[cc], pv[u].v[e], acc[cc][e & 3]);
                 }
             }
         }
         for (; v < nvec; v += 256) {
-            d4 pv = ld_cached(p + 4 * (size_t)v);
+            PV<VE> pv = PV<VE>::load(p + (size_t)VE * v);
 #pragma unroll
             for (int cc = 0; cc < C; cc++) {
-                d4 a = ld_stream(col[cc] + 4 * (size_t)v);
-                acc[cc][0] = fma(a.x - m[cc], pv.x, acc[cc][0]);
-                acc[cc][1] = fma(a.y - m[cc], pv.y, acc[cc][1]);
-                acc[cc][2] = fma(a.z - m[cc], pv.z, acc[cc][2]);
-                acc[cc][3] = fma(a.w - m[cc], pv.w, acc[cc][3]);
+                V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
+#pragma unroll
+                for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.v[e] - m[cc], pv.v[e], acc[cc][e & 3]);
             }
         }
 #pragma unroll
@@ -691,30 +710,30 @@ int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* 
 template <typename T>
 __global__ void __launch_bounds__(256) k_loo_sums(const T* __restrict__ A, size_t ld, const double* __restrict__ w,
                                                   long long M, double* __restrict__ sums) {
+    constexpr int VE = V32<T>::VE;
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-    const int nvec = (int)(ld >> 2);
+    const int nvec = (int)(ld / VE);
     for (long long j = warp; j < M; j += nwarps) {
         const T* col = A + (size_t)j * ld;
         double sx = 0, sxx = 0, sxw = 0, tx = 0, txx = 0, txw = 0;
         int v = lane;
         for (; v + 32 < nvec; v += 64) {
-            d4 a = ld_stream(col + 4 * (size_t)v), b = ld_stream(col + 4 * (size_t)(v + 32));
-            d4 wa = ld_cached(w + 4 * (size_t)v), wb = ld_cached(w + 4 * (size_t)(v + 32));
-            sx += (a.x + a.y) + (a.z + a.w);
-            tx += (b.x + b.y) + (b.z + b.w);
-            sxx = fma(a.x, a.x, sxx); sxx = fma(a.y, a.y, sxx); sxx = fma(a.z, a.z, sxx); sxx = fma(a.w, a.w, sxx);
-            txx = fma(b.x, b.x, txx); txx = fma(b.y, b.y, txx); txx = fma(b.z, b.z, txx); txx = fma(b.w, b.w, txx);
-            sxw = fma(a.x, wa.x, sxw); sxw = fma(a.y, wa.y, sxw); sxw = fma(a.z, wa.z, sxw); sxw = fma(a.w, wa.w, sxw);
-            txw = fma(b.x, wb.x, txw); txw = fma(b.y, wb.y, txw); txw = fma(b.z, wb.z, txw); txw = fma(b.w, wb.w, txw);
+            V32<T> a = V32<T>::stream(col + (size_t)VE * v), b = V32<T>::stream(col + (size_t)VE * (v + 32));
+            PV<VE> wa = PV<VE>::load(w + (size_t)VE * v), wb = PV<VE>::load(w + (size_t)VE * (v + 32));
+#pragma unroll
+            for (int e = 0; e < VE; e++) {
+                sx += a.v[e]; tx += b.v[e];
+                sxx = fma(a.v[e], a.v[e], sxx); txx = fma(b.v[e], b.v[e], txx);
+                sxw = fma(a.v[e], wa.v[e], sxw); txw = fma(b.v[e], wb.v[e], txw);
+            }
         }
         for (; v < nvec; v += 32) {
-            d4 a = ld_stream(col + 4 * (size_t)v);
-            d4 wa = ld_cached(w + 4 * (size_t)v);
-            sx += (a.x + a.y) + (a.z + a.w);
-            sxx = fma(a.x, a.x, sxx); sxx = fma(a.y, a.y, sxx); sxx = fma(a.z, a.z, sxx); sxx = fma(a.w, a.w, sxx);
-            sxw = fma(a.x, wa.x, sxw); sxw = fma(a.y, wa.y, sxw); sxw = fma(a.z, wa.z, sxw); sxw = fma(a.w, wa.w, sxw);
+            V32<T> a = V32<T>::stream(col + (size_t)VE * v);
+            PV<VE> wa = PV<VE>::load(w + (size_t)VE * v);
+#pragma unroll
+            for (int e = 0; e < VE; e++) { sx += a.v[e]; sxx = fma(a.v[e], a.v[e], sxx); sxw = fma(a.v[e], wa.v[e], sxw); }
         }
         sx = warp_sum(sx + tx); sxx = warp_sum(sxx + txx); sxw = warp_sum(sxw + txw);
         if (lane == 0) { sums[3 * j] = sx; sums[3 * j + 1] = sxx; sums[3 * j + 2] = sxw; }

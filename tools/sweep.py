@@ -59,7 +59,7 @@ if a.sustained:
     t(3, "loo_sustained", a.sustained)
     for k, v in base.items():
         sh.set_tuning(k, v)
-    sh.set_tuning("ax_rv", 2); sh.set_tuning("ax_unroll", 4); sh.set_tuning("atx_cols", 0); sh.set_tuning("atx_unroll", 0)
+    sh.set_tuning("ax_rv", 0); sh.set_tuning("ax_unroll", 0); sh.set_tuning("atx_cols", 0); sh.set_tuning("atx_unroll", 0)
     sh.set_tuning("atx_impl", 3)
     if a.quick:
         sys.exit(0)

@@ -776,7 +776,7 @@ int vampomi_stream(vampomi_ctx* c, void** stream) {
 int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
     VO_ARG(c && name, "set_tuning: NULL argument");
     struct { const char* n; int* p; int lo, hi; } knobs[] = {
-        {"ax_rv", &c->tune.ax_rv, 1, 4},           {"ax_unroll", &c->tune.ax_unroll, 2, 8},
+        {"ax_rv", &c->tune.ax_rv, 0, 4},           {"ax_unroll", &c->tune.ax_unroll, 0, 8},
         {"ax_ctas_per_sm", &c->tune.ax_ctas_per_sm, 0, 32}, {"atx_cols", &c->tune.atx_cols, 0, 4},
         {"atx_unroll", &c->tune.atx_unroll, 0, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
         {"cg_depth", &c->tune.cg_depth, 1, 32},     {"ax_impl", &c->tune.ax_impl, 0, 1},

@@ -72,8 +72,8 @@ struct CgScalars {                   // device-resident CG scalars (src/vamp.cpp
 };
 
 struct Tuning {
-    int ax_rv = 2;                   // 256-bit vectors per thread per column in Ax (tile = 1024*rv rows)
-    int ax_unroll = 4;               // columns in flight per thread
+    int ax_rv = 0;                   // 256-bit vectors per thread per column in Ax (0 = measured default: 2 for FP64 storage, 1 for FP32)
+    int ax_unroll = 0;               // columns in flight per thread (0 = measured default: 4 for FP64 storage, 2 for FP32)
     int ax_ctas_per_sm = 0;              // 0 = one resident wave (occupancy query)
     int atx_cols = 0;                // columns per pass in ATx (0 = default of the chosen implementation)
     int atx_unroll = 0;

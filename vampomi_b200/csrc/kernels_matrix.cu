@@ -390,12 +390,13 @@ static int resident_ctas(const void* kernel, int threads, size_t smem) {
 
 static AxPlan plan_ax(const vampomi_ctx* c) {
     AxPlan p;
-    p.rv = c->tune.ax_rv;
-    p.U = c->tune.ax_unroll;
-    if (ax_kernel<double>(p.rv, p.U) == nullptr) { p.rv = 2; p.U = 4; }
+    // measured defaults (profiles/r01_sweep_*): FP64 storage rv=2,U=4; FP32 storage rv=1,U=2 (8 accumulators per vector)
+    p.rv = c->tune.ax_rv > 0 ? c->tune.ax_rv : (c->storage == 1 ? 1 : 2);
+    p.U = c->tune.ax_unroll > 0 ? c->tune.ax_unroll : (c->storage == 1 ? 2 : 4);
+    if (ax_kernel<double>(p.rv, p.U) == nullptr) { p.rv = c->storage == 1 ? 1 : 2; p.U = c->storage == 1 ? 2 : 4; }
     const int ve = c->storage == 1 ? 8 : 4;                                  // elements per 32-byte vector
     while (p.rv > 1 && (size_t)(256 * ve * (p.rv / 2)) >= c->ld) p.rv /= 2;  // do not leave most lanes idle on small N
-    if (ax_kernel<double>(p.rv, p.U) == nullptr) p.U = 4;
+    if (ax_kernel<double>(p.rv, p.U) == nullptr) p.U = c->storage == 1 ? 2 : 4;
     int cap = 256 * ve * p.rv;
     p.ntiles = (int)((c->ld + cap - 1) / cap);
     size_t tr = (c->ld + p.ntiles - 1) / p.ntiles;

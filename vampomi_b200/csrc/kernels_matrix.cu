@@ -26,6 +26,7 @@ template <typename T> struct V32;
 template <> struct V32<double> {
     static constexpr int VE = 4;
     double v[4];
+    __device__ __forceinline__ double val(int e) const { return v[e]; }
     static __device__ __forceinline__ V32 stream(const double* p) {
         V32 r;
         asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -38,26 +39,21 @@ template <> struct V32<double> {
         return r;
     }
 };
-template <> struct V32<float> {
+template <> struct V32<float> {      // keeps the raw FP32 values (8 registers) and widens on use, so loads in flight stay cheap
     static constexpr int VE = 8;
-    double v[8];
-    static __device__ __forceinline__ V32 widen(const float (&f)[8]) {
+    float f[8];
+    __device__ __forceinline__ double val(int e) const { return (double)f[e]; }
+    static __device__ __forceinline__ V32 stream(const float* p) {
         V32 r;
-#pragma unroll
-        for (int e = 0; e < 8; e++) r.v[e] = (double)f[e];
+        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
         return r;
     }
-    static __device__ __forceinline__ V32 stream(const float* p) {
-        float f[8];
-        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
-        return widen(f);
-    }
     static __device__ __forceinline__ V32 cached(const float* p) {
-        float f[8];
+        V32 r;
         asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
-        return widen(f);
+                     : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
+        return r;
     }
 };
 // VE consecutive doubles of a small, reused N-vector (p in A^T p, w in the loo sums): L1-allocating 256-bit loads.
@@ -146,7 +142,7 @@ __global__ void __launch_bounds__(256) k_stats(const T* __restrict__ A, size_t l
         for (int v = lane; v < nvec; v += 32) {
             V32<T> a = V32<T>::cached(col + (size_t)VE * v);
 #pragma unroll
-            for (int e = 0; e < VE; e++) s[e & 3] += a.v[e];
+            for (int e = 0; e < VE; e++) s[e & 3] += a.val(e);
         }
         for (int i = nvec * VE + lane; i < N; i += 32) s[0] += (double)col[i];
         double mean = warp_sum((s[0] + s[1]) + (s[2] + s[3])) / (double)N;       // suma / nonas, src/data.cpp:258
@@ -154,7 +150,7 @@ __global__ void __launch_bounds__(256) k_stats(const T* __restrict__ A, size_t l
         for (int v = lane; v < nvec; v += 32) {
             V32<T> a = V32<T>::cached(col + (size_t)VE * v);
 #pragma unroll
-            for (int e = 0; e < VE; e++) { double d = a.v[e] - mean; s[e & 3] = fma(d, d, s[e & 3]); }
+            for (int e = 0; e < VE; e++) { double d = a.val(e) - mean; s[e & 3] = fma(d, d, s[e & 3]); }
         }
         for (int i = nvec * VE + lane; i < N; i += 32) { double d = (double)col[i] - mean; s[0] = fma(d, d, s[0]); }
         double sumsqr = warp_sum((s[0] + s[1]) + (s[2] + s[3]));
@@ -236,8 +232,8 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
                 if (valid[k]) {
 #pragma unroll
                     for (int e = 0; e < VE; e++) {
-                        if (SPLIT) acc[k][e] = fma(a[u][k].v[e], w[u], acc[k][e]);
-                        else acc[k][e] = fma(a[u][k].v[e] - m[u], w[u], acc[k][e]);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
+                        if (SPLIT) acc[k][e] = fma(a[u][k].val(e), w[u], acc[k][e]);
+                        else acc[k][e] = fma(a[u][k].val(e) - m[u], w[u], acc[k][e]);   // (meth[j] - ave) * sig_phen_i, src/data.cpp:360
                     }
                 }
             }
@@ -252,7 +248,7 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
             if (valid[k]) {
                 V32<T> a = V32<T>::stream(ap[k] + (size_t)j * ld);
 #pragma unroll
-                for (int e = 0; e < VE; e++) acc[k][e] = fma(a.v[e] - m, w, acc[k][e]);
+                for (int e = 0; e < VE; e++) acc[k][e] = fma(a.val(e) - m, w, acc[k][e]);
             }
         }
     }
@@ -515,7 +511,7 @@ __global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld,
                 for (int cc = 0; cc < C; cc++) {
 #pragma unroll
                     for (int e = 0; e < VE; e++)        // (meth[i] - mu) * phen[i], src/data.cpp:304
-                        acc[cc][e & 3] = fma(a[u][cc].v[e] - m[cc], pv[u].v[e], acc[cc][e & 3]);
+                        acc[cc][e & 3] = fma(a[u][cc].val(e) - m[cc], pv[u].v[e], acc[cc][e & 3]);
                 }
             }
         }
@@ -525,7 +521,7 @@ __global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld,
             for (int cc = 0; cc < C; cc++) {
                 V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
 #pragma unroll
-                for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.v[e] - m[cc], pv.v[e], acc[cc][e & 3]);
+                for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.val(e) - m[cc], pv.v[e], acc[cc][e & 3]);
             }
         }
 #pragma unroll
@@ -584,7 +580,7 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
                 for (int cc = 0; cc < C; cc++) {
 #pragma unroll
                     for (int e = 0; e < VE; e++)        // (meth[i] - mu) * phen[i], src/data.cpp:304
-                        acc[cc][e & 3] = fma(a[u][cc].v[e] - m[cc], pv[u].v[e], acc[cc][e & 3]);
+                        acc[cc][e & 3] = fma(a[u][cc].val(e) - m[cc], pv[u].v[e], acc[cc][e & 3]);
                 }
             }
         }
@@ -594,7 +590,7 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
             for (int cc = 0; cc < C; cc++) {
                 V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
 #pragma unroll
-                for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.v[e] - m[cc], pv.v[e], acc[cc][e & 3]);
+                for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.val(e) - m[cc], pv.v[e], acc[cc][e & 3]);
             }
         }
 #pragma unroll
@@ -725,16 +721,16 @@ __global__ void __launch_bounds__(256) k_loo_sums(const T* __restrict__ A, size_
             PV<VE> wa = PV<VE>::load(w + (size_t)VE * v), wb = PV<VE>::load(w + (size_t)VE * (v + 32));
 #pragma unroll
             for (int e = 0; e < VE; e++) {
-                sx += a.v[e]; tx += b.v[e];
-                sxx = fma(a.v[e], a.v[e], sxx); txx = fma(b.v[e], b.v[e], txx);
-                sxw = fma(a.v[e], wa.v[e], sxw); txw = fma(b.v[e], wb.v[e], txw);
+                sx += a.val(e); tx += b.val(e);
+                sxx = fma(a.val(e), a.val(e), sxx); txx = fma(b.val(e), b.val(e), txx);
+                sxw = fma(a.val(e), wa.v[e], sxw); txw = fma(b.val(e), wb.v[e], txw);
             }
         }
         for (; v < nvec; v += 32) {
             V32<T> a = V32<T>::stream(col + (size_t)VE * v);
             PV<VE> wa = PV<VE>::load(w + (size_t)VE * v);
 #pragma unroll
-            for (int e = 0; e < VE; e++) { sx += a.v[e]; sxx = fma(a.v[e], a.v[e], sxx); sxw = fma(a.v[e], wa.v[e], sxw); }
+            for (int e = 0; e < VE; e++) { sx += a.val(e); sxx = fma(a.val(e), a.val(e), sxx); sxw = fma(a.val(e), wa.v[e], sxw); }
         }
         sx = warp_sum(sx + tx); sxx = warp_sum(sxx + txx); sxw = warp_sum(sxw + txw);
         if (lane == 0) { sums[3 * j] = sx; sums[3 * j + 1] = sxx; sums[3 * j + 2] = sxw; }

@@ -27,10 +27,22 @@ template <> struct V32<double> {
     static constexpr int VE = 4;
     double v[4];
     __device__ __forceinline__ double val(int e) const { return v[e]; }
+    // H: L2 hint of the streaming load — 0 none, 1 L2::256B prefetch, 2 L2::evict_first, 3 both
+    template <int H = 0>
     static __device__ __forceinline__ V32 stream(const double* p) {
         V32 r;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
-                     : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+        if (H == 1)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+        else if (H == 2)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+        else if (H == 3)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::256B.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(p));
         return r;
     }
     static __device__ __forceinline__ V32 cached(const double* p) {
@@ -43,10 +55,21 @@ template <> struct V32<float> {      // keeps the raw FP32 values (8 registers) 
     static constexpr int VE = 8;
     float f[8];
     __device__ __forceinline__ double val(int e) const { return (double)f[e]; }
+    template <int H = 0>
     static __device__ __forceinline__ V32 stream(const float* p) {
         V32 r;
-        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
+        if (H == 1)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
+        else if (H == 2)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
+        else if (H == 3)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.L2::256B.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=f"(r.f[0]), "=f"(r.f[1]), "=f"(r.f[2]), "=f"(r.f[3]), "=f"(r.f[4]), "=f"(r.f[5]), "=f"(r.f[6]), "=f"(r.f[7]) : "l"(p));
         return r;
     }
     static __device__ __forceinline__ V32 cached(const float* p) {
@@ -184,7 +207,7 @@ int launch_stats(vampomi_ctx* c, double alpha_scale) {
 // SPLIT = false: (a - mave_j) * w_j per element, exactly the reference's expression (src/data.cpp:360).
 // SPLIT = true : a * w_j per element and one subtraction of sum_j mave_j * w_j per row at the end — one FP64 instruction
 //                less per element (less power under the 1 kW cap); same value up to summation order.
-template <typename T, int RV, int U, bool SPLIT>
+template <typename T, int RV, int U, bool SPLIT, int H = 0>
 __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                     const double* __restrict__ msig, const double* __restrict__ x,
                                                     int tile_rows, int cols_per_chunk, long long M,
@@ -218,7 +241,7 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
         for (int u = 0; u < U; u++) {
 #pragma unroll
             for (int k = 0; k < RV; k++)
-                if (valid[k]) a[u][k] = V32<T>::stream(ap[k] + (size_t)(j + u) * ld);
+                if (valid[k]) a[u][k] = V32<T>::template stream<H>(ap[k] + (size_t)(j + u) * ld);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -246,7 +269,7 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
 #pragma unroll
         for (int k = 0; k < RV; k++) {
             if (valid[k]) {
-                V32<T> a = V32<T>::stream(ap[k] + (size_t)j * ld);
+                V32<T> a = V32<T>::template stream<H>(ap[k] + (size_t)j * ld);
 #pragma unroll
                 for (int e = 0; e < VE; e++) acc[k][e] = fma(a.val(e) - m, w, acc[k][e]);
             }
@@ -372,8 +395,18 @@ static ax_kernel_t<T> ax_kernel(int rv, int U, bool split = false) {
         default: return nullptr;
     }
 }
+// the two measured default shapes also exist with an L2 hint on the streaming loads (knob ld_hint)
+template <typename T>
+static ax_kernel_t<T> ax_kernel_hint(int rv, int U, bool split, int hint) {
+    if (!split && hint >= 1 && hint <= 3) {
+        if (rv == 2 && U == 4) return hint == 1 ? k_ax_partial<T, 2, 4, false, 1> : hint == 2 ? k_ax_partial<T, 2, 4, false, 2> : k_ax_partial<T, 2, 4, false, 3>;
+        if (rv == 1 && U == 2) return hint == 1 ? k_ax_partial<T, 1, 2, false, 1> : hint == 2 ? k_ax_partial<T, 1, 2, false, 2> : k_ax_partial<T, 1, 2, false, 3>;
+    }
+    return ax_kernel<T>(rv, U, split);
+}
 static const void* ax_kernel_any(const vampomi_ctx* c, int rv, int U, bool split) {
-    return c->storage == 1 ? (const void*)ax_kernel<float>(rv, U, split) : (const void*)ax_kernel<double>(rv, U, split);
+    return c->storage == 1 ? (const void*)ax_kernel_hint<float>(rv, U, split, c->tune.ld_hint)
+                           : (const void*)ax_kernel_hint<double>(rv, U, split, c->tune.ld_hint);
 }
 
 // CTAs of `kernel` that fit on one SM (registers / shared memory) — grids are sized to exactly one resident wave so
@@ -430,10 +463,10 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
         dim3 grid(p.ntiles, p.nchunks);
         sp = prof_begin(c, 0, a_bytes);
         if (c->storage == 1)
-            ax_kernel<float>(p.rv, p.U, c->tune.center_split != 0)<<<grid, 256, 0, c->stream>>>(
+            ax_kernel_hint<float>(p.rv, p.U, c->tune.center_split != 0, c->tune.ld_hint)<<<grid, 256, 0, c->stream>>>(
                 c->A32, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag);
         else
-            ax_kernel<double>(p.rv, p.U, c->tune.center_split != 0)<<<grid, 256, 0, c->stream>>>(
+            ax_kernel_hint<double>(p.rv, p.U, c->tune.center_split != 0, c->tune.ld_hint)<<<grid, 256, 0, c->stream>>>(
                 c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag);
         prof_end(c, sp);
         VO_CUDA(cudaGetLastError());
@@ -538,7 +571,7 @@ __global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld,
 // CTA-cooperative form of A^T p (atx_impl = 2): the 8 warps of a CTA walk the SAME C columns together, 8 KB of each
 // column per step (U steps in flight), so the chip streams ~900 long sequential runs instead of ~3500 per-warp ones;
 // one block barrier per column group (partials double-buffered in shared memory), fixed reduction order.
-template <typename T, int C, int U>
+template <typename T, int C, int U, int H = 0>
 __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                  const double* __restrict__ msig, const double* __restrict__ p, long long M,
                                                  double scale, double* __restrict__ out, const int* __restrict__ done) {
@@ -570,7 +603,7 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
 #pragma unroll
             for (int u = 0; u < U; u++) {
 #pragma unroll
-                for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::stream(col[cc] + (size_t)VE * (v + 256 * u));
+                for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::template stream<H>(col[cc] + (size_t)VE * (v + 256 * u));
             }
 #pragma unroll
             for (int u = 0; u < U; u++) pv[u] = PV<VE>::load(p + (size_t)VE * (v + 256 * u));
@@ -588,7 +621,7 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
             PV<VE> pv = PV<VE>::load(p + (size_t)VE * v);
 #pragma unroll
             for (int cc = 0; cc < C; cc++) {
-                V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
+                V32<T> a = V32<T>::template stream<H>(col[cc] + (size_t)VE * v);
 #pragma unroll
                 for (int e = 0; e < VE; e++) acc[cc][e & 3] = fma(a.val(e) - m[cc], pv.v[e], acc[cc][e & 3]);
             }
@@ -661,6 +694,8 @@ static int launch_atx_t(vampomi_ctx* c, const T* A, int impl, int C, int U, cons
     if (impl == 2) {
         if (atx_cta_kernel<T>(C, U) == nullptr) { C = 2; U = 2; }
         atx_cta_kernel_t<T> k = atx_cta_kernel<T>(C, U);
+        if (C == 2 && U == 2 && c->tune.ld_hint >= 1 && c->tune.ld_hint <= 3)      // default shape with an L2 hint on the streaming loads
+            k = c->tune.ld_hint == 1 ? k_atx_cta<T, 2, 2, 1> : c->tune.ld_hint == 2 ? k_atx_cta<T, 2, 2, 2> : k_atx_cta<T, 2, 2, 3>;
         int occ = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)k, 256, 0);
         long long nb = (long long)c->num_sms * occ, ng = (c->M + C - 1) / C;
         if (nb > ng) nb = ng;

@@ -718,10 +718,11 @@ static int launch_atx_t(vampomi_ctx* c, const T* A, int impl, int C, int U, cons
 
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag) {
     int impl = c->tune.atx_impl;
-    if (impl == 3) impl = c->ld >= 4096 ? 2 : 0;          // short columns leave most of a CTA idle: keep one warp per column group
-    if (impl == 1 && c->storage == 1) impl = 2;           // the bulk-copy pipeline exists for FP64 storage only
-    // measured defaults (profiles/r01_sweep_*): CTA form C=2,U=2; warp form C=1,U=2
-    int C = c->tune.atx_cols > 0 ? c->tune.atx_cols : (impl == 2 ? 2 : 1);
+    // measured defaults (profiles/r01_sweep_*): FP64 storage — CTA form C=2,U=2 (short columns leave most of a CTA idle: one
+    // warp per column, C=1,U=2, below N = 4096); FP32 storage — warp form C=2,U=2
+    if (impl == 1 && c->storage == 1) impl = 3;           // the bulk-copy pipeline exists for FP64 storage only
+    if (impl == 3) impl = (c->storage == 0 && c->ld >= 4096) ? 2 : 0;
+    int C = c->tune.atx_cols > 0 ? c->tune.atx_cols : ((impl == 2 || c->storage == 1) ? 2 : 1);
     int U = c->tune.atx_unroll > 0 ? c->tune.atx_unroll : 2;
     const double scale = 1.0 / sqrt((double)c->N);                              // src/data.cpp:326-327
     int sp = prof_begin(c, 2, (double)c->M * c->N * (double)c->elem_bytes);

@@ -85,3 +85,24 @@ def test_cli_accepts_every_reference_flag(lib):
     res = subprocess.run([build.MAIN_METH] + argv, stdout=subprocess.PIPE, text=True)
     assert "unknown" not in res.stdout and "missing argument" not in res.stdout
     assert "--probit-var1" in res.stdout        # the reference echoes this flag without a space (src/options.cpp:199)
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    """Bad arguments are rejected with VAMPOMI_ERR_ARG (1) and a message before any CUDA call."""
+    import ctypes as C
+    h = C.c_void_p()
+    for args in ((0, 1, 10, 1, 0, 0), (0, 100, 0, 1, 0, 0), (0, 100, 10, 0, 0, 0), (0, 100, 10, 2, 2, 0), (0, 100, 3, 4, 0, 0),
+                 (0, 100, 10, 1, 0, 7)):
+        assert lib.vampomi_create_ex(*args, C.byref(h)) == 1
+        assert lib.vampomi_last_error()
+    assert lib.vampomi_create_ex(0, 100, 10, 1, 0, 0, None) == 1
+    M, S = C.c_longlong(), C.c_longlong()
+    assert lib.vampomi_divide_work(10, 0, 0, C.byref(M), C.byref(S)) == 1
+    assert lib.vampomi_divide_work(10, 2, 2, C.byref(M), C.byref(S)) == 1
+    assert lib.vampomi_shard(None, C.byref(M), C.byref(S)) == 1
+    assert lib.vampomi_set_tuning(None, b"ax_rv", 1) == 1
+    assert lib.vampomi_comm_get_unique_id(None) == 1
+    assert lib.vampomi_solver_create(None, None, None, None, None, None) == 1
+    buf = C.create_string_buffer(8)
+    assert lib.vampomi_host_csv_row(1, None, 0, buf, 8) == 6 and buf.value == b"    1\n"      # empty row: "%5d" + newline
+    assert lib.vampomi_host_csv_row(1, None, 0, buf, 3) == -1                               # does not fit

@@ -335,3 +335,38 @@ def test_f32_storage_generator_is_the_rounded_f64_generator():
     assert np.array_equal(b.download(), a.download().astype(np.float32).astype(np.float64))
     a.close()
     b.close()
+
+
+def test_instrumentation_and_error_paths():
+    N, M = 300, 800
+    sh, A, y, rng = make(N, M, seed=12)
+    assert sh.comm_mode() == 0 and sh.stream() is not None
+    sh.counters(reset=True)
+    sh.profile(True)
+    sh.profile_read(reset=True)
+    x = rng.standard_normal(M)
+    sh.set(V_V, x)
+    it, _, _ = sh.cg_solve(V_V, V_X2, 2.0, 1.5, tol=1e-6)
+    c = sh.counters()
+    assert c["matrix_passes"] == 2 * it and c["matrix_bytes"] == 2 * it * N * M * 8 and c["allreduces"] == 0
+    pr = sh.profile_read()
+    assert pr["ax_partial"]["launches"] == it and pr["atx"]["launches"] == it          # look-ahead no-op launches are not counted
+    assert pr["ax_partial"]["bytes"] == it * N * M * 8 and pr["ax_partial"]["ms"] > 0
+    sh.profile(False)
+    assert sh.time_kernel(0, 3) > 0 and sh.time_kernel(1, 3) > 0 and sh.time_kernel(2, 1) > 0 and sh.time_kernel(3, 1) > 0
+    # error paths: codes and messages, never a crash
+    with pytest.raises(capi.VampomiError, match="unknown knob"):
+        sh.set_tuning("no_such_knob", 1)
+    with pytest.raises(capi.VampomiError, match="must be in"):
+        sh.set_tuning("ax_rv", 99)
+    with pytest.raises(capi.VampomiError, match="distinct M-vectors"):
+        sh.cg_solve(V_V, V_V, 1.0, 1.0)
+    with pytest.raises(capi.VampomiError, match="bad vector id"):
+        sh.get(99)
+    with pytest.raises(capi.VampomiError, match="outside the shard"):
+        sh.upload(A, j0=10)
+    fresh = capi.Shard(N, M)
+    with pytest.raises(capi.VampomiError, match="before compute_stats"):
+        fresh.Ax(x)
+    fresh.close()
+    sh.close()

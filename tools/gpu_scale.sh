@@ -29,3 +29,9 @@ for n in ${SCALE_LIST:-1 $G}; do
   run_bench $n ""
   if [ "${AB:-0}" = "1" ] && [ "$n" != "1" ]; then VAMPOMI_XCHG=0 run_bench $n "_nccl"; fi
 done
+if [ "${F32:-0}" = "1" ]; then   # opt-in FP32-storage mode at full width, for the record (not the headline)
+  timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 \
+    bench.py --gpus $G --steps ${BENCH_STEPS:-3} --warmup ${BENCH_WARMUP:-3} --storage f32 > $OUT/bench_g${G}_of${G}_f32.log 2>&1
+  echo "bench n=$G f32 rc=$?" | tee -a $OUT/status_scale_$G.txt
+  grep -h '^{' $OUT/bench_g${G}_of${G}_f32.log | tail -1 | cut -c1-200
+fi

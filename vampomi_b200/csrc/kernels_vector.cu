@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_step(const double* __restric
 
 // scalar logic of one CG iteration (:708-726 onsager test, :731-751 beta and residual test) + p = z + beta p (:738-739).
 // Every block recomputes the scalars from read-only inputs (slot `parity`); block 0 publishes slot parity^1.
+// cg->done is written by block 0 while later-scheduled blocks of the SAME launch may already read it at their entry: if they
+// see it set they skip a p update that nothing will read any more (the solve is over), so the race is benign by construction.
 __global__ void __launch_bounds__(RED_THREADS) k_cg_finish(const double* __restrict__ z, double* __restrict__ p, long long M, int parity,
                                                            double gam2, double tol, int max_iter, int onsager_mode,
                                                            CgScalars* cg, const double* __restrict__ sums) {

@@ -63,3 +63,35 @@ def test_peer_exchange_equals_nccl(gpus, tmp_path):
         assert rel_l2(a, g["x1"][k - 1]) < 1e-9
     cg = lambda s: [l for l in s.splitlines() if l.startswith("[CG] LMMSE solve")]
     assert cg(outs["1"]) == cg(outs["0"])
+
+
+def test_association_and_test_modes_on_two_gpus(tmp_path):
+    """se / loo p-values and the out-of-sample test mode with the markers split over 2 GPUs: every shard writes its S*8
+    slice of the same output file; results equal the single-rank reference fixtures."""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from vampomi_b200 import sim
+    g = load_golden("linear_small")
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    last = int(g["iterations"])
+    for k in range(1, last + 1):
+        g["x1"][k - 1].tofile(f"{d}/out/g_it_{k}.bin")
+        g["r1"][k - 1].tofile(f"{d}/out/g_r1_it_{k}.bin")
+    common = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
+              "--gpus", 2]
+
+    def run(args):
+        res = subprocess.run([build.MAIN_METH] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-3000:]
+
+    run(common + ["--run-mode", "association_test", "--pval-method", "se", "--r1-file", f"{d}/out/g_r1_it_{last}.bin", "--gam1", repr(float(g["se_gam1"]))])
+    assert np.allclose(np.fromfile(f"{d}/out/g_it_{last}_pval_se.bin"), g["pval_se"], rtol=1e-10, atol=1e-300)
+    run(common + ["--run-mode", "association_test", "--pval-method", "loo", "--estimate-file", f"{d}/out/g_it_{last}.bin"])
+    assert np.allclose(np.fromfile(f"{d}/out/g_it_{last}_pval_loo.bin"), g["pval_loo"], rtol=1e-7, atol=1e-300)
+    Nt = int(g["N_test"])
+    sim.write_dataset(d, "tst", Nt, int(g["M"]), float(g["lam"]), float(g["h2"]), int(g["data_seed"]) + 1000)
+    run(["--meth-file-test", f"{d}/tst.bin", "--phen-file-test", f"{d}/tst.phen", "--N-test", Nt, "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
+         "--run-mode", "test", "--estimate-file", f"{d}/out/g_it_1.bin", "--test-iter-range", f"1,{last}", "--gpus", 2])
+    assert_rows_close(csv_rows(open(f"{d}/out/g_test.csv", "rb").read()), csv_rows(g["csv_test"]), 1e-8, "test.csv")

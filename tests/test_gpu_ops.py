@@ -76,7 +76,8 @@ def test_constant_column_and_alpha_scale():
                                    dict(center_split=1, atx_impl=0), dict(center_split=1, ax_rv=1, ax_unroll=8, atx_impl=0, atx_cols=1, atx_unroll=2),
                                    dict(atx_impl=2), dict(atx_impl=2, atx_cols=1, atx_unroll=8), dict(atx_impl=2, atx_cols=4, atx_unroll=2),
                                    dict(atx_impl=2, atx_cols=2, atx_unroll=2, atx_ctas_per_sm=5),
-                                   dict(ld_hint=1), dict(ld_hint=2), dict(ld_hint=3),
+                                   dict(ld_hint=1), dict(ld_hint=2), dict(ld_hint=3), dict(interleave=1), dict(interleave=1, ax_rv=1, ax_unroll=8, atx_cols=4),
+                                   dict(interleave=1, ax_ctas_per_sm=7, atx_ctas_per_sm=5),
                                    dict(ax_impl=1), dict(atx_impl=1), dict(ax_impl=1, ax_ctas_per_sm=1), dict(atx_impl=1, atx_ctas_per_sm=1)])
 def test_kernel_variants_agree(knobs):
     N, M = 4100, 1033

@@ -46,9 +46,9 @@ if a.sustained:
     base = dict(ax_impl=0, atx_impl=0, center_split=0, ax_ctas_per_sm=0, atx_ctas_per_sm=0)
     t(0, "ax_default", a.sustained)
     t(1, "atx_default", a.sustained)
-    for h in (1, 2, 3, 0):
-        t(0, "ax_default_hint", a.sustained, ld_hint=h)
-        t(1, "atx_default_hint", a.sustained, ld_hint=h)
+    for il in (1, 0, 1, 0):
+        t(0, "ax_default_interleave", a.sustained, interleave=il)
+        t(1, "atx_default_interleave", a.sustained, interleave=il)
     for split in (0,):
         for rv, u in ((2, 4), (4, 2)):
             t(0, "ax_sustained", a.sustained, **dict(base, ax_rv=rv, ax_unroll=u, center_split=split))

@@ -781,7 +781,8 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"atx_unroll", &c->tune.atx_unroll, 0, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
         {"cg_depth", &c->tune.cg_depth, 1, 32},     {"ax_impl", &c->tune.ax_impl, 0, 1},
         {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},
-        {"load_threads", &c->tune.load_threads, 1, 16}, {"ld_hint", &c->tune.ld_hint, 0, 3},       {"center_split", &c->tune.center_split, 0, 1},
+        {"load_threads", &c->tune.load_threads, 1, 16}, {"ld_hint", &c->tune.ld_hint, 0, 3},
+        {"interleave", &c->tune.interleave, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
     };
     for (auto& k : knobs)
         if (!strcmp(k.n, name)) {

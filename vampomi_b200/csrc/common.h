@@ -84,6 +84,7 @@ struct Tuning {
     int xchg = 1;                    // 1 = fused peer-memory all-reduce (xchg.cuh) when it could be set up, 0 = NCCL collectives
     int load_threads = 4;            // parallel pread -> pinned -> HBM pipelines of vampomi_load_file
     int ld_hint = 0;                 // L2 hint on the streaming loads of the default kernel shapes: 0 none, 1 L2::256B, 2 L2::evict_first, 3 both
+    int interleave = 0;              // experiment: deal column groups round-robin over the grid instead of one contiguous range per CTA
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 

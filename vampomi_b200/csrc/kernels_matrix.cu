@@ -211,14 +211,18 @@ template <typename T, int RV, int U, bool SPLIT, int H = 0>
 __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                     const double* __restrict__ msig, const double* __restrict__ x,
                                                     int tile_rows, int cols_per_chunk, long long M,
-                                                    double* __restrict__ partial, const int* __restrict__ done) {
+                                                    double* __restrict__ partial, const int* __restrict__ done, int interleave) {
     if (done != nullptr && *done != 0) return;
     constexpr int VE = V32<T>::VE;
     const int tid = threadIdx.x;
     const size_t rbase = (size_t)blockIdx.x * tile_rows;
-    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    // contiguous chunk [c0, c1) per blockIdx.y, or (experiment, knob `interleave`) groups of U columns dealt round-robin so
+    // that the whole grid walks ONE moving window of memory instead of gridDim.y separate ones
+    long long c0 = (long long)blockIdx.y * cols_per_chunk;
     long long c1 = c0 + cols_per_chunk;
     if (c1 > M) c1 = M;
+    long long jstep = U;
+    if (interleave) { c0 = (long long)blockIdx.y * U; c1 = M; jstep = (long long)gridDim.y * U; }
 
     double acc[RV][VE];
     const T* ap[RV];
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
     }
 
     long long j = c0;
-    for (; j + U <= c1; j += U) {
+    for (; j + U <= c1; j += jstep) {
         V32<T> a[U][RV];
         double m[U], w[U];
 #pragma unroll
@@ -262,6 +266,10 @@ __global__ void __launch_bounds__(256) k_ax_partial(const T* __restrict__ A, siz
             }
             if (SPLIT) corr = fma(m[u], w[u], corr);
         }
+    }
+    if (interleave) {                                     // the last, partial group of columns belongs to exactly one blockIdx.y
+        const long long full = M / U;
+        j = (full % gridDim.y == blockIdx.y) ? full * U : M;
     }
     for (; j < c1; j++) {
         double m = __ldg(mave + j), w = __ldg(msig + j) * __ldg(x + j);
@@ -378,7 +386,7 @@ int launch_scale_div(vampomi_ctx* c, double* dst, const double* src, double divi
 struct AxPlan { int rv, U, ntiles, tile_rows, nchunks, cols_per_chunk; };
 
 template <typename T>
-using ax_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, int, int, long long, double*, const int*);
+using ax_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, int, int, long long, double*, const int*, int);
 
 template <typename T>
 static ax_kernel_t<T> ax_kernel(int rv, int U, bool split = false) {
@@ -464,10 +472,10 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
         sp = prof_begin(c, 0, a_bytes);
         if (c->storage == 1)
             ax_kernel_hint<float>(p.rv, p.U, c->tune.center_split != 0, c->tune.ld_hint)<<<grid, 256, 0, c->stream>>>(
-                c->A32, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag);
+                c->A32, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag, c->tune.interleave);
         else
             ax_kernel_hint<double>(p.rv, p.U, c->tune.center_split != 0, c->tune.ld_hint)<<<grid, 256, 0, c->stream>>>(
-                c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag);
+                c->A, c->ld, c->mave, c->msig, x_dev, p.tile_rows, p.cols_per_chunk, c->M, c->ax_partial, done_flag, c->tune.interleave);
         prof_end(c, sp);
         VO_CUDA(cudaGetLastError());
     }
@@ -574,7 +582,7 @@ __global__ void __launch_bounds__(256) k_atx(const T* __restrict__ A, size_t ld,
 template <typename T, int C, int U, int H = 0>
 __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                  const double* __restrict__ msig, const double* __restrict__ p, long long M,
-                                                 double scale, double* __restrict__ out, const int* __restrict__ done) {
+                                                 double scale, double* __restrict__ out, const int* __restrict__ done, int interleave) {
     if (done != nullptr && *done != 0) return;
     constexpr int VE = V32<T>::VE;
     __shared__ double red[2][8][C];
@@ -582,10 +590,11 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
     const int nvec = (int)(ld / VE);
     const long long ngroups = (M + C - 1) / C;
     const long long per = (ngroups + gridDim.x - 1) / gridDim.x;
-    long long g0 = (long long)blockIdx.x * per, g1 = g0 + per;
+    long long g0 = (long long)blockIdx.x * per, g1 = g0 + per, gstep = 1;
     if (g1 > ngroups) g1 = ngroups;
+    if (interleave) { g0 = blockIdx.x; g1 = ngroups; gstep = gridDim.x; }      // round-robin column groups (knob `interleave`)
     int par = 0;
-    for (long long g = g0; g < g1; g++) {
+    for (long long g = g0; g < g1; g += gstep) {
         const long long j0 = g * C;
         const T* col[C];
         double m[C], acc[C][4];
@@ -643,7 +652,7 @@ __global__ void __launch_bounds__(256) k_atx_cta(const T* __restrict__ A, size_t
 }
 
 template <typename T>
-using atx_cta_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, long long, double, double*, const int*);
+using atx_cta_kernel_t = void (*)(const T*, size_t, const double*, const double*, const double*, long long, double, double*, const int*, int);
 template <typename T>
 static atx_cta_kernel_t<T> atx_cta_kernel(int C, int U) {
     switch (C * 10 + U) {
@@ -699,7 +708,7 @@ static int launch_atx_t(vampomi_ctx* c, const T* A, int impl, int C, int U, cons
         int occ = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident_ctas((const void*)k, 256, 0);
         long long nb = (long long)c->num_sms * occ, ng = (c->M + C - 1) / C;
         if (nb > ng) nb = ng;
-        k<<<(unsigned)nb, 256, 0, c->stream>>>(A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag);
+        k<<<(unsigned)nb, 256, 0, c->stream>>>(A, c->ld, c->mave, c->msig, p_dev, c->M, scale, out_dev, done_flag, c->tune.interleave);
         return VAMPOMI_OK;
     }
     if (atx_kernel<T>(C, U) == nullptr) { C = 1; U = 2; }

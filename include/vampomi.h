@@ -193,7 +193,9 @@ int vampomi_loo_sums(vampomi_ctx* ctx, int w_vec, double* sums_3M);
  * [2] bytes those passes streamed, [3] all-reduces issued. */
 int vampomi_counters(vampomi_ctx* ctx, long long out[4], int reset);
 /* Times `reps` back-to-back launches of one matrix kernel with CUDA events on the context's stream.
- * which: 0 = Ax (partial + reduce), 1 = ATx, 2 = stats, 3 = loo sums. Returns average milliseconds per launch. */
+ * which: 0 = Ax (partial + reduce), 1 = ATx, 2 = stats, 3 = loo sums, 4 = read-bandwidth probe (a plain linear streaming
+ * read of the whole marker block, not part of the VAMP path: the live ceiling the matrix kernels are compared with).
+ * Returns average milliseconds per launch. */
 int vampomi_time_kernel(vampomi_ctx* ctx, int which, int reps, double* ms_avg);
 /* Per-kernel device timing of the matrix passes (CUDA events on the context stream around every launch while enabled).
  * read(): out[3k] = launches, out[3k+1] = total ms, out[3k+2] = bytes of A streamed, for k = 0 (k_ax_partial),

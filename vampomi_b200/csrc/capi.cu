@@ -719,8 +719,8 @@ int vampomi_counters(vampomi_ctx* c, long long out[4], int reset) {
 }
 
 int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
-    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 3, "time_kernel: bad arguments");
-    if (which != 2) NEED_STATS(c, "time_kernel");
+    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 4, "time_kernel: bad arguments");
+    if (which != 2 && which != 4) NEED_STATS(c, "time_kernel");
     VO_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
     VO_CUDA(cudaEventCreate(&e0));
@@ -737,6 +737,7 @@ int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
             case 0: rc = launch_ax(c, c->mvec[VAMPOMI_V_TMP_M1], c->nvec[VAMPOMI_V_TMP_N1 - 32], nullptr); break;
             case 1: rc = launch_atx(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], c->mvec[VAMPOMI_V_TMP_M1], nullptr); break;
             case 2: rc = launch_stats(c, 1.0); break;
+            case 4: rc = launch_read_probe(c); break;
             default: rc = launch_loo_sums(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], dsums); break;
         }
     }

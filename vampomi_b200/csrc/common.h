@@ -154,6 +154,7 @@ int launch_stats(vampomi_ctx* c, double alpha_scale);
 int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* done_flag);     // incl. all-reduce and 1/sqrt(N)
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
 int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev);
+int launch_read_probe(vampomi_ctx* c);
 int launch_f64_to_f32(vampomi_ctx* c, float* dst, const double* src_dense, long long ncols, cudaStream_t st);
 int launch_f32_to_f64(vampomi_ctx* c, double* dst_dense, const float* src, long long ncols, cudaStream_t st);
 // ---- launchers (kernels_bulk.cu) ----

@@ -782,6 +782,33 @@ __global__ void __launch_bounds__(256) k_loo_sums(const T* __restrict__ A, size_
     }
 }
 
+// Read-bandwidth probe: the plainest possible streaming read of the whole marker block (linear addresses like a copy
+// kernel, 256-bit non-allocating loads, one FP64 add per value, no other input). It is not part of the VAMP path; it gives
+// the live "how fast can this GPU read this buffer at all" number that the matrix kernels are compared with.
+__global__ void __launch_bounds__(256) k_read_probe(const double* __restrict__ A, size_t nvec, double* __restrict__ out) {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < nvec; v += 4 * stride) {
+        V32<double> a = V32<double>::stream(A + 4 * v), b = V32<double>::stream(A + 4 * (v + stride));
+        V32<double> c = V32<double>::stream(A + 4 * (v + 2 * stride)), d = V32<double>::stream(A + 4 * (v + 3 * stride));
+        s0 += (a.v[0] + a.v[1]) + (a.v[2] + a.v[3]); s1 += (b.v[0] + b.v[1]) + (b.v[2] + b.v[3]);
+        s2 += (c.v[0] + c.v[1]) + (c.v[2] + c.v[3]); s3 += (d.v[0] + d.v[1]) + (d.v[2] + d.v[3]);
+    }
+    for (; v < nvec; v += stride) { V32<double> a = V32<double>::stream(A + 4 * v); s0 += (a.v[0] + a.v[1]) + (a.v[2] + a.v[3]); }
+    double s = warp_sum((s0 + s1) + (s2 + s3));
+    if ((threadIdx.x & 31) == 0 && s == 1.2345e300) out[0] = s;      // keeps the loads alive without a real store
+}
+
+int launch_read_probe(vampomi_ctx* c) {
+    const void* base = c->storage == 1 ? (const void*)c->A32 : (const void*)c->A;
+    const size_t bytes = (size_t)c->M * c->ld * (size_t)c->elem_bytes;
+    int occ = resident_ctas((const void*)k_read_probe, 256, 0);
+    k_read_probe<<<c->num_sms * occ, 256, 0, c->stream>>>((const double*)base, bytes / 32, c->psum);
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
 int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev) {
     if (c->storage == 1) k_loo_sums<float><<<c->num_sms * 8, 256, 0, c->stream>>>(c->A32, c->ld, w_dev, c->M, sums_dev);
     else k_loo_sums<double><<<c->num_sms * 8, 256, 0, c->stream>>>(c->A, c->ld, w_dev, c->M, sums_dev);

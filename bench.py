@@ -227,6 +227,11 @@ def main_ours(args):
     y = y * math.sqrt((N - 1) / float(((y - y.mean()) ** 2).sum()))         # data::read_phen scaling, src/data.cpp:97-99
     setup_s = time.time() - t_setup
 
+    # live read ceiling of this GPU on this very buffer: plain linear streaming read (vampomi_time_kernel which=4), burst of 5
+    sh.time_kernel(4, 2)
+    probe_ms = sh.time_kernel(4, 5)
+    probe_gbs = sh.M * ((N + 15) // 16 * 16) * (8 if args.storage == "f64" else 4) / (probe_ms * 1e-3) / 1e9
+
     stream = torch.cuda.ExternalStream(sh.stream(), device=torch.device("cuda", local))
     y_pinned = torch.from_numpy(y.copy()).pin_memory()
     x1_host = torch.empty(sh.M, dtype=torch.float64).pin_memory()
@@ -299,7 +304,9 @@ def main_ours(args):
     matrix_ms = sum(prof_dev[k]["ms"] for k in prof_dev)
     traffic, traffic_src = ncu_traffic("k_" + dom, N, sh.M, bytes_per_launch)
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "frac_of_8TBs_spec": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
+                "frac_of_8TBs_spec": achieved / 8000.0, "read_probe_gbs": probe_gbs, "frac_of_read_probe": achieved / probe_gbs,
+                "read_probe_note": "plain linear LDG.256 streaming read of the same buffer, burst of 5 launches before the timed region",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "launches_timed": pd["launches"],
                 "other_kernel": {k: (prof_dev[k]["bytes"] / max(prof_dev[k]["ms"], 1e-9) / 1e6) for k in ("ax_partial", "atx")},
                 "matrix_kernel_share_of_step": (prof_dev["ax_partial"]["ms"] + prof_dev["atx"]["ms"]) / ms_dev,

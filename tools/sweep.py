@@ -44,6 +44,7 @@ def t(which, label, reps=None, **knobs):
 
 if a.sustained:
     base = dict(ax_impl=0, atx_impl=0, center_split=0, ax_ctas_per_sm=0, atx_ctas_per_sm=0)
+    t(4, "read_probe_sustained", a.sustained)
     t(0, "ax_default", a.sustained)
     t(1, "atx_default", a.sustained)
     for il in (1, 0, 1, 0):
@@ -79,6 +80,8 @@ for o in ([0] if a.quick else [0, 1, 2, 3]):
     t(1, "atx", atx_impl=1, atx_ctas_per_sm=o)
 sh.set_tuning("ax_impl", 0)
 sh.set_tuning("atx_impl", 0)
+t(4, "read_probe")
+t(4, "read_probe_sustained", 200)
 t(2, "stats")
 t(3, "loo")
 best = {k: max((r for r in results if r["kernel"] == k), key=lambda r: r["gbs"]) for k in ("ax", "atx")}

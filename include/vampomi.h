@@ -154,6 +154,11 @@ int vampomi_draw_probe(vampomi_ctx* ctx, unsigned long long seed, int it);
 /* Operators on device vectors (no host traffic): out = A x (x: M-vector id, out: N-vector id) and out = A^T p. */
 int vampomi_ax_dev(vampomi_ctx* ctx, int x_vec, int out_vec);
 int vampomi_atx_dev(vampomi_ctx* ctx, int p_vec, int out_vec);
+/* The same operators applied to K vectors in ONE pass over the marker block (K <= 4 for A x, K <= 2 for A^T p): every
+ * pass is bound by streaming A from HBM, so K independent products cost one read of A instead of K. Each vector keeps the
+ * arithmetic of the single-vector call. out_k = A x_k (x: M-vector ids, out: distinct N-vector ids) / out_k = A^T p_k. */
+int vampomi_ax_multi_dev(vampomi_ctx* ctx, int K, const int* x_vecs, const int* out_vecs);
+int vampomi_atx_multi_dev(vampomi_ctx* ctx, int K, const int* p_vecs, const int* out_vecs);
 
 /* ---- Gaussian-mixture denoiser: vamp::g1 / vamp::g1d, src/vamp.cpp:440-492, as used at :203-223 ------------- */
 /* X1_PREV <- X1; X1 <- g1(R1, gam1) (then rho*X1 + (1-rho)*X1_PREV if damp != 0); *sum_g1d = sum over ALL shards of
@@ -194,7 +199,8 @@ int vampomi_loo_sums(vampomi_ctx* ctx, int w_vec, double* sums_3M);
 int vampomi_counters(vampomi_ctx* ctx, long long out[4], int reset);
 /* Times `reps` back-to-back launches of one matrix kernel with CUDA events on the context's stream.
  * which: 0 = Ax (partial + reduce), 1 = ATx, 2 = stats, 3 = loo sums, 4 = read-bandwidth probe (a plain linear streaming
- * read of the whole marker block, not part of the VAMP path: the live ceiling the matrix kernels are compared with).
+ * read of the whole marker block, not part of the VAMP path: the live ceiling the matrix kernels are compared with),
+ * 5 = A x for 2 vectors in one pass, 6 = A^T p for 2 vectors in one pass, 7 = the row-tiled A^T p kernel with 1 vector.
  * Returns average milliseconds per launch. */
 int vampomi_time_kernel(vampomi_ctx* ctx, int which, int reps, double* ms_avg);
 /* Per-kernel device timing of the matrix passes (CUDA events on the context stream around every launch while enabled).

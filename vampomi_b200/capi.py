@@ -74,6 +74,8 @@ _SIGNATURES = {
     "vampomi_draw_probe": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_int]),
     "vampomi_ax_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vampomi_atx_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "vampomi_ax_multi_dev": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p]),
+    "vampomi_atx_multi_dev": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p]),
     "vampomi_denoise": (C.c_int, [C.c_void_p, C.c_double, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double, c_double_p]),
     "vampomi_em_sums": (C.c_int, [C.c_void_p, C.c_double, C.c_double, c_double_p, c_double_p, C.c_int, c_double_p]),
     "vampomi_cg_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
@@ -295,6 +297,16 @@ class Shard:
 
     def atx_dev(self, p_vec, out_vec):
         _check(self.lib.vampomi_atx_dev(self.h, p_vec, out_vec), "atx_dev")
+
+    def ax_multi_dev(self, x_vecs, out_vecs):
+        """out_k = A x_k for up to 4 M-vectors in ONE pass over the marker block."""
+        K = len(x_vecs)
+        _check(self.lib.vampomi_ax_multi_dev(self.h, K, (C.c_int * K)(*x_vecs), (C.c_int * K)(*out_vecs)), "ax_multi_dev")
+
+    def atx_multi_dev(self, p_vecs, out_vecs):
+        """out_k = A^T p_k for up to 2 N-vectors in ONE pass over the marker block."""
+        K = len(p_vecs)
+        _check(self.lib.vampomi_atx_multi_dev(self.h, K, (C.c_int * K)(*p_vecs), (C.c_int * K)(*out_vecs)), "atx_multi_dev")
 
     # ---- VAMP pieces ----
     def denoise(self, gam1, probs, vars_internal, damp=False, rho=0.5):

@@ -121,12 +121,12 @@ static int xchg_setup(vampomi_ctx* c) {
     if (env && env[0] == '0') c->tune.xchg = 0;
     Xchg& x = c->xchg;
     x = Xchg{};
-    x.G = c->nranks; x.rank = c->rank; x.ld = c->ld;
-    x.maxb = (int)((c->ld + 31) / 32);
+    x.G = c->nranks; x.rank = c->rank; x.ld = (unsigned long long)XCHG_KMAX * c->ld;
+    x.maxb = XCHG_KMAX * (int)((c->ld + 31) / 32);
     size_t off = 0;
     x.off_flag_vec = off; off = align(off + (size_t)x.G * x.maxb * sizeof(unsigned int));
     x.off_flag_sc = off;  off = align(off + (size_t)x.G * 32 * sizeof(unsigned int));
-    x.off_recv_vec = off; off = align(off + (size_t)2 * x.G * c->ld * sizeof(double));
+    x.off_recv_vec = off; off = align(off + (size_t)2 * x.G * XCHG_KMAX * c->ld * sizeof(double));
     x.off_recv_sc = off;  off = align(off + (size_t)2 * x.G * XCHG_SCALARS * sizeof(double));
     const size_t region_bytes = off;
     XchgInfo mine{};
@@ -329,7 +329,7 @@ int vampomi_destroy(vampomi_ctx* c) {
     cudaFree(c->A); cudaFree(c->A32); cudaFree(c->mave); cudaFree(c->msig);
     for (auto p : c->mvec) cudaFree(p);
     for (auto p : c->nvec) cudaFree(p);
-    cudaFree(c->psum);
+    cudaFree(c->psum); cudaFree(c->atx_partial);
     cudaFree(c->ax_partial); cudaFree(c->red_partials); cudaFree(c->red_tickets); cudaFree(c->sums); cudaFree(c->cg);
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->cg_poll_host) cudaFreeHost(c->cg_poll_host);
@@ -641,6 +641,36 @@ int vampomi_draw_probe(vampomi_ctx* c, unsigned long long seed, int it) {
     return launch_probe(c, seed, it);
 }
 
+static int fill_multi(vampomi_ctx* c, int K, const int* in_vecs, const int* out_vecs, bool in_is_m, MultiVec* mv) {
+    VO_ARG(c && in_vecs && out_vecs && K >= 1 && K <= XCHG_KMAX, "multi: need 1..%d vectors", XCHG_KMAX);
+    mv->K = K;
+    for (int k = 0; k < XCHG_KMAX; k++) { mv->in[k] = nullptr; mv->out[k] = nullptr; mv->done[k] = nullptr; }
+    for (int k = 0; k < K; k++) {
+        VO_ARG(vec_ptr(c, in_vecs[k]) && vec_ptr(c, out_vecs[k]) && is_mvec(in_vecs[k]) == in_is_m && is_mvec(out_vecs[k]) != in_is_m,
+               "multi: vector %d has the wrong kind", k);
+        for (int q = 0; q < k; q++) VO_ARG(out_vecs[q] != out_vecs[k], "multi: output vectors must be distinct");
+        mv->in[k] = vec_ptr(c, in_vecs[k]);
+        mv->out[k] = vec_ptr(c, out_vecs[k]);
+    }
+    return VAMPOMI_OK;
+}
+
+int vampomi_ax_multi_dev(vampomi_ctx* c, int K, const int* x_vecs, const int* out_vecs) {
+    MultiVec mv;
+    VO_CHECK(fill_multi(c, K, x_vecs, out_vecs, true, &mv));
+    NEED_STATS(c, "ax_multi_dev");
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_ax_multi(c, mv);
+}
+
+int vampomi_atx_multi_dev(vampomi_ctx* c, int K, const int* p_vecs, const int* out_vecs) {
+    MultiVec mv;
+    VO_CHECK(fill_multi(c, K, p_vecs, out_vecs, false, &mv));
+    NEED_STATS(c, "atx_multi_dev");
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_atx_multi(c, mv);
+}
+
 int vampomi_ax_dev(vampomi_ctx* c, int x_vec, int out_vec) {
     VO_ARG(c && is_mvec(x_vec) && vec_ptr(c, out_vec) && !is_mvec(out_vec), "ax_dev: need M-vector in, N-vector out");
     NEED_STATS(c, "ax_dev");
@@ -719,7 +749,7 @@ int vampomi_counters(vampomi_ctx* c, long long out[4], int reset) {
 }
 
 int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
-    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 4, "time_kernel: bad arguments");
+    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 7, "time_kernel: bad arguments");
     if (which != 2 && which != 4) NEED_STATS(c, "time_kernel");
     VO_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
@@ -738,6 +768,20 @@ int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
             case 1: rc = launch_atx(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], c->mvec[VAMPOMI_V_TMP_M1], nullptr); break;
             case 2: rc = launch_stats(c, 1.0); break;
             case 4: rc = launch_read_probe(c); break;
+            case 5: case 6: case 7: {
+                MultiVec mv{};
+                mv.K = which == 7 ? 1 : 2;
+                if (which == 5) {
+                    mv.in[0] = c->mvec[VAMPOMI_V_TMP_M1]; mv.in[1] = c->mvec[VAMPOMI_V_TMP_M0];
+                    mv.out[0] = c->nvec[VAMPOMI_V_TMP_N1 - 32]; mv.out[1] = c->nvec[VAMPOMI_V_TMP_N0 - 32];
+                    rc = launch_ax_multi(c, mv);
+                } else {
+                    mv.in[0] = c->nvec[VAMPOMI_V_TMP_N1 - 32]; mv.in[1] = c->nvec[VAMPOMI_V_TMP_N0 - 32];
+                    mv.out[0] = c->mvec[VAMPOMI_V_TMP_M1]; mv.out[1] = c->mvec[VAMPOMI_V_TMP_M0];
+                    rc = launch_atx_multi(c, mv);
+                }
+                break;
+            }
             default: rc = launch_loo_sums(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], dsums); break;
         }
     }

@@ -55,6 +55,13 @@ constexpr int RED_THREADS = 256;
 constexpr int MAX_DOTS = 16;         // reductions per vampomi_dots() call
 constexpr int MAX_SUMS = 64;         // doubles in the packed scalar all-reduce buffer
 
+struct MultiVec {                    // K vectors handled by one multi-right-hand-side pass (kernels_multi.cu)
+    int K;
+    const double* in[XCHG_KMAX];
+    double* out[XCHG_KMAX];
+    const int* done[XCHG_KMAX];      // per-slot "skip me" flag in device memory (nullptr = always active)
+};
+
 struct MixParams {                   // passed by value to the denoiser / EM kernels
     int L;
     double probs[MAX_MIX];           // probs (denoiser) or omegas (EM)
@@ -105,8 +112,10 @@ struct vampomi_ctx {
     double* msig = nullptr;
     double* mvec[VAMPOMI_V_NUM_M] = {};
     double* nvec[VAMPOMI_V_NUM_N] = {};
-    double* ax_partial = nullptr;    // [ax_chunks][ld]
+    double* ax_partial = nullptr;    // [K][ax_chunks][ld]
     size_t ax_partial_elems = 0;
+    double* atx_partial = nullptr;   // [row tiles][K][M] of the tiled A^T kernels
+    size_t atx_partial_elems = 0;
     double* red_partials = nullptr;  // [MAX_DOTS][RED_BLOCKS][MAX_SUMS] scratch of the deterministic reductions
     unsigned int* red_tickets = nullptr;
     double* sums = nullptr;          // [MAX_SUMS] packed scalars (device), all-reduced in place
@@ -155,6 +164,9 @@ int launch_ax(vampomi_ctx* c, const double* x_dev, double* out_dev, const int* d
 int launch_atx(vampomi_ctx* c, const double* p_dev, double* out_dev, const int* done_flag);
 int launch_loo_sums(vampomi_ctx* c, const double* w_dev, double* sums_dev);
 int launch_read_probe(vampomi_ctx* c);
+// ---- launchers (kernels_multi.cu): one pass over A for K vectors ----
+int launch_ax_multi(vampomi_ctx* c, const MultiVec& mv);
+int launch_atx_multi(vampomi_ctx* c, const MultiVec& mv);
 int launch_f64_to_f32(vampomi_ctx* c, float* dst, const double* src_dense, long long ncols, cudaStream_t st);
 int launch_f32_to_f64(vampomi_ctx* c, double* dst_dense, const float* src, long long ncols, cudaStream_t st);
 // ---- launchers (kernels_bulk.cu) ----

@@ -1,0 +1,366 @@
+// Multi-right-hand-side passes over the marker block: ONE read of A serves K vectors.
+//
+// The VAMP iteration contains pairs of matrix passes that are independent of each other: the LMMSE solve and the Onsager
+// (trace) solve are two CG solves with the same operator tau*A^T A + gam2*I (src/vamp.cpp:308-311 and :494-501), and
+// A x1_hat / A mu_start (:232,:681) as well as A x2_hat / A Q^-1 u (:508,:518) apply A to two known vectors. The
+// reference runs them one after the other; since every pass is bound by streaming A from HBM, running them side by side on
+// the same stream of A halves the bytes of those passes while each right-hand side keeps exactly its own arithmetic.
+//
+//   k_ax_multi      out_k[i] partials = sum_j (A[i,j]-mave[j]) * (msig[j] * x_k[j]),  k < K     (mirror of k_ax_partial)
+//   k_ax_reduce_multi (+ fused cross-GPU sum)                                                    (mirror of k_ax_reduce[_xchg])
+//   k_atx_tiled     out_k[j] partials over a row tile = sum_i (A[i,j]-mave[j]) * p_k[i]; the K tiles of p live in
+//                   registers, so the K vectors cost no extra memory traffic at all (the CTA-per-column form would have to
+//                   re-read K*N*8 bytes of p per column group through L2)
+//   k_atx_reduce    out_k[j] = msig[j] * (sum over row tiles) * (1/sqrt(N))
+//
+// A slot whose `done` flag is set (a CG solve that has already stopped) is skipped by every kernel, consistently on all GPUs.
+#include "common.h"
+#include "vec32.cuh"
+
+namespace vampomi {
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int K, int U>
+__global__ void __launch_bounds__(256) k_ax_multi(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                  const double* __restrict__ msig, MultiVec mv, int tile_rows, int cols_per_chunk,
+                                                  long long M, double* __restrict__ partial, int nchunks) {
+    constexpr int VE = V32<T>::VE;
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = mv.done[k] == nullptr || *mv.done[k] == 0; any |= active[k]; }
+    if (!any) return;
+    const int tid = threadIdx.x;
+    const size_t rbase = (size_t)blockIdx.x * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+    const int off = tid * VE;
+    const bool valid = off < tile_rows && rbase + off < ld;
+    const T* ap = A + rbase + (valid ? off : 0);
+    double acc[K][VE];
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int e = 0; e < VE; e++) acc[k][e] = 0.0;
+
+    long long j = c0;
+    for (; j + U <= c1; j += U) {
+        V32<T> a[U];
+        double m[U], w[K][U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (valid) a[u] = V32<T>::stream(ap + (size_t)(j + u) * ld);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            m[u] = __ldg(mave + j + u);
+            const double sg = __ldg(msig + j + u);
+#pragma unroll
+            for (int k = 0; k < K; k++) w[k][u] = active[k] ? sg * __ldg(mv.in[k] + j + u) : 0.0;     // sig_phen_i, src/data.cpp:354
+        }
+        if (valid) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int e = 0; e < VE; e++) {
+                    const double d = a[u].val(e) - m[u];                                              // meth[j] - ave, src/data.cpp:360
+#pragma unroll
+                    for (int k = 0; k < K; k++) acc[k][e] = fma(d, w[k][u], acc[k][e]);
+                }
+            }
+        }
+    }
+    for (; j < c1; j++) {
+        const double m = __ldg(mave + j), sg = __ldg(msig + j);
+        if (valid) {
+            V32<T> a = V32<T>::stream(ap + (size_t)j * ld);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const double w = active[k] ? sg * __ldg(mv.in[k] + j) : 0.0;
+#pragma unroll
+                for (int e = 0; e < VE; e++) acc[k][e] = fma(a.val(e) - m, w, acc[k][e]);
+            }
+        }
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (!active[k]) continue;
+        double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase + off;
+#pragma unroll
+        for (int q = 0; q < VE / 4; q++) st256(prow + 4 * q, d4{acc[k][4 * q], acc[k][4 * q + 1], acc[k][4 * q + 2], acc[k][4 * q + 3]});
+    }
+}
+
+// out_k[i] = (sum_c partial[k][c][i]) / divisor; blockIdx.y = k. With x.enabled the cross-GPU sum happens here (xchg.cuh).
+template <int SL>
+__global__ void __launch_bounds__(256) k_ax_reduce_multi(const double* __restrict__ partial, size_t ld, int nchunks, int N,
+                                                         double divisor, MultiVec mv, Xchg x, int use_xchg) {
+    __shared__ double sm[SL][256 / SL];
+    __shared__ unsigned int s_seq;
+    constexpr int ROWS = 256 / SL;
+    static_assert(ROWS == 32, "one warp owns the CTA's rows in the exchange");
+    const int k = blockIdx.y;
+    const bool active = mv.done[k] == nullptr || *mv.done[k] == 0;
+    const int r = threadIdx.x % ROWS, s = threadIdx.x / ROWS;
+    const int i = blockIdx.x * ROWS + r;
+    if (use_xchg && threadIdx.x == 0) s_seq = ld_volatile_u32(x.seq) + 1u;
+    double acc = 0.0;
+    if (active && i < N) {
+        const double* base = partial + (size_t)k * nchunks * ld;
+        for (int cidx = s; cidx < nchunks; cidx += SL) acc += __ldcg(base + (size_t)cidx * ld + i);
+    }
+    sm[s][r] = acc;
+    __syncthreads();
+    if (s != 0) return;
+    double t = sm[0][r];
+#pragma unroll
+    for (int q = 1; q < SL; q++) t += sm[q][r];
+    double* out = mv.out[k];
+    if (!use_xchg) {
+        if (active && i < N) out[i] = t / divisor;
+        return;
+    }
+    // slot k of this exchange: rows of rank g land at recv[slot][g][k*ld_vec + i]; flags are indexed by (k, CTA)
+    const unsigned int seq = s_seq, slot = seq & 1u;
+    const size_t koff = (size_t)k * (x.ld / XCHG_KMAX);
+    const int cta = k * gridDim.x + blockIdx.x;
+    if (active) {
+        if (i < N)
+            for (int g = 0; g < x.G; g++) xchg_recv_vec(x, g, slot, x.rank)[koff + i] = t;
+        __threadfence_system();
+        __syncwarp();
+        if (r < x.G) {
+            st_release_sys(xchg_flag_vec(x, r, x.rank, cta), seq);
+            xchg_wait_flag(xchg_flag_vec(x, x.rank, r, cta), seq);
+        }
+        __syncwarp();
+        if (i < N) {
+            double tot = 0.0;
+            for (int g = 0; g < x.G; g++) tot += __ldcg(xchg_recv_vec(x, x.rank, slot, g) + koff + i);
+            out[i] = tot / divisor;
+        }
+        __syncwarp();
+    }
+    if (r == 0) {                                             // the last CTA of the whole (rows x K) grid publishes the sequence number
+        __threadfence();
+        if (atomicAdd(x.ticket, 1u) == gridDim.x * gridDim.y - 1) { x.seq[0] = seq; *x.ticket = 0u; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A^T [p_0 .. p_{K-1}] over a row tile: thread t keeps its rows of all K vectors in registers; CB columns per step.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int K, int RV, int CB>
+__global__ void __launch_bounds__(256) k_atx_tiled(const T* __restrict__ A, size_t ld, const double* __restrict__ mave, MultiVec mv,
+                                                   int tile_rows, int cols_per_chunk, long long M, double* __restrict__ partial) {
+    constexpr int VE = V32<T>::VE;
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = mv.done[k] == nullptr || *mv.done[k] == 0; any |= active[k]; }
+    if (!any) return;
+    __shared__ double red[2][8][K * CB];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t rbase = (size_t)blockIdx.x * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+
+    const T* ap[RV];
+    bool valid[RV];
+    double pr[K][RV][VE];
+#pragma unroll
+    for (int rv = 0; rv < RV; rv++) {
+        const int off = (rv * 256 + tid) * VE;
+        valid[rv] = off < tile_rows && rbase + off < ld;
+        ap[rv] = A + rbase + (valid[rv] ? off : 0);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+            for (int e = 0; e < VE; e++) pr[k][rv][e] = 0.0;
+            if (valid[rv] && active[k]) {
+                PV<VE> pv = PV<VE>::load(mv.in[k] + rbase + off);          // pad rows of p are zero
+#pragma unroll
+                for (int e = 0; e < VE; e++) pr[k][rv][e] = pv.v[e];
+            }
+        }
+    }
+    // partial layout: [tile][k][M]
+    double* pout = partial + (size_t)blockIdx.x * K * M;
+    int par = 0;
+    for (long long j = c0; j < c1; j += CB) {
+        const int ncol = (int)(c1 - j < CB ? c1 - j : CB);
+        V32<T> a[CB][RV];
+        double m[CB];
+#pragma unroll
+        for (int cc = 0; cc < CB; cc++) {
+            const long long jj = cc < ncol ? j + cc : j;
+            m[cc] = __ldg(mave + jj);
+#pragma unroll
+            for (int rv = 0; rv < RV; rv++)
+                if (valid[rv]) a[cc][rv] = V32<T>::stream(ap[rv] + (size_t)jj * ld);
+        }
+        double acc[K][CB];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int cc = 0; cc < CB; cc++) acc[k][cc] = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < CB; cc++) {
+#pragma unroll
+            for (int rv = 0; rv < RV; rv++) {
+                if (valid[rv]) {
+#pragma unroll
+                    for (int e = 0; e < VE; e++) {
+                        const double d = a[cc][rv].val(e) - m[cc];                   // meth[i] - mu, src/data.cpp:304
+#pragma unroll
+                        for (int k = 0; k < K; k++) acc[k][cc] = fma(d, pr[k][rv][e], acc[k][cc]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int cc = 0; cc < CB; cc++) {
+                const double sw = warp_sum(acc[k][cc]);
+                if (lane == 0) red[par][wid][k * CB + cc] = sw;
+            }
+        __syncthreads();
+        if (tid < K * CB) {
+            const int k = tid / CB, cc = tid % CB;
+            if (cc < ncol && active[k]) {
+                double t = red[par][0][tid];
+#pragma unroll
+                for (int w = 1; w < 8; w++) t += red[par][w][tid];
+                pout[(size_t)k * M + j + cc] = t;
+            }
+        }
+        par ^= 1;
+    }
+}
+
+// out_k[j] = (msig[j] * sum_tiles partial[tile][k][j]) * scale; blockIdx.y = k
+__global__ void __launch_bounds__(256) k_atx_reduce(const double* __restrict__ partial, int ntiles, int K, long long M,
+                                                    const double* __restrict__ msig, double scale, MultiVec mv) {
+    const int k = blockIdx.y;
+    if (mv.done[k] != nullptr && *mv.done[k] != 0) return;
+    double* out = mv.out[k];
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
+        double t = 0.0;
+        for (int tile = 0; tile < ntiles; tile++) t += __ldcg(partial + ((size_t)tile * K + k) * M + j);
+        out[j] = (__ldg(msig + j) * t) * scale;                                      // sigma_inv * dpa (:306), then * scale (:330)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+static int resident(const void* kernel) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) n = 1;
+    return n;
+}
+static int ensure_buf(vampomi_ctx* c, double** buf, size_t* cap, size_t need) {
+    if (need <= *cap) return VAMPOMI_OK;
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    if (*buf) VO_CUDA(cudaFree(*buf));
+    *buf = nullptr; *cap = 0;
+    VO_CUDA(cudaMalloc(buf, need * sizeof(double)));
+    *cap = need;
+    return VAMPOMI_OK;
+}
+
+template <typename T, int K>
+static int ax_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+    constexpr int VE = V32<T>::VE;
+    constexpr int U = sizeof(T) == 8 ? 4 : 2;
+    auto kern = k_ax_multi<T, K, U>;
+    const int cap = 256 * VE;
+    const int ntiles = (int)((c->ld + cap - 1) / cap);
+    const size_t tr = (c->ld + ntiles - 1) / ntiles;
+    const int tile_rows = (int)((tr + 15) / 16 * 16);
+    const int per_sm = c->tune.ax_ctas_per_sm > 0 ? c->tune.ax_ctas_per_sm : resident((const void*)kern);
+    long long nch = (long long)c->num_sms * per_sm / ntiles;
+    if (nch < 1) nch = 1;
+    if (nch > c->M) nch = c->M;
+    const int cols_per_chunk = (int)((c->M + nch - 1) / nch);
+    const int nchunks = (int)((c->M + cols_per_chunk - 1) / cols_per_chunk);
+    VO_CHECK(ensure_buf(c, &c->ax_partial, &c->ax_partial_elems, (size_t)K * nchunks * c->ld));
+    if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
+    int sp = prof_begin(c, 0, (double)c->M * c->N * (double)c->elem_bytes);
+    kern<<<dim3(ntiles, nchunks), 256, 0, c->stream>>>(A, c->ld, c->mave, c->msig, mv, tile_rows, cols_per_chunk, c->M, c->ax_partial, nchunks);
+    prof_end(c, sp);
+    VO_CUDA(cudaGetLastError());
+    sp = prof_begin(c, 1, 0.0);
+    const double sqrtN = sqrt((double)c->N);
+    constexpr int SL = 8;
+    const int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
+    const bool fused = c->nranks > 1 && c->xchg.enabled;
+    k_ax_reduce_multi<SL><<<dim3(rblocks, K), 256, 0, c->stream>>>(c->ax_partial, c->ld, nchunks, c->N,
+                                                                    (c->nranks == 1 || fused) ? sqrtN : 1.0, mv, c->xchg, fused ? 1 : 0);
+    VO_CUDA(cudaGetLastError());
+    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
+    if (c->nranks > 1 && !fused) {
+        for (int k = 0; k < K; k++) {
+            VO_CHECK(allreduce_inplace(c, mv.out[k], (size_t)c->N));
+            VO_CHECK(launch_scale_div(c, mv.out[k], mv.out[k], sqrtN, c->N, mv.done[k]));
+        }
+    }
+    prof_end(c, sp);
+    return VAMPOMI_OK;
+}
+
+int launch_ax_multi(vampomi_ctx* c, const MultiVec& mv) {
+    if (mv.K < 1 || mv.K > XCHG_KMAX) { set_error("ax_multi: 1..%d vectors", XCHG_KMAX); return VAMPOMI_ERR_ARG; }
+    if (c->storage == 1) {
+        switch (mv.K) { case 1: return ax_multi_t<float, 1>(c, c->A32, mv); case 2: return ax_multi_t<float, 2>(c, c->A32, mv);
+                        case 3: return ax_multi_t<float, 3>(c, c->A32, mv); default: return ax_multi_t<float, 4>(c, c->A32, mv); }
+    }
+    switch (mv.K) { case 1: return ax_multi_t<double, 1>(c, c->A, mv); case 2: return ax_multi_t<double, 2>(c, c->A, mv);
+                    case 3: return ax_multi_t<double, 3>(c, c->A, mv); default: return ax_multi_t<double, 4>(c, c->A, mv); }
+}
+
+template <typename T, int K>
+static int atx_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+    constexpr int VE = V32<T>::VE;
+    constexpr int RV = sizeof(T) == 8 ? 2 : 1;
+    constexpr int CB = 4;
+    auto kern = k_atx_tiled<T, K, RV, CB>;
+    const int cap = 256 * VE * RV;
+    const int ntiles = (int)((c->ld + cap - 1) / cap);
+    const size_t tr = (c->ld + ntiles - 1) / ntiles;
+    const int tile_rows = (int)((tr + 15) / 16 * 16);
+    const int per_sm = c->tune.atx_ctas_per_sm > 0 ? c->tune.atx_ctas_per_sm : resident((const void*)kern);
+    long long nch = (long long)c->num_sms * per_sm / ntiles;
+    if (nch < 1) nch = 1;
+    if (nch > c->M) nch = c->M;
+    int cols_per_chunk = (int)((c->M + nch - 1) / nch);
+    cols_per_chunk = (cols_per_chunk + CB - 1) / CB * CB;
+    const int nchunks = (int)((c->M + cols_per_chunk - 1) / cols_per_chunk);
+    VO_CHECK(ensure_buf(c, &c->atx_partial, &c->atx_partial_elems, (size_t)ntiles * K * c->M));
+    if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
+    int sp = prof_begin(c, 2, (double)c->M * c->N * (double)c->elem_bytes);
+    kern<<<dim3(ntiles, nchunks), 256, 0, c->stream>>>(A, c->ld, c->mave, mv, tile_rows, cols_per_chunk, c->M, c->atx_partial);
+    VO_CUDA(cudaGetLastError());
+    long long rb = (c->M + 255) / 256;
+    if (rb > 4 * c->num_sms) rb = 4 * c->num_sms;
+    k_atx_reduce<<<dim3((unsigned)rb, K), 256, 0, c->stream>>>(c->atx_partial, ntiles, K, c->M, c->msig, 1.0 / sqrt((double)c->N), mv);
+    prof_end(c, sp);
+    VO_CUDA(cudaGetLastError());
+    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
+    return VAMPOMI_OK;
+}
+
+int launch_atx_multi(vampomi_ctx* c, const MultiVec& mv) {
+    if (mv.K < 1 || mv.K > XCHG_KMAX) { set_error("atx_multi: 1..%d vectors", XCHG_KMAX); return VAMPOMI_ERR_ARG; }
+    if (c->storage == 1) {
+        switch (mv.K) { case 1: return atx_multi_t<float, 1>(c, c->A32, mv); case 2: return atx_multi_t<float, 2>(c, c->A32, mv);
+                        default: set_error("atx_multi: at most 2 vectors"); return VAMPOMI_ERR_ARG; }
+    }
+    switch (mv.K) { case 1: return atx_multi_t<double, 1>(c, c->A, mv); case 2: return atx_multi_t<double, 2>(c, c->A, mv);
+                    default: set_error("atx_multi: at most 2 vectors"); return VAMPOMI_ERR_ARG; }
+}
+
+}  // namespace vampomi

@@ -23,12 +23,13 @@ namespace vampomi {
 
 constexpr int XCHG_MAX_RANKS = 8;
 constexpr int XCHG_SCALARS = 64;        // doubles per scalar exchange (>= MAX_SUMS)
+constexpr int XCHG_KMAX = 4;            // vectors one exchange can carry (multi-right-hand-side A x)
 
 struct Xchg {                           // passed by value to kernels; all offsets identical on every rank
     int enabled;
     int G, rank;
     int maxb;                           // CTA slots per rank in the vector flag array
-    unsigned long long ld;              // length of one vector contribution (doubles)
+    unsigned long long ld;              // stride between the contributions of two ranks (doubles): XCHG_KMAX vectors of length ld_vec
     unsigned long long off_flag_vec, off_flag_sc, off_recv_vec, off_recv_sc;   // byte offsets inside a region
     unsigned char* peer[XCHG_MAX_RANKS];   // base of every rank's region as mapped into THIS rank's address space
     unsigned int* seq;                  // local: [0] vector exchanges done, [1] scalar exchanges done

@@ -52,7 +52,9 @@ enum {
     VAMPOMI_V_CG_R = 12, VAMPOMI_V_CG_Z = 13, VAMPOMI_V_CG_P = 14, VAMPOMI_V_CG_D = 15,   /* src/vamp.cpp:679-692 */
     VAMPOMI_V_USER_M0 = 16,    /* never touched by the library itself (TMP_* and CG_* are clobbered by its calls) */
     VAMPOMI_V_USER_M1 = 17,
-    VAMPOMI_V_NUM_M = 18,
+    VAMPOMI_V_CG2_R = 18, VAMPOMI_V_CG2_Z = 19, VAMPOMI_V_CG2_P = 20, VAMPOMI_V_CG2_D = 21,   /* second system of a paired solve */
+    VAMPOMI_V_ATA_X2 = 22,     /* A^T A x2_hat, kept from one iteration to the next (the warm start's residual needs it) */
+    VAMPOMI_V_NUM_M = 23,
 
     VAMPOMI_V_Y = 32,          /* phenotype y                 src/vamp.hpp:23 */
     VAMPOMI_V_Z1 = 33,         /* z1 = A x1_hat               src/vamp.hpp:24 */
@@ -182,6 +184,21 @@ int vampomi_em_sums(vampomi_ctx* ctx, double gam1, double lambda, const double* 
 int vampomi_cg_solve(vampomi_ctx* ctx, int rhs_vec, int sol_vec, int warm_start, double tau, double gam2,
                      double tol, int max_iter, int onsager_mode, int* iters, double* rel_err, double* rhs_dot_sol);
 
+/* Two solves with the SAME operator (tau A^T A + gam2 I) advanced in lock-step: system 0 and system 1 share every matrix
+ * pass (one read of the marker block per A p and per A^T (A p) for both), while each keeps exactly the scalars, the
+ * stopping tests and the iteration count it would have in vampomi_cg_solve — a system that has converged is skipped by
+ * all later launches. This is how one VAMP iteration runs its LMMSE solve (src/vamp.cpp:308-311) and its Onsager / trace
+ * solve (:494-501) in max(k1, k2) instead of k1 + k2 CG iterations' worth of passes.
+ *   warm_ata_vec[s]: only read when warm_start[s] != 0 — id of an M-vector that already holds A^T A sol_s (e.g. from a
+ *     vampomi_atx_multi_dev of an earlier A sol_s), or -1 to compute it here with two extra passes.
+ *   extra_x_vec / extra_out_vec: if extra_x_vec >= 0, extra_out = A extra_x is computed by the first A p pass of the solve
+ *     (a third vector on the same read); pass -1 for none.
+ * rhs/sol must be distinct, non-work M-vectors. Outputs are arrays of two. */
+int vampomi_cg_solve_pair(vampomi_ctx* ctx, const int rhs_vec[2], const int sol_vec[2], const int warm_start[2],
+                          const int warm_ata_vec[2], double tau, double gam2, double tol, int max_iter,
+                          const int onsager_mode[2], int extra_x_vec, int extra_out_vec, int iters[2], double rel_err[2],
+                          double rhs_dot_sol[2]);
+
 /* ---- probit z-channel: vamp::g1_bin_class / g1d_bin_class, src/vamp_probit.cpp:469-488 as used at :213-236 --- */
 /* Z1HAT <- g1_bin_class(P1, tau1, Y, 0); *sum_g1d = sum_i g1d_bin_class(P1_i, tau1, Y_i, 0). */
 int vampomi_probit_zdenoise(vampomi_ctx* ctx, double tau1, double* sum_g1d);
@@ -200,7 +217,8 @@ int vampomi_counters(vampomi_ctx* ctx, long long out[4], int reset);
 /* Times `reps` back-to-back launches of one matrix kernel with CUDA events on the context's stream.
  * which: 0 = Ax (partial + reduce), 1 = ATx, 2 = stats, 3 = loo sums, 4 = read-bandwidth probe (a plain linear streaming
  * read of the whole marker block, not part of the VAMP path: the live ceiling the matrix kernels are compared with),
- * 5 = A x for 2 vectors in one pass, 6 = A^T p for 2 vectors in one pass, 7 = the row-tiled A^T p kernel with 1 vector.
+ * 5 = A x for 2 vectors in one pass, 6 = A^T p for 2 vectors in one pass, 7 = the multi-vector A^T p kernel with 1 vector,
+ * 8 = A x for 3 vectors in one pass.
  * Returns average milliseconds per launch. */
 int vampomi_time_kernel(vampomi_ctx* ctx, int which, int reps, double* ms_avg);
 /* Per-kernel device timing of the matrix passes (CUDA events on the context stream around every launch while enabled).

@@ -7,7 +7,7 @@ import pytest
 
 from oracle import vamp_oracle as vo
 from vampomi_b200 import capi
-from vampomi_b200.capi import (DIFF2, DOT, SQDEV, V_ATY, V_BERN, V_P1, V_QINV_BERN, V_R1, V_R2, V_TRUE, V_USER_M0,
+from vampomi_b200.capi import (V_ATA_X2, V_USER_M1, V_Z2, DIFF2, DOT, SQDEV, V_ATY, V_BERN, V_P1, V_QINV_BERN, V_R1, V_R2, V_TRUE, V_USER_M0,
                                V_USER_N0, V_USER_N1, V_V, V_X1, V_X1_PREV, V_X2, V_Y, V_Z1, V_Z1HAT)
 from helpers import rel_l2
 
@@ -293,6 +293,122 @@ def test_association_pvalues_match_oracle():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+MULTI_KNOBS = [dict(), dict(multi_ax_rv=1, multi_ax_unroll=2), dict(multi_ax_rv=1, multi_ax_unroll=8), dict(multi_ax_rv=2, multi_ax_unroll=2),
+               dict(multi_ax_rv=2, multi_ax_unroll=4), dict(multi_atx_impl=0), dict(multi_atx_cols=1, multi_atx_unroll=2),
+               dict(multi_atx_cols=1, multi_atx_unroll=4), dict(multi_atx_cols=2, multi_atx_unroll=4), dict(multi_atx_cols=4, multi_atx_unroll=2),
+               dict(multi_atx_tile=256), dict(multi_atx_tile=1000, atx_ctas_per_sm=3), dict(ax_ctas_per_sm=5)]
+
+
+@pytest.mark.parametrize("storage", ["f64", "f32"])
+@pytest.mark.parametrize("N,M", SHAPES + [(9000, 77)])
+def test_multi_vector_passes_match_oracle(N, M, storage):
+    """One read of the marker block for K vectors (vampomi_ax_multi_dev / vampomi_atx_multi_dev): every vector must get the
+    product the single-vector call (and the oracle) gives, for every kernel shape, on ragged sizes."""
+    rng = np.random.default_rng(N * 3 + M)
+    A = rng.standard_normal((M, N)) * 0.1 + 0.5
+    if storage == "f32":
+        A = A.astype(np.float32).astype(np.float64)
+    y = rng.standard_normal(N)
+    sh = capi.Shard(N, M, storage=storage)
+    sh.upload(A)
+    sh.compute_stats()
+    d = vo.Data(A, y)
+    xs = [rng.standard_normal(M) for _ in range(4)]
+    ps = [rng.standard_normal(N) for _ in range(2)]
+    xin, xout = [V_X1, V_X2, V_V, V_USER_M0], [V_Z1, V_Z2, V_USER_N0, V_USER_N1]
+    pin, pout = [V_USER_N0, V_USER_N1], [V_R1, V_R2]
+    want_ax = [d.Ax(x) for x in xs]
+    want_atx = [d.ATx(p) for p in ps]
+    for knobs in MULTI_KNOBS:
+        for k, v in knobs.items():
+            sh.set_tuning(k, v)
+        for K in (1, 2, 3, 4):
+            for i in range(4):
+                sh.set(xin[i], xs[i])
+                sh.fill(xout[i], -7.0)
+            sh.ax_multi_dev(xin[:K], xout[:K])
+            for i in range(K):
+                assert rel_l2(sh.get(xout[i]), want_ax[i]) < 1e-12, (knobs, K, i)
+            for i in range(K, 4):
+                assert np.all(sh.get(xout[i]) == -7.0)           # untouched
+        for K in (1, 2):
+            for i in range(2):
+                sh.set(pin[i], ps[i])
+                sh.fill(pout[i], -7.0)
+            sh.atx_multi_dev(pin[:K], pout[:K])
+            for i in range(K):
+                assert rel_l2(sh.get(pout[i]), want_atx[i]) < 1e-12, (knobs, K, i)
+            for i in range(K, 2):
+                assert np.all(sh.get(pout[i]) == -7.0)
+        for k in knobs:
+            sh.set_tuning(k, 1 if k == "multi_atx_impl" else 0)
+    # bitwise reproducible from run to run
+    sh.ax_multi_dev(xin[:2], xout[:2]); a = sh.get(xout[1]).copy()
+    sh.ax_multi_dev(xin[:2], xout[:2]); assert np.array_equal(a, sh.get(xout[1]))
+    sh.atx_multi_dev(pin, pout); b = sh.get(pout[1]).copy()
+    sh.atx_multi_dev(pin, pout); assert np.array_equal(b, sh.get(pout[1]))
+    with pytest.raises(capi.VampomiError):
+        sh.ax_multi_dev([V_X1, V_X2], [V_Z1, V_Z1])              # outputs must be distinct
+    with pytest.raises(capi.VampomiError):
+        sh.atx_multi_dev([V_USER_N0, V_USER_N1, V_Z1], [V_R1, V_R2, V_V])   # at most two
+    with pytest.raises(capi.VampomiError):
+        sh.ax_multi_dev([V_Z1], [V_X1])                          # wrong kinds
+    sh.close()
+
+
+@pytest.mark.parametrize("N,M", [(400, 1000), (333, 517), (2050, 300)])
+def test_paired_solve_equals_two_single_solves(N, M):
+    """vampomi_cg_solve_pair: two systems with one operator in lock-step. Each system must stop after exactly the
+    iterations the single solve (and the oracle) takes and return the same solution; the rider A x on the first pass and a
+    warm start from a cached A^T A x must behave like their separate calls."""
+    sh, A, y, rng = make(N, M, seed=N + 1)
+    d = vo.Data(A, y)
+    o = vo.Vamp(d, CG_err_tol=1e-7)
+    gam2, tau = 1.9, 2.3
+    o.gam2 = gam2
+    v, u, x1 = rng.standard_normal(M), np.sign(rng.standard_normal(M)) / math.sqrt(M), rng.standard_normal(M)
+    mu0 = rng.standard_normal(M) * 0.1
+    sh.set(V_V, v); sh.set(V_BERN, u); sh.set(V_X1, x1)
+    want0 = o.precondCG_solver(v, None, tau, 1); k0 = o.cg_iters[-1][2]
+    want1 = o.precondCG_solver(u, None, tau, 0); k1 = o.cg_iters[-1][2]
+    for depth in (2, 1, 5):
+        sh.set_tuning("cg_depth", depth)
+        sh.fill(V_Z1, 0.0)
+        c0 = sh.counters(reset=True)
+        res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, tol=1e-7, extra=(V_X1, V_Z1))
+        assert (res[0][0], res[1][0]) == (k0, k1)
+        assert rel_l2(sh.get(V_X2), want0) < 1e-11 and rel_l2(sh.get(V_QINV_BERN), want1) < 1e-11
+        assert abs(res[1][2] - u @ want1) < 1e-11 * abs(u @ want1)
+        assert rel_l2(sh.get(V_Z1), d.Ax(x1)) < 1e-12
+        assert sh.counters()["matrix_passes"] == 2 * max(k0, k1)            # one pass per product pair, idle look-ahead not counted
+    # the same answers as the single-system entry point, to rounding of the reduction order
+    it_s, _, _ = sh.cg_solve(V_V, V_USER_M0, tau, gam2, tol=1e-7)
+    assert it_s == k0 and rel_l2(sh.get(V_USER_M0), sh.get(V_X2)) < 1e-12
+    # warm start of system 0: (a) A^T A mu0 computed inside, (b) handed in from a multi pass
+    want_w = o.precondCG_solver(v, mu0, tau, 1); kw = o.cg_iters[-1][2]
+    sh.set(V_X2, mu0)
+    res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, warm_start=(True, False), tol=1e-7)
+    assert (res[0][0], res[1][0]) == (kw, k1) and rel_l2(sh.get(V_X2), want_w) < 1e-11
+    sh.set(V_X2, mu0)
+    sh.ax_multi_dev([V_X2], [V_Z2])
+    sh.atx_multi_dev([V_Z2], [V_ATA_X2])
+    c = sh.counters(reset=True)
+    res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, warm_start=(True, False), warm_ata_vecs=(V_ATA_X2, -1), tol=1e-7)
+    assert (res[0][0], res[1][0]) == (kw, k1) and rel_l2(sh.get(V_X2), want_w) < 1e-11
+    assert sh.counters()["matrix_passes"] == 2 * max(kw, k1)
+    # iteration cap applies to both
+    res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, tol=1e-30, max_iter=3, onsager_mode=(False, False))
+    assert (res[0][0], res[1][0]) == (3, 3)
+    # argument validation
+    with pytest.raises(capi.VampomiError):
+        sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_X2], tau, gam2)
+    with pytest.raises(capi.VampomiError):
+        sh.cg_solve_pair([V_V, V_BERN], [V_X2, capi.V_CG2_P], tau, gam2)
+    with pytest.raises(capi.VampomiError):
+        sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, extra=(V_X1, capi.V_TMP_N0))
+    sh.close()
+
+
 # opt-in FP32 storage of the marker block (vampomi_create_ex): every value is rounded once, arithmetic stays FP64, so the
 # results must equal the oracle's on the ROUNDED matrix
 # ---------------------------------------------------------------------------------------------------------------------

@@ -32,13 +32,19 @@ def solver_for(g, A, y_txt, beta, **over):
     return sh, capi.Solver(sh, y, model=model, true_signal=beta, x1hat_init=g.get("x1hat_init"), **kw)
 
 
+# schedules of the matrix passes: "fused" (default: products that are known together share one read of the block),
+# "plain" (one product per pass, A^T y and A x2_hat cached), "reference" (plain + the passes the reference repeats)
+SCHEDULES = {"fused": dict(fuse_passes=1, redundant_passes=0), "plain": dict(fuse_passes=0, redundant_passes=0),
+             "reference": dict(fuse_passes=0, redundant_passes=1)}
+
+
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("redundant", [0, 1])
-def test_solver_matches_reference_fixture(name, redundant):
+@pytest.mark.parametrize("schedule", list(SCHEDULES))
+def test_solver_matches_reference_fixture(name, schedule):
     g = load_golden(name)
     rel_vec, rel_csv = tolerances(g)
     A, y_txt, beta = golden_inputs(g)
-    sh, sol = solver_for(g, A, y_txt, beta, redundant_passes=redundant)
+    sh, sol = solver_for(g, A, y_txt, beta, **SCHEDULES[schedule])
     want_params, want_metrics = csv_rows(g["csv_params"]), csv_rows(g["csv_metrics"])
     got_params, got_metrics = {}, {}
     for k in range(1, int(g["iterations"]) + 1):
@@ -50,10 +56,17 @@ def test_solver_matches_reference_fixture(name, redundant):
         if g["model"] == "linear":
             assert (r["k1"], r["k2"]) == tuple(g["cg_iters"][k - 1]), f"CG iteration counts it {k}"
             base = 2 * (r["k1"] + r["k2"])
-            if redundant:       # the reference's own pass count: 6 (it = 1) / 8 (it > 1) + 2(k1+k2), SURVEY.md §3.1
+            if schedule == "reference":   # the reference's own pass count: 6 (it = 1) / 8 (it > 1) + 2(k1+k2), SURVEY.md §3.1
                 assert r["matrix_passes"] == base + (6 if k == 1 else 8)
-            else:               # A^T y cached, A x2_hat computed once
+            elif schedule == "plain":     # A^T y cached, A x2_hat computed once
                 assert r["matrix_passes"] == base + (5 if k == 1 else 6)
+            else:                         # A^T y once; both solves in lock-step; A [x2, Q^-1 u] and A^T [.., A x2] one pass each
+                assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (3 if k == 1 else 2)
+        else:
+            if schedule == "fused":       # A^T p2, lock-step solves, A [x2, x2/sqrt(N)]
+                assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + 2
+            else:
+                assert r["matrix_passes"] == 2 * (r["k1"] + r["k2"]) + 4
     assert_rows_close(got_params, want_params, rel_csv, "params")
     assert_rows_close(got_metrics, want_metrics, rel_csv, "metrics")
     if float(g.get("stop_thr", 0)) > 0:          # the reference stopped here on its own NMSE test (src/vamp.cpp:419-423)
@@ -82,6 +95,28 @@ def run_cli(args, **kw):
     res = subprocess.run([build.MAIN_METH] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
     assert res.returncode == 0, res.stdout[-3000:]
     return res.stdout
+
+
+@pytest.mark.parametrize("schedule", ["fused", "plain", "reference"])
+def test_main_meth_schedule_flag(schedule, tmp_path):
+    """--schedule only changes which products share a read of the block: same files for all three."""
+    g = load_golden("linear_wellcond")
+    rel_vec, rel_csv = tolerances(g)
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    its = int(g["iterations"])
+    out = run_cli(["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out",
+                   "--out-name", "g", "--iterations", its, "--true-signal-file", f"{d}/ex_ts.bin", "--stop-criteria-thr", 0,
+                   "--seed", g["probe_seed"], "--schedule", schedule] + list(g["extra"]))
+    assert f"--schedule {schedule}" in out
+    for k in range(1, its + 1):
+        assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), g["x1"][k - 1]) < rel_vec
+        assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < rel_vec
+    for kind in ("params", "metrics"):
+        assert_rows_close(csv_rows(open(f"{d}/out/g_{kind}.csv", "rb").read()), csv_rows(bytes(g[f"csv_{kind}"])), rel_csv, kind)
+    res = subprocess.run([build.MAIN_METH, "--schedule", "sideways"], stdout=subprocess.PIPE, text=True)
+    assert res.returncode == 1 and "FATAL" in res.stdout
 
 
 @pytest.mark.parametrize("name", ["linear_small", "probit_small", "linear_stops_early", "linear_warm_start", "linear_alpha_scale",

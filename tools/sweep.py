@@ -18,6 +18,8 @@ ap.add_argument("--M", type=int, default=106250)
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--storage", default="f64", choices=["f64", "f32"])
+ap.add_argument("--multi", type=int, default=0, help="only the multi-vector kernels (one read of A for K vectors), with this many "
+                "back-to-back reps per variant")
 ap.add_argument("--sustained", type=int, default=0, help="also time a short list of variants with this many back-to-back reps "
                 "(seconds-long, i.e. under the power cap) instead of a burst")
 a = ap.parse_args()
@@ -41,6 +43,33 @@ def t(which, label, reps=None, **knobs):
     results.append(rec)
     print(json.dumps(rec), flush=True)
 
+
+if a.multi:
+    t(4, "read_probe", a.multi)
+    t(0, "ax_single_default", a.multi)
+    t(1, "atx_single_default", a.multi)
+    for rv, u in ((1, 4), (1, 8), (2, 2), (2, 4), (1, 2)):
+        t(5, "ax_multi_K2", a.multi, multi_ax_rv=rv, multi_ax_unroll=u)
+        t(8, "ax_multi_K3", a.multi, multi_ax_rv=rv, multi_ax_unroll=u)
+    for o in (1, 2, 3, 4):
+        t(5, "ax_multi_K2", a.multi, multi_ax_rv=1, multi_ax_unroll=4, ax_ctas_per_sm=o)
+    sh.set_tuning("ax_ctas_per_sm", 0); sh.set_tuning("multi_ax_rv", 0); sh.set_tuning("multi_ax_unroll", 0)
+    t(6, "atx_multi_K2_regtile", a.multi, multi_atx_impl=0)
+    t(7, "atx_multi_K1_regtile", a.multi, multi_atx_impl=0)
+    for tile in (4096, 2048, 8192):
+        for c_, u in ((2, 2), (2, 4), (1, 2), (1, 4), (4, 2)):
+            if tile != 4096 and (c_, u) not in ((2, 2), (2, 4)):
+                continue
+            t(6, "atx_multi_K2_smem", a.multi, multi_atx_impl=1, multi_atx_cols=c_, multi_atx_unroll=u, multi_atx_tile=tile)
+            t(7, "atx_multi_K1_smem", a.multi, multi_atx_impl=1, multi_atx_cols=c_, multi_atx_unroll=u, multi_atx_tile=tile)
+    for o in (1, 2, 3, 4):
+        t(6, "atx_multi_K2_smem", a.multi, multi_atx_impl=1, multi_atx_cols=2, multi_atx_unroll=2, multi_atx_tile=4096, atx_ctas_per_sm=o)
+    best = {}
+    for r in results:
+        if r["kernel"] not in best or r["gbs"] > best[r["kernel"]]["gbs"]:
+            best[r["kernel"]] = r
+    print("BEST", json.dumps(best))
+    sys.exit(0)
 
 if a.sustained:
     base = dict(ax_impl=0, atx_impl=0, center_split=0, ax_ctas_per_sm=0, atx_ctas_per_sm=0)

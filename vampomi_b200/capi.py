@@ -20,6 +20,7 @@ MAX_MIX = 32
 # vector ids (include/vampomi.h)
 V_X1, V_X1_PREV, V_R1, V_R2, V_X2, V_V, V_BERN, V_QINV_BERN, V_TRUE, V_ATY, V_TMP_M0, V_TMP_M1 = range(12)
 V_CG_R, V_CG_Z, V_CG_P, V_CG_D, V_USER_M0, V_USER_M1 = 12, 13, 14, 15, 16, 17
+V_CG2_R, V_CG2_Z, V_CG2_P, V_CG2_D, V_ATA_X2 = 18, 19, 20, 21, 22
 V_Y, V_Z1, V_Z2, V_P1, V_P2, V_Z1HAT, V_TMP_N0, V_TMP_N1, V_USER_N0, V_USER_N1 = range(32, 42)
 DOT, DIFF2, SQDEV = 0, 1, 2
 
@@ -29,7 +30,8 @@ class SolverConfig(C.Structure):
                 ("CG_max_iter", C.c_int), ("CG_err_tol", C.c_double), ("EM_max_iter", C.c_int),
                 ("EM_err_thr", C.c_double), ("learn_vars", C.c_int), ("learn_prior_delay", C.c_int),
                 ("merge_vars_thr", C.c_double), ("L", C.c_int), ("probs", C.c_double * MAX_MIX),
-                ("vars", C.c_double * MAX_MIX), ("seed", C.c_ulonglong), ("redundant_passes", C.c_int)]
+                ("vars", C.c_double * MAX_MIX), ("seed", C.c_ulonglong), ("redundant_passes", C.c_int),
+                ("fuse_passes", C.c_int)]
 
 
 class IterResult(C.Structure):
@@ -80,6 +82,8 @@ _SIGNATURES = {
     "vampomi_em_sums": (C.c_int, [C.c_void_p, C.c_double, C.c_double, c_double_p, c_double_p, C.c_int, c_double_p]),
     "vampomi_cg_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                    C.c_int, c_int_p, c_double_p, c_double_p]),
+    "vampomi_cg_solve_pair": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                        c_int_p, C.c_int, C.c_int, c_int_p, c_double_p, c_double_p]),
     "vampomi_probit_zdenoise": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "vampomi_pvals_se": (C.c_int, [C.c_void_p, c_double_p, C.c_double, c_double_p]),
     "vampomi_loo_sums": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
@@ -328,6 +332,18 @@ class Shard:
         _check(self.lib.vampomi_cg_solve(self.h, rhs_vec, sol_vec, int(bool(warm_start)), tau, gam2, tol, max_iter,
                                          int(bool(onsager_mode)), C.byref(iters), C.byref(rel), C.byref(vmu)), "cg_solve")
         return iters.value, rel.value, vmu.value
+
+    def cg_solve_pair(self, rhs_vecs, sol_vecs, tau, gam2, warm_start=(False, False), warm_ata_vecs=(-1, -1), tol=1e-5,
+                      max_iter=500, onsager_mode=(False, True), extra=None):
+        """Two solves with the same operator in lock-step (one read of the marker block per pass for both).
+        extra: optional (x_vec, out_vec) — out = A x computed on the first pass. Returns [(iters, rel_err, <rhs,sol>)] * 2."""
+        i2 = C.c_int * 2
+        iters, rel, vmu = i2(), (C.c_double * 2)(), (C.c_double * 2)()
+        ex, eo = extra if extra is not None else (-1, -1)
+        _check(self.lib.vampomi_cg_solve_pair(self.h, i2(*rhs_vecs), i2(*sol_vecs), i2(*[int(bool(w)) for w in warm_start]),
+                                              i2(*warm_ata_vecs), tau, gam2, tol, max_iter,
+                                              i2(*[int(bool(o)) for o in onsager_mode]), ex, eo, iters, rel, vmu), "cg_solve_pair")
+        return [(iters[s], rel[s], vmu[s]) for s in range(2)]
 
     def probit_zdenoise(self, tau1):
         s = C.c_double()

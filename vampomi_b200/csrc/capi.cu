@@ -305,8 +305,8 @@ int vampomi_create_ex(int device, int N, long long Mt, int nranks, int rank, int
         VO_CUDA(cudaMemsetAsync(c->sums, 0, MAX_SUMS * sizeof(double), c->stream));
         VO_CUDA(cudaMallocHost(&c->sums_host, MAX_SUMS * sizeof(double)));
         VO_CUDA(cudaMalloc(&c->psum, sizeof(double)));
-        VO_CUDA(cudaMalloc(&c->cg, sizeof(CgScalars)));
-        VO_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgScalars), c->stream));
+        VO_CUDA(cudaMalloc(&c->cg, 2 * sizeof(CgScalars)));          // one per system of a paired solve
+        VO_CUDA(cudaMemsetAsync(c->cg, 0, 2 * sizeof(CgScalars), c->stream));
         VO_CUDA(cudaMallocHost(&c->cg_poll_host, 64 * sizeof(int)));
         size_t st = (size_t)(3 * c->M > (long long)c->ld ? 3 * c->M : (long long)c->ld);
         VO_CHECK(ensure_stage(c, st));
@@ -749,7 +749,7 @@ int vampomi_counters(vampomi_ctx* c, long long out[4], int reset) {
 }
 
 int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
-    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 7, "time_kernel: bad arguments");
+    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 8, "time_kernel: bad arguments");
     if (which != 2 && which != 4) NEED_STATS(c, "time_kernel");
     VO_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
@@ -768,12 +768,12 @@ int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
             case 1: rc = launch_atx(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], c->mvec[VAMPOMI_V_TMP_M1], nullptr); break;
             case 2: rc = launch_stats(c, 1.0); break;
             case 4: rc = launch_read_probe(c); break;
-            case 5: case 6: case 7: {
+            case 5: case 6: case 7: case 8: {
                 MultiVec mv{};
-                mv.K = which == 7 ? 1 : 2;
-                if (which == 5) {
-                    mv.in[0] = c->mvec[VAMPOMI_V_TMP_M1]; mv.in[1] = c->mvec[VAMPOMI_V_TMP_M0];
-                    mv.out[0] = c->nvec[VAMPOMI_V_TMP_N1 - 32]; mv.out[1] = c->nvec[VAMPOMI_V_TMP_N0 - 32];
+                mv.K = which == 7 ? 1 : which == 8 ? 3 : 2;
+                if (which == 5 || which == 8) {
+                    mv.in[0] = c->mvec[VAMPOMI_V_TMP_M1]; mv.in[1] = c->mvec[VAMPOMI_V_TMP_M0]; mv.in[2] = c->mvec[VAMPOMI_V_USER_M1];
+                    mv.out[0] = c->nvec[VAMPOMI_V_TMP_N1 - 32]; mv.out[1] = c->nvec[VAMPOMI_V_TMP_N0 - 32]; mv.out[2] = c->nvec[VAMPOMI_V_USER_N1 - 32];
                     rc = launch_ax_multi(c, mv);
                 } else {
                     mv.in[0] = c->nvec[VAMPOMI_V_TMP_N1 - 32]; mv.in[1] = c->nvec[VAMPOMI_V_TMP_N0 - 32];
@@ -828,6 +828,9 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},
         {"load_threads", &c->tune.load_threads, 1, 16}, {"ld_hint", &c->tune.ld_hint, 0, 3},
         {"interleave", &c->tune.interleave, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
+        {"multi_ax_rv", &c->tune.multi_ax_rv, 0, 2},     {"multi_ax_unroll", &c->tune.multi_ax_unroll, 0, 8},
+        {"multi_atx_impl", &c->tune.multi_atx_impl, 0, 1}, {"multi_atx_cols", &c->tune.multi_atx_cols, 0, 4},
+        {"multi_atx_unroll", &c->tune.multi_atx_unroll, 0, 4}, {"multi_atx_tile", &c->tune.multi_atx_tile, 0, 16384},
     };
     for (auto& k : knobs)
         if (!strcmp(k.n, name)) {

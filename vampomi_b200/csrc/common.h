@@ -78,6 +78,22 @@ struct CgScalars {                   // device-resident CG scalars (src/vamp.cpp
     int iters;
 };
 
+struct CgSys {                       // one linear system of a CG batch (cg.cu); all pointers are device memory
+    const double* v;                 // right-hand side
+    double* mu;                      // solution (start vector when warm)
+    double *r, *z, *p, *d;           // CG work vectors
+    double* atx_out;                 // A^T A mu_start while the solve is set up (warm), then = atx_work
+    double* atx_work;                // A^T A p of the current iteration
+    double* tmpN;                    // A p
+    CgScalars* cg;
+    int warm;
+    int onsager_mode;
+};
+struct CgBatch {
+    int S;
+    CgSys s[2];
+};
+
 struct Tuning {
     int ax_rv = 0;                   // 256-bit vectors per thread per column in Ax (0 = measured default: 2 for FP64 storage, 1 for FP32)
     int ax_unroll = 0;               // columns in flight per thread (0 = measured default: 4 for FP64 storage, 2 for FP32)
@@ -92,6 +108,12 @@ struct Tuning {
     int load_threads = 4;            // parallel pread -> pinned -> HBM pipelines of vampomi_load_file
     int ld_hint = 0;                 // L2 hint on the streaming loads of the default kernel shapes: 0 none, 1 L2::256B, 2 L2::evict_first, 3 both
     int interleave = 0;              // experiment: deal column groups round-robin over the grid instead of one contiguous range per CTA
+    int multi_ax_rv = 0;             // multi-vector A x: 32-byte vectors per thread per column (0 = 1)
+    int multi_ax_unroll = 0;         // multi-vector A x: columns in flight (0 = 4 for FP64 storage, 2 for FP32)
+    int multi_atx_impl = 1;          // multi-vector A^T p: 0 = p tiles in registers, 1 = p tiles in shared memory
+    int multi_atx_cols = 0;          // shared-memory form: columns per warp pass (0 = 2)
+    int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 2)
+    int multi_atx_tile = 0;          // shared-memory form: rows of p per tile (0 = 4096)
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 
@@ -156,6 +178,10 @@ inline long long vec_len(const vampomi_ctx* c, int id) {
     return -1;
 }
 inline bool is_mvec(int id) { return id >= 0 && id < VAMPOMI_V_NUM_M; }
+// M-vectors the library's own calls clobber (TMP_*, CG_*, CG2_*): not usable as rhs / sol of a solve
+inline bool is_work_mvec(int id) {
+    return (id >= VAMPOMI_V_TMP_M0 && id <= VAMPOMI_V_CG_D) || (id >= VAMPOMI_V_CG2_R && id <= VAMPOMI_V_CG2_D);
+}
 
 // ---- launchers (kernels_matrix.cu) ----
 int launch_generate_iid(vampomi_ctx* c, uint64_t seed);
@@ -183,12 +209,11 @@ int launch_denoise(vampomi_ctx* c, double gam1, const MixParams& mp, int damp, d
 int launch_em_sums(vampomi_ctx* c, double gam1, double lambda, const MixParams& mp, double* sums_dev);
 int launch_probit_z(vampomi_ctx* c, double tau1, double* sums_dev);
 int launch_pvals_se(vampomi_ctx* c, const double* r1_dev, double sd, double* out_dev);
-int launch_cg_init(vampomi_ctx* c, const double* v, double* mu, const double* atx_out, int warm, double tau, double gam2,
-                   double diag, double* sums_dev);
-int launch_cg_init_finish(vampomi_ctx* c, const double* sums_dev);
-int launch_cg_dp(vampomi_ctx* c, const double* atx_out, double tau, double gam2, double* sums_dev);
-int launch_cg_step(vampomi_ctx* c, const double* v, double* mu, double diag, int parity, const double* dp_dev, double* sums_dev);
-int launch_cg_finish(vampomi_ctx* c, int parity, double gam2, double tol, int max_iter, int onsager_mode, const double* sums_dev);
+int launch_cg_init(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, double* sums_dev);
+int launch_cg_init_finish(vampomi_ctx* c, const CgBatch& b, const double* sums_dev);
+int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double* sums_dev);
+int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev);
+int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double tol, int max_iter, const double* sums_dev);
 // all-reduce `n` doubles in place on the context stream (no-op for nranks == 1)
 int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n);
 // profiling spans: begin returns an index (or -1 when profiling is off), end closes it

@@ -114,6 +114,14 @@ bool Options::parse(int argc, char** argv, std::string* echo) {
                 return false;
             }
             ss << "--storage " << storage << "\n";
+        } else if (!strcmp(a, "--schedule")) {
+            if (!need_value()) return false;
+            schedule = argv[++i];
+            if (schedule != "fused" && schedule != "plain" && schedule != "reference") {
+                std::cout << "FATAL  : option --schedule has to be fused, plain or reference! (" << schedule << " was passed)" << std::endl;
+                return false;
+            }
+            ss << "--schedule " << schedule << "\n";
         } else if (!strcmp(a, "--gpus")) {
             if (!need_value()) return false;
             gpus = atoi(argv[++i]);

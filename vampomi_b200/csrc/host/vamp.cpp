@@ -62,6 +62,7 @@ int Vamp::init(const double* y, const double* true_signal, const double* x1hat_i
     VH(vampomi_vec_fill(ctx_, VAMPOMI_V_R2, 0.0));
     it_ = 0;
     aty_ready_ = false;
+    ata_x2_ready_ = false;
     if (cfg_.model == 1) {                                                      // src/vamp_probit.cpp:35-61
         tau1_ = gam1_;
         std::vector<double> p1 = probit_p1(cfg_.seed, N_);
@@ -162,17 +163,24 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         for (double p : probs_) std::cout << p << ' ';
         std::cout << std::endl;
     }
+    // fused schedule (cfg.fuse_passes): matrix passes whose inputs are known at the same time share ONE read of the block —
+    //   A x1_hat rides on the first A p pass of the solves, the LMMSE and the Onsager solve advance in lock-step,
+    //   A x2_hat and A Q^-1 u are one pass, A^T (A Q^-1 u) and A^T (A x2_hat) (next iteration's warm-start residual) another —
+    // 2 max(k1,k2) + 2 passes per iteration instead of 2 (k1+k2) + 6; every product keeps its own arithmetic.
+    const bool fuse = cfg_.fuse_passes != 0 && cfg_.redundant_passes == 0;
     double sum_d = 0;
     VH(vampomi_denoise(ctx_, gam1_, probs_.data(), vars_.data(), (int)probs_.size(), it > 1, rho, &sum_d));   // :203-219
     alpha1_ = sum_d / (double)Mt_;                                              // :221-223
     eta1_ = gam1_ / alpha1_;
-    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X1, VAMPOMI_V_Z1));                       // :232
+    if (!fuse) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X1, VAMPOMI_V_Z1));            // :232
     VH(dump(x1_scaled, r1_scaled));                                             // :235-249
     gam2_ = clampg(eta1_ - gam1_);                                              // :255-256
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R2, eta1_, VAMPOMI_V_X1, -gam1_, VAMPOMI_V_R1, gam2_));   // :259-261
 
-    // err_measures(1) (:760-852), true-gam2 diagnostic (:264-270) and the NMSE sums (:409-413) in one reduction launch
-    {
+    // err_measures(1) (:760-852), true-gam2 diagnostic (:264-270) and the NMSE sums (:409-413) in one reduction launch;
+    // needs z1 = A x1_hat, so in the fused schedule it runs after the first pass of the solves
+    const double gam1_used = gam1_;
+    auto measures1 = [&]() -> int {
         const int kind[10] = {VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DIFF2, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT,
                               VAMPOMI_SQDEV, VAMPOMI_DIFF2, VAMPOMI_DOT};
         const int a[10] = {VAMPOMI_V_X1, VAMPOMI_V_X1, VAMPOMI_V_TRUE, VAMPOMI_V_Y, VAMPOMI_V_Y, VAMPOMI_V_Z1, VAMPOMI_V_Z1,
@@ -192,12 +200,13 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
             std::cout << "Corr(x1_hat, x0) = " << corr << std::endl;
             std::cout << "Corr(y_hat, y)^2 = " << corr_y * corr_y << std::endl << "R2 = " << R2 << std::endl
                       << "L2(y_hat, y) = " << l2_pred_err << std::endl;
+            std::cout << "alpha1 = " << alpha1_ << std::endl << "gam1 = " << gam1_used << std::endl << "gam2 = " << gam2_ << std::endl
+                      << "true gam2 = " << res->true_gam2 << std::endl << "______________________" << std::endl << "->LMMSE" << std::endl;
         }
-    }
+        return VAMPOMI_OK;
+    };
     res->params[0] = alpha1_; res->params[1] = gam1_;                           // :275-276
-    if (verbose)
-        std::cout << "alpha1 = " << alpha1_ << std::endl << "gam1 = " << gam1_ << std::endl << "gam2 = " << gam2_ << std::endl
-                  << "true gam2 = " << res->true_gam2 << std::endl << "______________________" << std::endl << "->LMMSE" << std::endl;
+    if (!fuse) VH(measures1());
 
     VH(vampomi_draw_probe(ctx_, cfg_.seed, it));                                // :295-296
     if (cfg_.redundant_passes || !aty_ready_) {                                 // v = gamw * A^T y + gam2 * r2, :303-306
@@ -207,10 +216,21 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_V, gamw_, VAMPOMI_V_ATY, gam2_, VAMPOMI_V_R2, 1.0));
     int k1 = 0, k2 = 0;
     double rel = 0, vmu = 0;
-    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, it > 1, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel,
-                        nullptr));                                              // :308-311
-    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2,
-                        &rel, &vmu));                                           // g2d_onsager, :494-501
+    if (!fuse) {
+        VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, it > 1, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel,
+                            nullptr));                                          // :308-311
+        VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2,
+                            &rel, &vmu));                                       // g2d_onsager, :494-501
+    } else {
+        const int rhs[2] = {VAMPOMI_V_V, VAMPOMI_V_BERN}, sol[2] = {VAMPOMI_V_X2, VAMPOMI_V_QINV_BERN};
+        const int warm[2] = {it > 1 ? 1 : 0, 0}, ata[2] = {ata_x2_ready_ ? VAMPOMI_V_ATA_X2 : -1, -1}, ons[2] = {0, 1};
+        int its[2] = {0, 0};
+        double rels[2], vmus[2];
+        VH(vampomi_cg_solve_pair(ctx_, rhs, sol, warm, ata, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, ons, VAMPOMI_V_X1,
+                                 VAMPOMI_V_Z1, its, rels, vmus));
+        k1 = its[0]; k2 = its[1]; vmu = vmus[1];
+        VH(measures1());
+    }
     alpha2_ = gam2_ * vmu;
     res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
     eta2_ = gam2_ / alpha2_;                                                    // :341
@@ -220,10 +240,18 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R1, eta2_, VAMPOMI_V_X2, -gam2_, VAMPOMI_V_R2, gam1_));   // :348-350
 
     // updateNoisePrec (:504-529) + err_measures(2) share A x2_hat; the reference computes it twice (:508, :826)
-    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
-    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));           // :518
-    VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));            // :519
-    if (cfg_.redundant_passes) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    if (!fuse) {
+        VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+        VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));       // :518
+        VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));        // :519
+        if (cfg_.redundant_passes) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    } else {
+        const int xin[2] = {VAMPOMI_V_X2, VAMPOMI_V_QINV_BERN}, xout[2] = {VAMPOMI_V_Z2, VAMPOMI_V_USER_N0};
+        VH(vampomi_ax_multi_dev(ctx_, 2, xin, xout));
+        const int pin[2] = {VAMPOMI_V_USER_N0, VAMPOMI_V_Z2}, pout[2] = {VAMPOMI_V_USER_M0, VAMPOMI_V_ATA_X2};
+        VH(vampomi_atx_multi_dev(ctx_, 2, pin, pout));                          // A^T A x2_hat: the next iteration's :681-684
+        ata_x2_ready_ = true;
+    }
     {
         const int kind[9] = {VAMPOMI_DIFF2, VAMPOMI_DOT, VAMPOMI_SQDEV, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT, VAMPOMI_DOT,
                              VAMPOMI_DOT, VAMPOMI_DOT};
@@ -305,10 +333,8 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     if (verbose)
         std::cout << "alpha1 = " << alpha1_ << std::endl << "beta1 = " << beta1 << std::endl << "tau1 = " << tau1_ << std::endl;
 
-    auto confusion = [&](int xvec, double* out6, double corr) -> int {          // :271-282 / :403-415
-        // A (x/sqrt(N)) then probit prediction at threshold 0.5 and the confusion matrix, on the host (N values)
-        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, xvec, 0.0, xvec, sqrtN));
-        VH(vampomi_ax_dev(ctx_, VAMPOMI_V_USER_M0, VAMPOMI_V_USER_N0));
+    // A (x/sqrt(N)) (:271, :403), then the probit prediction at threshold 0.5 and the confusion matrix on the host (N values)
+    auto confusion_eval = [&](double* out6, double corr) -> int {               // :272-282 / :404-415
         VH(vampomi_vec_get(ctx_, VAMPOMI_V_USER_N0, zbuf_.data()));
         int TP = 0, TN = 0, FP = 0, FN = 0;
         for (int i = 0; i < N_; i++) {
@@ -324,9 +350,18 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         out6[5] = corr;
         return VAMPOMI_OK;
     };
-    VH(confusion(VAMPOMI_V_X1, res->metrics, x1_corr));
-    if (verbose) std::cout << "Corr(x1_hat,x0) = " << x1_corr << std::endl << "Accuracy1 = " << res->metrics[4] << std::endl
-                           << std::endl << "->LMMSE" << std::endl;
+    auto confusion = [&](int xvec, double* out6, double corr) -> int {
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M1, 1.0, xvec, 0.0, xvec, sqrtN));
+        VH(vampomi_ax_dev(ctx_, VAMPOMI_V_USER_M1, VAMPOMI_V_USER_N0));
+        return confusion_eval(out6, corr);
+    };
+    const bool fuse = cfg_.fuse_passes != 0 && cfg_.redundant_passes == 0;      // see step_linear
+    auto report1 = [&]() {
+        if (verbose) std::cout << "Corr(x1_hat,x0) = " << x1_corr << std::endl << "Accuracy1 = " << res->metrics[4] << std::endl
+                               << std::endl << "->LMMSE" << std::endl;
+    };
+    if (!fuse) { VH(confusion(VAMPOMI_V_X1, res->metrics, x1_corr)); report1(); }
+    else VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M1, 1.0, VAMPOMI_V_X1, 0.0, VAMPOMI_V_X1, sqrtN));
 
     // LMMSE for x (:296-349)
     VH(vampomi_draw_probe(ctx_, cfg_.seed, it));
@@ -334,8 +369,20 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_V, tau2, VAMPOMI_V_USER_M0, gam2_, VAMPOMI_V_R2, 1.0));   // :302-303
     int k1 = 0, k2 = 0;
     double rel = 0, vmu = 0;
-    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel, nullptr));   // :307
-    VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2, &rel, &vmu));
+    if (!fuse) {
+        VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel, nullptr));   // :307
+        VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2, &rel, &vmu));
+    } else {                                                                    // both solves in lock-step; A (x1/sqrt(N)) rides on their first pass
+        const int rhs[2] = {VAMPOMI_V_V, VAMPOMI_V_BERN}, sol[2] = {VAMPOMI_V_X2, VAMPOMI_V_QINV_BERN};
+        const int warm[2] = {0, 0}, ata[2] = {-1, -1}, ons[2] = {0, 1};
+        int its[2] = {0, 0};
+        double rels[2], vmus[2];
+        VH(vampomi_cg_solve_pair(ctx_, rhs, sol, warm, ata, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, ons, VAMPOMI_V_USER_M1,
+                                 VAMPOMI_V_USER_N0, its, rels, vmus));
+        k1 = its[0]; k2 = its[1]; vmu = vmus[1];
+        VH(confusion_eval(res->metrics, x1_corr));
+        report1();
+    }
     const double alpha2 = gam2_ * vmu;                                          // :311
     res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
     double x2_corr;
@@ -351,7 +398,12 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R1, 1.0, VAMPOMI_V_X2, -alpha2, VAMPOMI_V_R2, 1 - alpha2));   // :337-338
     gam1_ = clampg(gam2_ * (1 - alpha2) / alpha2);                              // :345-346
     // LMMSE for z (:352-376)
-    VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    if (!fuse) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
+    else {                                                                      // A x2_hat and A (x2_hat/sqrt(N)) (:403) in one pass
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M1, 1.0, VAMPOMI_V_X2, 0.0, VAMPOMI_V_X2, sqrtN));
+        const int xin[2] = {VAMPOMI_V_X2, VAMPOMI_V_USER_M1}, xout[2] = {VAMPOMI_V_Z2, VAMPOMI_V_USER_N0};
+        VH(vampomi_ax_multi_dev(ctx_, 2, xin, xout));
+    }
     const double beta2 = (double)Mt_ / N_ * (1 - alpha2);
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_P1, 1.0, VAMPOMI_V_Z2, -beta2, VAMPOMI_V_P2, 1 - beta2));     // :367-368
     tau1_ = clampg(tau2 * (1 - beta2) / beta2);                                 // :375-376
@@ -359,7 +411,8 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     if (verbose)
         std::cout << "alpha2 = " << alpha2 << std::endl << "beta2 = " << beta2 << std::endl << "gam1 = " << gam1_ << std::endl
                   << "gam2 = " << gam2_ << std::endl << "tau2 = " << tau2 << std::endl;
-    VH(confusion(VAMPOMI_V_X2, res->metrics + 6, x2_corr));
+    if (!fuse) VH(confusion(VAMPOMI_V_X2, res->metrics + 6, x2_corr));
+    else VH(confusion_eval(res->metrics + 6, x2_corr));
     if (verbose) std::cout << "Corr(x2_hat, x0) = " << x2_corr << std::endl << "Accuracy2 = " << res->metrics[10] << std::endl;
     res->n_params = 8; res->n_metrics = 12;
     alpha2_ = alpha2;
@@ -452,6 +505,7 @@ void vampomi_solver_default_config(vampomi_solver_config* cfg) {
     for (int i = 0; i < 10; i++) { cfg->vars[i] = vars[i]; cfg->probs[i] = probs[i]; }
     cfg->seed = 0;
     cfg->redundant_passes = 0;
+    cfg->fuse_passes = 1;
 }
 
 }  // extern "C"

@@ -39,6 +39,7 @@ private:
     std::vector<double> probs_, vars_;     // vars_ are the internal ones (x N, src/vamp.cpp:87-88)
     std::vector<double> y_host_, zbuf_;
     bool aty_ready_ = false;
+    bool ata_x2_ready_ = false;   // VAMPOMI_V_ATA_X2 holds A^T A x2_hat of the previous iteration (fused schedule)
     long long passes_at_start_ = 0;
 };
 

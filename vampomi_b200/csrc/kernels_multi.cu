@@ -20,8 +20,8 @@
 namespace vampomi {
 
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int K, int U>
-__global__ void __launch_bounds__(256) k_ax_multi(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
+template <typename T, int K, int RV, int U>
+__global__ void __launch_bounds__(256, (K * RV >= 4 ? 1 : 2)) k_ax_multi(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                   const double* __restrict__ msig, MultiVec mv, int tile_rows, int cols_per_chunk,
                                                   long long M, double* __restrict__ partial, int nchunks) {
     constexpr int VE = V32<T>::VE;
@@ -35,60 +35,76 @@ __global__ void __launch_bounds__(256) k_ax_multi(const T* __restrict__ A, size_
     const long long c0 = (long long)blockIdx.y * cols_per_chunk;
     long long c1 = c0 + cols_per_chunk;
     if (c1 > M) c1 = M;
-    const int off = tid * VE;
-    const bool valid = off < tile_rows && rbase + off < ld;
-    const T* ap = A + rbase + (valid ? off : 0);
-    double acc[K][VE];
+    const T* ap[RV];
+    bool valid[RV];
+    double acc[K][RV][VE];
 #pragma unroll
-    for (int k = 0; k < K; k++)
+    for (int rv = 0; rv < RV; rv++) {
+        const int off = (rv * 256 + tid) * VE;
+        valid[rv] = off < tile_rows && rbase + off < ld;
+        ap[rv] = A + rbase + (valid[rv] ? off : 0);
 #pragma unroll
-        for (int e = 0; e < VE; e++) acc[k][e] = 0.0;
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int e = 0; e < VE; e++) acc[k][rv][e] = 0.0;
+    }
 
     long long j = c0;
     for (; j + U <= c1; j += U) {
-        V32<T> a[U];
-        double m[U], w[K][U];
+        V32<T> a[U][RV];
 #pragma unroll
         for (int u = 0; u < U; u++)
-            if (valid) a[u] = V32<T>::stream(ap + (size_t)(j + u) * ld);
+#pragma unroll
+            for (int rv = 0; rv < RV; rv++)
+                if (valid[rv]) a[u][rv] = V32<T>::stream(ap[rv] + (size_t)(j + u) * ld);
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            m[u] = __ldg(mave + j + u);
-            const double sg = __ldg(msig + j + u);
+            const double m = __ldg(mave + j + u), sg = __ldg(msig + j + u);
+            double w[K];
 #pragma unroll
-            for (int k = 0; k < K; k++) w[k][u] = active[k] ? sg * __ldg(mv.in[k] + j + u) : 0.0;     // sig_phen_i, src/data.cpp:354
-        }
-        if (valid) {
+            for (int k = 0; k < K; k++) w[k] = active[k] ? sg * __ldg(mv.in[k] + j + u) : 0.0;       // sig_phen_i, src/data.cpp:354
 #pragma unroll
-            for (int u = 0; u < U; u++) {
+            for (int rv = 0; rv < RV; rv++) {
+                if (valid[rv]) {
 #pragma unroll
-                for (int e = 0; e < VE; e++) {
-                    const double d = a[u].val(e) - m[u];                                              // meth[j] - ave, src/data.cpp:360
+                    for (int e = 0; e < VE; e++) {
+                        const double d = a[u][rv].val(e) - m;                                         // meth[j] - ave, src/data.cpp:360
 #pragma unroll
-                    for (int k = 0; k < K; k++) acc[k][e] = fma(d, w[k][u], acc[k][e]);
+                        for (int k = 0; k < K; k++) acc[k][rv][e] = fma(d, w[k], acc[k][rv][e]);
+                    }
                 }
             }
         }
     }
     for (; j < c1; j++) {
         const double m = __ldg(mave + j), sg = __ldg(msig + j);
-        if (valid) {
-            V32<T> a = V32<T>::stream(ap + (size_t)j * ld);
+        double w[K];
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const double w = active[k] ? sg * __ldg(mv.in[k] + j) : 0.0;
+        for (int k = 0; k < K; k++) w[k] = active[k] ? sg * __ldg(mv.in[k] + j) : 0.0;
 #pragma unroll
-                for (int e = 0; e < VE; e++) acc[k][e] = fma(a.val(e) - m, w, acc[k][e]);
+        for (int rv = 0; rv < RV; rv++) {
+            if (valid[rv]) {
+                V32<T> a = V32<T>::stream(ap[rv] + (size_t)j * ld);
+#pragma unroll
+                for (int e = 0; e < VE; e++) {
+                    const double d = a.val(e) - m;
+#pragma unroll
+                    for (int k = 0; k < K; k++) acc[k][rv][e] = fma(d, w[k], acc[k][rv][e]);
+                }
             }
         }
     }
-    if (!valid) return;
 #pragma unroll
     for (int k = 0; k < K; k++) {
         if (!active[k]) continue;
-        double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase + off;
+        double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase;
 #pragma unroll
-        for (int q = 0; q < VE / 4; q++) st256(prow + 4 * q, d4{acc[k][4 * q], acc[k][4 * q + 1], acc[k][4 * q + 2], acc[k][4 * q + 3]});
+        for (int rv = 0; rv < RV; rv++) {
+            if (!valid[rv]) continue;
+#pragma unroll
+            for (int q = 0; q < VE / 4; q++)
+                st256(prow + (rv * 256 + tid) * VE + 4 * q, d4{acc[k][rv][4 * q], acc[k][rv][4 * q + 1], acc[k][rv][4 * q + 2], acc[k][rv][4 * q + 3]});
+        }
     }
 }
 
@@ -101,6 +117,11 @@ __global__ void __launch_bounds__(256) k_ax_reduce_multi(const double* __restric
     constexpr int ROWS = 256 / SL;
     static_assert(ROWS == 32, "one warp owns the CTA's rows in the exchange");
     const int k = blockIdx.y;
+    // nothing to do for any vector (look-ahead launch of a finished solve): leave the exchange sequence untouched, exactly
+    // like the single-vector kernel — the sequence number advances only for launches in which an exchange really runs
+    bool any = false;
+    for (int q = 0; q < mv.K; q++) any |= mv.done[q] == nullptr || *mv.done[q] == 0;
+    if (!any) return;
     const bool active = mv.done[k] == nullptr || *mv.done[k] == 0;
     const int r = threadIdx.x % ROWS, s = threadIdx.x / ROWS;
     const int i = blockIdx.x * ROWS + r;
@@ -241,6 +262,106 @@ __global__ void __launch_bounds__(256) k_atx_tiled(const T* __restrict__ A, size
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// A^T [p_0 .. p_{K-1}] over a row tile with the K tiles of p staged in SHARED memory: every warp walks its own C columns
+// down the tile (U steps in flight), reads p with conflict-free LDS.128 — each piece of p serves C columns, so shared
+// memory carries K/C bytes per byte of A — and needs one warp reduction per (vector, column) at the end of the tile:
+// no block barrier in the loop, few registers (two or three CTAs per SM).
+// ---------------------------------------------------------------------------------------------------------------
+// Position (in doubles) of the q-th pair of the VE values that belong to 32-byte vector `v` of the tile: the 32 lanes of a warp
+// read 32 consecutive vectors, so pair q of lane l sits at ((q*32 + l)*2) inside the block — consecutive lanes, consecutive
+// 16-byte words, no bank conflicts (the natural layout would put lanes 32 or 64 bytes apart).
+template <int VE>
+__device__ __forceinline__ int sp_pos(int v, int q) { return (v >> 5) * (32 * VE) + ((q << 5) + (v & 31)) * 2; }
+
+template <typename T, int K, int C, int U>
+__global__ void __launch_bounds__(256) k_atx_smem(const T* __restrict__ A, size_t ld, const double* __restrict__ mave, MultiVec mv,
+                                                  int tile_rows, int cols_per_chunk, long long M, double* __restrict__ partial) {
+    constexpr int VE = V32<T>::VE;
+    extern __shared__ __align__(32) double sp[];                 // [K][sp_stride], swizzled (sp_pos)
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = mv.done[k] == nullptr || *mv.done[k] == 0; any |= active[k]; }
+    if (!any) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t rbase = (size_t)blockIdx.x * tile_rows;
+    int rows = tile_rows;
+    if (rbase + rows > ld) rows = (int)(ld - rbase);             // ld is a multiple of 16, so is tile_rows -> whole vectors
+    const int sp_stride = (tile_rows + 32 * VE - 1) / (32 * VE) * (32 * VE);      // one vector of p, padded to whole 32-lane blocks
+#pragma unroll
+    for (int k = 0; k < K; k++)
+        for (int i = tid * 4; i < rows; i += 256 * 4) {
+            double2 lo = make_double2(0.0, 0.0), hi = lo;
+            if (active[k]) { PV<4> pv = PV<4>::load(mv.in[k] + rbase + i); lo = make_double2(pv.v[0], pv.v[1]); hi = make_double2(pv.v[2], pv.v[3]); }
+            const int v = i / VE, q0 = (i % VE) / 2;
+            *reinterpret_cast<double2*>(sp + (size_t)k * sp_stride + sp_pos<VE>(v, q0)) = lo;
+            *reinterpret_cast<double2*>(sp + (size_t)k * sp_stride + sp_pos<VE>(v, q0 + 1)) = hi;
+        }
+    __syncthreads();
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+    const int nvec = rows / VE;
+    const T* abase = A + rbase;
+    double* pout = partial + (size_t)blockIdx.x * K * M;         // [tile][k][M]
+    for (long long j0 = c0 + (long long)wid * C; j0 < c1; j0 += 8 * C) {
+        const T* col[C];
+        double m[C], acc[K][C][2];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            const long long j = j0 + cc < c1 ? j0 + cc : c1 - 1;
+            col[cc] = abase + (size_t)j * ld;
+            m[cc] = __ldg(mave + j);
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k][cc][0] = acc[k][cc][1] = 0.0;
+        }
+        int v = lane;
+        for (; v + 32 * (U - 1) < nvec; v += 32 * U) {
+            V32<T> a[U][C];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::stream(col[cc] + (size_t)VE * (v + 32 * u));
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    double pv[VE];
+#pragma unroll
+                    for (int q = 0; q < VE / 2; q++) {
+                        const double2 t = *reinterpret_cast<const double2*>(sp + (size_t)k * sp_stride + sp_pos<VE>(v + 32 * u, q));
+                        pv[2 * q] = t.x; pv[2 * q + 1] = t.y;
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                        for (int e = 0; e < VE; e++)              // (meth[i] - mu) * phen[i], src/data.cpp:304
+                            acc[k][cc][e & 1] = fma(a[u][cc].val(e) - m[cc], pv[e], acc[k][cc][e & 1]);
+                }
+            }
+        }
+        for (; v < nvec; v += 32) {
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
+#pragma unroll
+                for (int k = 0; k < K; k++)
+#pragma unroll
+                    for (int e = 0; e < VE; e++)
+                        acc[k][cc][e & 1] = fma(a.val(e) - m[cc], sp[(size_t)k * sp_stride + sp_pos<VE>(v, e / 2) + (e & 1)], acc[k][cc][e & 1]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++)
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                const double sw = warp_sum(acc[k][cc][0] + acc[k][cc][1]);
+                if (lane == 0 && active[k] && j0 + cc < c1) pout[(size_t)k * M + j0 + cc] = sw;
+            }
+    }
+}
+
 // out_k[j] = (msig[j] * sum_tiles partial[tile][k][j]) * scale; blockIdx.y = k
 __global__ void __launch_bounds__(256) k_atx_reduce(const double* __restrict__ partial, int ntiles, int K, long long M,
                                                     const double* __restrict__ msig, double scale, MultiVec mv) {
@@ -272,12 +393,11 @@ static int ensure_buf(vampomi_ctx* c, double** buf, size_t* cap, size_t need) {
     return VAMPOMI_OK;
 }
 
-template <typename T, int K>
-static int ax_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+template <typename T, int K, int RV, int U>
+static int ax_multi_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     constexpr int VE = V32<T>::VE;
-    constexpr int U = sizeof(T) == 8 ? 4 : 2;
-    auto kern = k_ax_multi<T, K, U>;
-    const int cap = 256 * VE;
+    auto kern = k_ax_multi<T, K, RV, U>;
+    const int cap = 256 * VE * RV;
     const int ntiles = (int)((c->ld + cap - 1) / cap);
     const size_t tr = (c->ld + ntiles - 1) / ntiles;
     const int tile_rows = (int)((tr + 15) / 16 * 16);
@@ -312,6 +432,22 @@ static int ax_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     return VAMPOMI_OK;
 }
 
+// tile shape (32-byte vectors per thread per column, columns in flight): knobs multi_ax_rv / multi_ax_unroll, 0 = default
+template <typename T, int K>
+static int ax_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+    int rv = c->tune.multi_ax_rv, u = c->tune.multi_ax_unroll;
+    if (rv == 0) rv = 1;
+    if (u == 0) u = sizeof(T) == 8 ? 4 : 2;
+    switch (rv * 10 + u) {
+        case 12: return ax_multi_launch<T, K, 1, 2>(c, A, mv);
+        case 14: return ax_multi_launch<T, K, 1, 4>(c, A, mv);
+        case 18: return ax_multi_launch<T, K, 1, 8>(c, A, mv);
+        case 22: return ax_multi_launch<T, K, 2, 2>(c, A, mv);
+        case 24: return ax_multi_launch<T, K, 2, 4>(c, A, mv);
+        default: set_error("ax_multi: unsupported tile shape rv=%d unroll=%d", rv, u); return VAMPOMI_ERR_ARG;
+    }
+}
+
 int launch_ax_multi(vampomi_ctx* c, const MultiVec& mv) {
     if (mv.K < 1 || mv.K > XCHG_KMAX) { set_error("ax_multi: 1..%d vectors", XCHG_KMAX); return VAMPOMI_ERR_ARG; }
     if (c->storage == 1) {
@@ -322,8 +458,18 @@ int launch_ax_multi(vampomi_ctx* c, const MultiVec& mv) {
                     case 3: return ax_multi_t<double, 3>(c, c->A, mv); default: return ax_multi_t<double, 4>(c, c->A, mv); }
 }
 
+static int atx_reduce_launch(vampomi_ctx* c, int ntiles, int K, const MultiVec& mv) {
+    long long rb = (c->M + 255) / 256;
+    if (rb > 4 * c->num_sms) rb = 4 * c->num_sms;
+    k_atx_reduce<<<dim3((unsigned)rb, K), 256, 0, c->stream>>>(c->atx_partial, ntiles, K, c->M, c->msig, 1.0 / sqrt((double)c->N), mv);
+    VO_CUDA(cudaGetLastError());
+    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
+    return VAMPOMI_OK;
+}
+
+// register-tiled form (knob multi_atx_impl = 0)
 template <typename T, int K>
-static int atx_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+static int atx_tiled_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     constexpr int VE = V32<T>::VE;
     constexpr int RV = sizeof(T) == 8 ? 2 : 1;
     constexpr int CB = 4;
@@ -344,23 +490,75 @@ static int atx_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     int sp = prof_begin(c, 2, (double)c->M * c->N * (double)c->elem_bytes);
     kern<<<dim3(ntiles, nchunks), 256, 0, c->stream>>>(A, c->ld, c->mave, mv, tile_rows, cols_per_chunk, c->M, c->atx_partial);
     VO_CUDA(cudaGetLastError());
-    long long rb = (c->M + 255) / 256;
-    if (rb > 4 * c->num_sms) rb = 4 * c->num_sms;
-    k_atx_reduce<<<dim3((unsigned)rb, K), 256, 0, c->stream>>>(c->atx_partial, ntiles, K, c->M, c->msig, 1.0 / sqrt((double)c->N), mv);
+    int rc = atx_reduce_launch(c, ntiles, K, mv);
     prof_end(c, sp);
+    return rc;
+}
+
+// shared-memory form (knob multi_atx_impl = 1, the default): rows per tile from knob multi_atx_tile (0 = 4096 / K-independent)
+template <typename T, int K, int C, int U>
+static int atx_smem_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+    constexpr int VE = V32<T>::VE;
+    auto kern = k_atx_smem<T, K, C, U>;
+    int want = c->tune.multi_atx_tile > 0 ? c->tune.multi_atx_tile : 4096;
+    want = (want + 32 * VE - 1) / (32 * VE) * (32 * VE);
+    const int ntiles = (int)((c->ld + want - 1) / want);
+    const size_t tr = (c->ld + ntiles - 1) / ntiles;
+    const int tile_rows = (int)((tr + 15) / 16 * 16);
+    const int sp_stride = (tile_rows + 32 * VE - 1) / (32 * VE) * (32 * VE);
+    const size_t smem = (size_t)K * sp_stride * sizeof(double);
+    static thread_local const void* attr_set[8] = {};
+    static thread_local size_t attr_bytes[8] = {};
+    {   // raise the dynamic shared-memory limit of this instantiation once per (thread, kernel, size)
+        int slot = -1;
+        for (int i = 0; i < 8; i++) if (attr_set[i] == (const void*)kern) { slot = i; break; }
+        if (slot < 0) for (int i = 0; i < 8; i++) if (attr_set[i] == nullptr) { slot = i; break; }
+        if (slot < 0) slot = 0;
+        if (attr_set[slot] != (const void*)kern || attr_bytes[slot] < smem) {
+            VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[slot] = (const void*)kern; attr_bytes[slot] = smem;
+        }
+    }
+    int per_sm = c->tune.atx_ctas_per_sm;
+    if (per_sm <= 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    long long nch = (long long)c->num_sms * per_sm / ntiles;
+    if (nch < 1) nch = 1;
+    long long maxch = (c->M + 8 * C - 1) / (8 * C);
+    if (nch > maxch) nch = maxch;
+    int cols_per_chunk = (int)((c->M + nch - 1) / nch);
+    const int nchunks = (int)((c->M + cols_per_chunk - 1) / cols_per_chunk);
+    VO_CHECK(ensure_buf(c, &c->atx_partial, &c->atx_partial_elems, (size_t)ntiles * K * c->M));
+    if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
+    int sp = prof_begin(c, 2, (double)c->M * c->N * (double)c->elem_bytes);
+    kern<<<dim3(ntiles, nchunks), 256, smem, c->stream>>>(A, c->ld, c->mave, mv, tile_rows, cols_per_chunk, c->M, c->atx_partial);
     VO_CUDA(cudaGetLastError());
-    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
-    return VAMPOMI_OK;
+    int rc = atx_reduce_launch(c, ntiles, K, mv);
+    prof_end(c, sp);
+    return rc;
+}
+
+template <typename T, int K>
+static int atx_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
+    if (c->tune.multi_atx_impl == 0) return atx_tiled_launch<T, K>(c, A, mv);
+    int cc = c->tune.multi_atx_cols, u = c->tune.multi_atx_unroll;
+    if (cc == 0) cc = 2;
+    if (u == 0) u = 2;
+    switch (cc * 10 + u) {
+        case 12: return atx_smem_launch<T, K, 1, 2>(c, A, mv);
+        case 14: return atx_smem_launch<T, K, 1, 4>(c, A, mv);
+        case 22: return atx_smem_launch<T, K, 2, 2>(c, A, mv);
+        case 24: return atx_smem_launch<T, K, 2, 4>(c, A, mv);
+        case 42: return atx_smem_launch<T, K, 4, 2>(c, A, mv);
+        default: set_error("atx_multi: unsupported shape cols=%d unroll=%d", cc, u); return VAMPOMI_ERR_ARG;
+    }
 }
 
 int launch_atx_multi(vampomi_ctx* c, const MultiVec& mv) {
-    if (mv.K < 1 || mv.K > XCHG_KMAX) { set_error("atx_multi: 1..%d vectors", XCHG_KMAX); return VAMPOMI_ERR_ARG; }
-    if (c->storage == 1) {
-        switch (mv.K) { case 1: return atx_multi_t<float, 1>(c, c->A32, mv); case 2: return atx_multi_t<float, 2>(c, c->A32, mv);
-                        default: set_error("atx_multi: at most 2 vectors"); return VAMPOMI_ERR_ARG; }
-    }
-    switch (mv.K) { case 1: return atx_multi_t<double, 1>(c, c->A, mv); case 2: return atx_multi_t<double, 2>(c, c->A, mv);
-                    default: set_error("atx_multi: at most 2 vectors"); return VAMPOMI_ERR_ARG; }
+    if (mv.K < 1 || mv.K > 2) { set_error("atx_multi: 1 or 2 vectors"); return VAMPOMI_ERR_ARG; }
+    if (c->storage == 1) return mv.K == 1 ? atx_multi_t<float, 1>(c, c->A32, mv) : atx_multi_t<float, 2>(c, c->A32, mv);
+    return mv.K == 1 ? atx_multi_t<double, 1>(c, c->A, mv) : atx_multi_t<double, 2>(c, c->A, mv);
 }
 
 }  // namespace vampomi

@@ -308,153 +308,187 @@ int launch_pvals_se(vampomi_ctx* c, const double* r1_dev, double sd, double* out
 
 // ---------------------------------------------------------------------------------------------------------------
 // Preconditioned CG vector steps (src/vamp.cpp:671-757). All scalars live in CgScalars on the device.
+// Every kernel handles the S <= 2 systems of a batch (cg.cu: the LMMSE solve and the Onsager solve of one VAMP iteration
+// share the operator and run in lock-step): one launch, one grid reduction and one cross-GPU exchange for all of them.
+// A system whose done flag is set is skipped; the flags are identical on all GPUs, so the skips agree everywhere.
+// Packed sums: sums[s] = <d,p>; sums[4 + 3s .. 4 + 3s + 2] = <v,mu>, <r,z>, <r,r> (init: sums[4 + 2s], [4 + 2s + 1] = <r,z>, <v,v>).
 // ---------------------------------------------------------------------------------------------------------------
-// r = v - (tau*AtA mu + gam2*mu) [warm] or r = v; z = r/diag; p = z; sums[0] = <r,z>, sums[1] = <v,v>   (:679-690)
-__global__ void __launch_bounds__(RED_THREADS) k_cg_init(const double* __restrict__ v, double* __restrict__ mu,
-                                                         const double* __restrict__ atx_out, double* __restrict__ r,
-                                                         double* __restrict__ z, double* __restrict__ p, long long M, int warm,
-                                                         double tau, double gam2, double diag, double* __restrict__ partials,
-                                                         unsigned int* ticket, double* __restrict__ out, Xchg xc) {
-    double acc[2] = {0.0, 0.0};
-    GRID_STRIDE(i, M) {
-        const double vi = v[i];
-        double ri;
-        if (warm) {
-            double res = atx_out[i] * tau;          // lmmse_mult, :656-659
-            res += gam2 * mu[i];
-            ri = vi - res;
-        } else {
-            mu[i] = 0.0;
-            ri = vi;
+// r = v - (tau*AtA mu + gam2*mu) [warm] or r = v; z = r/diag; p = z   (:679-690)
+template <int S>
+__global__ void __launch_bounds__(RED_THREADS) k_cg_init(CgBatch b, long long M, double tau, double gam2, double diag,
+                                                         double* __restrict__ partials, unsigned int* ticket,
+                                                         double* __restrict__ out, Xchg xc) {
+    double acc[2 * S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const CgSys& q = b.s[s];
+        double a0 = 0.0, a1 = 0.0;
+        GRID_STRIDE(i, M) {
+            const double vi = q.v[i];
+            double ri;
+            if (q.warm) {
+                double res = q.atx_out[i] * tau;        // lmmse_mult, :656-659
+                res += gam2 * q.mu[i];
+                ri = vi - res;
+            } else {
+                q.mu[i] = 0.0;
+                ri = vi;
+            }
+            const double zi = ri / diag;
+            q.r[i] = ri; q.z[i] = zi; q.p[i] = zi;
+            a0 = fma(ri, zi, a0);
+            a1 = fma(vi, vi, a1);
         }
-        const double zi = ri / diag;
-        r[i] = ri; z[i] = zi; p[i] = zi;
-        acc[0] = fma(ri, zi, acc[0]);
-        acc[1] = fma(vi, vi, acc[1]);
+        acc[2 * s] = a0; acc[2 * s + 1] = a1;
     }
-    grid_reduce(acc, 2, partials, ticket, out, &xc);
+    grid_reduce(acc, 2 * S, partials, ticket, out, &xc);
 }
 
-__global__ void k_cg_init_finish(CgScalars* cg, const double* __restrict__ sums) {
-    cg->rz[0] = sums[0]; cg->rz[1] = sums[0];
-    cg->vv = sums[1];
+__global__ void k_cg_init_finish(CgBatch b, const double* __restrict__ sums) {
+    const int s = threadIdx.x;
+    if (s >= b.S) return;
+    CgScalars* cg = b.s[s].cg;
+    cg->rz[0] = sums[2 * s]; cg->rz[1] = sums[2 * s];
+    cg->vv = sums[2 * s + 1];
     cg->prev_onsager[0] = 0.0; cg->prev_onsager[1] = 0.0;
     cg->rel_err = CUDART_NAN; cg->vmu = 0.0;
     cg->done = 0; cg->iters = 0;
 }
 
-// d = tau * AtA p + gam2 * p (lmmse_mult, :656-659); sums[0] = <d,p>
-__global__ void __launch_bounds__(RED_THREADS) k_cg_dp(const double* __restrict__ atx_out, const double* __restrict__ p,
-                                                       double* __restrict__ d, long long M, double tau, double gam2,
-                                                       const CgScalars* __restrict__ cg, double* __restrict__ partials,
-                                                       unsigned int* ticket, double* __restrict__ out, Xchg xc) {
-    if (cg->done) return;
-    double acc = 0.0;
-    GRID_STRIDE(i, M) {
-        const double pi = p[i];
-        double di = atx_out[i] * tau;
-        di += gam2 * pi;
-        d[i] = di;
-        acc = fma(di, pi, acc);
+// d = tau * AtA p + gam2 * p (lmmse_mult, :656-659); out[s] = <d,p>
+template <int S>
+__global__ void __launch_bounds__(RED_THREADS) k_cg_dp(CgBatch b, long long M, double tau, double gam2,
+                                                       double* __restrict__ partials, unsigned int* ticket,
+                                                       double* __restrict__ out, Xchg xc) {
+    bool active[S], any = false;
+#pragma unroll
+    for (int s = 0; s < S; s++) { active[s] = b.s[s].cg->done == 0; any |= active[s]; }
+    if (!any) return;
+    double acc[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const CgSys& q = b.s[s];
+        double a = 0.0;
+        if (active[s]) {
+            GRID_STRIDE(i, M) {
+                const double pi = q.p[i];
+                double di = q.atx_out[i] * tau;
+                di += gam2 * pi;
+                q.d[i] = di;
+                a = fma(di, pi, a);
+            }
+        }
+        acc[s] = a;
     }
-    grid_reduce(&acc, 1, partials, ticket, out, &xc);
+    grid_reduce(acc, S, partials, ticket, out, &xc);
 }
 
-// alpha = <r,z>/<d,p>; mu += alpha p; r -= alpha d; z = r/diag; sums[1..3] = <v,mu>, <r,z>, <r,r>   (:701-706, :728-734)
-__global__ void __launch_bounds__(RED_THREADS) k_cg_step(const double* __restrict__ v, double* __restrict__ mu, double* __restrict__ r,
-                                                         double* __restrict__ z, const double* __restrict__ p,
-                                                         const double* __restrict__ d, long long M, double diag, int parity,
-                                                         const CgScalars* __restrict__ cg, const double* __restrict__ dp,
-                                                         double* __restrict__ partials, unsigned int* ticket,
-                                                         double* __restrict__ out, Xchg xc) {
-    if (cg->done) return;
-    const double alpha = cg->rz[parity] / dp[0];
-    double acc[3] = {0.0, 0.0, 0.0};
-    GRID_STRIDE(i, M) {
-        const double mui = mu[i] + alpha * p[i];
-        const double ri = r[i] - d[i] * alpha;
-        const double zi = ri / diag;
-        mu[i] = mui; r[i] = ri; z[i] = zi;
-        acc[0] = fma(v[i], mui, acc[0]);
-        acc[1] = fma(ri, zi, acc[1]);
-        acc[2] = fma(ri, ri, acc[2]);
+// alpha = <r,z>/<d,p>; mu += alpha p; r -= alpha d; z = r/diag; out[3s..3s+2] = <v,mu>, <r,z>, <r,r>   (:701-706, :728-734)
+template <int S>
+__global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M, double diag, int parity,
+                                                         const double* __restrict__ dp, double* __restrict__ partials,
+                                                         unsigned int* ticket, double* __restrict__ out, Xchg xc) {
+    bool active[S], any = false;
+#pragma unroll
+    for (int s = 0; s < S; s++) { active[s] = b.s[s].cg->done == 0; any |= active[s]; }
+    if (!any) return;
+    double acc[3 * S];
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const CgSys& q = b.s[s];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (active[s]) {
+            const double alpha = q.cg->rz[parity] / dp[s];
+            GRID_STRIDE(i, M) {
+                const double mui = q.mu[i] + alpha * q.p[i];
+                const double ri = q.r[i] - q.d[i] * alpha;
+                const double zi = ri / diag;
+                q.mu[i] = mui; q.r[i] = ri; q.z[i] = zi;
+                a0 = fma(q.v[i], mui, a0);
+                a1 = fma(ri, zi, a1);
+                a2 = fma(ri, ri, a2);
+            }
+        }
+        acc[3 * s] = a0; acc[3 * s + 1] = a1; acc[3 * s + 2] = a2;
     }
-    grid_reduce(acc, 3, partials, ticket, out, &xc);
+    grid_reduce(acc, 3 * S, partials, ticket, out, &xc);
 }
 
 // scalar logic of one CG iteration (:708-726 onsager test, :731-751 beta and residual test) + p = z + beta p (:738-739).
 // Every block recomputes the scalars from read-only inputs (slot `parity`); block 0 publishes slot parity^1.
 // cg->done is written by block 0 while later-scheduled blocks of the SAME launch may already read it at their entry: if they
-// see it set they skip a p update that nothing will read any more (the solve is over), so the race is benign by construction.
-__global__ void __launch_bounds__(RED_THREADS) k_cg_finish(const double* __restrict__ z, double* __restrict__ p, long long M, int parity,
-                                                           double gam2, double tol, int max_iter, int onsager_mode,
-                                                           CgScalars* cg, const double* __restrict__ sums) {
-    if (cg->done) return;
-    const double rz_old = cg->rz[parity];
-    const double vmu = sums[1], rz_new = sums[2], rr = sums[3];
-    int done = 0;
-    double prev_onsager = cg->prev_onsager[parity];
-    if (onsager_mode) {
-        const double onsager = gam2 * vmu;
-        double rel = 1.0;
-        if (onsager != 0.0) rel = fabs((onsager - prev_onsager) / onsager);
-        if (rel < 1e-8) done = 1;
-        prev_onsager = onsager;
-    }
-    double rel_err = CUDART_NAN;
-    if (!done) {
-        double beta = 1.0 / rz_old;                   // pow(<r,z>, -1), :731
-        beta *= rz_new;                               // :736
-        GRID_STRIDE(i, M) p[i] = z[i] + beta * p[i];
-        rel_err = sqrt(rr) / sqrt(cg->vv);            // :742-744
-        if (rel_err < tol) done = 2;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const int iters = cg->iters + 1;
-        if (!done && iters >= max_iter) done = 3;
-        cg->rz[parity ^ 1] = rz_new;
-        cg->prev_onsager[parity ^ 1] = prev_onsager;
-        cg->rel_err = rel_err;
-        cg->vmu = vmu;
-        cg->iters = iters;
-        __threadfence();
-        cg->done = done;
+// see it set they skip a p update that nothing will read any more (that solve is over), so the race is benign by construction.
+template <int S>
+__global__ void __launch_bounds__(RED_THREADS) k_cg_finish(CgBatch b, long long M, int parity, double gam2, double tol, int max_iter,
+                                                           const double* __restrict__ sums) {
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const CgSys& q = b.s[s];
+        CgScalars* cg = q.cg;
+        if (cg->done) continue;
+        const double rz_old = cg->rz[parity];
+        const double vmu = sums[3 * s], rz_new = sums[3 * s + 1], rr = sums[3 * s + 2];
+        int done = 0;
+        double prev_onsager = cg->prev_onsager[parity];
+        if (q.onsager_mode) {
+            const double onsager = gam2 * vmu;
+            double rel = 1.0;
+            if (onsager != 0.0) rel = fabs((onsager - prev_onsager) / onsager);
+            if (rel < 1e-8) done = 1;
+            prev_onsager = onsager;
+        }
+        double rel_err = CUDART_NAN;
+        if (!done) {
+            double beta = 1.0 / rz_old;                   // pow(<r,z>, -1), :731
+            beta *= rz_new;                               // :736
+            GRID_STRIDE(i, M) q.p[i] = q.z[i] + beta * q.p[i];
+            rel_err = sqrt(rr) / sqrt(cg->vv);            // :742-744
+            if (rel_err < tol) done = 2;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const int iters = cg->iters + 1;
+            if (!done && iters >= max_iter) done = 3;
+            cg->rz[parity ^ 1] = rz_new;
+            cg->prev_onsager[parity ^ 1] = prev_onsager;
+            cg->rel_err = rel_err;
+            cg->vmu = vmu;
+            cg->iters = iters;
+            __threadfence();
+            cg->done = done;
+        }
     }
 }
 
-int launch_cg_init(vampomi_ctx* c, const double* v, double* mu, const double* atx_out, int warm, double tau, double gam2,
-                   double diag, double* sums_dev) {
-    k_cg_init<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(v, mu, atx_out, c->mvec[VAMPOMI_V_CG_R], c->mvec[VAMPOMI_V_CG_Z],
-                                                              c->mvec[VAMPOMI_V_CG_P], c->M, warm, tau, gam2, diag,
-                                                              c->red_partials, c->red_tickets, sums_dev, c->xchg);
+int launch_cg_init(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, double* sums_dev) {
+    if (b.S == 1) k_cg_init<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, tau, gam2, diag, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    else k_cg_init<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, tau, gam2, diag, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
-int launch_cg_init_finish(vampomi_ctx* c, const double* sums_dev) {
-    k_cg_init_finish<<<1, 1, 0, c->stream>>>(c->cg, sums_dev);
+int launch_cg_init_finish(vampomi_ctx* c, const CgBatch& b, const double* sums_dev) {
+    k_cg_init_finish<<<1, 32, 0, c->stream>>>(b, sums_dev);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
-int launch_cg_dp(vampomi_ctx* c, const double* atx_out, double tau, double gam2, double* sums_dev) {
-    k_cg_dp<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(atx_out, c->mvec[VAMPOMI_V_CG_P], c->mvec[VAMPOMI_V_CG_D], c->M, tau, gam2,
-                                                            c->cg, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double* sums_dev) {
+    if (b.S == 1) k_cg_dp<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, tau, gam2, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    else k_cg_dp<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, tau, gam2, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
-int launch_cg_step(vampomi_ctx* c, const double* v, double* mu, double diag, int parity, const double* dp_dev, double* sums_dev) {
-    k_cg_step<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(v, mu, c->mvec[VAMPOMI_V_CG_R], c->mvec[VAMPOMI_V_CG_Z],
-                                                              c->mvec[VAMPOMI_V_CG_P], c->mvec[VAMPOMI_V_CG_D], c->M, diag, parity,
-                                                              c->cg, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev) {
+    if (b.S == 1) k_cg_step<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    else k_cg_step<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
-int launch_cg_finish(vampomi_ctx* c, int parity, double gam2, double tol, int max_iter, int onsager_mode, const double* sums_dev) {
-    k_cg_finish<<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(c->mvec[VAMPOMI_V_CG_Z], c->mvec[VAMPOMI_V_CG_P], c->M, parity, gam2,
-                                                                tol, max_iter, onsager_mode, c->cg, sums_dev);
+int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double tol, int max_iter, const double* sums_dev) {
+    if (b.S == 1) k_cg_finish<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, parity, gam2, tol, max_iter, sums_dev);
+    else k_cg_finish<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, parity, gam2, tol, max_iter, sums_dev);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;

@@ -47,9 +47,11 @@ def parse_args():
     ap.add_argument("--Mt", type=int, default=850000)
     ap.add_argument("--cpu-sample-M", type=int, default=4000, help="markers of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--schedule", default="fused", choices=["fused", "plain"],
-                    help="fused (default): matrix products that are known together share one read of the block (lock-step LMMSE + "
-                         "Onsager solves); plain: one product per pass in the reference's order")
+    ap.add_argument("--schedule", default="recycled", choices=["recycled", "fused", "plain"],
+                    help="recycled (default): lock-step LMMSE + Onsager solves sharing every read of the block, products of their "
+                         "solutions kept by the solves themselves; fused: the same without that recycling (every product computed "
+                         "by a pass, sharing reads); plain: one product per pass in the reference's order")
+    ap.add_argument("--no-ab", action="store_true", help="skip the short device-resident legs of the other schedules")
     ap.add_argument("--storage", default="f64", choices=["f64", "f32"],
                     help="f32 = opt-in mode that holds the matrix rounded to FP32 in HBM (arithmetic FP64); NOT the headline configuration")
     return ap.parse_args()
@@ -245,9 +247,9 @@ def main_ours(args):
         sampler.start()
     windows = []
 
-    def leg(e2e):
+    def leg(e2e, schedule=None):
         sol = capi.Solver(sh, y, model="linear", true_signal=beta_sh, gamw=1.0 / (1.0 - H2), seed=PROBE_SEED,
-                          fuse_passes=1 if args.schedule == "fused" else 0)
+                          fuse_passes={"recycled": 2, "fused": 1, "plain": 0}[schedule or args.schedule])
         hist = []
         for _ in range(args.warmup):
             hist.append(sol.step(want_vectors=False))
@@ -284,6 +286,16 @@ def main_ours(args):
 
     ms_dev, hist_dev, prof_dev, cnt_dev = leg(e2e=False)
     ms_e2e, hist_e2e, prof_e2e, cnt_e2e = leg(e2e=True)
+    # the other schedules on the same box, same iterations (device-resident leg only): what each level of pass sharing buys
+    ab = {}
+    if not args.no_ab:
+        for sched in ("plain", "fused", "recycled"):
+            if sched == args.schedule:
+                continue
+            ms_s, hist_s, _, _ = leg(e2e=False, schedule=sched)
+            ab[sched] = {"value": args.steps / (ms_s / 1e3), "ms_per_step": ms_s / args.steps,
+                         "passes": sum(h["matrix_passes"] for h in hist_s),
+                         "cg_iters_per_step": [[h["k1"], h["k2"]] for h in hist_s]}
     if rank == 0:
         sampler.stop()
 
@@ -307,7 +319,7 @@ def main_ours(args):
     iter_gbs_per_gpu = iter_bytes / (ms_dev * 1e-3) / 1e9 / world
     matrix_ms = sum(prof_dev[k]["ms"] for k in prof_dev)
     # kernel behind each profiling slot: in the fused schedule every pass of iterations > 1 is a multi-vector kernel
-    knames = ({"ax_partial": "k_ax_multi", "atx": "k_atx_smem"} if args.schedule == "fused" else {"ax_partial": "k_ax_partial", "atx": "k_atx_cta"})
+    knames = ({"ax_partial": "k_ax_multi", "atx": "k_atx_smem"} if args.schedule != "plain" else {"ax_partial": "k_ax_partial", "atx": "k_atx_cta"})
     products = sum(2 * (h["k1"] + h["k2"]) + 6 for h in hist_dev)                # matrix-vector products the iterations need (the reference streams A for each, plus 2 repeats)
     traffic, traffic_src = ncu_traffic(knames[dom], N, sh.M, bytes_per_launch)
     roofline = {"bound": "hbm", "kernel": knames[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -319,7 +331,7 @@ def main_ours(args):
                 "matrix_kernel_share_of_step": (prof_dev["ax_partial"]["ms"] + prof_dev["atx"]["ms"]) / ms_dev,
                 "phase_ms_per_step": {knames["ax_partial"]: prof_dev["ax_partial"]["ms"] / args.steps,
                                       "k_ax_reduce+allreduce+scale": prof_dev["ax_reduce"]["ms"] / args.steps,
-                                      knames["atx"] + ("+k_atx_reduce" if args.schedule == "fused" else ""): prof_dev["atx"]["ms"] / args.steps,
+                                      knames["atx"] + ("+k_atx_reduce" if args.schedule != "plain" else ""): prof_dev["atx"]["ms"] / args.steps,
                                       "everything_else": (ms_dev - matrix_ms) / args.steps,
                                       "ax_reduce_avg_us": 1e3 * prof_dev["ax_reduce"]["ms"] / max(prof_dev["ax_reduce"]["launches"], 1)},
                 "whole_iteration": {"passes": passes, "gbs_per_gpu": iter_gbs_per_gpu, "frac_of_peak": iter_gbs_per_gpu / peak,
@@ -342,6 +354,11 @@ def main_ours(args):
                     "note": "vampomi_solver_step through the host-buffer C ABI; per step: phenotype H2D, x1_hat and r1 D2H"},
             "gpu_launches": int(cnt_dev["kernels"]),
             "clocks": sampler.summary(windows)}
+    if ab:
+        ab[args.schedule] = {"value": value, "ms_per_step": ms_dev / args.steps, "passes": passes,
+                             "cg_iters_per_step": [[h["k1"], h["k2"]] for h in hist_dev]}
+        line["schedules"] = {"unit": UNIT, "note": "same W+1..W+K iterations, device-resident leg, one after the other on this box; "
+                             "`value` above is the default schedule's", **ab}
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_baseline(N, Mt, args.cpu_sample_M, 1, 2)
         if cb:

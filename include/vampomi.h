@@ -193,11 +193,16 @@ int vampomi_cg_solve(vampomi_ctx* ctx, int rhs_vec, int sol_vec, int warm_start,
  *     vampomi_atx_multi_dev of an earlier A sol_s), or -1 to compute it here with two extra passes.
  *   extra_x_vec / extra_out_vec: if extra_x_vec >= 0, extra_out = A extra_x is computed by the first A p pass of the solve
  *     (a third vector on the same read); pass -1 for none.
+ *   track_ax_vec (may be NULL; entries -1 = off): N-vector that the solve keeps equal to A sol_s from its OWN products —
+ *     it must hold A sol_s on entry when warm_start[s] (it is zeroed for a zero start) and is advanced by alpha * (A p) in
+ *     every iteration, the same recurrence that advances sol_s by alpha * p. After the solve A sol_s is there without a
+ *     pass of its own (the reference computes A x2_hat and A Q^-1 u with extra passes, src/vamp.cpp:508,518). Likewise
+ *     A^T A sol_s follows from the solve's residual: (rhs - r - gam2 sol)/tau with r in VAMPOMI_V_CG_R / _CG2_R.
  * rhs/sol must be distinct, non-work M-vectors. Outputs are arrays of two. */
 int vampomi_cg_solve_pair(vampomi_ctx* ctx, const int rhs_vec[2], const int sol_vec[2], const int warm_start[2],
                           const int warm_ata_vec[2], double tau, double gam2, double tol, int max_iter,
-                          const int onsager_mode[2], int extra_x_vec, int extra_out_vec, int iters[2], double rel_err[2],
-                          double rhs_dot_sol[2]);
+                          const int onsager_mode[2], int extra_x_vec, int extra_out_vec, const int track_ax_vec[2],
+                          int iters[2], double rel_err[2], double rhs_dot_sol[2]);
 
 /* ---- probit z-channel: vamp::g1_bin_class / g1d_bin_class, src/vamp_probit.cpp:469-488 as used at :213-236 --- */
 /* Z1HAT <- g1_bin_class(P1, tau1, Y, 0); *sum_g1d = sum_i g1d_bin_class(P1_i, tau1, Y_i, 0). */

@@ -43,12 +43,17 @@ typedef struct vampomi_solver_config {
     unsigned long long seed;   /* Hutchinson probe / probit start */
     int redundant_passes;      /* 1 = also recompute A^T y and A x2 where the reference does (src/vamp.cpp:303,826);
                                   0 = reuse them (same results, 2 fewer matrix passes per iteration) */
-    int fuse_passes;           /* 1 (default) = matrix products whose inputs are known at the same time share ONE read of
+    int fuse_passes;           /* 1 = matrix products whose inputs are known at the same time share ONE read of
                                   the marker block: the LMMSE and the Onsager solve advance in lock-step
                                   (vampomi_cg_solve_pair), A x1_hat rides on their first pass, A x2_hat / A Q^-1 u and the two
                                   A^T products after the solves are one pass each — 2 max(k1,k2) + 2 passes per iteration
                                   instead of 2 (k1+k2) + 6, same arithmetic per product. 0 = one product per pass, in the
-                                  reference's order. Ignored (0) when redundant_passes = 1. */
+                                  reference's order. 2 (default) = fused, and additionally the products of the solves' SOLUTIONS are
+                                  not computed by passes of their own but kept by the solves: A x2_hat and A Q^-1 u advance
+                                  by alpha * (A p) next to the solutions (vampomi_cg_solve_pair track_ax_vec), A^T A of
+                                  both follows from the solves' residuals — 2 max(k1,k2) passes per iteration; the values
+                                  differ from separately computed products by recurrence rounding only (~1e-15 relative).
+                                  Ignored (0) when redundant_passes = 1. */
 } vampomi_solver_config;
 
 typedef struct vampomi_iter_result {

@@ -396,6 +396,22 @@ def test_paired_solve_equals_two_single_solves(N, M):
     res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, warm_start=(True, False), warm_ata_vecs=(V_ATA_X2, -1), tol=1e-7)
     assert (res[0][0], res[1][0]) == (kw, k1) and rel_l2(sh.get(V_X2), want_w) < 1e-11
     assert sh.counters()["matrix_passes"] == 2 * max(kw, k1)
+    # products of the solutions kept by the solve itself: A sol (track_ax_vecs) and A^T A sol = (rhs - r - gam2 sol)/tau
+    sh.set(V_X2, mu0)
+    sh.ax_multi_dev([V_X2], [V_Z2])                                             # A mu0 on entry (warm system)
+    sh.fill(V_USER_N0, 123.0)                                                   # cold system: zeroed by the solve
+    res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, warm_start=(True, False), tol=1e-7,
+                           track_ax_vecs=(V_Z2, V_USER_N0))
+    assert (res[0][0], res[1][0]) == (kw, k1)
+    x2, w = sh.get(V_X2), sh.get(V_QINV_BERN)
+    assert rel_l2(sh.get(V_Z2), d.Ax(x2)) < 1e-13 and rel_l2(sh.get(V_USER_N0), d.Ax(w)) < 1e-13
+    sh.lincomb(V_ATA_X2, 1.0, V_V, -1.0, capi.V_CG_R, 1.0)
+    sh.lincomb(V_ATA_X2, 1.0, V_ATA_X2, -gam2, V_X2, tau)
+    sh.lincomb(V_USER_M0, 1.0, V_BERN, -1.0, capi.V_CG2_R, 1.0)
+    sh.lincomb(V_USER_M0, 1.0, V_USER_M0, -gam2, V_QINV_BERN, tau)
+    assert rel_l2(sh.get(V_ATA_X2), d.ATx(d.Ax(x2))) < 1e-12 and rel_l2(sh.get(V_USER_M0), d.ATx(d.Ax(w))) < 1e-12
+    with pytest.raises(capi.VampomiError):
+        sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, track_ax_vecs=(V_Z2, V_Z2))
     # iteration cap applies to both
     res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, tol=1e-30, max_iter=3, onsager_mode=(False, False))
     assert (res[0][0], res[1][0]) == (3, 3)

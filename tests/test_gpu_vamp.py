@@ -32,9 +32,10 @@ def solver_for(g, A, y_txt, beta, **over):
     return sh, capi.Solver(sh, y, model=model, true_signal=beta, x1hat_init=g.get("x1hat_init"), **kw)
 
 
-# schedules of the matrix passes: "fused" (default: products that are known together share one read of the block),
+# schedules of the matrix passes: "recycled" (fused + A x2_hat, A Q^-1 u and A^T A of both kept by the solves themselves),
+# "fused" (products that are known together share one read of the block),
 # "plain" (one product per pass, A^T y and A x2_hat cached), "reference" (plain + the passes the reference repeats)
-SCHEDULES = {"fused": dict(fuse_passes=1, redundant_passes=0), "plain": dict(fuse_passes=0, redundant_passes=0),
+SCHEDULES = {"recycled": dict(fuse_passes=2, redundant_passes=0), "fused": dict(fuse_passes=1, redundant_passes=0), "plain": dict(fuse_passes=0, redundant_passes=0),
              "reference": dict(fuse_passes=0, redundant_passes=1)}
 
 
@@ -60,11 +61,15 @@ def test_solver_matches_reference_fixture(name, schedule):
                 assert r["matrix_passes"] == base + (6 if k == 1 else 8)
             elif schedule == "plain":     # A^T y cached, A x2_hat computed once
                 assert r["matrix_passes"] == base + (5 if k == 1 else 6)
-            else:                         # A^T y once; both solves in lock-step; A [x2, Q^-1 u] and A^T [.., A x2] one pass each
+            elif schedule == "fused":     # A^T y once; both solves in lock-step; A [x2, Q^-1 u] and A^T [.., A x2] one pass each
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (3 if k == 1 else 2)
+            else:                         # nothing but the lock-step solves (and A^T y once)
+                assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (1 if k == 1 else 0)
         else:
             if schedule == "fused":       # A^T p2, lock-step solves, A [x2, x2/sqrt(N)]
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + 2
+            elif schedule == "recycled":  # A^T p2, lock-step solves
+                assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + 1
             else:
                 assert r["matrix_passes"] == 2 * (r["k1"] + r["k2"]) + 4
     assert_rows_close(got_params, want_params, rel_csv, "params")
@@ -97,7 +102,7 @@ def run_cli(args, **kw):
     return res.stdout
 
 
-@pytest.mark.parametrize("schedule", ["fused", "plain", "reference"])
+@pytest.mark.parametrize("schedule", ["recycled", "fused", "plain", "reference"])
 def test_main_meth_schedule_flag(schedule, tmp_path):
     """--schedule only changes which products share a read of the block: same files for all three."""
     g = load_golden("linear_wellcond")

@@ -83,7 +83,7 @@ _SIGNATURES = {
     "vampomi_cg_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
                                    C.c_int, c_int_p, c_double_p, c_double_p]),
     "vampomi_cg_solve_pair": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_double, C.c_double, C.c_double, C.c_int,
-                                        c_int_p, C.c_int, C.c_int, c_int_p, c_double_p, c_double_p]),
+                                        c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_double_p, c_double_p]),
     "vampomi_probit_zdenoise": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "vampomi_pvals_se": (C.c_int, [C.c_void_p, c_double_p, C.c_double, c_double_p]),
     "vampomi_loo_sums": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
@@ -334,15 +334,17 @@ class Shard:
         return iters.value, rel.value, vmu.value
 
     def cg_solve_pair(self, rhs_vecs, sol_vecs, tau, gam2, warm_start=(False, False), warm_ata_vecs=(-1, -1), tol=1e-5,
-                      max_iter=500, onsager_mode=(False, True), extra=None):
+                      max_iter=500, onsager_mode=(False, True), extra=None, track_ax_vecs=(-1, -1)):
         """Two solves with the same operator in lock-step (one read of the marker block per pass for both).
-        extra: optional (x_vec, out_vec) — out = A x computed on the first pass. Returns [(iters, rel_err, <rhs,sol>)] * 2."""
+        extra: optional (x_vec, out_vec) — out = A x computed on the first pass. track_ax_vecs: N-vectors kept equal to
+        A sol by the solve's own recurrence. Returns [(iters, rel_err, <rhs,sol>)] * 2."""
         i2 = C.c_int * 2
         iters, rel, vmu = i2(), (C.c_double * 2)(), (C.c_double * 2)()
         ex, eo = extra if extra is not None else (-1, -1)
         _check(self.lib.vampomi_cg_solve_pair(self.h, i2(*rhs_vecs), i2(*sol_vecs), i2(*[int(bool(w)) for w in warm_start]),
                                               i2(*warm_ata_vecs), tau, gam2, tol, max_iter,
-                                              i2(*[int(bool(o)) for o in onsager_mode]), ex, eo, iters, rel, vmu), "cg_solve_pair")
+                                              i2(*[int(bool(o)) for o in onsager_mode]), ex, eo, i2(*track_ax_vecs), iters, rel, vmu),
+               "cg_solve_pair")
         return [(iters[s], rel[s], vmu[s]) for s in range(2)]
 
     def probit_zdenoise(self, tau1):

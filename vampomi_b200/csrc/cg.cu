@@ -145,6 +145,7 @@ static void fill_sys(vampomi_ctx* c, CgSys* q, int s, int rhs_vec, int sol_vec, 
     q->atx_out = q->atx_work;
     q->tmpN = c->nvec[(s == 0 ? VAMPOMI_V_TMP_N0 : VAMPOMI_V_TMP_N1) - 32];
     q->cg = c->cg + s;
+    q->amu = nullptr;
     q->warm = warm ? 1 : 0;
     q->onsager_mode = onsager_mode ? 1 : 0;
 }
@@ -169,8 +170,8 @@ extern "C" int vampomi_cg_solve(vampomi_ctx* c, int rhs_vec, int sol_vec, int wa
 
 extern "C" int vampomi_cg_solve_pair(vampomi_ctx* c, const int rhs_vec[2], const int sol_vec[2], const int warm_start[2],
                                      const int warm_ata_vec[2], double tau, double gam2, double tol, int max_iter,
-                                     const int onsager_mode[2], int extra_x_vec, int extra_out_vec, int iters[2],
-                                     double rel_err[2], double rhs_dot_sol[2]) {
+                                     const int onsager_mode[2], int extra_x_vec, int extra_out_vec, const int track_ax_vec[2],
+                                     int iters[2], double rel_err[2], double rhs_dot_sol[2]) {
     using namespace vampomi;
     VO_ARG(c && rhs_vec && sol_vec && warm_start && onsager_mode, "cg_solve_pair: NULL argument");
     for (int s = 0; s < 2; s++) {
@@ -199,6 +200,13 @@ extern "C" int vampomi_cg_solve_pair(vampomi_ctx* c, const int rhs_vec[2], const
     for (int s = 0; s < 2; s++) {
         fill_sys(c, &b.s[s], s, rhs_vec[s], sol_vec[s], warm_start[s], onsager_mode[s]);
         if (warm_start[s] && warm_ata_vec && warm_ata_vec[s] >= 0) { b.s[s].atx_out = vec_ptr(c, warm_ata_vec[s]); given[s] = 1; }
+        if (track_ax_vec && track_ax_vec[s] >= 0) {
+            const int t = track_ax_vec[s];
+            VO_ARG(vec_ptr(c, t) && !is_mvec(t) && t != VAMPOMI_V_TMP_N0 && t != VAMPOMI_V_TMP_N1 && t != extra_out_vec &&
+                   (s == 0 || !track_ax_vec || t != track_ax_vec[0]),
+                   "cg_solve_pair: track_ax_vec must name distinct non-work N-vectors");
+            b.s[s].amu = vec_ptr(c, t);
+        }
     }
     return cg_run(c, b, given, tau, gam2, tol, max_iter, extra, iters, rel_err, rhs_dot_sol);
 }

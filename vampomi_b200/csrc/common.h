@@ -85,6 +85,7 @@ struct CgSys {                       // one linear system of a CG batch (cg.cu);
     double* atx_out;                 // A^T A mu_start while the solve is set up (warm), then = atx_work
     double* atx_work;                // A^T A p of the current iteration
     double* tmpN;                    // A p
+    double* amu;                     // optional N-vector kept equal to A mu by the solve itself (amu += alpha * A p); nullptr = off
     CgScalars* cg;
     int warm;
     int onsager_mode;
@@ -111,8 +112,8 @@ struct Tuning {
     int multi_ax_rv = 0;             // multi-vector A x: 32-byte vectors per thread per column (0 = 1)
     int multi_ax_unroll = 0;         // multi-vector A x: columns in flight (0 = 4 for FP64 storage, 2 for FP32)
     int multi_atx_impl = 1;          // multi-vector A^T p: 0 = p tiles in registers, 1 = p tiles in shared memory
-    int multi_atx_cols = 0;          // shared-memory form: columns per warp pass (0 = 2)
-    int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 2)
+    int multi_atx_cols = 0;          // shared-memory form: columns per warp pass (0 = 2 for two vectors, 1 for one)
+    int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 4)
     int multi_atx_tile = 0;          // shared-memory form: rows of p per tile (0 = 4096)
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
@@ -209,7 +210,7 @@ int launch_denoise(vampomi_ctx* c, double gam1, const MixParams& mp, int damp, d
 int launch_em_sums(vampomi_ctx* c, double gam1, double lambda, const MixParams& mp, double* sums_dev);
 int launch_probit_z(vampomi_ctx* c, double tau1, double* sums_dev);
 int launch_pvals_se(vampomi_ctx* c, const double* r1_dev, double sd, double* out_dev);
-int launch_cg_init(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, double* sums_dev);
+int launch_cg_init(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, double* sums_dev);   // also zeroes amu of cold systems
 int launch_cg_init_finish(vampomi_ctx* c, const CgBatch& b, const double* sums_dev);
 int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double* sums_dev);
 int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev);

@@ -2,7 +2,7 @@
 // Same flags, same defaults (the code's, not the README's), same FATAL messages and exit status. Two additions
 // that the reference does not have: --seed (counter-hash seed of the Hutchinson probe / probit start) and --gpus; and two
 // that choose HOW the same numbers are computed: --storage (FP32 residency of the block, opt-in) and --schedule (which matrix
-// products share a read of the block: fused (default) / plain / reference, see vampomi_solver_config::fuse_passes).
+// products share a read of the block: recycled (default) / fused / plain / reference, see vampomi_solver_config::fuse_passes).
 #pragma once
 #include <string>
 #include <vector>
@@ -29,7 +29,7 @@ struct Options {
     // additions
     unsigned long long seed = 0;
     int gpus = 1;
-    std::string schedule = "fused";  // fused | plain | reference (vampomi_solver_config::fuse_passes / redundant_passes)
+    std::string schedule = "recycled";  // recycled | fused | plain | reference (vampomi_solver_config::fuse_passes / redundant_passes)
     std::string storage = "f64";     // "f32": hold the marker block rounded to FP32 in HBM (arithmetic stays FP64)
 
     // Parses argv. On error prints the reference's FATAL line to stdout and returns false (caller exits 1).

@@ -168,6 +168,8 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     //   A x2_hat and A Q^-1 u are one pass, A^T (A Q^-1 u) and A^T (A x2_hat) (next iteration's warm-start residual) another —
     // 2 max(k1,k2) + 2 passes per iteration instead of 2 (k1+k2) + 6; every product keeps its own arithmetic.
     const bool fuse = cfg_.fuse_passes != 0 && cfg_.redundant_passes == 0;
+    const bool recycle = fuse && cfg_.fuse_passes >= 2;
+    double tau_solved = gamw_;
     double sum_d = 0;
     VH(vampomi_denoise(ctx_, gam1_, probs_.data(), vars_.data(), (int)probs_.size(), it > 1, rho, &sum_d));   // :203-219
     alpha1_ = sum_d / (double)Mt_;                                              // :221-223
@@ -226,8 +228,12 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         const int warm[2] = {it > 1 ? 1 : 0, 0}, ata[2] = {ata_x2_ready_ ? VAMPOMI_V_ATA_X2 : -1, -1}, ons[2] = {0, 1};
         int its[2] = {0, 0};
         double rels[2], vmus[2];
+        // recycled schedule: the solves also keep Z2 = A x2_hat (it holds A x2_hat of the previous iteration, the warm start)
+        // and USER_N0 = A Q^-1 u up to date from their own A p products
+        const int track[2] = {recycle ? VAMPOMI_V_Z2 : -1, recycle ? VAMPOMI_V_USER_N0 : -1};
         VH(vampomi_cg_solve_pair(ctx_, rhs, sol, warm, ata, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, ons, VAMPOMI_V_X1,
-                                 VAMPOMI_V_Z1, its, rels, vmus));
+                                 VAMPOMI_V_Z1, track, its, rels, vmus));
+        tau_solved = gamw_;
         k1 = its[0]; k2 = its[1]; vmu = vmus[1];
         VH(measures1());
     }
@@ -245,11 +251,19 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));       // :518
         VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));        // :519
         if (cfg_.redundant_passes) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
-    } else {
+    } else if (!recycle) {
         const int xin[2] = {VAMPOMI_V_X2, VAMPOMI_V_QINV_BERN}, xout[2] = {VAMPOMI_V_Z2, VAMPOMI_V_USER_N0};
         VH(vampomi_ax_multi_dev(ctx_, 2, xin, xout));
         const int pin[2] = {VAMPOMI_V_USER_N0, VAMPOMI_V_Z2}, pout[2] = {VAMPOMI_V_USER_M0, VAMPOMI_V_ATA_X2};
         VH(vampomi_atx_multi_dev(ctx_, 2, pin, pout));                          // A^T A x2_hat: the next iteration's :681-684
+        ata_x2_ready_ = true;
+    } else {
+        // no pass at all: Z2 = A x2_hat and A Q^-1 u were kept by the solves; A^T A of both solutions follows from the solves'
+        // own residuals, r = rhs - (tau A^T A + gam2 I) sol  =>  A^T A sol = (rhs - r - gam2 sol) / tau
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_V, -1.0, VAMPOMI_V_CG_R, 1.0));
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_ATA_X2, -gam2_, VAMPOMI_V_X2, tau_solved));
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_BERN, -1.0, VAMPOMI_V_CG2_R, 1.0));
+        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_USER_M0, -gam2_, VAMPOMI_V_QINV_BERN, tau_solved));
         ata_x2_ready_ = true;
     }
     {
@@ -334,8 +348,8 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         std::cout << "alpha1 = " << alpha1_ << std::endl << "beta1 = " << beta1 << std::endl << "tau1 = " << tau1_ << std::endl;
 
     // A (x/sqrt(N)) (:271, :403), then the probit prediction at threshold 0.5 and the confusion matrix on the host (N values)
-    auto confusion_eval = [&](double* out6, double corr) -> int {               // :272-282 / :404-415
-        VH(vampomi_vec_get(ctx_, VAMPOMI_V_USER_N0, zbuf_.data()));
+    auto confusion_eval = [&](int zvec, double* out6, double corr) -> int {     // :272-282 / :404-415
+        VH(vampomi_vec_get(ctx_, zvec, zbuf_.data()));
         int TP = 0, TN = 0, FP = 0, FN = 0;
         for (int i = 0; i < N_; i++) {
             const double yhat = normal_cdf(zbuf_[i]) >= 0.5 ? 1.0 : 0.0;       // predict_probit, :619-629
@@ -353,9 +367,10 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     auto confusion = [&](int xvec, double* out6, double corr) -> int {
         VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M1, 1.0, xvec, 0.0, xvec, sqrtN));
         VH(vampomi_ax_dev(ctx_, VAMPOMI_V_USER_M1, VAMPOMI_V_USER_N0));
-        return confusion_eval(out6, corr);
+        return confusion_eval(VAMPOMI_V_USER_N0, out6, corr);
     };
     const bool fuse = cfg_.fuse_passes != 0 && cfg_.redundant_passes == 0;      // see step_linear
+    const bool recycle = fuse && cfg_.fuse_passes >= 2;
     auto report1 = [&]() {
         if (verbose) std::cout << "Corr(x1_hat,x0) = " << x1_corr << std::endl << "Accuracy1 = " << res->metrics[4] << std::endl
                                << std::endl << "->LMMSE" << std::endl;
@@ -377,10 +392,11 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         const int warm[2] = {0, 0}, ata[2] = {-1, -1}, ons[2] = {0, 1};
         int its[2] = {0, 0};
         double rels[2], vmus[2];
+        const int track[2] = {recycle ? VAMPOMI_V_Z2 : -1, -1};                 // recycled: the solve keeps Z2 = A x2_hat itself
         VH(vampomi_cg_solve_pair(ctx_, rhs, sol, warm, ata, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, ons, VAMPOMI_V_USER_M1,
-                                 VAMPOMI_V_USER_N0, its, rels, vmus));
+                                 VAMPOMI_V_USER_N0, track, its, rels, vmus));
         k1 = its[0]; k2 = its[1]; vmu = vmus[1];
-        VH(confusion_eval(res->metrics, x1_corr));
+        VH(confusion_eval(VAMPOMI_V_USER_N0, res->metrics, x1_corr));
         report1();
     }
     const double alpha2 = gam2_ * vmu;                                          // :311
@@ -399,7 +415,7 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     gam1_ = clampg(gam2_ * (1 - alpha2) / alpha2);                              // :345-346
     // LMMSE for z (:352-376)
     if (!fuse) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
-    else {                                                                      // A x2_hat and A (x2_hat/sqrt(N)) (:403) in one pass
+    else if (!recycle) {                                                        // A x2_hat and A (x2_hat/sqrt(N)) (:403) in one pass
         VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M1, 1.0, VAMPOMI_V_X2, 0.0, VAMPOMI_V_X2, sqrtN));
         const int xin[2] = {VAMPOMI_V_X2, VAMPOMI_V_USER_M1}, xout[2] = {VAMPOMI_V_Z2, VAMPOMI_V_USER_N0};
         VH(vampomi_ax_multi_dev(ctx_, 2, xin, xout));
@@ -412,7 +428,8 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         std::cout << "alpha2 = " << alpha2 << std::endl << "beta2 = " << beta2 << std::endl << "gam1 = " << gam1_ << std::endl
                   << "gam2 = " << gam2_ << std::endl << "tau2 = " << tau2 << std::endl;
     if (!fuse) VH(confusion(VAMPOMI_V_X2, res->metrics + 6, x2_corr));
-    else VH(confusion_eval(res->metrics + 6, x2_corr));
+    else if (!recycle) VH(confusion_eval(VAMPOMI_V_USER_N0, res->metrics + 6, x2_corr));
+    else VH(confusion_eval(VAMPOMI_V_Z2, res->metrics + 6, x2_corr));          // the 0.5 threshold only needs the sign of A x2_hat: no 1/sqrt(N) pass
     if (verbose) std::cout << "Corr(x2_hat, x0) = " << x2_corr << std::endl << "Accuracy2 = " << res->metrics[10] << std::endl;
     res->n_params = 8; res->n_metrics = 12;
     alpha2_ = alpha2;
@@ -505,7 +522,7 @@ void vampomi_solver_default_config(vampomi_solver_config* cfg) {
     for (int i = 0; i < 10; i++) { cfg->vars[i] = vars[i]; cfg->probs[i] = probs[i]; }
     cfg->seed = 0;
     cfg->redundant_passes = 0;
-    cfg->fuse_passes = 1;
+    cfg->fuse_passes = 2;
 }
 
 }  // extern "C"

@@ -275,7 +275,7 @@ template <int VE>
 __device__ __forceinline__ int sp_pos(int v, int q) { return (v >> 5) * (32 * VE) + ((q << 5) + (v & 31)) * 2; }
 
 template <typename T, int K, int C, int U>
-__global__ void __launch_bounds__(256) k_atx_smem(const T* __restrict__ A, size_t ld, const double* __restrict__ mave, MultiVec mv,
+__global__ void __launch_bounds__(256, (C * U >= 8 ? 2 : C * U >= 4 ? 3 : 4)) k_atx_smem(const T* __restrict__ A, size_t ld, const double* __restrict__ mave, MultiVec mv,
                                                   int tile_rows, int cols_per_chunk, long long M, double* __restrict__ partial) {
     constexpr int VE = V32<T>::VE;
     extern __shared__ __align__(32) double sp[];                 // [K][sp_stride], swizzled (sp_pos)
@@ -316,40 +316,35 @@ __global__ void __launch_bounds__(256) k_atx_smem(const T* __restrict__ A, size_
 #pragma unroll
             for (int k = 0; k < K; k++) acc[k][cc][0] = acc[k][cc][1] = 0.0;
         }
-        int v = lane;
-        for (; v + 32 * (U - 1) < nvec; v += 32 * U) {
+        // U steps of 32 lanes x 32 bytes per column in flight; the last, partial group of steps is predicated rather than
+        // peeled into a serial tail (a tile of 4000 rows is 31.25 steps: a peeled tail would expose the memory latency twice)
+        for (int v0 = lane; v0 < nvec; v0 += 32 * U) {
             V32<T> a[U][C];
 #pragma unroll
-            for (int u = 0; u < U; u++)
-#pragma unroll
-                for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::stream(col[cc] + (size_t)VE * (v + 32 * u));
-#pragma unroll
             for (int u = 0; u < U; u++) {
+                if (v0 + 32 * u < nvec) {
 #pragma unroll
-                for (int k = 0; k < K; k++) {
-                    double pv[VE];
-#pragma unroll
-                    for (int q = 0; q < VE / 2; q++) {
-                        const double2 t = *reinterpret_cast<const double2*>(sp + (size_t)k * sp_stride + sp_pos<VE>(v + 32 * u, q));
-                        pv[2 * q] = t.x; pv[2 * q + 1] = t.y;
-                    }
-#pragma unroll
-                    for (int cc = 0; cc < C; cc++)
-#pragma unroll
-                        for (int e = 0; e < VE; e++)              // (meth[i] - mu) * phen[i], src/data.cpp:304
-                            acc[k][cc][e & 1] = fma(a[u][cc].val(e) - m[cc], pv[e], acc[k][cc][e & 1]);
+                    for (int cc = 0; cc < C; cc++) a[u][cc] = V32<T>::stream(col[cc] + (size_t)VE * (v0 + 32 * u));
                 }
             }
-        }
-        for (; v < nvec; v += 32) {
 #pragma unroll
-            for (int cc = 0; cc < C; cc++) {
-                V32<T> a = V32<T>::stream(col[cc] + (size_t)VE * v);
+            for (int u = 0; u < U; u++) {
+                if (v0 + 32 * u < nvec) {
 #pragma unroll
-                for (int k = 0; k < K; k++)
+                    for (int k = 0; k < K; k++) {
+                        double pv[VE];
 #pragma unroll
-                    for (int e = 0; e < VE; e++)
-                        acc[k][cc][e & 1] = fma(a.val(e) - m[cc], sp[(size_t)k * sp_stride + sp_pos<VE>(v, e / 2) + (e & 1)], acc[k][cc][e & 1]);
+                        for (int q = 0; q < VE / 2; q++) {
+                            const double2 t = *reinterpret_cast<const double2*>(sp + (size_t)k * sp_stride + sp_pos<VE>(v0 + 32 * u, q));
+                            pv[2 * q] = t.x; pv[2 * q + 1] = t.y;
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                            for (int e = 0; e < VE; e++)              // (meth[i] - mu) * phen[i], src/data.cpp:304
+                                acc[k][cc][e & 1] = fma(a[u][cc].val(e) - m[cc], pv[e], acc[k][cc][e & 1]);
+                    }
+                }
             }
         }
 #pragma unroll
@@ -543,8 +538,8 @@ template <typename T, int K>
 static int atx_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     if (c->tune.multi_atx_impl == 0) return atx_tiled_launch<T, K>(c, A, mv);
     int cc = c->tune.multi_atx_cols, u = c->tune.multi_atx_unroll;
-    if (cc == 0) cc = 2;
-    if (u == 0) u = 2;
+    if (cc == 0) cc = K >= 2 ? 2 : 1;                   // measured defaults (profiles/r01_sweep_multi_vector_kernels*.jsonl)
+    if (u == 0) u = 4;
     switch (cc * 10 + u) {
         case 12: return atx_smem_launch<T, K, 1, 2>(c, A, mv);
         case 14: return atx_smem_launch<T, K, 1, 4>(c, A, mv);

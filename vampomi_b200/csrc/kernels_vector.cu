@@ -315,7 +315,7 @@ int launch_pvals_se(vampomi_ctx* c, const double* r1_dev, double sd, double* out
 // ---------------------------------------------------------------------------------------------------------------
 // r = v - (tau*AtA mu + gam2*mu) [warm] or r = v; z = r/diag; p = z   (:679-690)
 template <int S>
-__global__ void __launch_bounds__(RED_THREADS) k_cg_init(CgBatch b, long long M, double tau, double gam2, double diag,
+__global__ void __launch_bounds__(RED_THREADS) k_cg_init(CgBatch b, long long M, int N, double tau, double gam2, double diag,
                                                          double* __restrict__ partials, unsigned int* ticket,
                                                          double* __restrict__ out, Xchg xc) {
     double acc[2 * S];
@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_init(CgBatch b, long long M,
             a0 = fma(ri, zi, a0);
             a1 = fma(vi, vi, a1);
         }
+        if (q.amu != nullptr && !q.warm) GRID_STRIDE(i, N) q.amu[i] = 0.0;      // A mu_start of a zero start
         acc[2 * s] = a0; acc[2 * s + 1] = a1;
     }
     grid_reduce(acc, 2 * S, partials, ticket, out, &xc);
@@ -384,8 +385,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_dp(CgBatch b, long long M, d
 }
 
 // alpha = <r,z>/<d,p>; mu += alpha p; r -= alpha d; z = r/diag; out[3s..3s+2] = <v,mu>, <r,z>, <r,r>   (:701-706, :728-734)
+// A system with `amu` also advances amu += alpha * (A p), so that amu stays A mu without a pass of its own.
 template <int S>
-__global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M, double diag, int parity,
+__global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M, int N, double diag, int parity,
                                                          const double* __restrict__ dp, double* __restrict__ partials,
                                                          unsigned int* ticket, double* __restrict__ out, Xchg xc) {
     bool active[S], any = false;
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M,
                 a1 = fma(ri, zi, a1);
                 a2 = fma(ri, ri, a2);
             }
+            if (q.amu != nullptr) GRID_STRIDE(i, N) q.amu[i] += alpha * q.tmpN[i];
         }
         acc[3 * s] = a0; acc[3 * s + 1] = a1; acc[3 * s + 2] = a2;
     }
@@ -460,8 +463,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_finish(CgBatch b, long long 
 }
 
 int launch_cg_init(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, double* sums_dev) {
-    if (b.S == 1) k_cg_init<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, tau, gam2, diag, c->red_partials, c->red_tickets, sums_dev, c->xchg);
-    else k_cg_init<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, tau, gam2, diag, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    if (b.S == 1) k_cg_init<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, tau, gam2, diag, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    else k_cg_init<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, tau, gam2, diag, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
@@ -480,8 +483,8 @@ int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, doub
     return VAMPOMI_OK;
 }
 int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev) {
-    if (b.S == 1) k_cg_step<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
-    else k_cg_step<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    if (b.S == 1) k_cg_step<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    else k_cg_step<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;

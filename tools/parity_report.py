@@ -16,13 +16,15 @@ from vampomi_b200 import capi  # noqa: E402
 
 CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
          "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged"]
-out = {}
+SCHED = {"recycled": 2, "fused": 1, "plain": 0}
+schedule = sys.argv[1] if len(sys.argv) > 1 else "recycled"
+out = {"_schedule": schedule}
 for name in CASES:
     g = load_golden(name)
     A, y_txt, beta = golden_inputs(g)
     model = g["model"]
     y = standardize_phen(y_txt) if model == "linear" else y_txt
-    kw = dict(gamw=2.0, seed=int(g["probe_seed"]))
+    kw = dict(gamw=2.0, seed=int(g["probe_seed"]), fuse_passes=SCHED[schedule])
     kw.update(extra_kwargs(g))
     sh = capi.Shard(int(g["N"]), int(g["M"]))
     sh.upload(A)

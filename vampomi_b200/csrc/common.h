@@ -115,6 +115,7 @@ struct Tuning {
     int multi_atx_cols = 0;          // shared-memory form: columns per warp pass (0 = 2 for two vectors, 1 for one)
     int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 4)
     int multi_atx_tile = 0;          // shared-memory form: rows of p per tile (0 = 4096)
+    int grid_balance = 1;            // 1 = (row tile x column chunk) grids sized to full waves of resident CTAs (balanced_chunks), 0 = one, possibly partly filled, wave
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 
@@ -178,6 +179,28 @@ inline long long vec_len(const vampomi_ctx* c, int id) {
     if (id >= 32 && id < 32 + VAMPOMI_V_NUM_N) return c->N;
     return -1;
 }
+// Column chunks for a (row tiles x column chunks) grid of a streaming matrix kernel. `slots` = resident CTAs of the device
+// (SMs x CTAs per SM). One wave is floor(slots / ntiles) chunks, which leaves slots idle whenever ntiles does not divide
+// slots (20 row tiles on 296 slots: 280 CTAs, 5 % of the machine unused for the whole kernel). Take the smallest number of
+// waves w for which floor(w * slots / ntiles) chunks fill the w waves to within 1 %: every wave is (almost) full, and with
+// w > 1 a CTA that finishes early is replaced at once, so the tail is one smaller CTA long.
+inline long long balanced_chunks(long long slots, int ntiles, long long M, int min_cols, bool balance) {
+    long long nch = slots / ntiles;
+    if (balance) {
+        for (int w = 1; w <= 8; w++) {
+            const long long n = w * slots / ntiles;
+            if (n < 1) continue;
+            nch = n;
+            if ((double)(n * ntiles) >= 0.99 * (double)(w * slots)) break;
+        }
+    }
+    if (min_cols < 1) min_cols = 1;
+    const long long cap = (M + min_cols - 1) / min_cols;        // keep at least min_cols columns per chunk
+    if (nch > cap) nch = cap;
+    if (nch < 1) nch = 1;
+    return nch;
+}
+
 inline bool is_mvec(int id) { return id >= 0 && id < VAMPOMI_V_NUM_M; }
 // M-vectors the library's own calls clobber (TMP_*, CG_*, CG2_*): not usable as rhs / sol of a solve
 inline bool is_work_mvec(int id) {

@@ -358,9 +358,7 @@ static AxPlan plan_ax(const vampomi_ctx* c) {
     int per_sm = c->tune.ax_ctas_per_sm > 0 ? c->tune.ax_ctas_per_sm
                                             : resident_ctas(ax_kernel_any(c, p.rv, p.U, c->tune.center_split != 0), 256, 0);
     long long slots = (long long)c->num_sms * per_sm;
-    long long nch = slots / p.ntiles;
-    if (nch < 1) nch = 1;
-    if (nch > c->M) nch = c->M;
+    long long nch = balanced_chunks(slots, p.ntiles, c->M, 4 * p.U, c->tune.grid_balance != 0 && c->tune.ax_ctas_per_sm == 0);
     p.cols_per_chunk = (int)((c->M + nch - 1) / nch);
     p.nchunks = (int)((c->M + p.cols_per_chunk - 1) / p.cols_per_chunk);
     return p;

@@ -397,9 +397,7 @@ static int ax_multi_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     const size_t tr = (c->ld + ntiles - 1) / ntiles;
     const int tile_rows = (int)((tr + 15) / 16 * 16);
     const int per_sm = c->tune.ax_ctas_per_sm > 0 ? c->tune.ax_ctas_per_sm : resident((const void*)kern);
-    long long nch = (long long)c->num_sms * per_sm / ntiles;
-    if (nch < 1) nch = 1;
-    if (nch > c->M) nch = c->M;
+    const long long nch = balanced_chunks((long long)c->num_sms * per_sm, ntiles, c->M, 4 * U, c->tune.grid_balance != 0 && c->tune.ax_ctas_per_sm == 0);
     const int cols_per_chunk = (int)((c->M + nch - 1) / nch);
     const int nchunks = (int)((c->M + cols_per_chunk - 1) / cols_per_chunk);
     VO_CHECK(ensure_buf(c, &c->ax_partial, &c->ax_partial_elems, (size_t)K * nchunks * c->ld));
@@ -518,10 +516,7 @@ static int atx_smem_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     if (per_sm <= 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     }
-    long long nch = (long long)c->num_sms * per_sm / ntiles;
-    if (nch < 1) nch = 1;
-    long long maxch = (c->M + 8 * C - 1) / (8 * C);
-    if (nch > maxch) nch = maxch;
+    const long long nch = balanced_chunks((long long)c->num_sms * per_sm, ntiles, c->M, 8 * C, c->tune.grid_balance != 0 && c->tune.atx_ctas_per_sm == 0);
     int cols_per_chunk = (int)((c->M + nch - 1) / nch);
     const int nchunks = (int)((c->M + cols_per_chunk - 1) / cols_per_chunk);
     VO_CHECK(ensure_buf(c, &c->atx_partial, &c->atx_partial_elems, (size_t)ntiles * K * c->M));

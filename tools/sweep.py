@@ -48,6 +48,11 @@ if a.multi:
     t(4, "read_probe", a.multi)
     t(0, "ax_single_default", a.multi)
     t(1, "atx_single_default", a.multi)
+    for gbal in (0, 1, 0, 1):                         # full-wave grid sizing on / off, twice (order effects)
+        t(0, "ax_single_default", a.multi, grid_balance=gbal)
+        t(5, "ax_multi_K2_default", a.multi, grid_balance=gbal)
+        t(8, "ax_multi_K3_default", a.multi, grid_balance=gbal)
+        t(6, "atx_multi_K2_default", a.multi, grid_balance=gbal)
     for rv, u in ((1, 4), (1, 8), (2, 2), (2, 4), (1, 2)):
         t(5, "ax_multi_K2", a.multi, multi_ax_rv=rv, multi_ax_unroll=u)
         t(8, "ax_multi_K3", a.multi, multi_ax_rv=rv, multi_ax_unroll=u)
@@ -56,9 +61,9 @@ if a.multi:
     sh.set_tuning("ax_ctas_per_sm", 0); sh.set_tuning("multi_ax_rv", 0); sh.set_tuning("multi_ax_unroll", 0)
     t(6, "atx_multi_K2_regtile", a.multi, multi_atx_impl=0)
     t(7, "atx_multi_K1_regtile", a.multi, multi_atx_impl=0)
-    for tile in (4096, 2048, 8192):
+    for tile in (4096, 2048):
         for c_, u in ((2, 2), (2, 4), (1, 2), (1, 4), (4, 2)):
-            if tile != 4096 and (c_, u) not in ((2, 2), (2, 4)):
+            if tile != 4096 and (c_, u) not in ((2, 4),):
                 continue
             t(6, "atx_multi_K2_smem", a.multi, multi_atx_impl=1, multi_atx_cols=c_, multi_atx_unroll=u, multi_atx_tile=tile)
             t(7, "atx_multi_K1_smem", a.multi, multi_atx_impl=1, multi_atx_cols=c_, multi_atx_unroll=u, multi_atx_tile=tile)

@@ -114,7 +114,7 @@ struct Tuning {
     int multi_atx_impl = 1;          // multi-vector A^T p: 0 = p tiles in registers, 1 = p tiles in shared memory
     int multi_atx_cols = 0;          // shared-memory form: columns per warp pass (0 = 2 for two vectors, 1 for one)
     int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 4)
-    int multi_atx_tile = 0;          // shared-memory form: rows of p per tile (0 = 4096)
+    int multi_atx_tile = 0;          // shared-memory form: rows of p per tile (0 = 2048)
     int grid_balance = 1;            // 1 = (row tile x column chunk) grids sized to full waves of resident CTAs (balanced_chunks), 0 = one, possibly partly filled, wave
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };

@@ -488,12 +488,12 @@ static int atx_tiled_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     return rc;
 }
 
-// shared-memory form (knob multi_atx_impl = 1, the default): rows per tile from knob multi_atx_tile (0 = 4096 / K-independent)
+// shared-memory form (knob multi_atx_impl = 1, the default): rows per tile from knob multi_atx_tile (0 = 2048)
 template <typename T, int K, int C, int U>
 static int atx_smem_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     constexpr int VE = V32<T>::VE;
     auto kern = k_atx_smem<T, K, C, U>;
-    int want = c->tune.multi_atx_tile > 0 ? c->tune.multi_atx_tile : 4096;
+    int want = c->tune.multi_atx_tile > 0 ? c->tune.multi_atx_tile : 2048;
     want = (want + 32 * VE - 1) / (32 * VE) * (32 * VE);
     const int ntiles = (int)((c->ld + want - 1) / want);
     const size_t tr = (c->ld + ntiles - 1) / ntiles;

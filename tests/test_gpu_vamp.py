@@ -184,6 +184,16 @@ def test_association_and_test_modes(tmp_path):
     want = bytes(g["csv_test"])
     assert len(got) == len(want) and got[:39] == want[:39]
     assert_rows_close(csv_rows(got), csv_rows(want), 1e-8, "test.csv")
+    # four saved estimates share one pass over the test matrix (ranges that are not a multiple of four, a missing file:
+    # like the reference, an unreadable estimate is a zero vector, src/utilities.cpp:251-267, i.e. R2 = 1 - |y|^2/(sd^2 n))
+    os.remove(f"{d}/out/g_test.csv")
+    run_cli(["--meth-file-test", f"{d}/tst.bin", "--phen-file-test", f"{d}/tst.phen", "--N-test", Nt, "--Mt", g["M"], "--out-dir",
+             f"{d}/out", "--out-name", "g", "--run-mode", "test", "--estimate-file", f"{d}/out/g_it_1.bin", "--test-iter-range",
+             f"1,{last + 2}"])
+    rows = csv_rows(open(f"{d}/out/g_test.csv", "rb").read())
+    assert sorted(rows) == list(range(1, last + 3))
+    assert_rows_close({k: rows[k] for k in range(1, last + 1)}, csv_rows(want), 1e-8, "test.csv, longer range")
+    assert rows[last + 1][0] == rows[last + 2][0] and rows[last + 1][0] < 0.01
     # README's literal association command (test-file flags) fails like the reference: FATAL, exit 1
     res = subprocess.run([build.MAIN_METH, "--meth-file-test", f"{d}/ex.bin", "--phen-file-test", f"{d}/ex.phen", "--N", "300", "--Mt", "800",
                           "--run-mode", "association_test"], stdout=subprocess.PIPE, text=True)

@@ -1,6 +1,7 @@
 // main_meth's program logic (reference: src/main_meth.cpp:9-270) over the kernel ABI. One "rank" = one marker shard on
 // one GPU; with --gpus G the G ranks run as threads of this process and meet in NCCL collectives, where the reference
 // runs G MPI processes. Output files, their byte layout, stdout landmarks and exit codes follow the reference.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -9,6 +10,7 @@
 #include <iostream>
 #include <mutex>
 #include <stdexcept>
+#include <exception>
 #include <thread>
 #include <vector>
 #include "../../../include/vampomi_host.h"
@@ -204,24 +206,47 @@ int run_test(Rank& r) {                                                         
     const size_t pos_it = est.rfind("it");
     if (r.root()) std::cout << "est_file_name = " << est << std::endl
                             << "iter range = [" << o.test_iter_range[0] << ", " << o.test_iter_range[1] << "]" << std::endl;
+    // The reference applies A to one saved estimate per pass (:178). Every pass is bound by streaming the test matrix, so
+    // up to four iteration files share one read of it (vampomi_ax_multi_dev); rows are still written in iteration order,
+    // and a file that cannot be read stops the run exactly after the rows of the iterations before it.
     std::vector<double> z((size_t)N_test);
-    for (int it = o.test_iter_range[0]; it <= o.test_iter_range[1]; it++) {
-        const std::string f = est.substr(0, pos_it) + "it_" + std::to_string(it) + "." + ext;  // :166
-        std::vector<double> x = ext == "bin" ? read_vec(f, r.M, r.S) : read_text_vec(f, r.M, r.S);
-        for (double& v : x) v *= std::sqrt((double)N_test);                                    // :174-175
-        if (vampomi_ax(r.ctx, x.data(), z.data()) != VAMPOMI_OK) return fatal_abi(r, "Ax");    // :178
-        double l2 = 0, zy = 0, zz = 0, yy = 0;
-        for (int i = 0; i < N_test; i++) {
-            l2 += (y[i] - z[i]) * (y[i] - z[i]);
-            zy += z[i] * y[i]; zz += z[i] * z[i]; yy += y[i] * y[i];
+    const int in_vec[4] = {VAMPOMI_V_X1, VAMPOMI_V_X2, VAMPOMI_V_R1, VAMPOMI_V_R2};
+    const int out_vec[4] = {VAMPOMI_V_Z1, VAMPOMI_V_Z2, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_N1};
+    const double sd = calc_stdev(y);
+    double yy = 0;
+    for (int i = 0; i < N_test; i++) yy += y[i] * y[i];
+    for (int it0 = o.test_iter_range[0]; it0 <= o.test_iter_range[1]; it0 += 4) {
+        const int nb = std::min(4, o.test_iter_range[1] - it0 + 1);
+        int got = 0;
+        std::exception_ptr err;
+        for (int b = 0; b < nb; b++) {
+            const std::string f = est.substr(0, pos_it) + "it_" + std::to_string(it0 + b) + "." + ext;  // :166
+            try {
+                std::vector<double> x = ext == "bin" ? read_vec(f, r.M, r.S) : read_text_vec(f, r.M, r.S);
+                for (double& v : x) v *= std::sqrt((double)N_test);                            // :174-175
+                if (vampomi_vec_set(r.ctx, in_vec[b], x.data()) != VAMPOMI_OK) return fatal_abi(r, "vec_set");
+                got++;
+            } catch (...) {
+                err = std::current_exception();
+                break;
+            }
         }
-        const double sd = calc_stdev(y);
-        const double r2 = 1 - l2 / (sd * sd * y.size());                                       // :187-188
-        const double corr_y = (zy * r.nranks) / std::sqrt((zz * r.nranks) * (yy * r.nranks));  // :191 (sync=1 on replicated vectors)
-        if (r.root()) {
-            std::cout << r2 << ", ";
-            csv.row(it, {r2, corr_y * corr_y});
+        if (got > 0 && vampomi_ax_multi_dev(r.ctx, got, in_vec, out_vec) != VAMPOMI_OK) return fatal_abi(r, "Ax");   // :178
+        for (int b = 0; b < got; b++) {
+            if (vampomi_vec_get(r.ctx, out_vec[b], z.data()) != VAMPOMI_OK) return fatal_abi(r, "vec_get");
+            double l2 = 0, zy = 0, zz = 0;
+            for (int i = 0; i < N_test; i++) {
+                l2 += (y[i] - z[i]) * (y[i] - z[i]);
+                zy += z[i] * y[i]; zz += z[i] * z[i];
+            }
+            const double r2 = 1 - l2 / (sd * sd * y.size());                                   // :187-188
+            const double corr_y = (zy * r.nranks) / std::sqrt((zz * r.nranks) * (yy * r.nranks));  // :191 (sync=1 on replicated vectors)
+            if (r.root()) {
+                std::cout << r2 << ", ";
+                csv.row(it0 + b, {r2, corr_y * corr_y});
+            }
         }
+        if (err) std::rethrow_exception(err);
     }
     return 0;
 }

@@ -276,6 +276,15 @@ def main_ours(args):
         cnt = sh.counters()
         sol.close()
         if world > 1:
+            # per-rank device time of the two matrix kernels and of the exchange tail: tells systematic from random rank skew
+            mine = torch.tensor([prof["ax_partial"]["ms"] / max(prof["ax_partial"]["launches"], 1),
+                                 prof["atx"]["ms"] / max(prof["atx"]["launches"], 1),
+                                 1e3 * prof["ax_reduce"]["ms"] / max(prof["ax_reduce"]["launches"], 1), ms], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            prof["per_rank"] = {"ax_avg_ms": [round(float(a[0]), 4) for a in allr], "atx_avg_ms": [round(float(a[1]), 4) for a in allr],
+                                "ax_exchange_tail_avg_us": [round(float(a[2]), 1) for a in allr],
+                                "leg_ms": [round(float(a[3]), 3) for a in allr]}
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -317,6 +326,8 @@ def main_ours(args):
     passes = sum(h["matrix_passes"] for h in hist_dev)
     iter_bytes = passes * float(N) * float(Mt) * (8.0 if args.storage == "f64" else 4.0)                       # whole job: P * N * Mt * 8 over the timed region
     iter_gbs_per_gpu = iter_bytes / (ms_dev * 1e-3) / 1e9 / world
+    per_rank = prof_dev.pop("per_rank", None)
+    prof_e2e.pop("per_rank", None)
     matrix_ms = sum(prof_dev[k]["ms"] for k in prof_dev)
     # kernel behind each profiling slot: in the fused schedule every pass of iterations > 1 is a multi-vector kernel
     knames = ({"ax_partial": "k_ax_multi", "atx": "k_atx_smem"} if args.schedule != "plain" else {"ax_partial": "k_ax_partial", "atx": "k_atx_cta"})
@@ -340,6 +351,8 @@ def main_ours(args):
                                     "note": "passes = reads of the whole marker block actually made in the timed steps (bytes = passes x N x Mt x 8); "
                                             "matrix_vector_products = products those steps computed — the one-product-per-pass schedule "
                                             "reads the block once for each"}}
+    if per_rank:
+        roofline["per_rank"] = per_rank
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.storage == "f64" else "f64 arithmetic on a matrix held as f32 (opt-in mode, not the headline)",

@@ -233,6 +233,11 @@ int vampomi_profile_enable(vampomi_ctx* ctx, int on);
 int vampomi_profile_read(vampomi_ctx* ctx, double out[9], int reset);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on — for callers that time with their own events. */
 int vampomi_stream(vampomi_ctx* ctx, void** stream);
+/* Pure host helper (no GPU needed): the number of column chunks the (row tile x column chunk) grids of the tiled matrix
+ * kernels use for `slots` resident CTAs (SMs x CTAs per SM) and `ntiles` row tiles — the smallest number of full waves that
+ * fills the slots to 99 % (balance != 0) or one, possibly partly filled, wave (balance == 0); at least `min_cols` columns
+ * per chunk. Returns the chunk count (>= 1). */
+long long vampomi_plan_chunks(long long slots, int ntiles, long long M, int min_cols, int balance);
 /* Tuning knobs (kernel variants); see DESIGN.md. Unknown names fail with VAMPOMI_ERR_ARG. */
 int vampomi_set_tuning(vampomi_ctx* ctx, const char* name, int value);
 

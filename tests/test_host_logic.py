@@ -97,3 +97,21 @@ def test_merge_components_matches_oracle(lib, vars_, probs, thr):
     assert L == len(p_want)
     assert np.allclose(p[:L], p_want, rtol=1e-15) and np.allclose(v[:L], v_want, rtol=1e-15)
     assert math.isclose(sum(p[:L]), sum(probs), rel_tol=1e-14)
+
+
+def test_grid_planning_fills_whole_waves():
+    """vampomi_plan_chunks: (row tile x column chunk) grids use the smallest number of full waves that leaves at most 1 % of
+    the resident-CTA slots empty; never fewer than min_cols columns per chunk."""
+    slots = 296                                             # 148 SMs x 2 CTAs
+    assert capi.plan_chunks(slots, 20, 106250, 16, balance=False) == 14          # one wave: 280 of 296 slots
+    n = capi.plan_chunks(slots, 20, 106250, 16)
+    assert n == 44 and 20 * n <= 3 * slots and 20 * n >= 0.99 * 3 * slots        # three waves of 880 CTAs on 888 slots
+    assert capi.plan_chunks(slots, 5, 106250, 16) == 59                          # 295 of 296: one wave is already full
+    assert capi.plan_chunks(slots, 10, 106250, 16) == 59                         # two waves: 590 of 592
+    assert capi.plan_chunks(slots, 1, 106250, 16) == 296
+    assert capi.plan_chunks(slots, 20, 100, 16) == 7                             # small M: at least 16 columns per chunk
+    assert capi.plan_chunks(slots, 400, 106250, 16) >= 1                         # more tiles than slots
+    for ntiles in range(1, 64):
+        n = capi.plan_chunks(slots, ntiles, 10 ** 6, 1)
+        waves = -(-ntiles * n // slots)
+        assert ntiles * n >= 0.99 * waves * slots or waves >= 8, (ntiles, n)

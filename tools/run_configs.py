@@ -43,6 +43,7 @@ for k in range(5):
     r = sol.step()
     its.append(dict(it=r["it"], s=round(time.time() - t, 4), k1=r["k1"], k2=r["k2"], passes=r["matrix_passes"],
                     acc1=r["metrics"][4], acc2=r["metrics"][10], corr_x2=r["metrics"][11]))
+out["schedule"] = "recycled (default)"
 out["C4_probit_N20000_M400000"] = dict(iterations=its, gbs=[round(i["passes"] * N * Mt * 8 / i["s"] / 1e9) for i in its],
                                        finite=bool(np.all(np.isfinite(r["x1"]))))
 sol.close()
@@ -69,11 +70,21 @@ sums = sh.loo_sums(capi.V_USER_N1)
 t_loo = time.time() - t
 loo_kernel_ms = sh.time_kernel(3, 5)
 t = time.time(); z = sh.Ax(x1s * math.sqrt(N)); t_test = time.time() - t
+# test mode as main_meth runs it: four saved estimates per pass over the test matrix (vampomi_ax_multi_dev)
+for v_ in (capi.V_X1, capi.V_X2, capi.V_R1, capi.V_R2):
+    sh.set(v_, x1s * math.sqrt(N))
+sh.ax_multi_dev([capi.V_X1, capi.V_X2, capi.V_R1, capi.V_R2], [capi.V_Z1, capi.V_Z2, capi.V_USER_N0, capi.V_USER_N1])
+sh.get(capi.V_Z1)
+t = time.time()
+sh.ax_multi_dev([capi.V_X1, capi.V_X2, capi.V_R1, capi.V_R2], [capi.V_Z1, capi.V_Z2, capi.V_USER_N0, capi.V_USER_N1])
+z4 = sh.get(capi.V_USER_N1)
+t_test4 = time.time() - t
 out["C5_assoc_test_N20000_M850000"] = dict(se_s=round(t_se, 4), se_frac_below_0_05=float((p_se < 0.05).mean()),
                                            loo_end_to_end_s=round(t_loo, 4), loo_prepare_s=round(t_prep, 4),
                                            loo_sums_kernel_ms=round(loo_kernel_ms, 3),
                                            loo_sums_kernel_gbs=round(N * Mt * 8 / loo_kernel_ms / 1e6),
-                                           test_mode_pass_s=round(t_test, 4), sums_finite=bool(np.all(np.isfinite(sums))),
+                                           test_mode_pass_s=round(t_test, 4), test_mode_four_estimates_pass_s=round(t_test4, 4),
+                                           four_pass_matches_single=bool(np.allclose(z4, z, rtol=1e-12, atol=1e-14)), sums_finite=bool(np.all(np.isfinite(sums))),
                                            sum_x_matches_mean=bool(np.allclose(sums[:1000, 0] / N, sh.stats()[0][:1000], rtol=1e-10, atol=1e-12)))
 sh.close()
 print(json.dumps(out, indent=1))

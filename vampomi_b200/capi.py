@@ -90,6 +90,7 @@ _SIGNATURES = {
     "vampomi_counters": (C.c_int, [C.c_void_p, c_ll_p, C.c_int]),
     "vampomi_time_kernel": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p]),
     "vampomi_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "vampomi_plan_chunks": (C.c_longlong, [C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_int]),
     "vampomi_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vampomi_profile_read": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
     "vampomi_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -162,6 +163,11 @@ def divide_work(Mt, nranks, rank):
     M, S = C.c_longlong(), C.c_longlong()
     _check(load_library().vampomi_divide_work(Mt, nranks, rank, C.byref(M), C.byref(S)), "divide_work")
     return M.value, S.value
+
+
+def plan_chunks(slots, ntiles, M, min_cols=1, balance=True):
+    """Column chunks of the tiled matrix kernels' grids (include/vampomi.h: vampomi_plan_chunks)."""
+    return load_library().vampomi_plan_chunks(slots, ntiles, M, min_cols, int(bool(balance)))
 
 
 def device_count():

@@ -818,6 +818,11 @@ int vampomi_stream(vampomi_ctx* c, void** stream) {
     return VAMPOMI_OK;
 }
 
+long long vampomi_plan_chunks(long long slots, int ntiles, long long M, int min_cols, int balance) {
+    if (slots < 1 || ntiles < 1 || M < 1) return 1;
+    return balanced_chunks(slots, ntiles, M, min_cols, balance != 0);
+}
+
 int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
     VO_ARG(c && name, "set_tuning: NULL argument");
     struct { const char* n; int* p; int lo, hi; } knobs[] = {

@@ -162,6 +162,16 @@ def test_vector_ops_and_dots():
     assert np.allclose(sh.get(V_X1, divisor=math.sqrt(N)), a / math.sqrt(N), rtol=1e-15)
     sh.copy(V_X2, V_X1)
     assert np.array_equal(sh.get(V_X2), a)
+    # asynchronous read-out: the value at begin() is what arrives, whatever happens to the vector afterwards
+    sh.dump_begin(0, V_X1, math.sqrt(N))
+    sh.dump_begin(1, V_Y)
+    sh.fill(V_X1, -1.0)
+    with pytest.raises(capi.VampomiError):
+        sh.dump_begin(0, V_R1)                     # slot still pending
+    assert np.array_equal(sh.dump_wait(0), a / math.sqrt(N)) and np.array_equal(sh.dump_wait(1), y)
+    with pytest.raises(capi.VampomiError):
+        sh.dump_wait(0, np.empty(M))               # nothing pending
+    sh.set(V_X1, a)
     sh.fill(V_V, 3.0)
     got = sh.dots([(DOT, V_X1, V_R1), (DIFF2, V_X1, V_R1), (SQDEV, V_X1, V_R1, 2.0), (DOT, V_Y, V_Y), (DOT, V_V, V_V)])
     want = [a @ b, ((a - b) ** 2).sum(), ((a - 2 * b) ** 2).sum(), y @ y, 9.0 * M]

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "vampomi_vec_set": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vampomi_vec_get": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vampomi_vec_get_scaled": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_double_p]),
+    "vampomi_dump_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double]),
+    "vampomi_dump_wait": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vampomi_vec_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "vampomi_vec_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vampomi_vec_lincomb": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double]),
@@ -277,6 +279,18 @@ class Shard:
             _check(self.lib.vampomi_vec_get(self.h, vec, po), "vec_get")
         else:
             _check(self.lib.vampomi_vec_get_scaled(self.h, vec, divisor, po), "vec_get_scaled")
+        return out
+
+    def dump_begin(self, slot, vec, divisor=1.0):
+        """Starts an asynchronous read-out of vec/divisor (snapshot now, copy underneath later work)."""
+        _check(self.lib.vampomi_dump_begin(self.h, slot, vec, divisor), "dump_begin")
+        if not hasattr(self, "_dump_len"):
+            self._dump_len = {}
+        self._dump_len[slot] = self.vlen(vec)
+
+    def dump_wait(self, slot, out=None):
+        out = np.empty(self._dump_len.pop(slot)) if out is None else out
+        _check(self.lib.vampomi_dump_wait(self.h, slot, out.ctypes.data_as(c_double_p)), "dump_wait")
         return out
 
     def fill(self, vec, value):

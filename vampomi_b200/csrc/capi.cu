@@ -334,6 +334,12 @@ int vampomi_destroy(vampomi_ctx* c) {
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->cg_poll_host) cudaFreeHost(c->cg_poll_host);
     if (c->stage) cudaFreeHost(c->stage);
+    for (int k = 0; k < 2; k++) {
+        if (c->dump_dev[k]) cudaFree(c->dump_dev[k]);
+        if (c->dump_host[k]) cudaFreeHost(c->dump_host[k]);
+        if (c->dump_ready[k]) cudaEventDestroy(c->dump_ready[k]);
+        if (c->dump_done[k]) cudaEventDestroy(c->dump_done[k]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -594,6 +600,40 @@ int vampomi_vec_get_scaled(vampomi_ctx* c, int vec, double divisor, double* host
     double* tmp = m ? c->mvec[VAMPOMI_V_TMP_M1] : c->nvec[VAMPOMI_V_TMP_N1 - 32];
     VO_CHECK(launch_scale_div(c, tmp, vec_ptr(c, vec), divisor, vec_len(c, vec), nullptr));
     return d2h_vec(c, host, tmp, vec_len(c, vec));
+}
+int vampomi_dump_begin(vampomi_ctx* c, int slot, int vec, double divisor) {
+    VO_ARG(c && (slot == 0 || slot == 1) && vec_ptr(c, vec), "dump_begin: bad slot %d or vector id %d", slot, vec);
+    if (c->dump_len[slot] > 0) { set_error("dump_begin: slot %d still holds a read-out that was not waited for", slot); return VAMPOMI_ERR_STATE; }
+    VO_CUDA(cudaSetDevice(c->device));
+    const long long n = vec_len(c, vec);
+    if ((size_t)n > c->dump_elems[slot]) {
+        if (c->dump_dev[slot]) VO_CUDA(cudaFree(c->dump_dev[slot]));
+        if (c->dump_host[slot]) VO_CUDA(cudaFreeHost(c->dump_host[slot]));
+        c->dump_dev[slot] = nullptr; c->dump_host[slot] = nullptr; c->dump_elems[slot] = 0;
+        VO_CUDA(cudaMalloc(&c->dump_dev[slot], (size_t)n * sizeof(double)));
+        VO_CUDA(cudaMallocHost(&c->dump_host[slot], (size_t)n * sizeof(double)));
+        c->dump_elems[slot] = (size_t)n;
+    }
+    if (!c->dump_ready[slot]) {
+        VO_CUDA(cudaEventCreateWithFlags(&c->dump_ready[slot], cudaEventDisableTiming));
+        VO_CUDA(cudaEventCreateWithFlags(&c->dump_done[slot], cudaEventDisableTiming));
+    }
+    VO_CHECK(launch_scale_div(c, c->dump_dev[slot], vec_ptr(c, vec), divisor, n, nullptr));      // snapshot: vec may change right after
+    VO_CUDA(cudaEventRecord(c->dump_ready[slot], c->stream));
+    VO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->dump_ready[slot], 0));
+    VO_CUDA(cudaMemcpyAsync(c->dump_host[slot], c->dump_dev[slot], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    VO_CUDA(cudaEventRecord(c->dump_done[slot], c->copy_stream));
+    c->dump_len[slot] = n;
+    return VAMPOMI_OK;
+}
+int vampomi_dump_wait(vampomi_ctx* c, int slot, double* host) {
+    VO_ARG(c && (slot == 0 || slot == 1) && host, "dump_wait: bad slot %d or NULL buffer", slot);
+    if (c->dump_len[slot] <= 0) { set_error("dump_wait: nothing pending in slot %d", slot); return VAMPOMI_ERR_STATE; }
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CUDA(cudaEventSynchronize(c->dump_done[slot]));
+    memcpy(host, c->dump_host[slot], (size_t)c->dump_len[slot] * sizeof(double));
+    c->dump_len[slot] = 0;
+    return VAMPOMI_OK;
 }
 int vampomi_vec_fill(vampomi_ctx* c, int vec, double value) {
     VO_ARG(c && vec_ptr(c, vec), "vec_fill: bad vector id %d", vec);

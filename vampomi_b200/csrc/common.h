@@ -149,6 +149,12 @@ struct vampomi_ctx {
     int* cg_poll_host = nullptr;     // pinned ring of done flags
     double* stage = nullptr;         // pinned staging for host<->device vector traffic (max(M,N,3M) doubles)
     size_t stage_elems = 0;
+    // asynchronous vector read-out (vampomi_dump_begin / _wait)
+    double* dump_dev[2] = {nullptr, nullptr};
+    double* dump_host[2] = {nullptr, nullptr};   // pinned
+    size_t dump_elems[2] = {0, 0};
+    long long dump_len[2] = {0, 0};              // > 0 while a read-out is pending in the slot
+    cudaEvent_t dump_ready[2] = {nullptr, nullptr}, dump_done[2] = {nullptr, nullptr};
     vampomi::Xchg xchg = {};         // peer-memory exchange descriptor (enabled == 0 -> NCCL path)
     bool xchg_ready = false;         // set up successfully at comm_init
     unsigned char* xchg_region = nullptr;

@@ -86,11 +86,20 @@ void Vamp::fill_prior(vampomi_iter_result* res) const {
     }
 }
 
+// x1_hat/sqrt(N) and r1/sqrt(N) as the reference stores them at this point of the iteration (src/vamp.cpp:237-249). The
+// values are snapshotted now and travel to the host underneath the LMMSE solve; step() collects them before it returns.
 int Vamp::dump(double* x1_scaled, double* r1_scaled) {
     const double sq = std::sqrt((double)N_);
-    if (x1_scaled) VH(vampomi_vec_get_scaled(ctx_, VAMPOMI_V_X1, sq, x1_scaled));   // src/vamp.cpp:237-239
-    if (r1_scaled) VH(vampomi_vec_get_scaled(ctx_, VAMPOMI_V_R1, sq, r1_scaled));   // :246-249
+    if (x1_scaled) { VH(vampomi_dump_begin(ctx_, 0, VAMPOMI_V_X1, sq)); pending_x1_ = x1_scaled; }   // src/vamp.cpp:237-239
+    if (r1_scaled) { VH(vampomi_dump_begin(ctx_, 1, VAMPOMI_V_R1, sq)); pending_r1_ = r1_scaled; }   // :246-249
     return VAMPOMI_OK;
+}
+
+int Vamp::collect_dump() {
+    int rc = VAMPOMI_OK;
+    if (pending_x1_) { int r = vampomi_dump_wait(ctx_, 0, pending_x1_); if (r != VAMPOMI_OK) rc = r; pending_x1_ = nullptr; }
+    if (pending_r1_) { int r = vampomi_dump_wait(ctx_, 1, pending_r1_); if (r != VAMPOMI_OK) rc = r; pending_r1_ = nullptr; }
+    return rc;
 }
 
 // src/vamp.cpp:531-643 — the per-marker sums come from the device, everything else is L-length host arithmetic
@@ -142,7 +151,9 @@ int Vamp::step(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
     it_++;
     res->it = it_;
     int rc = cfg_.model == 0 ? step_linear(res, x1_scaled, r1_scaled) : step_probit(res, x1_scaled, r1_scaled);
+    const int rc_dump = collect_dump();                                          // also on failure: leaves no read-out pending
     if (rc != VAMPOMI_OK) return rc;
+    if (rc_dump != VAMPOMI_OK) return rc_dump;
     VH(vampomi_counters(ctx_, c1, 0));
     res->matrix_passes = c1[1] - c0[1];
     res->gam1_next = gam1_;

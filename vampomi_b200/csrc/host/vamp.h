@@ -28,6 +28,7 @@ private:
     int step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled);
     int update_prior();
     int dump(double* x1_scaled, double* r1_scaled);
+    int collect_dump();
     void fill_prior(vampomi_iter_result* res) const;
 
     vampomi_ctx* ctx_;
@@ -38,6 +39,8 @@ private:
     double gam1_, gamw_, gam2_ = 0, eta1_ = 0, eta2_ = 0, alpha1_ = 0, alpha2_ = 0, tau1_ = 0;
     std::vector<double> probs_, vars_;     // vars_ are the internal ones (x N, src/vamp.cpp:87-88)
     std::vector<double> y_host_, zbuf_;
+    double* pending_x1_ = nullptr;   // host buffers of read-outs begun by dump() and not yet collected
+    double* pending_r1_ = nullptr;
     bool aty_ready_ = false;
     bool ata_x2_ready_ = false;   // VAMPOMI_V_ATA_X2 holds A^T A x2_hat of the previous iteration (fused schedule)
     long long passes_at_start_ = 0;

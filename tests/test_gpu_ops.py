@@ -168,7 +168,7 @@ def test_vector_ops_and_dots():
     sh.fill(V_X1, -1.0)
     with pytest.raises(capi.VampomiError):
         sh.dump_begin(0, V_R1)                     # slot still pending
-    assert np.array_equal(sh.dump_wait(0), a / math.sqrt(N)) and np.array_equal(sh.dump_wait(1), y)
+    assert np.allclose(sh.dump_wait(0), a / math.sqrt(N), rtol=1e-15) and np.array_equal(sh.dump_wait(1), y)
     with pytest.raises(capi.VampomiError):
         sh.dump_wait(0, np.empty(M))               # nothing pending
     sh.set(V_X1, a)

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iostream>
 #include <mutex>
 #include <stdexcept>
@@ -145,10 +146,18 @@ int run_infere(Rank& r) {
         }
     }
 
-    std::vector<double> x1s((size_t)r.M), r1s((size_t)r.M);
+    // The two per-iteration vector files (src/vamp.cpp:235-249) are written by a helper thread while the next iteration
+    // already runs on the GPU: two sets of host buffers, at most one write in flight, joined before a buffer is reused and
+    // before leaving.
+    std::vector<double> x1buf[2] = {std::vector<double>((size_t)r.M), std::vector<double>((size_t)r.M)};
+    std::vector<double> r1buf[2] = {std::vector<double>((size_t)r.M), std::vector<double>((size_t)r.M)};
+    std::future<bool> writer;
+    std::string writer_file;
+    auto join_writer = [&]() -> bool { return !writer.valid() || writer.get(); };
     double total_time = 0;
     const int max_iter = (int)o.iterations;
     for (int it = 1; it <= max_iter; it++) {
+        std::vector<double>&x1s = x1buf[it & 1], &r1s = r1buf[it & 1];
         if (r.root())
             std::cout << std::endl << "********************" << std::endl << "iteration = " << it << std::endl
                       << "********************" << std::endl;
@@ -158,8 +167,11 @@ int run_infere(Rank& r) {
         const double t1 = now_s();
         const std::string f_x1 = base + "_it_" + std::to_string(it) + ".bin";                  // src/vamp.cpp:235-249
         const std::string f_r1 = base + "_r1_it_" + std::to_string(it) + ".bin";
-        if (!store_vec(f_x1, x1s.data(), r.M, r.S) || !store_vec(f_r1, r1s.data(), r.M, r.S))
-            return fatal(r, "could not write " + f_x1);
+        if (!join_writer()) return fatal(r, "could not write " + writer_file);
+        writer_file = f_x1;
+        writer = std::async(std::launch::async, [f_x1, f_r1, &x1s, &r1s, M = r.M, S = r.S]() {
+            return store_vec(f_x1, x1s.data(), M, S) && store_vec(f_r1, r1s.data(), M, S);
+        });
         if (r.root()) {
             std::cout << "x1_hat filepath_out is " << f_x1 << std::endl << "r1_hat filepath_out is " << f_r1 << std::endl;
             std::cout << "[CG] LMMSE solve: " << res.cg_iters_lmmse << " iterations, onsager solve: " << res.cg_iters_onsager
@@ -187,6 +199,7 @@ int run_infere(Rank& r) {
         if (it == max_iter && r.root())
             std::cout << "...maximal number of iterations was achieved. The algorithm might not converge!" << std::endl;
     }
+    if (!join_writer()) return fatal(r, "could not write " + writer_file);
     return 0;
 }
 

@@ -143,9 +143,9 @@ int vampomi_vec_set(vampomi_ctx* ctx, int vec, const double* host);
 int vampomi_vec_get(vampomi_ctx* ctx, int vec, double* host);
 /* host[i] = vec[i] / divisor — the x/sqrt(N) dumps of src/vamp.cpp:237-249. */
 int vampomi_vec_get_scaled(vampomi_ctx* ctx, int vec, double divisor, double* host);
-/* The same read-out without stalling the GPU (the per-iteration dumps of a running solver): begin() snapshots vec/divisor
- * into a private device buffer on the context's stream and starts its copy to pinned host memory on the copy stream, so
- * later work of the context goes on underneath; wait() blocks until that copy has landed and hands it to `host`.
+/* The same read-out without a host round trip in the middle of an iteration (the per-iteration dumps of a running
+ * solver): begin() enqueues, on the context's stream, a snapshot of vec/divisor and its copy to pinned host memory and
+ * returns at once, so the caller keeps enqueueing work behind it; wait() blocks until that copy has landed and hands it to `host`.
  * Two independent slots (0, 1); a slot must be waited for before it is begun again. */
 int vampomi_dump_begin(vampomi_ctx* ctx, int slot, int vec, double divisor);
 int vampomi_dump_wait(vampomi_ctx* ctx, int slot, double* host);

@@ -87,7 +87,7 @@ void Vamp::fill_prior(vampomi_iter_result* res) const {
 }
 
 // x1_hat/sqrt(N) and r1/sqrt(N) as the reference stores them at this point of the iteration (src/vamp.cpp:237-249). The
-// values are snapshotted now and travel to the host underneath the LMMSE solve; step() collects them before it returns.
+// values are snapshotted and copied in stream order without a host round trip; step() collects them before it returns.
 int Vamp::dump(double* x1_scaled, double* r1_scaled) {
     const double sq = std::sqrt((double)N_);
     if (x1_scaled) { VH(vampomi_dump_begin(ctx_, 0, VAMPOMI_V_X1, sq)); pending_x1_ = x1_scaled; }   // src/vamp.cpp:237-239

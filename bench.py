@@ -51,6 +51,7 @@ def parse_args():
                     help="recycled (default): lock-step LMMSE + Onsager solves sharing every read of the block, products of their "
                          "solutions kept by the solves themselves; fused: the same without that recycling (every product computed "
                          "by a pass, sharing reads); plain: one product per pass in the reference's order")
+    ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE", help="vampomi_set_tuning knob for experiments (repeatable)")
     ap.add_argument("--no-ab", action="store_true", help="skip the short device-resident legs of the other schedules")
     ap.add_argument("--storage", default="f64", choices=["f64", "f32"],
                     help="f32 = opt-in mode that holds the matrix rounded to FP32 in HBM (arithmetic FP64); NOT the headline configuration")
@@ -217,6 +218,9 @@ def main_ours(args):
     N, Mt = args.N, args.Mt
     t_setup = time.time()
     sh = capi.Shard(N, Mt, device=local, nranks=world, rank=rank, nccl_id=nccl_id, storage=args.storage)
+    for kv in args.tune:
+        k_, v_ = kv.split("=")
+        sh.set_tuning(k_, int(v_))
     sh.generate_iid(DATA_SEED)
     sh.compute_stats()
     # phenotype of the simulated model y = A beta + noise (simulation/data_sim.py:37-47), built with the device operator
@@ -357,7 +361,7 @@ def main_ours(args):
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64" if args.storage == "f64" else "f64 arithmetic on a matrix held as f32 (opt-in mode, not the headline)",
             "data": "synthetic",
-            "config": {"workload": workload_name(N, Mt), "N": N, "Mt": Mt, "markers_per_gpu": sh.M, "parallelism": f"marker-shard x{world}", "schedule": args.schedule,
+            "config": {"workload": workload_name(N, Mt), "N": N, "Mt": Mt, "markers_per_gpu": sh.M, "parallelism": f"marker-shard x{world}", "schedule": args.schedule, **({"tune": args.tune} if args.tune else {}),
                        "l2_note": f"inputs larger than L2: every matrix pass streams {sh.M * N * 8 / 1e9:.1f} GB per GPU",
                        "cg_iters_per_step": [[h["k1"], h["k2"]] for h in hist_dev], "setup_s": round(setup_s, 2),
                        "cross_gpu_sums": {0: "none (1 GPU)", 1: "NCCL all-reduce", 2: "fused NVLink peer-memory all-reduce"}[sh.comm_mode()]},

@@ -204,6 +204,26 @@ static int h2d_vec(vampomi_ctx* c, double* dev, const double* host, long long n)
     VO_CUDA(cudaStreamSynchronize(c->stream));      // the staging buffer is reused by the next call
     return VAMPOMI_OK;
 }
+// buffers and events of the asynchronous read-outs (vampomi_dump_begin): allocated once, at context creation, so that no
+// allocation (pinning 2 x 6.8 MB takes tens of milliseconds) ever lands inside an iteration
+static int ensure_dump(vampomi_ctx* c) {
+    const size_t n = c->mpad > c->ld ? c->mpad : c->ld;
+    for (int k = 0; k < 2; k++) {
+        if (c->dump_elems[k] >= n) continue;
+        if (c->dump_dev[k]) VO_CUDA(cudaFree(c->dump_dev[k]));
+        if (c->dump_host[k]) VO_CUDA(cudaFreeHost(c->dump_host[k]));
+        c->dump_dev[k] = nullptr; c->dump_host[k] = nullptr; c->dump_elems[k] = 0;
+        VO_CUDA(cudaMalloc(&c->dump_dev[k], n * sizeof(double)));
+        VO_CUDA(cudaMallocHost(&c->dump_host[k], n * sizeof(double)));
+        c->dump_elems[k] = n;
+        if (!c->dump_ready[k]) {
+            VO_CUDA(cudaEventCreateWithFlags(&c->dump_ready[k], cudaEventDisableTiming));
+            VO_CUDA(cudaEventCreateWithFlags(&c->dump_done[k], cudaEventDisableTiming));
+        }
+    }
+    return VAMPOMI_OK;
+}
+
 static int d2h_vec(vampomi_ctx* c, double* host, const double* dev, long long n) {
     VO_CHECK(ensure_stage(c, (size_t)n));
     VO_CUDA(cudaMemcpyAsync(c->stage, dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -308,6 +328,7 @@ int vampomi_create_ex(int device, int N, long long Mt, int nranks, int rank, int
         VO_CUDA(cudaMalloc(&c->cg, 2 * sizeof(CgScalars)));          // one per system of a paired solve
         VO_CUDA(cudaMemsetAsync(c->cg, 0, 2 * sizeof(CgScalars), c->stream));
         VO_CUDA(cudaMallocHost(&c->cg_poll_host, 64 * sizeof(int)));
+        VO_CHECK(ensure_dump(c));
         size_t st = (size_t)(3 * c->M > (long long)c->ld ? 3 * c->M : (long long)c->ld);
         VO_CHECK(ensure_stage(c, st));
         VO_CUDA(cudaStreamSynchronize(c->stream));
@@ -606,25 +627,20 @@ int vampomi_dump_begin(vampomi_ctx* c, int slot, int vec, double divisor) {
     if (c->dump_len[slot] > 0) { set_error("dump_begin: slot %d still holds a read-out that was not waited for", slot); return VAMPOMI_ERR_STATE; }
     VO_CUDA(cudaSetDevice(c->device));
     const long long n = vec_len(c, vec);
-    if ((size_t)n > c->dump_elems[slot]) {
-        if (c->dump_dev[slot]) VO_CUDA(cudaFree(c->dump_dev[slot]));
-        if (c->dump_host[slot]) VO_CUDA(cudaFreeHost(c->dump_host[slot]));
-        c->dump_dev[slot] = nullptr; c->dump_host[slot] = nullptr; c->dump_elems[slot] = 0;
-        VO_CUDA(cudaMalloc(&c->dump_dev[slot], (size_t)n * sizeof(double)));
-        VO_CUDA(cudaMallocHost(&c->dump_host[slot], (size_t)n * sizeof(double)));
-        c->dump_elems[slot] = (size_t)n;
-    }
-    if (!c->dump_ready[slot]) {
-        VO_CUDA(cudaEventCreateWithFlags(&c->dump_ready[slot], cudaEventDisableTiming));
-        VO_CUDA(cudaEventCreateWithFlags(&c->dump_done[slot], cudaEventDisableTiming));
-    }
+    VO_CHECK(ensure_dump(c));
     VO_CHECK(launch_scale_div(c, c->dump_dev[slot], vec_ptr(c, vec), divisor, n, nullptr));      // snapshot: vec may change right after
-    // The copy is stream-ordered on the context's own stream: it costs its PCIe time there (0.3 ms for 6.8 MB) but no host
-    // round trip, and never competes with a running matrix kernel. (Measured alternative: the copy on the separate copy
-    // stream, overlapping the matrix kernels, made the whole iteration 18 % SLOWER on one GPU — the copy engine starves next
-    // to kernels that saturate HBM and holds up the solve's 4-byte completion polls queued behind it.)
-    VO_CUDA(cudaMemcpyAsync(c->dump_host[slot], c->dump_dev[slot], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaEventRecord(c->dump_done[slot], c->stream));
+    // Default: the copy is stream-ordered on the context's own stream — it costs its PCIe time there (0.3 ms for 6.8 MB) but
+    // no host round trip, and never competes with a running matrix kernel. Knob dump_stream = 1 puts it on the separate
+    // copy stream instead, underneath the following kernels (A/B: the copy engine competes with kernels that saturate HBM).
+    if (c->tune.dump_stream == 1) {
+        VO_CUDA(cudaEventRecord(c->dump_ready[slot], c->stream));
+        VO_CUDA(cudaStreamWaitEvent(c->copy_stream, c->dump_ready[slot], 0));
+        VO_CUDA(cudaMemcpyAsync(c->dump_host[slot], c->dump_dev[slot], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        VO_CUDA(cudaEventRecord(c->dump_done[slot], c->copy_stream));
+    } else {
+        VO_CUDA(cudaMemcpyAsync(c->dump_host[slot], c->dump_dev[slot], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        VO_CUDA(cudaEventRecord(c->dump_done[slot], c->stream));
+    }
     c->dump_len[slot] = n;
     return VAMPOMI_OK;
 }
@@ -875,7 +891,7 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},
         {"load_threads", &c->tune.load_threads, 1, 16}, {"ld_hint", &c->tune.ld_hint, 0, 3},
         {"interleave", &c->tune.interleave, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
-        {"grid_balance", &c->tune.grid_balance, 0, 1},
+        {"grid_balance", &c->tune.grid_balance, 0, 1},   {"dump_stream", &c->tune.dump_stream, 0, 1},
         {"multi_ax_rv", &c->tune.multi_ax_rv, 0, 2},     {"multi_ax_unroll", &c->tune.multi_ax_unroll, 0, 8},
         {"multi_atx_impl", &c->tune.multi_atx_impl, 0, 1}, {"multi_atx_cols", &c->tune.multi_atx_cols, 0, 4},
         {"multi_atx_unroll", &c->tune.multi_atx_unroll, 0, 4}, {"multi_atx_tile", &c->tune.multi_atx_tile, 0, 16384},

@@ -116,6 +116,7 @@ struct Tuning {
     int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 4)
     int multi_atx_tile = 0;          // shared-memory form: rows of p per tile (0 = 2048)
     int grid_balance = 1;            // 1 = (row tile x column chunk) grids sized to full waves of resident CTAs (balanced_chunks), 0 = one, possibly partly filled, wave
+    int dump_stream = 0;             // asynchronous read-outs copy on 0 = the context's stream (stream-ordered), 1 = the copy stream
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
 };
 

@@ -126,8 +126,8 @@ static int xchg_setup(vampomi_ctx* c) {
     size_t off = 0;
     x.off_flag_vec = off; off = align(off + (size_t)x.G * x.maxb * sizeof(unsigned int));
     x.off_flag_sc = off;  off = align(off + (size_t)x.G * 32 * sizeof(unsigned int));
-    x.off_recv_vec = off; off = align(off + (size_t)2 * x.G * XCHG_KMAX * c->ld * sizeof(double));
-    x.off_recv_sc = off;  off = align(off + (size_t)2 * x.G * XCHG_SCALARS * sizeof(double));
+    x.off_recv_vec = off; off = align(off + (size_t)2 * x.G * XCHG_KMAX * c->ld * 2 * sizeof(double));    // x 2: tagged words (xchg.cuh)
+    x.off_recv_sc = off;  off = align(off + (size_t)2 * x.G * XCHG_SCALARS * 2 * sizeof(double));
     const size_t region_bytes = off;
     XchgInfo mine{};
     mine.pid = (long long)getpid(); mine.device = c->device;
@@ -176,6 +176,7 @@ static int xchg_setup(vampomi_ctx* c) {
     x.seq = c->xchg_local; x.ticket = c->xchg_local + 2;
     c->xchg_ready = true;
     x.enabled = c->tune.xchg ? 1 : 0;
+    x.ll = c->tune.xchg_ll ? 1 : 0;
     return VAMPOMI_OK;
 }
 
@@ -893,6 +894,7 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"load_threads", &c->tune.load_threads, 1, 16}, {"ld_hint", &c->tune.ld_hint, 0, 3},
         {"interleave", &c->tune.interleave, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
         {"grid_balance", &c->tune.grid_balance, 0, 1},   {"dump_stream", &c->tune.dump_stream, 0, 1},
+        {"xchg_ll", &c->tune.xchg_ll, 0, 1},
         {"multi_ax_rv", &c->tune.multi_ax_rv, 0, 2},     {"multi_ax_unroll", &c->tune.multi_ax_unroll, 0, 8},
         {"multi_atx_impl", &c->tune.multi_atx_impl, 0, 1}, {"multi_atx_cols", &c->tune.multi_atx_cols, 0, 4},
         {"multi_atx_unroll", &c->tune.multi_atx_unroll, 0, 4}, {"multi_atx_tile", &c->tune.multi_atx_tile, 0, 16384},
@@ -902,6 +904,7 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
             VO_ARG(value >= k.lo && value <= k.hi, "set_tuning: %s must be in [%d,%d]", name, k.lo, k.hi);
             *k.p = value;
             c->xchg.enabled = (c->xchg_ready && c->tune.xchg) ? 1 : 0;
+            c->xchg.ll = c->tune.xchg_ll ? 1 : 0;
             return VAMPOMI_OK;
         }
     set_error("set_tuning: unknown knob %s", name);

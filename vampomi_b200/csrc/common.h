@@ -106,6 +106,7 @@ struct Tuning {
     int ax_impl = 0;                 // 0 = per-thread 256-bit LDG streaming, 1 = bulk-copy (cp.async.bulk + mbarrier) pipeline
     int atx_impl = 3;                // 0 = warp per column group, 1 = bulk-copy pipeline, 2 = CTA per column group, 3 = auto (2 when N >= 4096, else 0)
     int xchg = 1;                    // 1 = fused peer-memory all-reduce (xchg.cuh) when it could be set up, 0 = NCCL collectives
+    int xchg_ll = 1;                 // vector exchange: 1 = tagged words (no fence, no flags), 0 = payload + system fence + per-CTA flags
     int load_threads = 4;            // parallel pread -> pinned -> HBM pipelines of vampomi_load_file
     int ld_hint = 0;                 // L2 hint on the streaming loads of the default kernel shapes: 0 none, 1 L2::256B, 2 L2::evict_first, 3 both
     int interleave = 0;              // experiment: deal column groups round-robin over the grid instead of one contiguous range per CTA

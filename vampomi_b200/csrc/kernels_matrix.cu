@@ -261,19 +261,28 @@ __global__ void __launch_bounds__(256) k_ax_reduce_xchg(const double* __restrict
         double t = sm[0][r];
 #pragma unroll
         for (int q = 1; q < SL; q++) t += sm[q][r];
-        if (i < N)
-            for (int g = 0; g < x.G; g++) xchg_recv_vec(x, g, slot, x.rank)[i] = t;
-        __threadfence_system();
-        __syncwarp();
-        if (r < x.G) {
-            st_release_sys(xchg_flag_vec(x, r, x.rank, blockIdx.x), seq);
-            xchg_wait_flag(xchg_flag_vec(x, x.rank, r, blockIdx.x), seq);
-        }
-        __syncwarp();
-        if (i < N) {
-            double tot = 0.0;
-            for (int g = 0; g < x.G; g++) tot += __ldcg(xchg_recv_vec(x, x.rank, slot, g) + i);
-            out[i] = tot / divisor;
+        if (x.ll) {                                            // tagged words: the data is its own arrival signal (xchg.cuh)
+            if (i < N) {
+                for (int g = 0; g < x.G; g++) xchg_ll_store(xchg_recv_ll(x, g, slot, x.rank) + 2 * (size_t)i, t, seq);
+                double tot = 0.0;
+                for (int g = 0; g < x.G; g++) tot += xchg_ll_load(xchg_recv_ll(x, x.rank, slot, g) + 2 * (size_t)i, seq);
+                out[i] = tot / divisor;
+            }
+        } else {
+            if (i < N)
+                for (int g = 0; g < x.G; g++) xchg_recv_vec(x, g, slot, x.rank)[i] = t;
+            __threadfence_system();
+            __syncwarp();
+            if (r < x.G) {
+                st_release_sys(xchg_flag_vec(x, r, x.rank, blockIdx.x), seq);
+                xchg_wait_flag(xchg_flag_vec(x, x.rank, r, blockIdx.x), seq);
+            }
+            __syncwarp();
+            if (i < N) {
+                double tot = 0.0;
+                for (int g = 0; g < x.G; g++) tot += __ldcg(xchg_recv_vec(x, x.rank, slot, g) + i);
+                out[i] = tot / divisor;
+            }
         }
         __syncwarp();
         if (r == 0) {                                          // the last CTA to finish publishes the new sequence number

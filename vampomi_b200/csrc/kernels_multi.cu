@@ -146,7 +146,15 @@ __global__ void __launch_bounds__(256) k_ax_reduce_multi(const double* __restric
     const unsigned int seq = s_seq, slot = seq & 1u;
     const size_t koff = (size_t)k * (x.ld / XCHG_KMAX);
     const int cta = k * gridDim.x + blockIdx.x;
-    if (active) {
+    if (active && x.ll) {                                     // tagged words: the data is its own arrival signal (xchg.cuh)
+        if (i < N) {
+            for (int g = 0; g < x.G; g++) xchg_ll_store(xchg_recv_ll(x, g, slot, x.rank) + 2 * (koff + i), t, seq);
+            double tot = 0.0;
+            for (int g = 0; g < x.G; g++) tot += xchg_ll_load(xchg_recv_ll(x, x.rank, slot, g) + 2 * (koff + i), seq);
+            out[i] = tot / divisor;
+        }
+        __syncwarp();
+    } else if (active) {
         if (i < N)
             for (int g = 0; g < x.G; g++) xchg_recv_vec(x, g, slot, x.rank)[koff + i] = t;
         __threadfence_system();

@@ -11,6 +11,12 @@
 //   sum    it adds the G contributions from its local receive area in rank order 0..G-1 — every rank adds the same
 //          values in the same order, so results are bitwise identical on all GPUs and independent of timing
 //
+// Vector exchanges (the N doubles after A x) use a flag-less form of the same idea by default (Xchg::ll): every double travels
+// as two 8-byte words {low half | seq << 32} and {high half | seq << 32}. An 8-byte store is indivisible, so a word whose tag
+// equals `seq` IS the data of this exchange: the receiver polls the words themselves and needs neither a system-scope fence
+// behind the payload nor a flag — the per-CTA fence + flag round trip (~70 us for 1250 CTAs) becomes one NVLink store
+// latency. Tags of the previous use of a slot (seq - 2) never match. Twice the bytes (320 kB instead of 160 kB): immaterial.
+//
 // Slot reuse is safe with two slots: a rank can only start exchange s+2 after it has passed the wait of s+1, and a peer
 // raises its flag for s+1 only after it has finished reading slot (s & 1) of exchange s (stream order on that GPU).
 // `seq` lives in device memory and advances only when an exchange really ran, so launches that return early at the CG
@@ -28,6 +34,7 @@ constexpr int XCHG_KMAX = 4;            // vectors one exchange can carry (multi
 struct Xchg {                           // passed by value to kernels; all offsets identical on every rank
     int enabled;
     int G, rank;
+    int ll;                             // 1 = tagged-word vector exchange (no fence, no flags), 0 = payload + fence + per-CTA flags
     int maxb;                           // CTA slots per rank in the vector flag array
     unsigned long long ld;              // stride between the contributions of two ranks (doubles): XCHG_KMAX vectors of length ld_vec
     unsigned long long off_flag_vec, off_flag_sc, off_recv_vec, off_recv_sc;   // byte offsets inside a region
@@ -62,8 +69,29 @@ __device__ __forceinline__ double* xchg_recv_vec(const Xchg& x, int on_rank, uns
 __device__ __forceinline__ unsigned int* xchg_flag_vec(const Xchg& x, int on_rank, int from_rank, int cta) {
     return reinterpret_cast<unsigned int*>(x.peer[on_rank] + x.off_flag_vec) + (size_t)from_rank * x.maxb + cta;
 }
+// tagged-word form: value i of rank `from_rank` occupies two u64 at the same place, i.e. 16 bytes per value
+__device__ __forceinline__ unsigned long long* xchg_recv_ll(const Xchg& x, int on_rank, unsigned slot, int from_rank) {
+    return reinterpret_cast<unsigned long long*>(x.peer[on_rank] + x.off_recv_vec) + ((size_t)slot * x.G + from_rank) * x.ld * 2;
+}
+__device__ __forceinline__ void xchg_ll_store(unsigned long long* dst, double v, unsigned int seq) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v), tag = (unsigned long long)seq << 32;
+    const unsigned long long lo = (bits & 0xffffffffull) | tag, hi = (bits >> 32) | tag;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ double xchg_ll_load(const unsigned long long* src, unsigned int seq) {
+    unsigned long long lo, hi, spins = 0;
+    for (;;) {
+        asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
+        if ((unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq) break;
+        if (++spins > (1ull << 26)) __trap();        // a rank is gone — fault instead of hanging
+    }
+    return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+}
 __device__ __forceinline__ double* xchg_recv_sc(const Xchg& x, int on_rank, unsigned slot, int from_rank) {
     return reinterpret_cast<double*>(x.peer[on_rank] + x.off_recv_sc) + ((size_t)slot * x.G + from_rank) * XCHG_SCALARS;
+}
+__device__ __forceinline__ unsigned long long* xchg_recv_sc_ll(const Xchg& x, int on_rank, unsigned slot, int from_rank) {
+    return reinterpret_cast<unsigned long long*>(x.peer[on_rank] + x.off_recv_sc) + ((size_t)slot * x.G + from_rank) * XCHG_SCALARS * 2;
 }
 __device__ __forceinline__ unsigned int* xchg_flag_sc(const Xchg& x, int on_rank, int from_rank) {
     return reinterpret_cast<unsigned int*>(x.peer[on_rank] + x.off_flag_sc) + (size_t)from_rank * 32;   // one 128-byte line each
@@ -77,6 +105,18 @@ __device__ inline void xchg_allreduce_scalars(const Xchg& x, const double* vals,
     if (tid == 0) s_seq = ld_volatile_u32(x.seq + 1) + 1u;
     __syncthreads();
     const unsigned int seq = s_seq, slot = seq & 1u;
+    if (x.ll) {                                                             // tagged words: no fence, no flags
+        if (tid < K) {
+            const double v = vals[tid];
+            for (int g = 0; g < x.G; g++) xchg_ll_store(xchg_recv_sc_ll(x, g, slot, x.rank) + 2 * tid, v, seq);
+            double t = 0.0;
+            for (int g = 0; g < x.G; g++) t += xchg_ll_load(xchg_recv_sc_ll(x, x.rank, slot, g) + 2 * tid, seq);
+            out[tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) x.seq[1] = seq;
+        return;
+    }
     if (tid < K) {
         const double v = vals[tid];
         for (int g = 0; g < x.G; g++) xchg_recv_sc(x, g, slot, x.rank)[tid] = v;

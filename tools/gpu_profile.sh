@@ -23,6 +23,9 @@ step bench_ref timeout 900 python bench.py --impl reference --steps 2 --warmup 1
 if [ "${SKIP_C2:-0}" != "1" ]; then
   timeout 1500 python tools/parity_c2.py > $OUT/parity_c2.json 2> $OUT/parity_c2.err; echo "parity_c2 rc=$?" | tee -a $STATUS
 fi
+if [ "${SKIP_CONFIGS:-0}" != "1" ]; then
+  timeout 900 python tools/run_configs.py > $OUT/configs.json 2> $OUT/configs.err; echo "configs rc=$?" | tee -a $STATUS
+fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   NB="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-ab"
   step ncu_plain timeout 900 $NB && \

@@ -104,6 +104,9 @@ for s in ("recycled", "fused", "plain"):
             pass
 if rep:
     json.dump(rep, open(os.path.join(PROF, f"{tag}_parity_report_vs_reference_fixtures.json"), "w"), indent=1)
+p = os.path.join(OUT, "configs.json")
+if os.path.isfile(p):
+    shutil.copy(p, os.path.join(PROF, f"{tag}_configs_C4_C5.json"))
 p = os.path.join(OUT, "parity_c2.json")
 if os.path.isfile(p):
     shutil.copy(p, os.path.join(PROF, f"{tag}_parity_config2_vs_reference_binary.json"))

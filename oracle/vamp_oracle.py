@@ -7,7 +7,7 @@ cites the reference file:line it restates (paths relative to /root/reference).
 Parity pinning: the reference ships no tests or golden vectors. This restatement is pinned instead
 against outputs of the reference itself, compiled here by ``oracle/build_ref.py`` into ``oracle/_ref/main_meth_ref``
 (patched only to run and to be deterministic); the fixtures under ``tests/golden/`` were produced by that binary via
-``tools/make_golden.py`` and ``tests/test_oracle_vs_golden.py`` holds this module to them. The Boost special
+``tests/tools/make_golden.py`` and ``tests/test_oracle_vs_golden.py`` holds this module to them. The Boost special
 functions (normal cdf, Student-t tail) are *not* in /root/reference; they are restated from their published
 definitions and pinned against scipy (parity unpinned at the Boost boundary — see DESIGN.md).
 

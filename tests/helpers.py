@@ -1,4 +1,4 @@
-"""Shared helpers of the test suite: golden fixtures (made by tools/make_golden.py from the reference binary) and
+"""Shared helpers of the test suite: golden fixtures (made by tests/tools/make_golden.py from the reference binary) and
 the inputs they were computed on (rebuilt from seeds, checked against the recorded SHA-256)."""
 import hashlib
 import os

@@ -1,5 +1,5 @@
 """Pins the numpy oracle (oracle/vamp_oracle.py) to outputs of the reference itself (tests/golden/*.npz, produced by
-oracle/_ref/main_meth_ref via tools/make_golden.py): per-iteration x1_hat / r1 dumps, CSV values and byte layout,
+oracle/_ref/main_meth_ref via tests/tools/make_golden.py): per-iteration x1_hat / r1 dumps, CSV values and byte layout,
 CG iteration counts, p-values and test-mode rows."""
 import os
 

@@ -3,7 +3,7 @@ set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 OUT=gpurun_out; mkdir -p $OUT
 timeout 900 python tools/run_configs.py > $OUT/configs.json 2> $OUT/configs.err; echo "configs rc=$?"; tail -5 $OUT/configs.err
-timeout 1500 python tools/parity_c2.py > $OUT/parity_c2.json 2> $OUT/parity_c2.err; echo "parity rc=$?"; tail -5 $OUT/parity_c2.err
+timeout 1500 python tests/tools/parity_c2.py > $OUT/parity_c2.json 2> $OUT/parity_c2.err; echo "parity rc=$?"; tail -5 $OUT/parity_c2.err
 python - <<'PY'
 import json
 try:

@@ -15,13 +15,13 @@ step smoke timeout 600 python -c "import __graft_entry__ as g; g.smoke()"
 step pytest_gpu timeout 1500 python -m pytest tests -m gpu -q --timeout 600
 tail -3 $OUT/pytest_gpu.log
 for s in recycled fused plain; do
-  timeout 600 python tools/parity_report.py $s > $OUT/parity_report_$s.json 2> $OUT/parity_report_$s.err; echo "parity_report_$s rc=$?" | tee -a $STATUS
+  timeout 600 python tests/tools/parity_report.py $s > $OUT/parity_report_$s.json 2> $OUT/parity_report_$s.err; echo "parity_report_$s rc=$?" | tee -a $STATUS
 done
 BENCH="python bench.py --steps ${BENCH_STEPS:-5} --warmup ${BENCH_WARMUP:-3}"
 step bench timeout 1200 $BENCH
 step bench_ref timeout 900 python bench.py --impl reference --steps 2 --warmup 1
 if [ "${SKIP_C2:-0}" != "1" ]; then
-  timeout 1500 python tools/parity_c2.py > $OUT/parity_c2.json 2> $OUT/parity_c2.err; echo "parity_c2 rc=$?" | tee -a $STATUS
+  timeout 1500 python tests/tools/parity_c2.py > $OUT/parity_c2.json 2> $OUT/parity_c2.err; echo "parity_c2 rc=$?" | tee -a $STATUS
 fi
 if [ "${SKIP_CONFIGS:-0}" != "1" ]; then
   timeout 900 python tools/run_configs.py > $OUT/configs.json 2> $OUT/configs.err; echo "configs rc=$?" | tee -a $STATUS

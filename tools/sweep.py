@@ -53,6 +53,11 @@ if a.multi:
         t(5, "ax_multi_K2_default", a.multi, grid_balance=gbal)
         t(8, "ax_multi_K3_default", a.multi, grid_balance=gbal)
         t(6, "atx_multi_K2_default", a.multi, grid_balance=gbal)
+    for occ in (3, 0, 3, 0):
+        t(5, "ax_multi_K2_occ", a.multi, multi_ax_occ=occ)
+        t(8, "ax_multi_K3_occ", a.multi, multi_ax_occ=occ)
+    if a.quick:
+        sys.exit(0)
     for rv, u in ((1, 4), (1, 8), (2, 2), (2, 4), (1, 2)):
         t(5, "ax_multi_K2", a.multi, multi_ax_rv=rv, multi_ax_unroll=u)
         t(8, "ax_multi_K3", a.multi, multi_ax_rv=rv, multi_ax_unroll=u)

@@ -112,6 +112,7 @@ struct Tuning {
     int interleave = 0;              // experiment: deal column groups round-robin over the grid instead of one contiguous range per CTA
     int multi_ax_rv = 0;             // multi-vector A x: 32-byte vectors per thread per column (0 = 1)
     int multi_ax_unroll = 0;         // multi-vector A x: columns in flight (0 = 4 for FP64 storage, 2 for FP32)
+    int multi_ax_occ = 0;            // multi-vector A x, shape (1, 4): 3 = hold the kernel to 80 registers for three CTAs per SM (0 = two)
     int multi_atx_impl = 1;          // multi-vector A^T p: 0 = p tiles in registers, 1 = p tiles in shared memory
     int multi_atx_cols = 0;          // shared-memory form: columns per warp pass (0 = 2 for two vectors, 1 for one)
     int multi_atx_unroll = 0;        // shared-memory form: 32-byte steps in flight per column (0 = 4)

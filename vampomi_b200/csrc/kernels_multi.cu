@@ -20,8 +20,10 @@
 namespace vampomi {
 
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int K, int RV, int U>
-__global__ void __launch_bounds__(256, (K * RV >= 4 ? 1 : 2)) k_ax_multi(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
+// OCC: CTAs per SM the register allocation is held to (0 = 2, or 1 for the largest tiles). OCC = 3 (80 registers, no spills
+// for two vectors) trades registers for a third resident CTA: 96 instead of 64 KB of loads in flight per SM.
+template <typename T, int K, int RV, int U, int OCC = 0>
+__global__ void __launch_bounds__(256, (OCC > 0 ? OCC : (K * RV >= 4 ? 1 : 2))) k_ax_multi(const T* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                   const double* __restrict__ msig, MultiVec mv, int tile_rows, int cols_per_chunk,
                                                   long long M, double* __restrict__ partial, int nchunks) {
     constexpr int VE = V32<T>::VE;
@@ -396,10 +398,10 @@ static int ensure_buf(vampomi_ctx* c, double** buf, size_t* cap, size_t need) {
     return VAMPOMI_OK;
 }
 
-template <typename T, int K, int RV, int U>
+template <typename T, int K, int RV, int U, int OCC = 0>
 static int ax_multi_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     constexpr int VE = V32<T>::VE;
-    auto kern = k_ax_multi<T, K, RV, U>;
+    auto kern = k_ax_multi<T, K, RV, U, OCC>;
     const int cap = 256 * VE * RV;
     const int ntiles = (int)((c->ld + cap - 1) / cap);
     const size_t tr = (c->ld + ntiles - 1) / ntiles;
@@ -439,6 +441,7 @@ static int ax_multi_t(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     int rv = c->tune.multi_ax_rv, u = c->tune.multi_ax_unroll;
     if (rv == 0) rv = 1;
     if (u == 0) u = sizeof(T) == 8 ? 4 : 2;
+    if (rv == 1 && u == 4 && c->tune.multi_ax_occ == 3) return ax_multi_launch<T, K, 1, 4, 3>(c, A, mv);
     switch (rv * 10 + u) {
         case 12: return ax_multi_launch<T, K, 1, 2>(c, A, mv);
         case 14: return ax_multi_launch<T, K, 1, 4>(c, A, mv);

@@ -6,14 +6,19 @@
 // reference runs them one after the other; since every pass is bound by streaming A from HBM, running them side by side on
 // the same stream of A halves the bytes of those passes while each right-hand side keeps exactly its own arithmetic.
 //
-//   k_ax_multi      out_k[i] partials = sum_j (A[i,j]-mave[j]) * (msig[j] * x_k[j]),  k < K     (mirror of k_ax_partial)
-//   k_ax_reduce_multi (+ fused cross-GPU sum)                                                    (mirror of k_ax_reduce[_xchg])
-//   k_atx_tiled     out_k[j] partials over a row tile = sum_i (A[i,j]-mave[j]) * p_k[i]; the K tiles of p live in
-//                   registers, so the K vectors cost no extra memory traffic at all (the CTA-per-column form would have to
-//                   re-read K*N*8 bytes of p per column group through L2)
-//   k_atx_reduce    out_k[j] = msig[j] * (sum over row tiles) * (1/sqrt(N))
+//   k_ax_multi        out_k[i] partials = sum_j (A[i,j]-mave[j]) * (msig[j] * x_k[j]),  k < K <= 4   (mirror of k_ax_partial)
+//   k_ax_reduce_multi out_k[i] = (sum of the chunk partials [+ the other GPUs' over peer memory]) / sqrt(N)
+//                                                                                   (mirror of k_ax_reduce[_xchg])
+//   k_atx_smem        out_k[j] partials over a row tile = sum_i (A[i,j]-mave[j]) * p_k[i], K <= 2: the tile of the K vectors
+//                     is staged in shared memory once per CTA and every warp streams its own columns down the tile —
+//                     the default; 6.9 TB/s for two vectors, the same as the one-vector kernel
+//   k_atx_tiled       the same with the K tiles of p held in registers (162 registers for K = 2, one CTA per SM, 4.7 TB/s:
+//                     kept as knob multi_atx_impl = 0 for A/B)
+//   k_atx_reduce      out_k[j] = msig[j] * (sum over row tiles) * (1/sqrt(N))
 //
 // A slot whose `done` flag is set (a CG solve that has already stopped) is skipped by every kernel, consistently on all GPUs.
+// Grids are (row tile x column chunk) with the chunk count chosen so that whole waves of resident CTAs are filled
+// (balanced_chunks, common.h).
 #include "common.h"
 #include "vec32.cuh"
 

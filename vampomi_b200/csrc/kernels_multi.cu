@@ -516,16 +516,17 @@ static int atx_smem_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     const int tile_rows = (int)((tr + 15) / 16 * 16);
     const int sp_stride = (tile_rows + 32 * VE - 1) / (32 * VE) * (32 * VE);
     const size_t smem = (size_t)K * sp_stride * sizeof(double);
-    static thread_local const void* attr_set[8] = {};
-    static thread_local size_t attr_bytes[8] = {};
-    {   // raise the dynamic shared-memory limit of this instantiation once per (thread, kernel, size)
+    if (smem > 48 * 1024) {   // above the default limit the opt-in attribute is needed: set once per (device, instantiation, size)
+        static thread_local int attr_dev[16];
+        static thread_local const void* attr_fn[16] = {};
+        static thread_local size_t attr_bytes[16] = {};
         int slot = -1;
-        for (int i = 0; i < 8; i++) if (attr_set[i] == (const void*)kern) { slot = i; break; }
-        if (slot < 0) for (int i = 0; i < 8; i++) if (attr_set[i] == nullptr) { slot = i; break; }
+        for (int i = 0; i < 16; i++) if (attr_fn[i] == (const void*)kern && attr_dev[i] == c->device) { slot = i; break; }
+        if (slot < 0) for (int i = 0; i < 16; i++) if (attr_fn[i] == nullptr) { slot = i; break; }
         if (slot < 0) slot = 0;
-        if (attr_set[slot] != (const void*)kern || attr_bytes[slot] < smem) {
+        if (attr_fn[slot] != (const void*)kern || attr_dev[slot] != c->device || attr_bytes[slot] < smem) {
             VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set[slot] = (const void*)kern; attr_bytes[slot] = smem;
+            attr_fn[slot] = (const void*)kern; attr_dev[slot] = c->device; attr_bytes[slot] = smem;
         }
     }
     int per_sm = c->tune.atx_ctas_per_sm;

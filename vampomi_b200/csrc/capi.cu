@@ -61,6 +61,13 @@ int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n) {
     return VAMPOMI_OK;
 }
 
+// packed scalar sums over the GPUs: the peer-memory exchange when it is up (identically on all ranks), else NCCL
+static int sum_over_ranks(vampomi_ctx* c, double* dev, size_t n) {
+    if (c->nranks == 1) return VAMPOMI_OK;
+    if (c->xchg.enabled && n <= (size_t)XCHG_SCALARS) return launch_xchg_sums(c, dev, (int)n);
+    return allreduce_inplace(c, dev, n);
+}
+
 int prof_begin(vampomi_ctx* c, int kind, double bytes) {
     if (!c->profile) return -1;
     vampomi_ctx::ProfSpan sp;
@@ -191,7 +198,7 @@ static int ensure_stage(vampomi_ctx* c, size_t elems) {
 
 // device sums -> pinned host -> caller, after the (optional) packed all-reduce; ONE sync
 static int fetch_sums(vampomi_ctx* c, int n, bool reduce, double* out) {
-    if (reduce) VO_CHECK(allreduce_inplace(c, c->sums, (size_t)n));
+    if (reduce) VO_CHECK(sum_over_ranks(c, c->sums, (size_t)n));
     VO_CUDA(cudaMemcpyAsync(c->sums_host, c->sums, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; i++) out[i] = c->sums_host[i];
@@ -687,7 +694,7 @@ int vampomi_dots(vampomi_ctx* c, int n, const int* kind, const int* a, const int
     VO_CHECK(launch_dots(c, n, kind, pa, pb, len, scale, c->sums));
     if (c->nranks > 1 && any_m) {
         // N-vector items are replicated: divide them by nranks after the packed sum so that one all-reduce serves all
-        VO_CHECK(allreduce_inplace(c, c->sums, (size_t)n));
+        VO_CHECK(sum_over_ranks(c, c->sums, (size_t)n));
     }
     VO_CHECK(fetch_sums(c, n, false, out));
     if (c->nranks > 1 && any_m)

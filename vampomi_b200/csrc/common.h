@@ -247,6 +247,7 @@ int launch_cg_init_finish(vampomi_ctx* c, const CgBatch& b, const double* sums_d
 int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double* sums_dev);
 int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev);
 int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double tol, int max_iter, const double* sums_dev);
+int launch_xchg_sums(vampomi_ctx* c, double* sums_dev, int n);   // n <= XCHG_SCALARS packed sums over the GPUs via peer memory
 // all-reduce `n` doubles in place on the context stream (no-op for nranks == 1)
 int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n);
 // profiling spans: begin returns an index (or -1 when profiling is off), end closes it

@@ -144,6 +144,21 @@ int launch_dots(vampomi_ctx* c, int n, const int* kind, const double* const* a, 
     return VAMPOMI_OK;
 }
 
+// The per-iteration packed sums outside the CG loop (denoiser, EM, metrics): summed over the GPUs by ONE small block through
+// the same peer-memory exchange as the CG scalars, instead of an ncclAllReduce (~4 of them per VAMP iteration).
+__global__ void __launch_bounds__(64) k_xchg_sums(double* __restrict__ sums, int n, Xchg xc) {
+    __shared__ double v[XCHG_SCALARS];
+    if ((int)threadIdx.x < n) v[threadIdx.x] = sums[threadIdx.x];
+    __syncthreads();
+    xchg_allreduce_scalars(xc, v, n, sums);
+}
+int launch_xchg_sums(vampomi_ctx* c, double* sums_dev, int n) {
+    k_xchg_sums<<<1, 64, 0, c->stream>>>(sums_dev, n, c->xchg);
+    c->counters[0]++;
+    VO_CUDA(cudaGetLastError());
+    return VAMPOMI_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Hutchinson probe
 // ---------------------------------------------------------------------------------------------------------------

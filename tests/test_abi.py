@@ -87,6 +87,19 @@ def test_cli_accepts_every_reference_flag(lib):
     assert "--probit-var1" in res.stdout        # the reference echoes this flag without a space (src/options.cpp:199)
 
 
+def test_cli_additions_are_validated_before_any_gpu_work(lib):
+    """The flags the reference does not have (--gpus, --storage, --schedule, --seed) are parsed and echoed like its own;
+    bad values end with the reference's FATAL wording and exit status 1 without touching a GPU."""
+    for argv in (["--schedule", "sideways"], ["--storage", "f16"], ["--gpus", "0"], ["--schedule"]):
+        res = subprocess.run([build.MAIN_METH] + argv, stdout=subprocess.PIPE, text=True)
+        assert res.returncode == 1 and "FATAL" in res.stdout, argv
+    res = subprocess.run([build.MAIN_METH, "--meth-file", "x", "--phen-file", "y", "--out-dir", "/tmp", "--out-name", "t", "--schedule",
+                          "fused", "--storage", "f32", "--seed", "7", "--gpus", "2"], stdout=subprocess.PIPE, text=True)
+    assert res.returncode == 1            # --N / --Mt missing: stops after the echo, before any GPU work
+    for echo in ("--schedule fused", "--storage f32", "--seed 7", "--gpus 2"):
+        assert echo in res.stdout
+
+
 def test_argument_validation_needs_no_gpu(lib):
     """Bad arguments are rejected with VAMPOMI_ERR_ARG (1) and a message before any CUDA call."""
     import ctypes as C

@@ -115,3 +115,37 @@ def test_grid_planning_fills_whole_waves():
         n = capi.plan_chunks(slots, ntiles, 10 ** 6, 1)
         waves = -(-ntiles * n // slots)
         assert ntiles * n >= 0.99 * waves * slots or waves >= 8, (ntiles, n)
+
+
+def test_recycled_products_are_identities_of_the_cg_recurrences():
+    """The `recycled` schedule takes A x2_hat, A Q^-1 u and A^T A of both solutions from the solves instead of computing them
+    with passes of their own. In numpy, with the oracle's operators: running precondCG_solver's recurrences
+    (src/vamp.cpp:671-757) with the two extra updates the device makes — Amu += alpha * (A p) next to mu += alpha * p, and r
+    always advanced with mu — leaves Amu = A mu and (v - r - gam2 mu)/tau = A^T A mu to rounding, for a cold and a warm start."""
+    rng = np.random.default_rng(11)
+    N, M = 300, 700
+    A = rng.standard_normal((M, N)) * 0.1 + 0.5
+    d = vo.Data(A, rng.standard_normal(N))
+    tau, gam2 = 2.3, 1.9
+    diag = tau * (N - 1) / N + gam2
+    for warm in (False, True):
+        v = rng.standard_normal(M)
+        mu = rng.standard_normal(M) * 0.1 if warm else np.zeros(M)
+        Amu = d.Ax(mu) if warm else np.zeros(N)                 # the previous iteration's A x2_hat (warm) or zero
+        r = v - (tau * d.ATx(d.Ax(mu)) + gam2 * mu) if warm else v.copy()
+        z = r / diag
+        p = z.copy()
+        for _ in range(12):
+            Ap = d.Ax(p)
+            dvec = tau * d.ATx(Ap) + gam2 * p
+            alpha = (r @ z) / (dvec @ p)
+            mu = mu + alpha * p
+            Amu = Amu + alpha * Ap
+            rz_old = r @ z
+            r = r - dvec * alpha
+            z = r / diag
+            p = z + (r @ z) / rz_old * p
+        assert np.linalg.norm(Amu - d.Ax(mu)) < 1e-13 * np.linalg.norm(Amu)
+        ata = (v - r - gam2 * mu) / tau
+        want = d.ATx(d.Ax(mu))
+        assert np.linalg.norm(ata - want) < 1e-12 * np.linalg.norm(want)

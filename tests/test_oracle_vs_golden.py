@@ -12,7 +12,7 @@ from helpers import (REL_CSV, REL_VEC, assert_rows_close, csv_rows, golden_input
 
 
 ALL_CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
-             "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged"]
+             "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide"]
 
 
 @pytest.mark.parametrize("name", ALL_CASES)

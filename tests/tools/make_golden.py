@@ -38,6 +38,13 @@ CASES = {
                               extra=["--gam1", "1e-2"], warm_from=3),
     "probit_ragged": dict(N=333, M=217, lam=0.1, h2=0.5, data_seed=35, probe_seed=10, iterations=5, model="bin_class",
                           extra=["--gam1", "1e-2", "--rho", "0.8"]),
+    # the headline's aspect ratio (Mt/N = 42.5) in small: many more markers than samples, sparse effects, CLI-default prior
+    "linear_wide": dict(N=100, M=4000, lam=0.01, h2=0.5, data_seed=41, probe_seed=15, iterations=6, model="linear",
+                        extra=["--gam1", "1e-2"]),
+    # (probit needs a start that keeps tau1 off its 1e-11 clamp: once the z-channel precision collapses, 1 - alpha2 cancels to
+    # ~1e-13 and no two builds of the reference agree any more — N=160, M=2400, --gam1 1e-2 is such a case)
+    "probit_wide": dict(N=200, M=3000, lam=0.01, h2=0.5, data_seed=44, probe_seed=17, iterations=4, model="bin_class",
+                        extra=["--gam1", "1e-1"]),
     "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
                          extra=["--gam1", "1e-2"]),
 }

@@ -60,7 +60,7 @@ def extra_kwargs(g):
     names = {"--EM-max-iter": ("EM_max_iter", int), "--learn-prior-delay": ("learn_prior_delay", int), "--rho": ("rho", float),
              "--gam1": ("gam1", float), "--CG-err-tol": ("CG_err_tol", float), "--EM-err-thr": ("EM_err_thr", float),
              "--vars": ("vars", flist), "--probs": ("probs", flist), "--learn-vars": ("learn_vars", int),
-             "--merge-vars-thr": ("merge_vars_thr", float), "--alpha-scale": ("alpha_scale", float)}
+             "--merge-vars-thr": ("merge_vars_thr", float), "--alpha-scale": ("alpha_scale", float), "--CG-max-iter": ("CG_max_iter", int)}
     for k, v in zip(ex[::2], ex[1::2]):
         n, f = names[str(k)]
         kw[n] = f(v)

@@ -17,7 +17,8 @@ from helpers import (assert_rows_close, csv_rows, extra_kwargs, golden_inputs, l
 pytestmark = pytest.mark.gpu
 
 CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
-         "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide"]
+         "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
+         "linear_em_conv"]
 
 
 def solver_for(g, A, y_txt, beta, **over):

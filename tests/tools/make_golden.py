@@ -45,6 +45,14 @@ CASES = {
     # ~1e-13 and no two builds of the reference agree any more — N=160, M=2400, --gam1 1e-2 is such a case)
     "probit_wide": dict(N=200, M=3000, lam=0.01, h2=0.5, data_seed=44, probe_seed=17, iterations=4, model="bin_class",
                         extra=["--gam1", "1e-1"]),
+    # the CG iteration cap ends both solves (done = 3), a tight tolerance makes them long and unequal, and the EM loop
+    # runs to its own convergence test
+    "linear_cg_cap": dict(N=200, M=500, lam=0.05, h2=0.6, data_seed=51, probe_seed=21, iterations=4, model="linear",
+                          extra=["--gam1", "1e-2", "--CG-max-iter", "3"]),
+    "linear_tight_cg": dict(N=220, M=450, lam=0.05, h2=0.7, data_seed=52, probe_seed=22, iterations=4, model="linear",
+                            extra=["--gam1", "1e-2", "--CG-err-tol", "1e-9", "--rho", "1.0"]),
+    "linear_em_conv": dict(N=240, M=480, lam=0.08, h2=0.6, data_seed=53, probe_seed=23, iterations=5, model="linear",
+                           extra=["--gam1", "1e-2", "--EM-max-iter", "8", "--EM-err-thr", "0.05", "--learn-prior-delay", "0"]),
     "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
                          extra=["--gam1", "1e-2"]),
 }
@@ -58,18 +66,19 @@ def run_ref(args, seed, threads=4, binary=None):
     return res.stdout
 
 
-def cg_counts(log):
-    """Per VAMP iteration (k1, k2) from the --verbosity 1 log: '[CG] it = i' lines; the onsager solve prints one line
-    less than it iterates when its own test stops it (src/vamp.cpp:718-719 breaks before :747-748)."""
+def cg_counts(log, tol=1e-5, max_iter=500):
+    """Per VAMP iteration (k1, k2) from the --verbosity 1 log (src/vamp.cpp:696-751). Every executed iteration prints one
+    '[CG] it = i' line, except the one in which the onsager solve's own test fires: that one breaks before both prints
+    (:718-719). So k1 = number of '[CG]' lines, and k2 = that number + 1 unless the solve ended on the residual test (last
+    printed residual < tol) or on the iteration cap."""
     out = []
     for block in log.split("iteration = ")[1:]:
         lm, ons = block.split("CG took")[0], block.split("CG took")[1].split("onsager took")[0]
         k1 = len(re.findall(r"\[CG\] it = ", lm))
         n_cg = len(re.findall(r"\[CG\] it = ", ons))
-        n_on = len(re.findall(r"\[CG onsager\] it = ", ons))
         last_rel = re.findall(r"\|\|r_it\|\| / \|\|RHS\|\| = ([0-9.e+-]+)", ons)
-        # iterations executed = residual lines + 1 if the onsager test ended the solve
-        k2 = n_cg + (0 if n_on == n_cg and last_rel and float(last_rel[-1]) < 1e-5 else 1)
+        ended_by_residual = bool(last_rel) and float(last_rel[-1]) < tol
+        k2 = n_cg if (ended_by_residual or n_cg >= max_iter) else n_cg + 1
         out.append((k1, k2))
     return np.array(out, dtype=np.int64)
 
@@ -103,7 +112,8 @@ def make_case(name, c):
         if init is not None:
             fix["x1hat_init"] = init
         if c["model"] == "linear":
-            fix["cg_iters"] = cg_counts(log)
+            ex = dict(zip(c["extra"][::2], c["extra"][1::2]))
+            fix["cg_iters"] = cg_counts(log, float(ex.get("--CG-err-tol", 1e-5)), int(ex.get("--CG-max-iter", 500)))
         if name == "linear_small":
             # the same run by an IEEE-strict (-O2) build of the same patched sources: how far the reference is from
             # ITSELF when only compiler flags change — the floor any independent implementation can be held to

@@ -15,7 +15,8 @@ from helpers import csv_rows, extra_kwargs, golden_inputs, load_golden, rel_l2, 
 from vampomi_b200 import capi  # noqa: E402
 
 CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
-         "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide"]
+         "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
+         "linear_em_conv"]
 SCHED = {"recycled": 2, "fused": 1, "plain": 0}
 schedule = sys.argv[1] if len(sys.argv) > 1 else "recycled"
 out = {"_schedule": schedule}

@@ -60,7 +60,7 @@ def extra_kwargs(g):
     names = {"--EM-max-iter": ("EM_max_iter", int), "--learn-prior-delay": ("learn_prior_delay", int), "--rho": ("rho", float),
              "--gam1": ("gam1", float), "--CG-err-tol": ("CG_err_tol", float), "--EM-err-thr": ("EM_err_thr", float),
              "--vars": ("vars", flist), "--probs": ("probs", flist), "--learn-vars": ("learn_vars", int),
-             "--merge-vars-thr": ("merge_vars_thr", float), "--alpha-scale": ("alpha_scale", float), "--CG-max-iter": ("CG_max_iter", int)}
+             "--merge-vars-thr": ("merge_vars_thr", float), "--alpha-scale": ("alpha_scale", float), "--CG-max-iter": ("CG_max_iter", int), "--h2": ("h2", float)}
     for k, v in zip(ex[::2], ex[1::2]):
         n, f = names[str(k)]
         kw[n] = f(v)
@@ -104,11 +104,12 @@ def oracle_run(g, A, y_txt, beta, out_dir=None, comm=None, S=0, Mt=None, max_ite
     model = g["model"]
     y = standardize_phen(y_txt) if model == "linear" else y_txt
     kw = extra_kwargs(g)
+    h2 = kw.pop("h2", 0.5)                                   # gamw = 1/(1-h2), src/main_meth.cpp:52
     d = vo.Data(A, y, Mt=Mt, S=S, comm=comm, alpha_scale=kw.pop("alpha_scale", 1.0))
     init = g.get("x1hat_init")
     if init is not None:
         init = np.asarray(init)[S:S + A.shape[0]]
-    v = vo.Vamp(d, gamw=1.0 / (1.0 - 0.5), max_iter=int(max_iter or g["iterations"]), true_signal=beta, out_dir=out_dir, out_name="o",
+    v = vo.Vamp(d, gamw=1.0 / (1.0 - h2), max_iter=int(max_iter or g["iterations"]), true_signal=beta, out_dir=out_dir, out_name="o",
                 model=model, seed=int(g["probe_seed"]), stop_criteria_thr=float(g.get("stop_thr", 0.0)), x1hat_init=init, **kw)
     v.infere()
     return v

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
          "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
-         "linear_em_conv"]
+         "linear_em_conv", "linear_h2"]
 
 
 def solver_for(g, A, y_txt, beta, **over):
@@ -26,6 +26,8 @@ def solver_for(g, A, y_txt, beta, **over):
     y = standardize_phen(y_txt) if model == "linear" else y_txt
     kw = dict(gamw=2.0, seed=int(g["probe_seed"]))
     kw.update(extra_kwargs(g))
+    if "h2" in kw:
+        kw["gamw"] = 1.0 / (1.0 - kw.pop("h2"))              # src/main_meth.cpp:52
     kw.update(over)
     sh = capi.Shard(int(g["N"]), int(g["M"]))
     sh.upload(A)
@@ -248,6 +250,8 @@ def test_f32_storage_vamp_matches_oracle_on_rounded_matrix(name, tmp_path):
     sh.compute_stats()
     kw = dict(gamw=2.0, seed=int(g["probe_seed"]))
     kw.update(extra_kwargs(g))
+    if "h2" in kw:
+        kw["gamw"] = 1.0 / (1.0 - kw.pop("h2"))              # src/main_meth.cpp:52
     sol = capi.Solver(sh, y, model=model, true_signal=beta, **kw)
     for k in range(1, int(g["iterations"]) + 1):
         r = sol.step()

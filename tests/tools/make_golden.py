@@ -53,6 +53,8 @@ CASES = {
                             extra=["--gam1", "1e-2", "--CG-err-tol", "1e-9", "--rho", "1.0"]),
     "linear_em_conv": dict(N=240, M=480, lam=0.08, h2=0.6, data_seed=53, probe_seed=23, iterations=5, model="linear",
                            extra=["--gam1", "1e-2", "--EM-max-iter", "8", "--EM-err-thr", "0.05", "--learn-prior-delay", "0"]),
+    "linear_h2": dict(N=210, M=420, lam=0.1, h2=0.8, data_seed=54, probe_seed=24, iterations=4, model="linear",
+                      extra=["--gam1", "1e-2", "--h2", "0.8", "--rho", "0.3"]),
     "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
                          extra=["--gam1", "1e-2"]),
 }

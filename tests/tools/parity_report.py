@@ -16,7 +16,7 @@ from vampomi_b200 import capi  # noqa: E402
 
 CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
          "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
-         "linear_em_conv"]
+         "linear_em_conv", "linear_h2"]
 SCHED = {"recycled": 2, "fused": 1, "plain": 0}
 schedule = sys.argv[1] if len(sys.argv) > 1 else "recycled"
 out = {"_schedule": schedule}
@@ -27,6 +27,8 @@ for name in CASES:
     y = standardize_phen(y_txt) if model == "linear" else y_txt
     kw = dict(gamw=2.0, seed=int(g["probe_seed"]), fuse_passes=SCHED[schedule])
     kw.update(extra_kwargs(g))
+    if "h2" in kw:
+        kw["gamw"] = 1.0 / (1.0 - kw.pop("h2"))              # src/main_meth.cpp:52
     sh = capi.Shard(int(g["N"]), int(g["M"]))
     sh.upload(A)
     sh.compute_stats(kw.pop("alpha_scale", 1.0))

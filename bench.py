@@ -47,8 +47,8 @@ def parse_args():
     ap.add_argument("--Mt", type=int, default=850000)
     ap.add_argument("--cpu-sample-M", type=int, default=4000, help="markers of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--schedule", default="recycled", choices=["recycled", "fused", "plain"],
-                    help="recycled (default): lock-step LMMSE + Onsager solves sharing every read of the block, products of their "
+    ap.add_argument("--schedule", default="recycled", choices=["onepass", "recycled", "fused", "plain"],
+                    help="onepass: recycled + CG iterations that read the block once (fused A^T q / A A^T q pass); recycled (default): lock-step LMMSE + Onsager solves sharing every read of the block, products of their "
                          "solutions kept by the solves themselves; fused: the same without that recycling (every product computed "
                          "by a pass, sharing reads); plain: one product per pass in the reference's order")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE", help="vampomi_set_tuning knob for experiments (repeatable)")
@@ -253,7 +253,7 @@ def main_ours(args):
 
     def leg(e2e, schedule=None):
         sol = capi.Solver(sh, y, model="linear", true_signal=beta_sh, gamw=1.0 / (1.0 - H2), seed=PROBE_SEED,
-                          fuse_passes={"recycled": 2, "fused": 1, "plain": 0}[schedule or args.schedule])
+                          fuse_passes={"onepass": 3, "recycled": 2, "fused": 1, "plain": 0}[schedule or args.schedule])
         hist = []
         for _ in range(args.warmup):
             hist.append(sol.step(want_vectors=False))
@@ -302,7 +302,7 @@ def main_ours(args):
     # the other schedules on the same box, same iterations (device-resident leg only): what each level of pass sharing buys
     ab = {}
     if not args.no_ab:
-        for sched in ("plain", "fused", "recycled"):
+        for sched in ("plain", "fused", "recycled", "onepass"):
             if sched == args.schedule:
                 continue
             ms_s, hist_s, _, _ = leg(e2e=False, schedule=sched)
@@ -322,7 +322,7 @@ def main_ours(args):
     e2e_value = args.steps / (ms_e2e / 1e3)
     peak, peak_src = measured_peak()
     # dominant kernel: the matrix pass with the larger total device time in the timed region (rank 0's shard)
-    dom = max(("ax_partial", "atx"), key=lambda k: prof_dev[k]["ms"])
+    dom = max(("ax_partial", "atx", "gram"), key=lambda k: prof_dev[k]["ms"])
     pd = prof_dev[dom]
     bytes_per_launch = pd["bytes"] / max(pd["launches"], 1)
     avg_ms = pd["ms"] / max(pd["launches"], 1)
@@ -335,6 +335,7 @@ def main_ours(args):
     matrix_ms = sum(prof_dev[k]["ms"] for k in prof_dev)
     # kernel behind each profiling slot: in the fused schedule every pass of iterations > 1 is a multi-vector kernel
     knames = ({"ax_partial": "k_ax_multi", "atx": "k_atx_smem"} if args.schedule != "plain" else {"ax_partial": "k_ax_partial", "atx": "k_atx_cta"})
+    knames["gram"] = "k_gram"
     products = sum(2 * (h["k1"] + h["k2"]) + 6 for h in hist_dev)                # matrix-vector products the iterations need (the reference streams A for each, plus 2 repeats)
     traffic, traffic_src = ncu_traffic(knames[dom], N, sh.M, bytes_per_launch)
     roofline = {"bound": "hbm", "kernel": knames[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -342,11 +343,12 @@ def main_ours(args):
                 "read_probe_note": "plain linear LDG.256 streaming read of the same buffer, burst of 5 launches before the timed region",
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_ms,
                 "launches_timed": pd["launches"],
-                "other_kernel": {k: (prof_dev[k]["bytes"] / max(prof_dev[k]["ms"], 1e-9) / 1e6) for k in ("ax_partial", "atx")},
-                "matrix_kernel_share_of_step": (prof_dev["ax_partial"]["ms"] + prof_dev["atx"]["ms"]) / ms_dev,
+                "other_kernel": {k: (prof_dev[k]["bytes"] / max(prof_dev[k]["ms"], 1e-9) / 1e6) for k in ("ax_partial", "atx", "gram") if prof_dev[k]["launches"]},
+                "matrix_kernel_share_of_step": (prof_dev["ax_partial"]["ms"] + prof_dev["atx"]["ms"] + prof_dev["gram"]["ms"]) / ms_dev,
                 "phase_ms_per_step": {knames["ax_partial"]: prof_dev["ax_partial"]["ms"] / args.steps,
                                       "k_ax_reduce+allreduce+scale": prof_dev["ax_reduce"]["ms"] / args.steps,
                                       knames["atx"] + ("+k_atx_reduce" if args.schedule != "plain" else ""): prof_dev["atx"]["ms"] / args.steps,
+                                      "k_gram": prof_dev["gram"]["ms"] / args.steps,
                                       "everything_else": (ms_dev - matrix_ms) / args.steps,
                                       "ax_reduce_avg_us": 1e3 * prof_dev["ax_reduce"]["ms"] / max(prof_dev["ax_reduce"]["launches"], 1)},
                 "whole_iteration": {"passes": passes, "gbs_per_gpu": iter_gbs_per_gpu, "frac_of_peak": iter_gbs_per_gpu / peak,

@@ -66,7 +66,9 @@ enum {
     VAMPOMI_V_TMP_N1 = 39,
     VAMPOMI_V_USER_N0 = 40,
     VAMPOMI_V_USER_N1 = 41,
-    VAMPOMI_V_NUM_N = 10
+    VAMPOMI_V_GRAM_W0 = 42, VAMPOMI_V_GRAM_W1 = 43,     /* work: w = A A^T q of the one-pass CG, one per system */
+    VAMPOMI_V_GRAM_AR0 = 44, VAMPOMI_V_GRAM_AR1 = 45,   /* work: A r of the one-pass CG */
+    VAMPOMI_V_NUM_N = 14
 };
 
 /* Kinds for vampomi_dots(): out = sum_i f(a_i, b_i). */
@@ -168,6 +170,15 @@ int vampomi_atx_dev(vampomi_ctx* ctx, int p_vec, int out_vec);
 int vampomi_ax_multi_dev(vampomi_ctx* ctx, int K, const int* x_vecs, const int* out_vecs);
 int vampomi_atx_multi_dev(vampomi_ctx* ctx, int K, const int* p_vecs, const int* out_vecs);
 
+/* The FUSED pair of products t_k = A^T q_k (M-vectors) and w_k = A t_k = A A^T q_k (N-vectors, summed over all shards) for
+ * K <= 2 vectors in ONE pass over the marker block: each column is kept on chip between its dot product and its axpy
+ * (csrc/kernels_gram.cu). This is lmmse_mult's ATx(Ax(.)) (src/vamp.cpp:653-654) re-associated around the N-side vector, and
+ * what lets a CG iteration read the block once instead of twice (tuning knob cg_onepass / schedule "onepass"). Every
+ * product keeps the per-element arithmetic of vampomi_atx_dev / vampomi_ax_dev. Needs FP64 storage and N <= 20480
+ * (vampomi_aat_supported); q_vecs / w_out_vecs name N-vectors, t_out_vecs M-vectors, all distinct. */
+int vampomi_aat_multi_dev(vampomi_ctx* ctx, int K, const int* q_vecs, const int* t_out_vecs, const int* w_out_vecs);
+int vampomi_aat_supported(const vampomi_ctx* ctx, int* yes);
+
 /* ---- Gaussian-mixture denoiser: vamp::g1 / vamp::g1d, src/vamp.cpp:440-492, as used at :203-223 ------------- */
 /* X1_PREV <- X1; X1 <- g1(R1, gam1) (then rho*X1 + (1-rho)*X1_PREV if damp != 0); *sum_g1d = sum over ALL shards of
  * g1d(R1_j, gam1). `vars` are the internal (already multiplied by N, src/vamp.cpp:87-88) variances. L <= 32. */
@@ -229,7 +240,7 @@ int vampomi_counters(vampomi_ctx* ctx, long long out[4], int reset);
  * which: 0 = Ax (partial + reduce), 1 = ATx, 2 = stats, 3 = loo sums, 4 = read-bandwidth probe (a plain linear streaming
  * read of the whole marker block, not part of the VAMP path: the live ceiling the matrix kernels are compared with),
  * 5 = A x for 2 vectors in one pass, 6 = A^T p for 2 vectors in one pass, 7 = the multi-vector A^T p kernel with 1 vector,
- * 8 = A x for 3 vectors in one pass.
+ * 8 = A x for 3 vectors in one pass, 9 = the fused A^T q / A A^T q pass for 2 vectors, 10 = the same for 1 vector.
  * Returns average milliseconds per launch. */
 int vampomi_time_kernel(vampomi_ctx* ctx, int which, int reps, double* ms_avg);
 /* Per-kernel device timing of the matrix passes (CUDA events on the context stream around every launch while enabled).
@@ -237,6 +248,8 @@ int vampomi_time_kernel(vampomi_ctx* ctx, int which, int reps, double* ms_avg);
  * 1 (k_ax_reduce + all-reduce + scaling) and 2 (k_atx); synchronises the stream; `reset` clears the accumulators. */
 int vampomi_profile_enable(vampomi_ctx* ctx, int on);
 int vampomi_profile_read(vampomi_ctx* ctx, double out[9], int reset);
+/* The same for the first `nkinds` <= 4 kernel kinds (out[3*nkinds]); kind 3 = the fused A^T q / A A^T q pass (k_gram). */
+int vampomi_profile_read_ex(vampomi_ctx* ctx, int nkinds, double* out, int reset);
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on — for callers that time with their own events. */
 int vampomi_stream(vampomi_ctx* ctx, void** stream);
 /* Pure host helper (no GPU needed): the number of column chunks the (row tile x column chunk) grids of the tiled matrix

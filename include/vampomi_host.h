@@ -53,6 +53,11 @@ typedef struct vampomi_solver_config {
                                   by alpha * (A p) next to the solutions (vampomi_cg_solve_pair track_ax_vec), A^T A of
                                   both follows from the solves' residuals — 2 max(k1,k2) passes per iteration; the values
                                   differ from separately computed products by recurrence rounding only (~1e-15 relative).
+                                  3 = recycled, and every CG iteration reads the marker block ONCE instead of twice: the solves
+                                  keep q = A p as a vector of its own and one fused pass delivers A^T q (= A^T A p) and A A^T q
+                                  (what the recurrence of q needs), each column staying on chip between its two uses
+                                  (vampomi_aat_multi_dev) — max(k1,k2) + 1 passes per iteration; contexts that cannot run the
+                                  fused pass (FP32 storage, N > 20480) silently keep the two-pass iterations.
                                   Ignored (0) when redundant_passes = 1. */
 } vampomi_solver_config;
 

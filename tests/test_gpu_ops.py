@@ -366,6 +366,113 @@ def test_multi_vector_passes_match_oracle(N, M, storage):
     sh.close()
 
 
+@pytest.mark.parametrize("N,M", SHAPES + [(9000, 77), (20000, 300), (20480, 40)])
+def test_fused_gram_pass_matches_the_two_products(N, M):
+    """vampomi_aat_multi_dev: t = A^T q and w = A t from ONE read of the marker block (kernels_gram.cu). Both must equal what
+    the two separate products (and the oracle) give, for every kernel shape and every cluster size that holds N, for one and
+    two vectors, on ragged sizes; untouched outputs stay untouched; results are bitwise reproducible."""
+    rng = np.random.default_rng(N * 7 + M)
+    A = rng.standard_normal((M, N)) * 0.1 + 0.5
+    y = rng.standard_normal(N)
+    sh = capi.Shard(N, M)
+    sh.upload(A)
+    sh.compute_stats()
+    assert sh.aat_supported()
+    d = vo.Data(A, y)
+    qs = [rng.standard_normal(N) for _ in range(2)]
+    want_t = [d.ATx(q) for q in qs]
+    want_w = [d.Ax(t) for t in want_t]
+    qin, tout, wout = [V_USER_N0, V_USER_N1], [V_R1, V_R2], [V_Z1, V_Z2]
+    rows = {0: 2560, 1: 3072, 2: 2560, 3: 2560, 4: 2560, 5: 2560}
+    ran = 0
+    for shape in range(6):
+        sh.set_tuning("gram_shape", shape)
+        for cs in (0, 1, 2, 4, 8):
+            if cs and -(-((N + 15) // 16 * 16) // cs) > rows[shape]:
+                continue                                             # this cluster size cannot hold a column of N rows
+            sh.set_tuning("gram_cluster", cs)
+            for K in (1, 2):
+                for i in range(2):
+                    sh.set(qin[i], qs[i])
+                    sh.fill(tout[i], -7.0)
+                    sh.fill(wout[i], -7.0)
+                sh.aat_multi_dev(qin[:K], tout[:K], wout[:K])
+                for i in range(K):
+                    assert rel_l2(sh.get(tout[i]), want_t[i]) < 1e-12, (shape, cs, K, i)
+                    assert rel_l2(sh.get(wout[i]), want_w[i]) < 1e-12, (shape, cs, K, i)
+                for i in range(K, 2):
+                    assert np.all(sh.get(tout[i]) == -7.0) and np.all(sh.get(wout[i]) == -7.0)
+                ran += 1
+    assert ran >= 12
+    sh.set_tuning("gram_shape", 3)
+    sh.set_tuning("gram_cluster", 0)
+    for clusters in (1, 3, 1000):                                    # any number of column chunks, more than there are columns included
+        sh.set_tuning("gram_clusters", clusters)
+        sh.aat_multi_dev(qin, tout, wout)
+        assert rel_l2(sh.get(tout[1]), want_t[1]) < 1e-12 and rel_l2(sh.get(wout[1]), want_w[1]) < 1e-12
+    sh.set_tuning("gram_clusters", 0)
+    sh.aat_multi_dev(qin, tout, wout); a, b = sh.get(tout[1]).copy(), sh.get(wout[0]).copy()
+    sh.aat_multi_dev(qin, tout, wout); assert np.array_equal(a, sh.get(tout[1])) and np.array_equal(b, sh.get(wout[0]))
+    c0 = sh.counters(reset=True)
+    sh.aat_multi_dev(qin, tout, wout)
+    assert sh.counters()["matrix_passes"] == 1                       # two products, two vectors: ONE read of the block
+    with pytest.raises(capi.VampomiError):
+        sh.aat_multi_dev([V_USER_N0, V_USER_N1], [V_R1, V_R2], [V_Z1, V_Z1])
+    with pytest.raises(capi.VampomiError):
+        sh.aat_multi_dev([V_USER_N0], [V_R1], [V_USER_N0])
+    with pytest.raises(capi.VampomiError):
+        sh.aat_multi_dev([V_R1], [V_USER_N0], [V_Z1])
+    sh.close()
+    with capi.Shard(64, 10, storage="f32") as s32:
+        assert not s32.aat_supported()
+
+
+@pytest.mark.parametrize("N,M,cluster", [(400, 1000, 0), (333, 517, 4), (2050, 300, 8), (6000, 200, 0)])
+def test_onepass_cg_equals_two_pass_cg(N, M, cluster):
+    """Knob cg_onepass: the same solves with ONE read of the block per CG iteration (q = A p advanced by its recurrence, the
+    fused pass delivering A^T q and A A^T q). Iteration counts must be the oracle's, solutions and the tracked A sol must
+    agree to rounding, and the pass count is max(k0, k1) + 1 (+ the refresh passes of long solves)."""
+    sh, A, y, rng = make(N, M, seed=N + 3)
+    d = vo.Data(A, y)
+    o = vo.Vamp(d, CG_err_tol=1e-7)
+    gam2, tau = 1.9, 2.3
+    o.gam2 = gam2
+    v, u, x1 = rng.standard_normal(M), np.sign(rng.standard_normal(M)) / math.sqrt(M), rng.standard_normal(M)
+    mu0 = rng.standard_normal(M) * 0.1
+    sh.set(V_V, v); sh.set(V_BERN, u); sh.set(V_X1, x1)
+    want0 = o.precondCG_solver(v, None, tau, 1); k0 = o.cg_iters[-1][2]
+    want1 = o.precondCG_solver(u, None, tau, 0); k1 = o.cg_iters[-1][2]
+    want_w = o.precondCG_solver(v, mu0, tau, 1); kw = o.cg_iters[-1][2]
+    sh.set_tuning("cg_onepass", 1)
+    sh.set_tuning("gram_cluster", cluster)
+    for depth, refresh in ((2, 0), (1, 0), (5, 3)):
+        sh.set_tuning("cg_depth", depth)
+        sh.set_tuning("gram_refresh", refresh)
+        sh.fill(V_Z1, 0.0)
+        sh.counters(reset=True)
+        res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, tol=1e-7, extra=(V_X1, V_Z1), track_ax_vecs=(V_Z2, V_USER_N0))
+        assert (res[0][0], res[1][0]) == (k0, k1)
+        x2, w = sh.get(V_X2), sh.get(V_QINV_BERN)
+        assert rel_l2(x2, want0) < 1e-11 and rel_l2(w, want1) < 1e-11
+        assert abs(res[1][2] - u @ want1) < 1e-11 * abs(u @ want1)
+        assert rel_l2(sh.get(V_Z1), d.Ax(x1)) < 1e-12
+        assert rel_l2(sh.get(V_Z2), d.Ax(x2)) < 1e-12 and rel_l2(sh.get(V_USER_N0), d.Ax(w)) < 1e-12
+        kmax = max(k0, k1)
+        assert sh.counters()["matrix_passes"] == kmax + 1 + ((kmax - 1) // refresh if refresh else 0)
+    sh.set_tuning("gram_refresh", 0)
+    # single-system entry point and a warm start (A^T A mu0 computed inside: two more passes)
+    it_s, _, _ = sh.cg_solve(V_V, V_USER_M0, tau, gam2, tol=1e-7)
+    assert it_s == k0 and rel_l2(sh.get(V_USER_M0), want0) < 1e-11
+    sh.set(V_X2, mu0)
+    sh.counters(reset=True)
+    res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, warm_start=(True, False), tol=1e-7)
+    assert (res[0][0], res[1][0]) == (kw, k1) and rel_l2(sh.get(V_X2), want_w) < 1e-11
+    assert sh.counters()["matrix_passes"] == max(kw, k1) + 3
+    res = sh.cg_solve_pair([V_V, V_BERN], [V_X2, V_QINV_BERN], tau, gam2, tol=1e-30, max_iter=3, onsager_mode=(False, False))
+    assert (res[0][0], res[1][0]) == (3, 3)
+    sh.close()
+
+
 @pytest.mark.parametrize("N,M", [(400, 1000), (333, 517), (2050, 300)])
 def test_paired_solve_equals_two_single_solves(N, M):
     """vampomi_cg_solve_pair: two systems with one operator in lock-step. Each system must stop after exactly the

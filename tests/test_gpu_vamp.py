@@ -35,10 +35,10 @@ def solver_for(g, A, y_txt, beta, **over):
     return sh, capi.Solver(sh, y, model=model, true_signal=beta, x1hat_init=g.get("x1hat_init"), **kw)
 
 
-# schedules of the matrix passes: "recycled" (fused + A x2_hat, A Q^-1 u and A^T A of both kept by the solves themselves),
+# schedules of the matrix passes: "onepass" (recycled + CG iterations that read the block once: fused A^T q / A A^T q pass), "recycled" (fused + A x2_hat, A Q^-1 u and A^T A of both kept by the solves themselves),
 # "fused" (products that are known together share one read of the block),
 # "plain" (one product per pass, A^T y and A x2_hat cached), "reference" (plain + the passes the reference repeats)
-SCHEDULES = {"recycled": dict(fuse_passes=2, redundant_passes=0), "fused": dict(fuse_passes=1, redundant_passes=0), "plain": dict(fuse_passes=0, redundant_passes=0),
+SCHEDULES = {"onepass": dict(fuse_passes=3, redundant_passes=0), "recycled": dict(fuse_passes=2, redundant_passes=0), "fused": dict(fuse_passes=1, redundant_passes=0), "plain": dict(fuse_passes=0, redundant_passes=0),
              "reference": dict(fuse_passes=0, redundant_passes=1)}
 
 
@@ -66,6 +66,8 @@ def test_solver_matches_reference_fixture(name, schedule):
                 assert r["matrix_passes"] == base + (5 if k == 1 else 6)
             elif schedule == "fused":     # A^T y once; both solves in lock-step; A [x2, Q^-1 u] and A^T [.., A x2] one pass each
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (3 if k == 1 else 2)
+            elif schedule == "onepass":   # A [p0 p1 x1] once, then ONE fused pass per lock-step CG iteration (and A^T y once)
+                assert r["matrix_passes"] == max(r["k1"], r["k2"]) + 1 + (1 if k == 1 else 0)
             else:                         # nothing but the lock-step solves (and A^T y once)
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (1 if k == 1 else 0)
         else:
@@ -73,6 +75,8 @@ def test_solver_matches_reference_fixture(name, schedule):
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + 2
             elif schedule == "recycled":  # A^T p2, lock-step solves
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + 1
+            elif schedule == "onepass":   # A^T p2, A [p0 p1 x1/sqrt(N)], one fused pass per lock-step CG iteration
+                assert r["matrix_passes"] == max(r["k1"], r["k2"]) + 2
             else:
                 assert r["matrix_passes"] == 2 * (r["k1"] + r["k2"]) + 4
     assert_rows_close(got_params, want_params, rel_csv, "params")
@@ -105,7 +109,7 @@ def run_cli(args, **kw):
     return res.stdout
 
 
-@pytest.mark.parametrize("schedule", ["recycled", "fused", "plain", "reference"])
+@pytest.mark.parametrize("schedule", ["onepass", "recycled", "fused", "plain", "reference"])
 def test_main_meth_schedule_flag(schedule, tmp_path):
     """--schedule only changes which products share a read of the block: same files for all three."""
     g = load_golden("linear_wellcond")

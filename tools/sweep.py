@@ -22,6 +22,8 @@ ap.add_argument("--multi", type=int, default=0, help="only the multi-vector kern
                 "back-to-back reps per variant")
 ap.add_argument("--sustained", type=int, default=0, help="also time a short list of variants with this many back-to-back reps "
                 "(seconds-long, i.e. under the power cap) instead of a burst")
+ap.add_argument("--gram", type=int, default=0, help="only the fused A^T q / A A^T q pass (kernels_gram.cu) over its shapes and "
+                "cluster counts, with this many back-to-back reps per variant")
 a = ap.parse_args()
 
 sh = vb.Shard(a.N, a.M, storage=a.storage)
@@ -43,6 +45,31 @@ def t(which, label, reps=None, **knobs):
     results.append(rec)
     print(json.dumps(rec), flush=True)
 
+
+if a.gram:
+    t(4, "read_probe", a.gram)
+    t(5, "ax_multi_K2_default", a.gram)
+    t(6, "atx_multi_K2_default", a.gram)
+    for shape in range(6):
+        t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0)
+        t(10, "gram_K1", a.gram, gram_shape=shape, gram_clusters=0)
+    for shape in (0, 2):
+        for pfd in (0, 2, 4):
+            t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0, gram_prefetch=pfd)
+    if not a.quick:
+        for shape in (0, 1):
+            for ncl in (14, 15, 30, 45, 60):
+                t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=ncl)
+        for shape in (0, 1):
+            for cs, ncl in ((4, 0), (4, 33), (4, 66)):
+                if a.N <= cs * (3072 if shape == 1 else 2560):
+                    t(9, "gram_K2", a.gram, gram_shape=shape, gram_cluster=cs, gram_clusters=ncl)
+    best = {}
+    for r in results:
+        if r["kernel"] not in best or r["gbs"] > best[r["kernel"]]["gbs"]:
+            best[r["kernel"]] = r
+    print("BEST", json.dumps(best))
+    sys.exit(0)
 
 if a.multi:
     t(4, "read_probe", a.multi)

@@ -22,6 +22,7 @@ V_X1, V_X1_PREV, V_R1, V_R2, V_X2, V_V, V_BERN, V_QINV_BERN, V_TRUE, V_ATY, V_TM
 V_CG_R, V_CG_Z, V_CG_P, V_CG_D, V_USER_M0, V_USER_M1 = 12, 13, 14, 15, 16, 17
 V_CG2_R, V_CG2_Z, V_CG2_P, V_CG2_D, V_ATA_X2 = 18, 19, 20, 21, 22
 V_Y, V_Z1, V_Z2, V_P1, V_P2, V_Z1HAT, V_TMP_N0, V_TMP_N1, V_USER_N0, V_USER_N1 = range(32, 42)
+V_GRAM_W0, V_GRAM_W1, V_GRAM_AR0, V_GRAM_AR1 = range(42, 46)
 DOT, DIFF2, SQDEV = 0, 1, 2
 
 
@@ -80,6 +81,8 @@ _SIGNATURES = {
     "vampomi_atx_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "vampomi_ax_multi_dev": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p]),
     "vampomi_atx_multi_dev": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p]),
+    "vampomi_aat_multi_dev": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p, c_int_p]),
+    "vampomi_aat_supported": (C.c_int, [C.c_void_p, c_int_p]),
     "vampomi_denoise": (C.c_int, [C.c_void_p, C.c_double, c_double_p, c_double_p, C.c_int, C.c_int, C.c_double, c_double_p]),
     "vampomi_em_sums": (C.c_int, [C.c_void_p, C.c_double, C.c_double, c_double_p, c_double_p, C.c_int, c_double_p]),
     "vampomi_cg_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int,
@@ -95,6 +98,7 @@ _SIGNATURES = {
     "vampomi_plan_chunks": (C.c_longlong, [C.c_longlong, C.c_int, C.c_longlong, C.c_int, C.c_int]),
     "vampomi_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vampomi_profile_read": (C.c_int, [C.c_void_p, c_double_p, C.c_int]),
+    "vampomi_profile_read_ex": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int]),
     "vampomi_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     # host driver
     "vampomi_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
@@ -332,6 +336,17 @@ class Shard:
         K = len(p_vecs)
         _check(self.lib.vampomi_atx_multi_dev(self.h, K, (C.c_int * K)(*p_vecs), (C.c_int * K)(*out_vecs)), "atx_multi_dev")
 
+    def aat_multi_dev(self, q_vecs, t_out_vecs, w_out_vecs):
+        """t_k = A^T q_k and w_k = A t_k for up to 2 N-vectors in ONE pass over the marker block (kernels_gram.cu)."""
+        K = len(q_vecs)
+        _check(self.lib.vampomi_aat_multi_dev(self.h, K, (C.c_int * K)(*q_vecs), (C.c_int * K)(*t_out_vecs), (C.c_int * K)(*w_out_vecs)),
+               "aat_multi_dev")
+
+    def aat_supported(self):
+        y = C.c_int()
+        _check(self.lib.vampomi_aat_supported(self.h, C.byref(y)), "aat_supported")
+        return bool(y.value)
+
     # ---- VAMP pieces ----
     def denoise(self, gam1, probs, vars_internal, damp=False, rho=0.5):
         p, pp = _in(probs)
@@ -398,9 +413,9 @@ class Shard:
         _check(self.lib.vampomi_profile_enable(self.h, int(on)), "profile_enable")
 
     def profile_read(self, reset=False):
-        out, po = _out(9)
-        _check(self.lib.vampomi_profile_read(self.h, po, int(reset)), "profile_read")
-        names = ("ax_partial", "ax_reduce", "atx")
+        out, po = _out(12)
+        _check(self.lib.vampomi_profile_read_ex(self.h, 4, po, int(reset)), "profile_read")
+        names = ("ax_partial", "ax_reduce", "atx", "gram")
         return {n: dict(launches=int(out[3 * i]), ms=float(out[3 * i + 1]), bytes=float(out[3 * i + 2])) for i, n in enumerate(names)}
 
     def stream(self):

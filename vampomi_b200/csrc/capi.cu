@@ -738,6 +738,28 @@ int vampomi_atx_multi_dev(vampomi_ctx* c, int K, const int* p_vecs, const int* o
     return launch_atx_multi(c, mv);
 }
 
+int vampomi_aat_multi_dev(vampomi_ctx* c, int K, const int* q_vecs, const int* t_out_vecs, const int* w_out_vecs) {
+    MultiVec mq;
+    VO_ARG(K >= 1 && K <= 2 && w_out_vecs, "aat_multi_dev: 1 or 2 vectors");
+    VO_CHECK(fill_multi(c, K, q_vecs, t_out_vecs, false, &mq));
+    double* w_out[2] = {nullptr, nullptr};
+    for (int k = 0; k < K; k++) {
+        VO_ARG(vec_ptr(c, w_out_vecs[k]) && !is_mvec(w_out_vecs[k]) && w_out_vecs[k] != q_vecs[k] && (k == 0 || w_out_vecs[0] != w_out_vecs[1]),
+               "aat_multi_dev: w_out must name distinct N-vectors other than q");
+        w_out[k] = vec_ptr(c, w_out_vecs[k]);
+    }
+    NEED_STATS(c, "aat_multi_dev");
+    if (!gram_supported(c)) { set_error("aat_multi_dev: the fused pass needs FP64 storage and N <= 20480"); return VAMPOMI_ERR_STATE; }
+    VO_CUDA(cudaSetDevice(c->device));
+    return launch_gram(c, mq, w_out);
+}
+
+int vampomi_aat_supported(const vampomi_ctx* c, int* yes) {
+    VO_ARG(c && yes, "aat_supported: NULL argument");
+    *yes = gram_supported(c) ? 1 : 0;
+    return VAMPOMI_OK;
+}
+
 int vampomi_ax_dev(vampomi_ctx* c, int x_vec, int out_vec) {
     VO_ARG(c && is_mvec(x_vec) && vec_ptr(c, out_vec) && !is_mvec(out_vec), "ax_dev: need M-vector in, N-vector out");
     NEED_STATS(c, "ax_dev");
@@ -816,7 +838,7 @@ int vampomi_counters(vampomi_ctx* c, long long out[4], int reset) {
 }
 
 int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
-    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 8, "time_kernel: bad arguments");
+    VO_ARG(c && ms_avg && reps >= 1 && which >= 0 && which <= 10, "time_kernel: bad arguments");
     if (which != 2 && which != 4) NEED_STATS(c, "time_kernel");
     VO_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
@@ -849,6 +871,15 @@ int vampomi_time_kernel(vampomi_ctx* c, int which, int reps, double* ms_avg) {
                 }
                 break;
             }
+            case 9: case 10: {
+                MultiVec mq{};
+                mq.K = which == 9 ? 2 : 1;
+                mq.in[0] = c->nvec[VAMPOMI_V_TMP_N1 - 32]; mq.in[1] = c->nvec[VAMPOMI_V_TMP_N0 - 32];
+                mq.out[0] = c->mvec[VAMPOMI_V_TMP_M1]; mq.out[1] = c->mvec[VAMPOMI_V_TMP_M0];
+                double* w_out[2] = {c->nvec[VAMPOMI_V_GRAM_W0 - 32], c->nvec[VAMPOMI_V_GRAM_W1 - 32]};
+                rc = launch_gram(c, mq, w_out);
+                break;
+            }
             default: rc = launch_loo_sums(c, c->nvec[VAMPOMI_V_TMP_N1 - 32], dsums); break;
         }
     }
@@ -879,6 +910,14 @@ int vampomi_profile_read(vampomi_ctx* c, double out[9], int reset) {
     return VAMPOMI_OK;
 }
 
+int vampomi_profile_read_ex(vampomi_ctx* c, int nkinds, double* out, int reset) {
+    VO_ARG(c && out && nkinds >= 1 && nkinds <= 4, "profile_read_ex: 1..4 kinds");
+    VO_CUDA(cudaSetDevice(c->device));
+    VO_CHECK(prof_resolve(c));
+    for (int i = 0; i < 3 * nkinds; i++) { out[i] = c->prof_acc[i]; if (reset) c->prof_acc[i] = 0; }
+    return VAMPOMI_OK;
+}
+
 int vampomi_stream(vampomi_ctx* c, void** stream) {
     VO_ARG(c && stream, "stream: NULL argument");
     *stream = (void*)c->stream;
@@ -905,6 +944,9 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"multi_ax_rv", &c->tune.multi_ax_rv, 0, 2},     {"multi_ax_unroll", &c->tune.multi_ax_unroll, 0, 8},
         {"multi_atx_impl", &c->tune.multi_atx_impl, 0, 1}, {"multi_atx_cols", &c->tune.multi_atx_cols, 0, 4},
         {"multi_atx_unroll", &c->tune.multi_atx_unroll, 0, 4}, {"multi_atx_tile", &c->tune.multi_atx_tile, 0, 16384},
+        {"cg_onepass", &c->tune.cg_onepass, 0, 1},       {"gram_shape", &c->tune.gram_shape, 0, 5},         {"gram_prefetch", &c->tune.gram_prefetch, 0, 64},
+        {"gram_cluster", &c->tune.gram_cluster, 0, 8},
+        {"gram_clusters", &c->tune.gram_clusters, 0, 4096}, {"gram_refresh", &c->tune.gram_refresh, 0, 100000},
     };
     for (auto& k : knobs)
         if (!strcmp(k.n, name)) {

@@ -46,6 +46,25 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
     VO_CHECK(launch_cg_init_finish(c, b, sums_st));
     for (int s = 0; s < S; s++) b.s[s].atx_out = b.s[s].atx_work;            // from here on: A^T A p of the current iteration
 
+    // One-pass CG (knob cg_onepass, schedule "onepass"; kernels_gram.cu): q = A p is a vector of its own. It starts as A p_0
+    // (the only A x pass of the solve — it also carries the caller's extra product), A r starts as diag * q (p_0 = r_0/diag),
+    // and from then on ONE fused pass per iteration delivers t = A^T q (= A^T A p) and w = A t, from which k_cg_step /
+    // k_cg_finish advance A r and q next to r and p. Every `refresh` iterations q and A r are recomputed from p and z by a
+    // pass of their own, which bounds the drift of the recurrences in long solves.
+    const bool onepass = c->tune.cg_onepass != 0 && gram_supported(c);
+    const int refresh = c->tune.gram_refresh > 0 ? c->tune.gram_refresh : 32;
+    if (onepass) {
+        MultiVec mv{};
+        mv.K = S;
+        for (int s = 0; s < S; s++) {
+            b.s[s].gw = c->nvec[(s == 0 ? VAMPOMI_V_GRAM_W0 : VAMPOMI_V_GRAM_W1) - 32];
+            b.s[s].gar = c->nvec[(s == 0 ? VAMPOMI_V_GRAM_AR0 : VAMPOMI_V_GRAM_AR1) - 32];
+            mv.in[s] = b.s[s].p; mv.out[s] = b.s[s].tmpN; mv.done[s] = nullptr;
+        }
+        if (extra.x) { mv.in[S] = extra.x; mv.out[S] = extra.out; mv.done[S] = nullptr; mv.K = S + 1; }
+        VO_CHECK(launch_ax_multi(c, mv));
+        for (int s = 0; s < S; s++) VO_CHECK(launch_lincomb(c, b.s[s].gar, diag, b.s[s].tmpN, 0.0, b.s[s].tmpN, 1.0, c->N));
+    }
     int depth = c->tune.cg_depth;
     if (depth < 1) depth = 1;
     if (depth > 32) depth = 32;
@@ -56,6 +75,7 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
     // done flags were already set when they ran) are not reported as matrix passes / streamed bytes / timed launches
     int launched = 0;
     std::vector<size_t> span_mark;
+    std::vector<long long> pass_mark;                       // matrix-pass counter at the start of every enqueued iteration
     if (c->prof_pending.size() > 2048) VO_CHECK(prof_resolve(c));
     const long long pass_bytes = (long long)c->M * c->N * c->elem_bytes;
     const int* done0 = &b.s[0].cg->done;
@@ -68,8 +88,26 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
             if (all_done) break;
         }
         span_mark.push_back(c->prof_pending.size());
+        pass_mark.push_back(c->counters[1]);
         launched = i + 1;
-        if (S == 1 && !(i == 0 && extra.x)) {
+        if (onepass) {
+            if (i > 0 && i % refresh == 0) {                // q = A p and A r = diag * A z afresh (one pass for all of them)
+                MultiVec mv{};
+                mv.K = 2 * S;
+                for (int s = 0; s < S; s++) {
+                    mv.in[2 * s] = b.s[s].p; mv.out[2 * s] = b.s[s].tmpN; mv.done[2 * s] = &b.s[s].cg->done;
+                    mv.in[2 * s + 1] = b.s[s].z; mv.out[2 * s + 1] = b.s[s].gar; mv.done[2 * s + 1] = &b.s[s].cg->done;
+                }
+                if ((rc = launch_ax_multi(c, mv)) != VAMPOMI_OK) break;
+                for (int s = 0; s < S && rc == VAMPOMI_OK; s++) rc = launch_scale_div(c, b.s[s].gar, b.s[s].gar, 1.0 / diag, c->N, &b.s[s].cg->done);
+                if (rc != VAMPOMI_OK) break;
+            }
+            MultiVec mq{};
+            mq.K = S;
+            double* w_out[2] = {nullptr, nullptr};
+            for (int s = 0; s < S; s++) { mq.in[s] = b.s[s].tmpN; mq.out[s] = b.s[s].atx_out; mq.done[s] = &b.s[s].cg->done; w_out[s] = b.s[s].gw; }
+            if ((rc = launch_gram(c, mq, w_out)) != VAMPOMI_OK) break;
+        } else if (S == 1 && !(i == 0 && extra.x)) {
             if ((rc = launch_ax(c, b.s[0].p, b.s[0].tmpN, done0)) != VAMPOMI_OK) break;
             if ((rc = launch_atx(c, b.s[0].tmpN, b.s[0].atx_out, done0)) != VAMPOMI_OK) break;
         } else {
@@ -85,9 +123,9 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
         }
         if ((rc = launch_cg_dp(c, b, tau, gam2, sums_dp)) != VAMPOMI_OK) break;
         if (nccl_scalars && (rc = allreduce_inplace(c, sums_dp, S)) != VAMPOMI_OK) break;
-        if ((rc = launch_cg_step(c, b, diag, parity, sums_dp, sums_st)) != VAMPOMI_OK) break;
+        if ((rc = launch_cg_step(c, b, tau, gam2, diag, parity, sums_dp, sums_st)) != VAMPOMI_OK) break;
         if (nccl_scalars && (rc = allreduce_inplace(c, sums_st, 3 * S)) != VAMPOMI_OK) break;
-        if ((rc = launch_cg_finish(c, b, parity, gam2, tol, max_iter, sums_st)) != VAMPOMI_OK) break;
+        if ((rc = launch_cg_finish(c, b, parity, gam2, diag, tol, max_iter, sums_st)) != VAMPOMI_OK) break;
         bool ok = true;
         for (int s = 0; s < S; s++)
             ok = ok && cudaMemcpyAsync(&c->cg_poll_host[2 * slot + s], &b.s[s].cg->done, sizeof(int), cudaMemcpyDeviceToHost, c->stream) == cudaSuccess;
@@ -109,9 +147,9 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
             int ran = 0;                                    // iterations in which at least one system was still active
             for (int s = 0; s < S; s++) ran = fin[s].iters > ran ? fin[s].iters : ran;
             if (ran < launched) {
-                const int idle = launched - ran;
-                c->counters[1] -= 2LL * idle;
-                c->counters[2] -= 2LL * idle * pass_bytes;
+                const long long idle_passes = c->counters[1] - pass_mark[ran];     // passes enqueued by the idle iterations
+                c->counters[1] -= idle_passes;
+                c->counters[2] -= idle_passes * pass_bytes;
                 if (c->profile && (size_t)ran < span_mark.size() && span_mark[ran] <= c->prof_pending.size()) {
                     // drop the spans of the idle iterations
                     for (size_t k = span_mark[ran]; k < c->prof_pending.size(); k++) {
@@ -146,6 +184,7 @@ static void fill_sys(vampomi_ctx* c, CgSys* q, int s, int rhs_vec, int sol_vec, 
     q->tmpN = c->nvec[(s == 0 ? VAMPOMI_V_TMP_N0 : VAMPOMI_V_TMP_N1) - 32];
     q->cg = c->cg + s;
     q->amu = nullptr;
+    q->gw = nullptr; q->gar = nullptr;
     q->warm = warm ? 1 : 0;
     q->onsager_mode = onsager_mode ? 1 : 0;
 }

@@ -86,6 +86,8 @@ struct CgSys {                       // one linear system of a CG batch (cg.cu);
     double* atx_work;                // A^T A p of the current iteration
     double* tmpN;                    // A p
     double* amu;                     // optional N-vector kept equal to A mu by the solve itself (amu += alpha * A p); nullptr = off
+    double* gw;                      // one-pass CG: w = A A^T q of the current iteration (N); nullptr = two-pass CG
+    double* gar;                     // one-pass CG: A r, advanced by A r -= alpha (tau w + gam2 q) (N)
     CgScalars* cg;
     int warm;
     int onsager_mode;
@@ -120,6 +122,12 @@ struct Tuning {
     int grid_balance = 1;            // 1 = (row tile x column chunk) grids sized to full waves of resident CTAs (balanced_chunks), 0 = one, possibly partly filled, wave
     int dump_stream = 0;             // asynchronous read-outs copy on 0 = the context's stream (stream-ordered), 1 = the copy stream
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
+    int cg_onepass = 0;              // 1 = CG iterations read the marker block ONCE (fused A^T q / A A^T q pass, kernels_gram.cu) where supported
+    int gram_shape = 3;              // fused pass: kernel shape (threads, rows per thread, columns per step, steps in flight; kernels_gram.cu)
+    int gram_prefetch = 4;           // fused pass: steps ahead that one lane per CTA pulls into L2 (cp.async.bulk.prefetch), 0 = off
+    int gram_cluster = 0;            // fused pass: CTAs per cluster = row tiles of a column (0 = smallest of 1, 2, 4, 8 that holds N)
+    int gram_clusters = 0;           // fused pass: clusters in the grid (0 = as many as are co-resident, occupancy query)
+    int gram_refresh = 0;            // one-pass CG: recompute q = A p with a pass of its own every this many iterations (0 = 32)
 };
 
 }  // namespace vampomi
@@ -167,13 +175,14 @@ struct vampomi_ctx {
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;
     long long counters[4] = {0, 0, 0, 0};
+    int gram_clusters[8][4][2] = {};    // co-resident clusters of k_gram per (shape, cluster size 1/2/4/8, systems), 0 = not queried yet
     bool bulk_attr_ax = false, bulk_attr_atx = false;   // opt-in shared-memory size set for the bulk kernels on this device
     // optional per-launch device timing (vampomi_profile_*)
     bool profile = false;
     struct ProfSpan { int kind; cudaEvent_t e0, e1; double bytes; };
     std::vector<ProfSpan> prof_pending;
     std::vector<cudaEvent_t> prof_free;
-    double prof_acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // kinds: 0 A x, 1 A x reduce + exchange, 2 A^T p, 3 fused A^T q / A A^T q
 };
 
 namespace vampomi {
@@ -226,6 +235,11 @@ int launch_read_probe(vampomi_ctx* c);
 // ---- launchers (kernels_multi.cu): one pass over A for K vectors ----
 int launch_ax_multi(vampomi_ctx* c, const MultiVec& mv);
 int launch_atx_multi(vampomi_ctx* c, const MultiVec& mv);
+int ensure_ax_partial(vampomi_ctx* c, size_t elems);                              // scratch [K][chunks][ld] of the A x style kernels
+int launch_ax_reduce_multi(vampomi_ctx* c, int nchunks, const MultiVec& mv);      // chunk partials -> out_k (+ cross-GPU sum, / sqrt(N))
+// ---- launchers (kernels_gram.cu): t = A^T q and w = A t in ONE pass over A (K <= 2 systems) ----
+bool gram_supported(const vampomi_ctx* c);
+int launch_gram(vampomi_ctx* c, const MultiVec& mq, double* const* w_out);
 int launch_f64_to_f32(vampomi_ctx* c, float* dst, const double* src_dense, long long ncols, cudaStream_t st);
 int launch_f32_to_f64(vampomi_ctx* c, double* dst_dense, const float* src, long long ncols, cudaStream_t st);
 // ---- launchers (kernels_bulk.cu) ----
@@ -245,8 +259,8 @@ int launch_pvals_se(vampomi_ctx* c, const double* r1_dev, double sd, double* out
 int launch_cg_init(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, double* sums_dev);   // also zeroes amu of cold systems
 int launch_cg_init_finish(vampomi_ctx* c, const CgBatch& b, const double* sums_dev);
 int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double* sums_dev);
-int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev);
-int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double tol, int max_iter, const double* sums_dev);
+int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, int parity, const double* dp_dev, double* sums_dev);
+int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double diag, double tol, int max_iter, const double* sums_dev);
 int launch_xchg_sums(vampomi_ctx* c, double* sums_dev, int n);   // n <= XCHG_SCALARS packed sums over the GPUs via peer memory
 // all-reduce `n` doubles in place on the context stream (no-op for nranks == 1)
 int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n);

@@ -120,7 +120,7 @@ int run_infere(Rank& r) {
     for (int i = 0; i < cfg.L; i++) { cfg.probs[i] = o.probs[i]; cfg.vars[i] = o.vars[i]; }
     cfg.seed = o.seed;
     cfg.redundant_passes = o.schedule == "reference" ? 1 : 0;
-    cfg.fuse_passes = o.schedule == "recycled" ? 2 : o.schedule == "fused" ? 1 : 0;
+    cfg.fuse_passes = o.schedule == "onepass" ? 3 : o.schedule == "recycled" ? 2 : o.schedule == "fused" ? 1 : 0;
 
     Vamp vamp(r.ctx, cfg);
     vamp.verbose = r.root();

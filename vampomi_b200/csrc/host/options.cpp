@@ -117,8 +117,8 @@ bool Options::parse(int argc, char** argv, std::string* echo) {
         } else if (!strcmp(a, "--schedule")) {
             if (!need_value()) return false;
             schedule = argv[++i];
-            if (schedule != "fused" && schedule != "plain" && schedule != "reference" && schedule != "recycled") {
-                std::cout << "FATAL  : option --schedule has to be recycled, fused, plain or reference! (" << schedule << " was passed)" << std::endl;
+            if (schedule != "fused" && schedule != "plain" && schedule != "reference" && schedule != "recycled" && schedule != "onepass") {
+                std::cout << "FATAL  : option --schedule has to be onepass, recycled, fused, plain or reference! (" << schedule << " was passed)" << std::endl;
                 return false;
             }
             ss << "--schedule " << schedule << "\n";

@@ -1,0 +1,641 @@
+// ONE read of the marker block per conjugate-gradient iteration: t = A^T q and w = A t in the same pass.
+//
+// The operator of the LMMSE solve is tau*A^T A + gam2*I (vamp::lmmse_mult, src/vamp.cpp:645-662): the reference applies it
+// as ATx(Ax(p)) (:653-654), two sweeps over the marker block, and so does the two-pass schedule here. The same CG can be
+// advanced with ONE sweep per iteration: keep q = A p as a vector of its own (its recurrence follows from p = z + beta p,
+// cg.cu), and let the sweep deliver both t = A^T q (what the iteration needs as A^T A p) and w = A t = A A^T q (what the
+// recurrence of q needs). For a marker-major matrix these two products FUSE column by column:
+//
+//     t_j = msig_j * <a_j - mave_j, q> / sqrt(N)              data::dot_product, src/data.cpp:294-313
+//     w  += (a_j - mave_j) * (msig_j * t_j)                   inner loop of data::Ax, src/data.cpp:349-362
+//
+// Column j is needed twice, but only a dot product apart — so it is kept ON CHIP between the two uses instead of being read
+// from HBM again. One column is N*8 = 160 kB at N = 20 000, too much for one SM next to q and w, so a thread-block
+// CLUSTER of CS CTAs owns a column group: CTA r holds rows [r*tile, (r+1)*tile) of q (registers), of w (registers) and of
+// the C columns of the current step (registers); the partial dot products of the CS row tiles meet through distributed
+// shared memory (one st.shared::cluster per value + one cluster barrier per step), are added in rank order — every CTA gets
+// bitwise the same t_j — and the axpy runs on the registers that still hold the centred column. D steps of C columns are
+// in flight per thread, so the cluster barrier of one step overlaps the loads of the next ones.
+//
+// Output: t (M-vector, written by cluster rank 0) and the per-chunk partials of w, which go through the same
+// k_ax_reduce_multi (fixed-order reduction + fused peer-memory all-reduce + 1/sqrt(N)) as the A x passes.
+// Algorithmic bytes per launch: N*M_local*8, for t AND w, for up to two systems.
+#include "common.h"
+#include "vec32.cuh"
+
+namespace vampomi {
+
+namespace {
+
+struct GramVec {
+    const double* q[2];                // in: N-vectors (zero-padded to ld)
+    double* t[2];                      // out: M-vectors, t = A^T q
+    const int* done[2];                // "skip me" flags (nullptr = always active)
+};
+
+// Position (in doubles) of the h-th pair of the four values of 32-byte vector v of a row tile: the 32 lanes of a warp read
+// 32 consecutive vectors, so pair h of lane l sits at ((h*32 + l)*2) inside the block — consecutive lanes, consecutive
+// 16-byte words: conflict-free LDS.128 (the natural layout would put lanes 32 bytes apart).
+__device__ __forceinline__ int qs_pos(int v, int h) { return (v >> 5) * 128 + ((h << 5) + (v & 31)) * 2; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// 8-byte store into a peer CTA's shared memory that also counts 8 bytes on the peer's mbarrier: data and arrival in one message
+__device__ __forceinline__ void st_async_f64(uint32_t raddr, double v, uint32_t rbar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 ::"r"(raddr), "l"(__double_as_longlong(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins > (1ull << 28)) __trap();            // a protocol bug must fault, not hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Sums NV (1, 2, 4 or 8) values over the 32 lanes of a warp with 5 exchange levels in total: at each of the first log2(NV)
+// levels a lane hands half of its values to its partner and keeps the sums of the other half, so lane v * (32/NV) (and the
+// 32/NV - 1 lanes after it) ends up with the warp total of value v.
+template <int NV>
+__device__ __forceinline__ double warp_sum_multi(const double (&v)[NV], int lane) {
+    static_assert(NV == 1 || NV == 2 || NV == 4, "1, 2 or 4 values");
+    double t;
+    if constexpr (NV == 4) {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        const double a0 = (up16 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[2], 16);
+        const double a1 = (up16 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, up16 ? v[1] : v[3], 16);
+        t = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+    } else if constexpr (NV == 2) {
+        const bool up16 = (lane & 16) != 0;
+        t = (up16 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[1], 16);
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+    } else {
+        t = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 4);
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+
+// TPB threads, RV 32-byte vectors of a column per thread (TPB*RV*4 rows per CTA), C columns per step, D register buffers of
+// one step each, CS CTAs per cluster (row tiles of a column), QS: q held in shared memory (1) or in registers (0).
+// Register budget: 8 warps -> 255 per thread, 10 or 12 warps -> 168 (three warps share a 16 K-register scheduler partition).
+//
+// Step s of a cluster = C columns. The dot products of a step need all CS row tiles, i.e. a round trip through the cluster;
+// a step-by-step barrier would serialise that latency (~1.5 us) with the loads (0.7 us per step at HBM speed). So the
+// exchange is asynchronous and the axpy of a step is deferred by one step:
+//     iteration s:   dot(s) -> warp/CTA reduce -> st.async of the CK partial sums to every CTA of the cluster (slot s % 4)
+//                    wait for the partial sums of step s-1 (sent one iteration ago: normally already there) -> t_j
+//                    axpy(s-1) on the registers that still hold its centred columns -> reload that buffer with step s-1+D
+// Every partial sum travels as ONE st.async: an 8-byte store into the peer's shared memory that also completes 8 bytes on
+// the peer's mbarrier, so data and arrival are one message and nothing in the loop is a cluster-wide barrier. Four slots
+// make reuse safe: a CTA can only send step s+4 after it has received step s+3 from everybody, which every peer sends
+// after it has consumed step s. One lane per CTA pulls the column pieces `pf` steps ahead into L2 (cp.async.bulk.prefetch),
+// so the register loads of the D-2 steps in flight see L2 latency instead of HBM latency.
+template <int K, int TPB, int RV, int C, int D, int CS, int QS>
+__global__ void __launch_bounds__(TPB, 1) k_gram(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                 const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
+                                                 long long M, double scale, double* __restrict__ partial, int nchunks, int pf) {
+    constexpr int VE = 4, CK = C * K, NW = TPB / 32, QSTRIDE = TPB * RV * VE;
+    static_assert(CS * CK <= 32, "one warp sends the partial sums of a step");
+    static_assert(D >= 2, "the axpy of a step is deferred by one step");
+    extern __shared__ __align__(32) double qs[];                 // [K][QSTRIDE], swizzled (qs_pos); unused when QS == 0
+    __shared__ double red[2][NW][CK];
+    __shared__ __align__(16) double xbuf[4][CS][CK];
+    __shared__ __align__(8) uint64_t full[4];
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = gv.done[k] == nullptr || *gv.done[k] == 0; any |= active[k]; }
+    if (!any) return;                                            // identical decision in every CTA of the cluster
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { mbar_init(&full[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_expect_tx(&full[i], CS * CK * 8);
+    }
+    const size_t rbase = (size_t)crank * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+    const uint32_t piece_bytes = rbase < ld ? (uint32_t)((ld - rbase < (size_t)tile_rows ? ld - rbase : (size_t)tile_rows) * sizeof(double)) : 0u;
+
+    const double* ap[RV];
+    bool valid[RV];
+    double qr[QS ? 1 : K][QS ? 1 : RV][VE], acc[K][RV][VE];
+#pragma unroll
+    for (int rv = 0; rv < RV; rv++) {
+        const int vi = rv * TPB + tid, off = vi * VE;
+        valid[rv] = off < tile_rows && rbase + off < ld;
+        ap[rv] = A + rbase + (valid[rv] ? off : 0);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+#pragma unroll
+            for (int e = 0; e < VE; e++) acc[k][rv][e] = 0.0;
+            PV<4> pv;
+#pragma unroll
+            for (int e = 0; e < VE; e++) pv.v[e] = 0.0;
+            if (valid[rv] && active[k]) pv = PV<4>::load(gv.q[k] + rbase + off);   // pad rows of q are zero
+            if (QS) {                                                               // every thread reads back only what it wrote itself
+                *reinterpret_cast<double2*>(qs + (size_t)k * QSTRIDE + qs_pos(vi, 0)) = make_double2(pv.v[0], pv.v[1]);
+                *reinterpret_cast<double2*>(qs + (size_t)k * QSTRIDE + qs_pos(vi, 1)) = make_double2(pv.v[2], pv.v[3]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < VE; e++) qr[QS ? 0 : k][QS ? 0 : rv][e] = pv.v[e];
+            }
+        }
+    }
+    const long long nsteps = c1 > c0 ? (c1 - c0 + C - 1) / C : 0;
+    V32<double> a[D][C][RV];
+
+    auto col_of = [&](long long s, int cc) { const long long j = c0 + s * C + cc; return j < c1 ? j : c1 - 1; };   // ragged last step: a valid address, weight 0
+    auto load_step = [&](const int d, long long s) {
+        if (s < nsteps) {
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                const long long j = col_of(s, cc);
+#pragma unroll
+                for (int rv = 0; rv < RV; rv++)
+                    if (valid[rv]) a[d][cc][rv] = V32<double>::stream(ap[rv] + (size_t)j * ld);
+            }
+        }
+    };
+    // mave / msig of the step after the current one (loaded one step ahead: never on the critical path), of the current
+    // step, and msig of the previous one (its axpy is still to come)
+    double m_n[C], sg_n[C], sg_c[C], sg_p[C];
+#pragma unroll
+    for (int cc = 0; cc < C; cc++) {
+        const long long j = nsteps > 0 ? col_of(0, cc) : 0;
+        m_n[cc] = __ldg(mave + j); sg_n[cc] = __ldg(msig + j); sg_c[cc] = 0.0; sg_p[cc] = 0.0;
+    }
+    cluster_sync_all();                                          // every CTA's mbarriers are armed before anybody sends
+
+    auto dot_step = [&](const int d, long long s) {
+        double m[C], pd[C][K][2];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            m[cc] = m_n[cc]; sg_p[cc] = sg_c[cc]; sg_c[cc] = sg_n[cc];
+            const long long jn = col_of(s + 1 < nsteps ? s + 1 : s, cc);
+            m_n[cc] = __ldg(mave + jn); sg_n[cc] = __ldg(msig + jn);
+#pragma unroll
+            for (int k = 0; k < K; k++) pd[cc][k][0] = pd[cc][k][1] = 0.0;
+        }
+        if (pf > 0 && tid == 32 && piece_bytes != 0 && s + pf < nsteps) {
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) prefetch_l2_bulk(A + rbase + (size_t)col_of(s + pf, cc) * ld, piece_bytes);
+        }
+#pragma unroll
+        for (int rv = 0; rv < RV; rv++) {
+            if (valid[rv]) {
+                double qv[K][VE];
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    if (QS) {
+                        const double2 lo = *reinterpret_cast<const double2*>(qs + (size_t)k * QSTRIDE + qs_pos(rv * TPB + tid, 0));
+                        const double2 hi = *reinterpret_cast<const double2*>(qs + (size_t)k * QSTRIDE + qs_pos(rv * TPB + tid, 1));
+                        qv[k][0] = lo.x; qv[k][1] = lo.y; qv[k][2] = hi.x; qv[k][3] = hi.y;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VE; e++) qv[k][e] = qr[QS ? 0 : k][QS ? 0 : rv][e];
+                    }
+                }
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) {
+#pragma unroll
+                    for (int e = 0; e < VE; e++) {
+                        const double dd = a[d][cc][rv].v[e] - m[cc];           // meth[i] - mu, src/data.cpp:304 and :360
+                        a[d][cc][rv].v[e] = dd;                                 // kept centred for the deferred axpy
+#pragma unroll
+                        for (int k = 0; k < K; k++) pd[cc][k][e & 1] = fma(dd, qv[k][e], pd[cc][k][e & 1]);
+                    }
+                }
+            }
+        }
+        // partial dot products: warp (butterfly: lane v * 32/CK ends up with value v) -> CTA (fixed order) -> one message per
+        // (value, CTA of the cluster)
+        const int rb = (int)(s & 1);
+        {
+            double v[CK];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) v[cc * K + k] = pd[cc][k][0] + pd[cc][k][1];
+            const double sw = warp_sum_multi<CK>(v, lane);
+            if ((lane & (32 / CK - 1)) == 0) red[rb][wid][lane / (32 / CK)] = sw;
+        }
+        __syncthreads();
+        if (tid < CS * CK) {
+            const int ck = tid % CK, dest = tid / CK, slot = (int)(s & 3);
+            double ts = red[rb][0][ck];
+#pragma unroll
+            for (int w = 1; w < NW; w++) ts += red[rb][w][ck];
+            st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][ck]), (uint32_t)dest), ts, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
+        }
+    };
+    auto axpy_step = [&](const int d, long long sp) {
+        const int slot = (int)(sp & 3);
+        mbar_wait_cluster(&full[slot], (uint32_t)((sp >> 2) & 1));
+        const long long j0 = c0 + sp * C;
+        // lane (r, ck) of every warp reads ONE partial sum; the CS ranks meet by an xor butterfly (the same tree on the same
+        // values in every warp of every CTA: bitwise the same t_j everywhere), lane ck then holds the total of value ck
+        double wgt[C][K];
+        {
+            const int ck = lane % CK, r = lane / CK;
+            double tot = r < CS ? xbuf[slot][r < CS ? r : 0][ck] : 0.0;
+#pragma unroll
+            for (int o = CK; o < CK * CS && o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const int cc_l = ck / K, k_l = ck % K;
+            double sgl = sg_p[0];
+#pragma unroll
+            for (int cc = 1; cc < C; cc++) sgl = cc_l == cc ? sg_p[cc] : sgl;
+            const double tj = (sgl * tot) * scale;                              // sigma_inv * dpa (:306), then * scale (:330)
+            bool act = active[0];
+#pragma unroll
+            for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
+            const bool live = j0 + cc_l < c1 && act;
+            if (live && crank == 0 && tid < CK) (K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0])[j0 + cc_l] = tj;
+            const double wl = live ? sgl * tj : 0.0;                            // sig_phen_i = msig * x, src/data.cpp:354
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) wgt[cc][k] = __shfl_sync(0xffffffffu, wl, cc * K + k);
+        }
+        if (tid == 0) mbar_expect_tx(&full[slot], CS * CK * 8);                 // re-arm the slot for step sp + 4
+#pragma unroll
+        for (int cc = 0; cc < C; cc++)
+#pragma unroll
+            for (int rv = 0; rv < RV; rv++) {
+                if (valid[rv]) {
+#pragma unroll
+                    for (int e = 0; e < VE; e++)
+#pragma unroll
+                        for (int k = 0; k < K; k++) acc[k][rv][e] = fma(a[d][cc][rv].v[e], wgt[cc][k], acc[k][rv][e]);
+                }
+            }
+    };
+
+    // the loops over d are fully unrolled, so every index into a[][][] is a compile-time constant
+#pragma unroll
+    for (int d = 0; d < D; d++) load_step(d, (long long)d);
+    for (long long s0 = 0; s0 <= nsteps; s0 += D) {
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            const long long s = s0 + d;                                         // uniform over the cluster
+            if (s < nsteps) dot_step(d, s);
+            else if (s == nsteps) {                                             // drain: only the bookkeeping of the step that is not there
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) sg_p[cc] = sg_c[cc];
+            }
+            if (s >= 1 && s <= nsteps) {
+                axpy_step((d + D - 1) % D, s - 1);
+                load_step((d + D - 1) % D, s - 1 + D);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (!active[k]) continue;
+        double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase;
+#pragma unroll
+        for (int rv = 0; rv < RV; rv++)
+            if (valid[rv]) st256(prow + (rv * TPB + tid) * VE, d4{acc[k][rv][0], acc[k][rv][1], acc[k][rv][2], acc[k][rv][3]});
+    }
+    cluster_sync_all();                                          // nobody leaves while a peer may still write into its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same pass with the columns staged through SHARED memory by the bulk-copy engine (cp.async.bulk global -> shared,
+// completion on an mbarrier; SASS UBLKCP): a ring of R steps of C column pieces per CTA, so the bytes in flight per SM
+// ((R-1) * C * 20 kB at N = 20 000 with 8 row tiles) no longer cost registers — the register-staged form above can keep
+// only one or two steps in flight next to q, w and the deferred step (168 registers), i.e. 40-80 kB per SM against the
+// ~100 kB that HBM latency x bandwidth asks for. Every thread owns RP 16-byte row pairs (consecutive lanes, consecutive
+// 16-byte words: conflict-free LDS.128), copies its piece of the step from the ring into registers ONCE (the ring stage is
+// free again after the block barrier of the step) and keeps it there, centred, for the deferred axpy. q and w stay in registers.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins > (1ull << 28)) __trap();
+    } while (!ok);
+}
+
+template <int K, int TPB, int RP, int C, int R, int CS>
+__global__ void __launch_bounds__(TPB, 1) k_gram_bulk(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                      const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
+                                                      long long M, double scale, double* __restrict__ partial, int nchunks) {
+    constexpr int CK = C * K, NW = TPB / 32, PIECE = TPB * RP * 2;      // doubles per column piece slot in the ring
+    static_assert(CS * CK <= 32, "one warp sends the partial sums of a step");
+    extern __shared__ __align__(128) double ring[];              // [R][C][PIECE]
+    __shared__ double red[2][NW][CK];
+    __shared__ __align__(16) double xbuf[4][CS][CK];
+    __shared__ __align__(8) uint64_t full[4];
+    __shared__ __align__(8) uint64_t ringbar[R];
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = gv.done[k] == nullptr || *gv.done[k] == 0; any |= active[k]; }
+    if (!any) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const size_t rbase = (size_t)crank * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+    const long long nsteps = c1 > c0 ? (c1 - c0 + C - 1) / C : 0;
+    const uint32_t piece_bytes = rbase < ld ? (uint32_t)((ld - rbase < (size_t)tile_rows ? ld - rbase : (size_t)tile_rows) * sizeof(double)) : 0u;
+    auto col_of = [&](long long s, int cc) { const long long j = c0 + s * C + cc; return j < c1 ? j : c1 - 1; };
+    const bool producer = tid == TPB - 32;
+    auto issue_step = [&](long long s) {                         // producer lane: the C column pieces of step s into stage s % R
+        const int st = (int)(s % R);
+        mbar_expect_tx(&ringbar[st], C * piece_bytes);
+        if (piece_bytes != 0) {
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+                bulk_g2s(ring + ((size_t)st * C + cc) * PIECE, A + rbase + (size_t)col_of(s, cc) * ld, piece_bytes, &ringbar[st]);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_init(&full[i], 1);
+#pragma unroll
+        for (int i = 0; i < R; i++) mbar_init(&ringbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_expect_tx(&full[i], CS * CK * 8);
+    }
+    __syncthreads();
+    if (producer)
+        for (long long s = 0; s < R && s < nsteps; s++) issue_step(s);
+
+    bool valid[RP];
+    double qr[K][RP][2], acc[K][RP][2];
+#pragma unroll
+    for (int i = 0; i < RP; i++) {
+        const int off = (i * TPB + tid) * 2;
+        valid[i] = off < tile_rows && rbase + off < ld;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            acc[k][i][0] = acc[k][i][1] = 0.0;
+            double2 qv = make_double2(0.0, 0.0);
+            if (valid[i] && active[k]) qv = *reinterpret_cast<const double2*>(gv.q[k] + rbase + off);   // pad rows of q are zero
+            qr[k][i][0] = qv.x; qr[k][i][1] = qv.y;
+        }
+    }
+    double a[2][C][RP][2];                                       // the step being dotted and the step whose axpy is pending
+    double m_n[C], sg_n[C], sg_c[C], sg_p[C];
+#pragma unroll
+    for (int cc = 0; cc < C; cc++) {
+        const long long j = nsteps > 0 ? col_of(0, cc) : 0;
+        m_n[cc] = __ldg(mave + j); sg_n[cc] = __ldg(msig + j); sg_c[cc] = 0.0; sg_p[cc] = 0.0;
+    }
+    cluster_sync_all();                                          // every CTA's mbarriers are armed before anybody sends
+
+    auto dot_step = [&](const int b, long long s) {
+        double m[C], pd[C][K][2];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) {
+            m[cc] = m_n[cc]; sg_p[cc] = sg_c[cc]; sg_c[cc] = sg_n[cc];
+            const long long jn = col_of(s + 1 < nsteps ? s + 1 : s, cc);
+            m_n[cc] = __ldg(mave + jn); sg_n[cc] = __ldg(msig + jn);
+#pragma unroll
+            for (int k = 0; k < K; k++) pd[cc][k][0] = pd[cc][k][1] = 0.0;
+        }
+        const int st = (int)(s % R);
+        mbar_wait_cta(&ringbar[st], (uint32_t)((s / R) & 1));
+        const double* stage = ring + (size_t)st * C * PIECE;
+#pragma unroll
+        for (int cc = 0; cc < C; cc++)
+#pragma unroll
+            for (int i = 0; i < RP; i++) {
+                double2 v = make_double2(m[cc], m[cc]);          // rows this thread does not own: centred value 0
+                if (valid[i]) v = *reinterpret_cast<const double2*>(stage + (size_t)cc * PIECE + (i * TPB + tid) * 2);
+                const double d0 = v.x - m[cc], d1 = v.y - m[cc];  // meth[i] - mu, src/data.cpp:304 and :360
+                a[b][cc][i][0] = d0; a[b][cc][i][1] = d1;         // kept centred for the deferred axpy
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    pd[cc][k][0] = fma(d0, qr[k][i][0], pd[cc][k][0]);
+                    pd[cc][k][1] = fma(d1, qr[k][i][1], pd[cc][k][1]);
+                }
+            }
+        const int rb = (int)(s & 1);
+        {
+            double v[CK];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) v[cc * K + k] = pd[cc][k][0] + pd[cc][k][1];
+            const double sw = warp_sum_multi<CK>(v, lane);
+            if ((lane & (32 / CK - 1)) == 0) red[rb][wid][lane / (32 / CK)] = sw;
+        }
+        __syncthreads();                                         // also: every warp has copied stage s % R into registers
+        if (producer && s + R < nsteps) issue_step(s + R);
+        if (tid < CS * CK) {
+            const int ck = tid % CK, dest = tid / CK, slot = (int)(s & 3);
+            double ts = red[rb][0][ck];
+#pragma unroll
+            for (int w = 1; w < NW; w++) ts += red[rb][w][ck];
+            st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][ck]), (uint32_t)dest), ts, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
+        }
+    };
+    auto axpy_step = [&](const int b, long long sp) {
+        const int slot = (int)(sp & 3);
+        mbar_wait_cluster(&full[slot], (uint32_t)((sp >> 2) & 1));
+        const long long j0 = c0 + sp * C;
+        double wgt[C][K];
+        {
+            const int ck = lane % CK, r = lane / CK;
+            double tot = r < CS ? xbuf[slot][r < CS ? r : 0][ck] : 0.0;
+#pragma unroll
+            for (int o = CK; o < CK * CS && o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const int cc_l = ck / K, k_l = ck % K;
+            double sgl = sg_p[0];
+#pragma unroll
+            for (int cc = 1; cc < C; cc++) sgl = cc_l == cc ? sg_p[cc] : sgl;
+            const double tj = (sgl * tot) * scale;                              // sigma_inv * dpa (:306), then * scale (:330)
+            bool act = active[0];
+#pragma unroll
+            for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
+            const bool live = j0 + cc_l < c1 && act;
+            if (live && crank == 0 && tid < CK) (K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0])[j0 + cc_l] = tj;
+            const double wl = live ? sgl * tj : 0.0;                            // sig_phen_i = msig * x, src/data.cpp:354
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) wgt[cc][k] = __shfl_sync(0xffffffffu, wl, cc * K + k);
+        }
+        if (tid == 0) mbar_expect_tx(&full[slot], CS * CK * 8);                 // re-arm the slot for step sp + 4
+#pragma unroll
+        for (int cc = 0; cc < C; cc++)
+#pragma unroll
+            for (int i = 0; i < RP; i++)
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    acc[k][i][0] = fma(a[b][cc][i][0], wgt[cc][k], acc[k][i][0]);
+                    acc[k][i][1] = fma(a[b][cc][i][1], wgt[cc][k], acc[k][i][1]);
+                }
+    };
+    for (long long s0 = 0; s0 <= nsteps; s0 += 2) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const long long s = s0 + b;
+            if (s < nsteps) dot_step(b, s);
+            else if (s == nsteps) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) sg_p[cc] = sg_c[cc];
+            }
+            if (s >= 1 && s <= nsteps) axpy_step(b ^ 1, s - 1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (!active[k]) continue;
+        double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase;
+#pragma unroll
+        for (int i = 0; i < RP; i++)
+            if (valid[i]) *reinterpret_cast<double2*>(prow + (i * TPB + tid) * 2) = make_double2(acc[k][i][0], acc[k][i][1]);
+    }
+    cluster_sync_all();
+}
+
+template <int K, int C, int CS, typename Kern, typename... Extra>
+int gram_launch_any(vampomi_ctx* c, Kern kern, int TPB, int ROWS, size_t smem, int shape, const GramVec& gv, const MultiVec& mw, Extra... extra) {
+    const size_t tr = (c->ld + CS - 1) / CS;
+    const int tile_rows = (int)((tr + 15) / 16 * 16);
+    if (tile_rows > ROWS) { set_error("gram: N=%d needs more than %d rows per CTA at cluster size %d", c->N, ROWS, CS); return VAMPOMI_ERR_ARG; }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    // co-resident clusters of this (shape, cluster size, systems) on this device: queried once per context
+    constexpr int csi = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : 3;
+    int& ncl = c->gram_clusters[shape][csi][K - 1];
+    if (ncl <= 0) {
+        if (smem > 40 * 1024) VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg.gridDim = dim3(CS, c->num_sms);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = c->num_sms / CS; }
+        ncl = n < 1 ? 1 : n;
+    }
+    long long nch = c->tune.gram_clusters > 0 ? c->tune.gram_clusters : ncl;
+    const long long cap = (c->M + C - 1) / C;
+    if (nch > cap) nch = cap;
+    int cols_per_chunk = (int)((c->M + nch - 1) / nch);
+    cols_per_chunk = (cols_per_chunk + C - 1) / C * C;
+    const int nchunks = (int)((c->M + cols_per_chunk - 1) / cols_per_chunk);
+    VO_CHECK(ensure_ax_partial(c, (size_t)K * nchunks * c->ld));
+    cfg.gridDim = dim3(CS, nchunks);
+    if (c->prof_pending.size() > 8192) VO_CHECK(prof_resolve(c));
+    int sp = prof_begin(c, 3, (double)c->M * c->N * (double)c->elem_bytes);
+    const double scale = 1.0 / sqrt((double)c->N);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const double*)c->A, c->ld, (const double*)c->mave, (const double*)c->msig, gv, tile_rows,
+                                       cols_per_chunk, c->M, scale, c->ax_partial, nchunks, extra...);
+    prof_end(c, sp);
+    if (e != cudaSuccess) { set_error("gram kernel launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return VAMPOMI_ERR_CUDA; }
+    c->counters[0] += 1; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
+    return launch_ax_reduce_multi(c, nchunks, mw);
+}
+
+template <int K, int TPB, int RV, int C, int D, int CS, int QS>
+int gram_launch(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
+    constexpr int ROWS = TPB * RV * 4;
+    return gram_launch_any<K, C, CS>(c, k_gram<K, TPB, RV, C, D, CS, QS>, TPB, ROWS, QS ? (size_t)K * ROWS * sizeof(double) : 0, shape, gv, mw,
+                                     c->tune.gram_prefetch);
+}
+template <int K, int TPB, int RP, int C, int R, int CS>
+int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
+    constexpr int ROWS = TPB * RP * 2;
+    return gram_launch_any<K, C, CS>(c, k_gram_bulk<K, TPB, RP, C, R, CS>, TPB, ROWS, (size_t)R * C * ROWS * sizeof(double), shape, gv, mw);
+}
+
+// shapes (knob gram_shape)
+//   register-staged (k_gram): threads, 32-byte vectors per thread, columns per step, register buffers, q in shared memory
+//     0  320, 2, 2, 3, smem    1  256, 3, 2, 3, smem    2  320, 2, 2, 2, regs
+//   bulk-copy ring (k_gram_bulk): threads, 16-byte row pairs per thread, columns per step, ring stages
+//     3  256, 5, 2, 4          4  256, 5, 2, 3          5  256, 5, 1, 6
+constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : 2560; }
+
+template <int K, int CS>
+int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
+    switch (shape) {
+        case 0: return gram_launch<K, 320, 2, 2, 3, CS, 1>(c, gv, mw, shape);
+        case 1: return gram_launch<K, 256, 3, 2, 3, CS, 1>(c, gv, mw, shape);
+        case 2: return gram_launch<K, 320, 2, 2, 2, CS, 0>(c, gv, mw, shape);
+        case 3: return gram_launch_bulk<K, 256, 5, 2, 4, CS>(c, gv, mw, shape);
+        case 4: return gram_launch_bulk<K, 256, 5, 2, 3, CS>(c, gv, mw, shape);
+        case 5: return gram_launch_bulk<K, 256, 5, 1, 6, CS>(c, gv, mw, shape);
+        default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
+    }
+}
+
+template <int K>
+int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
+    const int shape = c->tune.gram_shape;
+    int cs = c->tune.gram_cluster;
+    if (cs == 0) { cs = 1; while (cs < 8 && (c->ld + cs - 1) / cs > (size_t)gram_rows_of_shape(shape)) cs *= 2; }
+    switch (cs) {
+        case 1: return gram_shape<K, 1>(c, gv, mw, shape);
+        case 2: return gram_shape<K, 2>(c, gv, mw, shape);
+        case 4: return gram_shape<K, 4>(c, gv, mw, shape);
+        case 8: return gram_shape<K, 8>(c, gv, mw, shape);
+        default: set_error("gram: cluster size must be 1, 2, 4 or 8"); return VAMPOMI_ERR_ARG;
+    }
+}
+
+}  // namespace
+
+bool gram_supported(const vampomi_ctx* c) { return c->storage == 0 && c->ld <= (size_t)8 * gram_rows_of_shape(c->tune.gram_shape); }
+
+// t_k = A^T q_k (M-vectors), w_k = A t_k (N-vectors, summed over the GPUs, / sqrt(N)) for K <= 2 systems in ONE pass.
+// mq: in = q_k (N-vectors), out = t_k (M-vectors); w_out: the N-vectors that receive w_k. done flags from mq.
+int launch_gram(vampomi_ctx* c, const MultiVec& mq, double* const* w_out) {
+    if (mq.K < 1 || mq.K > 2) { set_error("gram: 1 or 2 systems"); return VAMPOMI_ERR_ARG; }
+    if (!gram_supported(c)) { set_error("gram: needs FP64 storage and N <= %d", 8 * gram_rows_of_shape(c->tune.gram_shape)); return VAMPOMI_ERR_ARG; }
+    GramVec gv{};
+    MultiVec mw{};
+    mw.K = mq.K;
+    for (int k = 0; k < mq.K; k++) {
+        gv.q[k] = mq.in[k]; gv.t[k] = mq.out[k]; gv.done[k] = mq.done[k];
+        mw.in[k] = nullptr; mw.out[k] = w_out[k]; mw.done[k] = mq.done[k];
+    }
+    return mq.K == 1 ? gram_cluster<1>(c, gv, mw) : gram_cluster<2>(c, gv, mw);
+}
+
+}  // namespace vampomi

@@ -403,6 +403,30 @@ static int ensure_buf(vampomi_ctx* c, double** buf, size_t* cap, size_t need) {
     return VAMPOMI_OK;
 }
 
+int ensure_ax_partial(vampomi_ctx* c, size_t elems) { return ensure_buf(c, &c->ax_partial, &c->ax_partial_elems, elems); }
+
+// out_k = (sum of the chunk partials [+ the other GPUs' over peer memory, or NCCL]) / sqrt(N) for the mv.K vectors
+int launch_ax_reduce_multi(vampomi_ctx* c, int nchunks, const MultiVec& mv) {
+    const int K = mv.K;
+    int sp = prof_begin(c, 1, 0.0);
+    const double sqrtN = sqrt((double)c->N);
+    constexpr int SL = 8;
+    const int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
+    const bool fused = c->nranks > 1 && c->xchg.enabled;
+    k_ax_reduce_multi<SL><<<dim3(rblocks, K), 256, 0, c->stream>>>(c->ax_partial, c->ld, nchunks, c->N,
+                                                                    (c->nranks == 1 || fused) ? sqrtN : 1.0, mv, c->xchg, fused ? 1 : 0);
+    VO_CUDA(cudaGetLastError());
+    c->counters[0] += 1;
+    if (c->nranks > 1 && !fused) {
+        for (int k = 0; k < K; k++) {
+            VO_CHECK(allreduce_inplace(c, mv.out[k], (size_t)c->N));
+            VO_CHECK(launch_scale_div(c, mv.out[k], mv.out[k], sqrtN, c->N, mv.done[k]));
+        }
+    }
+    prof_end(c, sp);
+    return VAMPOMI_OK;
+}
+
 template <typename T, int K, int RV, int U, int OCC = 0>
 static int ax_multi_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     constexpr int VE = V32<T>::VE;
@@ -421,23 +445,8 @@ static int ax_multi_launch(vampomi_ctx* c, const T* A, const MultiVec& mv) {
     kern<<<dim3(ntiles, nchunks), 256, 0, c->stream>>>(A, c->ld, c->mave, c->msig, mv, tile_rows, cols_per_chunk, c->M, c->ax_partial, nchunks);
     prof_end(c, sp);
     VO_CUDA(cudaGetLastError());
-    sp = prof_begin(c, 1, 0.0);
-    const double sqrtN = sqrt((double)c->N);
-    constexpr int SL = 8;
-    const int rblocks = (c->N + (256 / SL) - 1) / (256 / SL);
-    const bool fused = c->nranks > 1 && c->xchg.enabled;
-    k_ax_reduce_multi<SL><<<dim3(rblocks, K), 256, 0, c->stream>>>(c->ax_partial, c->ld, nchunks, c->N,
-                                                                    (c->nranks == 1 || fused) ? sqrtN : 1.0, mv, c->xchg, fused ? 1 : 0);
-    VO_CUDA(cudaGetLastError());
-    c->counters[0] += 2; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
-    if (c->nranks > 1 && !fused) {
-        for (int k = 0; k < K; k++) {
-            VO_CHECK(allreduce_inplace(c, mv.out[k], (size_t)c->N));
-            VO_CHECK(launch_scale_div(c, mv.out[k], mv.out[k], sqrtN, c->N, mv.done[k]));
-        }
-    }
-    prof_end(c, sp);
-    return VAMPOMI_OK;
+    c->counters[0] += 1; c->counters[1]++; c->counters[2] += (long long)c->M * c->N * c->elem_bytes;
+    return launch_ax_reduce_multi(c, nchunks, mv);
 }
 
 // tile shape (32-byte vectors per thread per column, columns in flight): knobs multi_ax_rv / multi_ax_unroll, 0 = default

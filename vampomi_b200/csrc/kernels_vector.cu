@@ -401,8 +401,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_dp(CgBatch b, long long M, d
 
 // alpha = <r,z>/<d,p>; mu += alpha p; r -= alpha d; z = r/diag; out[3s..3s+2] = <v,mu>, <r,z>, <r,r>   (:701-706, :728-734)
 // A system with `amu` also advances amu += alpha * (A p), so that amu stays A mu without a pass of its own.
+// One-pass CG (gar != nullptr; kernels_gram.cu): tmpN holds q = A p and gw holds w = A A^T q, so A d = tau w + gam2 q and
+// A r follows r: A r -= alpha * A d — the N-side image of r -= alpha d.
 template <int S>
-__global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M, int N, double diag, int parity,
+__global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M, int N, double tau, double gam2, double diag, int parity,
                                                          const double* __restrict__ dp, double* __restrict__ partials,
                                                          unsigned int* ticket, double* __restrict__ out, Xchg xc) {
     bool active[S], any = false;
@@ -426,6 +428,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M,
                 a2 = fma(ri, ri, a2);
             }
             if (q.amu != nullptr) GRID_STRIDE(i, N) q.amu[i] += alpha * q.tmpN[i];
+            if (q.gar != nullptr) GRID_STRIDE(i, N) {
+                double adi = q.gw[i] * tau;
+                adi += gam2 * q.tmpN[i];
+                q.gar[i] -= adi * alpha;
+            }
         }
         acc[3 * s] = a0; acc[3 * s + 1] = a1; acc[3 * s + 2] = a2;
     }
@@ -436,9 +443,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_step(CgBatch b, long long M,
 // Every block recomputes the scalars from read-only inputs (slot `parity`); block 0 publishes slot parity^1.
 // cg->done is written by block 0 while later-scheduled blocks of the SAME launch may already read it at their entry: if they
 // see it set they skip a p update that nothing will read any more (that solve is over), so the race is benign by construction.
+// One-pass CG: q = A p follows p: q = (A r)/diag + beta q — the N-side image of p = z + beta p with z = r/diag.
 template <int S>
-__global__ void __launch_bounds__(RED_THREADS) k_cg_finish(CgBatch b, long long M, int parity, double gam2, double tol, int max_iter,
-                                                           const double* __restrict__ sums) {
+__global__ void __launch_bounds__(RED_THREADS) k_cg_finish(CgBatch b, long long M, int N, int parity, double gam2, double diag, double tol,
+                                                           int max_iter, const double* __restrict__ sums) {
 #pragma unroll
     for (int s = 0; s < S; s++) {
         const CgSys& q = b.s[s];
@@ -460,6 +468,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_finish(CgBatch b, long long 
             double beta = 1.0 / rz_old;                   // pow(<r,z>, -1), :731
             beta *= rz_new;                               // :736
             GRID_STRIDE(i, M) q.p[i] = q.z[i] + beta * q.p[i];
+            if (q.gar != nullptr) GRID_STRIDE(i, N) q.tmpN[i] = q.gar[i] / diag + beta * q.tmpN[i];
             rel_err = sqrt(rr) / sqrt(cg->vv);            // :742-744
             if (rel_err < tol) done = 2;
         }
@@ -497,16 +506,16 @@ int launch_cg_dp(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, doub
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
-int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double diag, int parity, const double* dp_dev, double* sums_dev) {
-    if (b.S == 1) k_cg_step<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
-    else k_cg_step<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+int launch_cg_step(vampomi_ctx* c, const CgBatch& b, double tau, double gam2, double diag, int parity, const double* dp_dev, double* sums_dev) {
+    if (b.S == 1) k_cg_step<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, tau, gam2, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
+    else k_cg_step<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, tau, gam2, diag, parity, dp_dev, c->red_partials, c->red_tickets, sums_dev, c->xchg);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;
 }
-int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double tol, int max_iter, const double* sums_dev) {
-    if (b.S == 1) k_cg_finish<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, parity, gam2, tol, max_iter, sums_dev);
-    else k_cg_finish<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, parity, gam2, tol, max_iter, sums_dev);
+int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, double diag, double tol, int max_iter, const double* sums_dev) {
+    if (b.S == 1) k_cg_finish<1><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, parity, gam2, diag, tol, max_iter, sums_dev);
+    else k_cg_finish<2><<<vec_blocks(c->M), RED_THREADS, 0, c->stream>>>(b, c->M, c->N, parity, gam2, diag, tol, max_iter, sums_dev);
     c->counters[0]++;
     VO_CUDA(cudaGetLastError());
     return VAMPOMI_OK;

@@ -47,8 +47,8 @@ def parse_args():
     ap.add_argument("--Mt", type=int, default=850000)
     ap.add_argument("--cpu-sample-M", type=int, default=4000, help="markers of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--schedule", default="recycled", choices=["onepass", "recycled", "fused", "plain"],
-                    help="onepass: recycled + CG iterations that read the block once (fused A^T q / A A^T q pass); recycled (default): lock-step LMMSE + Onsager solves sharing every read of the block, products of their "
+    ap.add_argument("--schedule", default="onepass", choices=["onepass", "recycled", "fused", "plain"],
+                    help="onepass (default): recycled + CG iterations that read the block once (fused A^T q / A A^T q pass); recycled: lock-step LMMSE + Onsager solves sharing every read of the block, products of their "
                          "solutions kept by the solves themselves; fused: the same without that recycling (every product computed "
                          "by a pass, sharing reads); plain: one product per pass in the reference's order")
     ap.add_argument("--tune", action="append", default=[], metavar="KNOB=VALUE", help="vampomi_set_tuning knob for experiments (repeatable)")

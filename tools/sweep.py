@@ -50,7 +50,7 @@ if a.gram:
     t(4, "read_probe", a.gram)
     t(5, "ax_multi_K2_default", a.gram)
     t(6, "atx_multi_K2_default", a.gram)
-    for shape in range(6):
+    for shape in range(8):
         t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0)
         t(10, "gram_K1", a.gram, gram_shape=shape, gram_clusters=0)
     for shape in (0, 2):

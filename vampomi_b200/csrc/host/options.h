@@ -29,7 +29,7 @@ struct Options {
     // additions
     unsigned long long seed = 0;
     int gpus = 1;
-    std::string schedule = "recycled";  // recycled | fused | plain | reference (vampomi_solver_config::fuse_passes / redundant_passes)
+    std::string schedule = "onepass";   // onepass | recycled | fused | plain | reference (vampomi_solver_config::fuse_passes / redundant_passes)
     std::string storage = "f64";     // "f32": hold the marker block rounded to FP32 in HBM (arithmetic stays FP64)
 
     // Parses argv. On error prints the reference's FATAL line to stdout and returns false (caller exits 1).

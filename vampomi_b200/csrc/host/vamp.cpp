@@ -537,7 +537,7 @@ void vampomi_solver_default_config(vampomi_solver_config* cfg) {
     for (int i = 0; i < 10; i++) { cfg->vars[i] = vars[i]; cfg->probs[i] = probs[i]; }
     cfg->seed = 0;
     cfg->redundant_passes = 0;
-    cfg->fuse_passes = 2;
+    cfg->fuse_passes = 3;
 }
 
 }  // extern "C"

@@ -534,6 +534,234 @@ __global__ void __launch_bounds__(TPB, 1) k_gram_bulk(const double* __restrict__
     cluster_sync_all();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised form of the bulk-copy pass: NCW compute warps + ONE communication warp per CTA.
+//
+// In k_gram_bulk every warp walks through the whole chain of a step — dot, warp reduction, block barrier, CTA sum, send, wait,
+// rank sum, weights, axpy — in lock-step, so the FP64 pipes idle during every exchange (measured: 1.04 us per step of 40 kB
+// against 0.69 us of HBM time). Here the chain is split:
+//   compute warp, step s:  wait ring stage -> LDS its rows -> centre, dot with q -> warp butterfly -> partial sums to red[s&1],
+//                          arrive on redbar[s&1];  wait wready[(s-1)&3] -> read the CK weights -> axpy(s-1) on the kept registers
+//   communication warp, s: wait redbar[s&1] (all compute warps have read stage s%R: lane 0 refills it with step s+R) ->
+//                          lane (dest, ck) adds the NCW warp sums in warp order and st.async's them to CTA dest (slot s&3);
+//                          wait full[s&3] -> lane (r, ck) reads one partial, xor butterfly over the ranks -> t_j, weight ->
+//                          wbuf[s&3], arrive on wready[s&3]; cluster rank 0 stores t_j
+// Compute warps never wait for the cluster round trip of the step they just dotted — only for the one before it, which the
+// communication warp has been carrying meanwhile.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// DIRECT = 1: every compute warp sends its own partial sums to all CTAs (one st.async per lane, no block-level stage in between)
+template <int K, int NCW, int RP, int C, int R, int CS, int DIRECT>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                              const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
+                                                              long long M, double scale, double* __restrict__ partial, int nchunks) {
+    constexpr int CK = C * K, CT = NCW * 32, PIECE = CT * RP * 2;      // compute threads; doubles per column piece slot in the ring
+    static_assert(CS * CK <= 32, "one warp sends the partial sums of a step");
+    extern __shared__ __align__(128) double ring[];              // [R][C][PIECE]
+    constexpr int NSRC = DIRECT ? NCW : 1;                       // partial sums per (rank, value) that arrive per step
+    static_assert(!DIRECT || CS <= 32 / CK, "the lanes that hold value ck after the butterfly send it to the CS ranks");
+    __shared__ double red[2][NCW][CK];
+    __shared__ __align__(16) double xbuf[4][CS][NSRC][CK];
+    __shared__ __align__(8) uint64_t empty[R];
+    __shared__ __align__(16) double wbuf[4][CK];
+    __shared__ __align__(8) uint64_t full[4], wready[4], redbar[2], ringbar[R];
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = gv.done[k] == nullptr || *gv.done[k] == 0; any |= active[k]; }
+    if (!any) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const size_t rbase = (size_t)crank * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+    const long long nsteps = c1 > c0 ? (c1 - c0 + C - 1) / C : 0;
+    const uint32_t piece_bytes = rbase < ld ? (uint32_t)((ld - rbase < (size_t)tile_rows ? ld - rbase : (size_t)tile_rows) * sizeof(double)) : 0u;
+    auto col_of = [&](long long s, int cc) { const long long j = c0 + s * C + cc; return j < c1 ? j : c1 - 1; };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) { mbar_init(&full[i], 1); mbar_init(&wready[i], 1); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) mbar_init(&redbar[i], NCW);
+#pragma unroll
+        for (int i = 0; i < R; i++) { mbar_init(&ringbar[i], 1); mbar_init(&empty[i], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_expect_tx(&full[i], CS * NSRC * CK * 8);
+    }
+    __syncthreads();
+    cluster_sync_all();                                          // every CTA's mbarriers are armed before anybody sends
+
+    if (wid == NCW) {
+        // ------------------------------------------- communication warp -------------------------------------------
+        auto issue_step = [&](long long s) {                     // lane 0: the C column pieces of step s into stage s % R
+            const int st = (int)(s % R);
+            mbar_expect_tx(&ringbar[st], C * piece_bytes);
+            if (piece_bytes != 0) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++)
+                    bulk_g2s(ring + ((size_t)st * C + cc) * PIECE, A + rbase + (size_t)col_of(s, cc) * ld, piece_bytes, &ringbar[st]);
+            }
+        };
+        if (lane == 0)
+            for (long long s = 0; s < R && s < nsteps; s++) issue_step(s);
+        const int ck = lane % CK, r = lane / CK, cc_l = ck / K, k_l = ck % K;
+        bool act = active[0];
+#pragma unroll
+        for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
+        double* tout = K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0];
+        double sg_next = nsteps > 0 ? __ldg(msig + col_of(0, cc_l)) : 0.0;
+        for (long long s = 0; s < nsteps; s++) {
+            const int rb = (int)(s & 1), slot = (int)(s & 3);
+            const double sgl = sg_next;
+            sg_next = __ldg(msig + col_of(s + 1 < nsteps ? s + 1 : s, cc_l));
+            if (DIRECT) {
+                if (lane == 0 && s + R < nsteps) {               // refill stage s % R once every compute warp has copied it into registers
+                    mbar_wait_cta(&empty[s % R], (uint32_t)((s / R) & 1));
+                    issue_step(s + R);
+                }
+            } else {
+                mbar_wait_cta(&redbar[rb], (uint32_t)((s >> 1) & 1));
+                if (lane == 0 && s + R < nsteps) issue_step(s + R);  // every compute warp has copied stage s % R into registers
+                if (lane < CS * CK) {                            // lane = (dest r, value ck)
+                    double ts = red[rb][0][ck];
+#pragma unroll
+                    for (int w = 1; w < NCW; w++) ts += red[rb][w][ck];
+                    st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][0][ck]), (uint32_t)r), ts, mapa_u32(smem_u32(&full[slot]), (uint32_t)r));
+                }
+            }
+            mbar_wait_cluster(&full[slot], (uint32_t)((s >> 2) & 1));
+            double tot = 0.0;
+            if (r < CS) {
+                double part[NSRC];
+#pragma unroll
+                for (int w = 0; w < NSRC; w++) part[w] = xbuf[slot][r][w][ck];
+#pragma unroll
+                for (int w = 0; w < NSRC; w++) tot += part[w];   // warp order: fixed
+            }
+#pragma unroll
+            for (int o = CK; o < CK * CS && o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // the same tree in every CTA
+            const long long j = c0 + s * C + cc_l;
+            const double tj = (sgl * tot) * scale;                              // sigma_inv * dpa (:306), then * scale (:330)
+            const bool live = j < c1 && act;
+            if (lane < CK) {
+                if (live && crank == 0) tout[j] = tj;
+                wbuf[slot][ck] = live ? sgl * tj : 0.0;                         // sig_phen_i = msig * x, src/data.cpp:354
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cta(&wready[slot]);
+                mbar_expect_tx(&full[slot], CS * NSRC * CK * 8);                // re-arm the slot for step s + 4
+            }
+        }
+    } else {
+        // ---------------------------------------------- compute warps ----------------------------------------------
+        bool valid[RP];
+        double qr[K][RP][2], acc[K][RP][2];
+#pragma unroll
+        for (int i = 0; i < RP; i++) {
+            const int off = (i * CT + tid) * 2;
+            valid[i] = off < tile_rows && rbase + off < ld;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                acc[k][i][0] = acc[k][i][1] = 0.0;
+                double2 qv = make_double2(0.0, 0.0);
+                if (valid[i] && active[k]) qv = *reinterpret_cast<const double2*>(gv.q[k] + rbase + off);   // pad rows of q are zero
+                qr[k][i][0] = qv.x; qr[k][i][1] = qv.y;
+            }
+        }
+        double a[2][C][RP][2];                                   // the step being dotted and the step whose axpy is pending
+        double m_n[C];
+#pragma unroll
+        for (int cc = 0; cc < C; cc++) m_n[cc] = __ldg(mave + (nsteps > 0 ? col_of(0, cc) : 0));
+
+        auto dot_step = [&](const int b, long long s) {
+            double m[C], pd[C][K][2];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++) {
+                m[cc] = m_n[cc];
+                m_n[cc] = __ldg(mave + col_of(s + 1 < nsteps ? s + 1 : s, cc));
+#pragma unroll
+                for (int k = 0; k < K; k++) pd[cc][k][0] = pd[cc][k][1] = 0.0;
+            }
+            const int st = (int)(s % R);
+            mbar_wait_cta(&ringbar[st], (uint32_t)((s / R) & 1));
+            const double* stage = ring + (size_t)st * C * PIECE;
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int i = 0; i < RP; i++) {
+                    double2 v = make_double2(m[cc], m[cc]);      // rows this thread does not own: centred value 0
+                    if (valid[i]) v = *reinterpret_cast<const double2*>(stage + (size_t)cc * PIECE + (i * CT + tid) * 2);
+                    const double d0 = v.x - m[cc], d1 = v.y - m[cc];            // meth[i] - mu, src/data.cpp:304 and :360
+                    a[b][cc][i][0] = d0; a[b][cc][i][1] = d1;                   // kept centred for the deferred axpy
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        pd[cc][k][0] = fma(d0, qr[k][i][0], pd[cc][k][0]);
+                        pd[cc][k][1] = fma(d1, qr[k][i][1], pd[cc][k][1]);
+                    }
+                }
+            if (DIRECT) {                                        // this warp's copy of the stage is in registers: release it
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(&empty[st]);
+            }
+            double v[CK];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) v[cc * K + k] = pd[cc][k][0] + pd[cc][k][1];
+            const double sw = warp_sum_multi<CK>(v, lane);      // lanes [ck*32/CK, (ck+1)*32/CK) hold the warp total of value ck
+            if (DIRECT) {
+                const int dest = lane & (32 / CK - 1), ck = lane / (32 / CK), slot = (int)(s & 3);
+                if (dest < CS)
+                    st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][wid][ck]), (uint32_t)dest), sw, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
+            } else {
+                if ((lane & (32 / CK - 1)) == 0) red[s & 1][wid][lane / (32 / CK)] = sw;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cta(&redbar[s & 1]);
+            }
+        };
+        auto axpy_step = [&](const int b, long long sp) {
+            const int slot = (int)(sp & 3);
+            mbar_wait_cta(&wready[slot], (uint32_t)((sp >> 2) & 1));
+            double wgt[CK];
+#pragma unroll
+            for (int i = 0; i < CK; i++) wgt[i] = wbuf[slot][i];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int i = 0; i < RP; i++)
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        acc[k][i][0] = fma(a[b][cc][i][0], wgt[cc * K + k], acc[k][i][0]);
+                        acc[k][i][1] = fma(a[b][cc][i][1], wgt[cc * K + k], acc[k][i][1]);
+                    }
+        };
+        for (long long s0 = 0; s0 <= nsteps; s0 += 2) {
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                const long long s = s0 + b;
+                if (s < nsteps) dot_step(b, s);
+                if (s >= 1 && s <= nsteps) axpy_step(b ^ 1, s - 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (!active[k]) continue;
+            double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase;
+#pragma unroll
+            for (int i = 0; i < RP; i++)
+                if (valid[i]) *reinterpret_cast<double2*>(prow + (i * CT + tid) * 2) = make_double2(acc[k][i][0], acc[k][i][1]);
+        }
+    }
+    cluster_sync_all();                                          // nobody leaves while a peer may still write into its shared memory
+}
+
 template <int K, int C, int CS, typename Kern, typename... Extra>
 int gram_launch_any(vampomi_ctx* c, Kern kern, int TPB, int ROWS, size_t smem, int shape, const GramVec& gv, const MultiVec& mw, Extra... extra) {
     const size_t tr = (c->ld + CS - 1) / CS;
@@ -579,6 +807,11 @@ int gram_launch(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape
     return gram_launch_any<K, C, CS>(c, k_gram<K, TPB, RV, C, D, CS, QS>, TPB, ROWS, QS ? (size_t)K * ROWS * sizeof(double) : 0, shape, gv, mw,
                                      c->tune.gram_prefetch);
 }
+template <int K, int NCW, int RP, int C, int R, int CS, int DIRECT>
+int gram_launch_ws(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
+    constexpr int ROWS = NCW * 32 * RP * 2;
+    return gram_launch_any<K, C, CS>(c, k_gram_ws<K, NCW, RP, C, R, CS, DIRECT>, (NCW + 1) * 32, ROWS, (size_t)R * C * ROWS * sizeof(double), shape, gv, mw);
+}
 template <int K, int TPB, int RP, int C, int R, int CS>
 int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
     constexpr int ROWS = TPB * RP * 2;
@@ -590,6 +823,8 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //     0  320, 2, 2, 3, smem    1  256, 3, 2, 3, smem    2  320, 2, 2, 2, regs
 //   bulk-copy ring (k_gram_bulk): threads, 16-byte row pairs per thread, columns per step, ring stages
 //     3  256, 5, 2, 4          4  256, 5, 2, 3          5  256, 5, 1, 6
+//   warp-specialised bulk-copy ring (k_gram_ws): compute warps, row pairs per thread, columns per step, ring stages
+//     6  10, 4, 2, 4           7  the same, every compute warp sending its own partial sums (no block-level stage)
 constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : 2560; }
 
 template <int K, int CS>
@@ -601,6 +836,8 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 3: return gram_launch_bulk<K, 256, 5, 2, 4, CS>(c, gv, mw, shape);
         case 4: return gram_launch_bulk<K, 256, 5, 2, 3, CS>(c, gv, mw, shape);
         case 5: return gram_launch_bulk<K, 256, 5, 1, 6, CS>(c, gv, mw, shape);
+        case 6: return gram_launch_ws<K, 10, 4, 2, 4, CS, 0>(c, gv, mw, shape);
+        case 7: return gram_launch_ws<K, 10, 4, 2, 4, CS, 1>(c, gv, mw, shape);
         default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
     }
 }

@@ -26,6 +26,22 @@ REF_SRC = os.environ.get("VAMPOMI_REFERENCE_SRC", "/root/reference/src")
 OUT_DIR = os.path.join(HERE, "_ref")
 OUT_BIN = os.path.join(OUT_DIR, "main_meth_ref")
 OUT_BIN_STRICT = os.path.join(OUT_DIR, "main_meth_ref_O2")      # IEEE-strict build (-O2, no fast-math), see DESIGN.md "parity floor"
+OUT_BIN_V4 = os.path.join(OUT_DIR, "main_meth_ref_v4")         # README flags for an AVX-512 host (-march=x86-64-v4): the TIMING binary
+
+
+def timing_binary():
+    """The reference build to TIME on this host: the README asks for -march=native (README.md:28), but the binary is built in
+    the build container and timed on the GPU box's CPU, so two ISA levels are built and the widest one this CPU runs is chosen
+    (x86-64-v4 = AVX-512 F/BW/CD/DQ/VL, else x86-64-v3 = AVX2 + FMA, the build the fixtures were made with)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = set(next(l for l in f if l.startswith("flags")).split(":", 1)[1].split())
+    except Exception:
+        flags = set()
+    if {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= flags and os.path.isfile(OUT_BIN_V4):
+        return OUT_BIN_V4, "-Ofast -march=x86-64-v4 (AVX-512: this host's level; README.md:28 asks for -march=native)"
+    return OUT_BIN, "-Ofast -march=x86-64-v3 (AVX2 + FMA)"
+
 
 PATCHES = {
     "vamp.cpp": [
@@ -62,9 +78,10 @@ def up_to_date(out_bin=None):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=True, strict=False):
-    out_bin = OUT_BIN_STRICT if strict else OUT_BIN
+def build(force=False, verbose=True, strict=False, v4=False):
+    out_bin = OUT_BIN_STRICT if strict else OUT_BIN_V4 if v4 else OUT_BIN
     opt = ["-O2"] if strict else ["-Ofast"]
+    march = "-march=x86-64-v4" if v4 else "-march=x86-64-v3"
     if not available():
         if verbose:
             print(f"[oracle/_ref] reference sources not present at {REF_SRC}; keeping prebuilt binary (if any)")
@@ -85,7 +102,7 @@ def build(force=False, verbose=True, strict=False):
                 with open(os.path.join(tmp, f), "w") as fh:
                     fh.write(text)
         shims = os.path.join(HERE, "ref_shims")
-        cmd = ["g++", "-std=c++17"] + opt + ["-march=x86-64-v3", "-fopenmp", "-w",
+        cmd = ["g++", "-std=c++17"] + opt + [march, "-fopenmp", "-w",
                "-I", shims, "-include", os.path.join(shims, "oracle_hooks.h")]
         cmd += [os.path.join(tmp, u) for u in UNITS]
         cmd += ["-o", out_bin + ".tmp"]
@@ -102,5 +119,6 @@ if __name__ == "__main__":
     ok = build(force="--force" in sys.argv)
     if "--strict" in sys.argv:
         ok = build(force="--force" in sys.argv, strict=True) and ok
+    ok = build(force="--force" in sys.argv, v4=True) and ok
     print(OUT_BIN if ok else "unavailable")
     sys.exit(0 if ok else 1)

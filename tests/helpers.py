@@ -16,15 +16,29 @@ REL_CSV = 1e-8     # ... and on the params / metrics CSV values
 # alpha1 = 1 + sigma*(pkdd/pk) with sigma = 1e6, which cancels to ~1e-8 (src/vamp.cpp:489), so ONE ulp of rounding in
 # pkdd/pk moves alpha1 — and with it gam2, x2_hat, r1 of every later iteration — by eps/alpha1 ~ 7e-9 relative. The
 # reference built with -O2 instead of the README's -Ofast already differs from itself by 4e-9..1.4e-8 on the
-# `linear_small` fixture (x1_O2 / r1_O2 there; see test_reference_is_not_1e9_reproducible_against_itself). Such runs are
-# therefore held to 1e-7 / 1e-6; every well-conditioned run (gam1 >= 1e-3, probit) is held to the stated 1e-9 / 1e-8.
-REL_VEC_ILLCOND = 1e-7
+# `linear_small` fixture and by 6e-8..4.4e-7 at the headline's aspect ratio (`linear_wide_default`); every default-gam1
+# fixture carries the -O2 build's vectors (x1_O2 / r1_O2; see test_reference_is_not_1e9_reproducible_against_itself). Such
+# runs are held to the MEASURED spread of the reference's own two builds on that very fixture (1.5 x the largest
+# per-iteration distance, never looser than 1e-6 and never tighter than the 1e-9 contract), not to a flat tolerance; every
+# well-conditioned run (gam1 >= 1e-3, probit) is held to the stated 1e-9 / 1e-8. The dedicated test
+# test_default_gam1_runs_sit_inside_the_reference_builds_own_spread applies the bound iteration by iteration.
+REL_VEC_ILLCOND = 1e-7     # oracle-side checks of the fixtures that predate the per-fixture spread
 REL_CSV_ILLCOND = 1e-6
+
+
+def builds_spread(g):
+    """Largest per-iteration relative distance between the reference's -Ofast and -O2 builds on this fixture (x1_hat, r1)."""
+    return max(max(rel_l2(g["x1_O2"][k], g["x1"][k]), rel_l2(g["r1_O2"][k], g["r1"][k])) for k in range(1, int(g["iterations"])))
 
 
 def tolerances(g):
     gam1 = extra_kwargs(g).get("gam1", 1e-6)
-    return (REL_VEC, REL_CSV) if gam1 >= 1e-3 else (REL_VEC_ILLCOND, REL_CSV_ILLCOND)
+    if gam1 >= 1e-3:
+        return REL_VEC, REL_CSV
+    if "x1_O2" in g:
+        rel_vec = min(max(REL_VEC, 1.5 * builds_spread(g)), 1e-6)
+        return rel_vec, max(REL_CSV, 10 * rel_vec)
+    return REL_VEC_ILLCOND, REL_CSV_ILLCOND
 
 
 def load_golden(name):

@@ -11,7 +11,7 @@ from helpers import (REL_CSV, REL_VEC, assert_rows_close, csv_rows, golden_input
                      standardize_phen, tolerances, REL_VEC_ILLCOND)
 
 
-ALL_CASES = ["linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+ALL_CASES = ["linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
              "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
          "linear_em_conv", "linear_h2"]
 
@@ -43,6 +43,7 @@ def test_oracle_matches_reference_run(name, tmp_path):
     assert len(got) == len(bytes(g["csv_prior"]))
     if g["model"] == "linear":
         assert got == bytes(g["csv_prior"])
+    if True:
         got_counts = np.array([[k for (it, kind, k) in v.cg_iters if it == i and kind == "lmmse"][0] for i in range(1, int(g["iterations"]) + 1)])
         got_ons = np.array([[k for (it, kind, k) in v.cg_iters if it == i and kind == "onsager"][0] for i in range(1, int(g["iterations"]) + 1)])
         assert np.array_equal(got_counts, g["cg_iters"][:, 0]), "LMMSE CG iteration counts"

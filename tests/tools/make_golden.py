@@ -55,6 +55,9 @@ CASES = {
                            extra=["--gam1", "1e-2", "--EM-max-iter", "8", "--EM-err-thr", "0.05", "--learn-prior-delay", "0"]),
     "linear_h2": dict(N=210, M=420, lam=0.1, h2=0.8, data_seed=54, probe_seed=24, iterations=4, model="linear",
                       extra=["--gam1", "1e-2", "--h2", "0.8", "--rho", "0.3"]),
+    # the headline's aspect ratio AND the CLI-default --gam1 1e-6 (the headline benchmark's own start): held to the measured
+    # distance between the reference's two builds (x1_O2 / r1_O2), see tests/helpers.py
+    "linear_wide_default": dict(N=100, M=4000, lam=0.01, h2=0.5, data_seed=41, probe_seed=15, iterations=6, model="linear", extra=[]),
     "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
                          extra=["--gam1", "1e-2"]),
 }
@@ -76,6 +79,23 @@ def cg_counts(log, tol=1e-5, max_iter=500):
     out = []
     for block in log.split("iteration = ")[1:]:
         lm, ons = block.split("CG took")[0], block.split("CG took")[1].split("onsager took")[0]
+        k1 = len(re.findall(r"\[CG\] it = ", lm))
+        n_cg = len(re.findall(r"\[CG\] it = ", ons))
+        last_rel = re.findall(r"\|\|r_it\|\| / \|\|RHS\|\| = ([0-9.e+-]+)", ons)
+        ended_by_residual = bool(last_rel) and float(last_rel[-1]) < tol
+        k2 = n_cg if (ended_by_residual or n_cg >= max_iter) else n_cg + 1
+        out.append((k1, k2))
+    return np.array(out, dtype=np.int64)
+
+
+def cg_counts_probit(log, tol=1e-5, max_iter=500):
+    """The probit loop (src/vamp_probit.cpp:296-311) prints no timing lines between its two solves; the Onsager solve marks its
+    iterations with '[CG onsager] it = i' (src/vamp.cpp:723-724), so the '[CG] it' lines before the first of those belong to
+    the LMMSE solve and the ones after it to the Onsager solve. Same rules as cg_counts for k2."""
+    out = []
+    for block in log.split("iteration = ")[1:]:
+        parts = block.split("[CG onsager]", 1)
+        lm, ons = parts[0], (parts[1] if len(parts) > 1 else "")
         k1 = len(re.findall(r"\[CG\] it = ", lm))
         n_cg = len(re.findall(r"\[CG\] it = ", ons))
         last_rel = re.findall(r"\|\|r_it\|\| / \|\|RHS\|\| = ([0-9.e+-]+)", ons)
@@ -113,9 +133,19 @@ def make_case(name, c):
         fix["stop_thr"] = float(c.get("stop_thr", "0"))
         if init is not None:
             fix["x1hat_init"] = init
+        ex = dict(zip(c["extra"][::2], c["extra"][1::2]))
         if c["model"] == "linear":
-            ex = dict(zip(c["extra"][::2], c["extra"][1::2]))
             fix["cg_iters"] = cg_counts(log, float(ex.get("--CG-err-tol", 1e-5)), int(ex.get("--CG-max-iter", 500)))
+        else:
+            fix["cg_iters"] = cg_counts_probit(log, float(ex.get("--CG-err-tol", 1e-5)), int(ex.get("--CG-max-iter", 500)))
+        if "--gam1" not in ex and name != "linear_small":
+            # CLI-default gam1 = 1e-6: the same run by the IEEE-strict (-O2) build, vectors and params rows (see linear_small below)
+            os.makedirs(os.path.join(d, "out2"))
+            args2 = [a.replace(f"{d}/out", f"{d}/out2") for a in args]
+            run_ref(args2, c["probe_seed"], binary=build_ref.OUT_BIN_STRICT)
+            fix["x1_O2"] = np.stack([np.fromfile(f"{d}/out2/g_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+            fix["r1_O2"] = np.stack([np.fromfile(f"{d}/out2/g_r1_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+            fix["csv_params_O2"] = np.frombuffer(open(f"{d}/out2/g_params.csv", "rb").read(), dtype=np.uint8)
         if name == "linear_small":
             # the same run by an IEEE-strict (-O2) build of the same patched sources: how far the reference is from
             # ITSELF when only compiler flags change — the floor any independent implementation can be held to
@@ -124,6 +154,7 @@ def make_case(name, c):
             run_ref(args2, c["probe_seed"], binary=build_ref.OUT_BIN_STRICT)
             fix["x1_O2"] = np.stack([np.fromfile(f"{d}/out2/g_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
             fix["r1_O2"] = np.stack([np.fromfile(f"{d}/out2/g_r1_it_{k}.bin") for k in range(1, c["iterations"] + 1)])
+            fix["csv_params_O2"] = np.frombuffer(open(f"{d}/out2/g_params.csv", "rb").read(), dtype=np.uint8)
             # association tests and out-of-sample test mode from this run's saved files (src/main_meth.cpp:112-265)
             params = vo.read_csv_rows(f"{d}/out/g_params.csv")
             last = c["iterations"]

@@ -117,6 +117,11 @@ int vampomi_comm_init(vampomi_ctx* ctx, const void* id128);
  * scalar reductions; csrc/xchg.cuh). Mode 2 is chosen at comm_init when every rank could map every peer (CUDA IPC
  * between processes, peer access between threads); the environment variable VAMPOMI_XCHG=0 forces mode 1. */
 int vampomi_comm_mode(const vampomi_ctx* ctx, int* mode);
+/* All ranks meet here (MPI_Barrier, src/data.cpp:148 / src/vamp.cpp:434): returns once every rank has called it and this rank's
+ * stream has drained. vampomi_compute_stats ends with one, so no rank starts an operator (and with it the wall-clock limit of
+ * the device-side peer waits, 120 s or VAMPOMI_XCHG_TIMEOUT_S) while another is still loading its shard. A peer wait that does
+ * run out raises a flag instead of faulting; the next synchronising call on that context fails with VAMPOMI_ERR_STATE. */
+int vampomi_barrier(vampomi_ctx* ctx);
 
 /* ---- design matrix: data::read_methylation_data, src/data.cpp:116-153 -------------------------------------- */
 /* Copies `ncols` columns (each N doubles, contiguous) starting at local column j0 from host memory to HBM. */

@@ -21,6 +21,10 @@ extern "C" {
 /* Runs main_meth's command line (argv[0] is ignored). Returns the process exit status (0 ok, 1 after a FATAL line).
  * With --gpus G > 1 it drives G marker shards from G host threads of this process, one GPU each. */
 int vampomi_main(int argc, char** argv);
+/* The same program entered as main_meth_probit (src/main_meth_probit.cpp:8-233; BASELINE.json configuration 4): --model is forced to
+ * bin_class, `--run-mode test` writes the probit confusion-matrix rows [TP, TN, FP, FN, ACC] of that driver (:104-200) and
+ * `--run-mode predict` its z_hat text file "<estimate file up to 'it'>.yhat" (:201-227). */
+int vampomi_main_probit(int argc, char** argv);
 
 #define VAMPOMI_MAX_MIX 32
 

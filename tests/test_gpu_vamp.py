@@ -388,3 +388,52 @@ def test_mid_size_run_matches_the_reference_binary_on_this_box(gpus, tmp_path):
         assert np.array_equal(np.frombuffer(got, dtype=np.uint8) == 0, np.frombuffer(want, dtype=np.uint8) == 0), f"{kind}.csv NUL layout"
         if kind != "prior":
             assert_rows_close(csv_rows(got), csv_rows(want), 1e-8, kind)
+
+
+def test_main_meth_probit_entry_point(tmp_path):
+    """bin/main_meth_probit (BASELINE.json configuration 4; src/main_meth_probit.cpp): the probit model without --model on the
+    command line, that driver's `test` run mode (confusion-matrix rows, no header, :104-200) and its `predict` mode (:201-227)."""
+    g = load_golden("probit_small")
+    d = str(tmp_path)
+    A, y_txt, beta = golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    its, N, M = 3, int(g["N"]), int(g["M"])
+    exe = build.MAIN_METH_PROBIT
+
+    def run(args):
+        res = subprocess.run([exe] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert res.returncode == 0, res.stdout[-3000:]
+        return res.stdout
+
+    out = run(["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", N, "--Mt", M, "--out-dir", f"{d}/out", "--out-name", "g",
+               "--iterations", its, "--true-signal-file", f"{d}/ex_ts.bin", "--stop-criteria-thr", 0, "--seed", g["probe_seed"]] + list(g["extra"]))
+    assert "--model" not in out.split("ardyh command line options:")[1].split("INFO")[0]
+    for k in range(1, its + 1):
+        assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), g["x1"][k - 1]) < 1e-9
+        assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < 1e-9
+    want = csv_rows(g["csv_params"])
+    got = csv_rows(open(f"{d}/out/g_params.csv", "rb").read())
+    assert_rows_close(got, {k: want[k] for k in range(1, its + 1)}, 1e-8, "params")
+    # probit test mode on an independent draw
+    Nt = 150
+    Xt, yt, _ = sim.write_dataset(d, "tst", Nt, M, float(g["lam"]), float(g["h2"]), int(g["data_seed"]) + 1000, binary=True)
+    run(["--meth-file-test", f"{d}/tst.bin", "--phen-file-test", f"{d}/tst.phen", "--N-test", Nt, "--Mt", M, "--out-dir", f"{d}/out", "--out-name", "g",
+         "--run-mode", "test", "--estimate-file", f"{d}/out/g_it_1.bin", "--test-iter-range", f"1,{its}"])
+    blob = open(f"{d}/out/g_test.csv", "rb").read()
+    rows = csv_rows(blob)
+    yt_txt = np.array([float("%0.10f" % v) for v in yt])
+    dt = vo.Data(Xt, yt_txt)
+    assert set(blob[:len(vo.csv_row(1, [0.0] * 5))]) == {0}                 # no header: the first row-length bytes are a hole
+    for k in range(1, its + 1):
+        z = dt.Ax(np.fromfile(f"{d}/out/g_it_{k}.bin") * math.sqrt(Nt))
+        yhat = (z >= 0).astype(float)                                        # normal_cdf(z) >= 0.5
+        TP, TN = int(((yt_txt == 1) & (yhat == 1)).sum()), int(((yt_txt == 0) & (yhat == 0)).sum())
+        FP, FN = int(((yt_txt == 0) & (yhat == 1)).sum()), int(((yt_txt == 1) & (yhat == 0)).sum())
+        assert rows[k][:4] == [TP, TN, FP, FN] and abs(rows[k][4] - (TP + TN) / Nt) < 1e-14
+    run(["--meth-file-test", f"{d}/tst.bin", "--phen-file-test", f"{d}/tst.phen", "--N-test", Nt, "--Mt", M, "--out-dir", f"{d}/out", "--out-name", "g",
+         "--run-mode", "predict", "--estimate-file", f"{d}/out/g_it_{its}.bin"])
+    zhat = np.loadtxt(f"{d}/out/g_.yhat")
+    assert zhat.shape == (Nt,) and np.allclose(zhat, dt.Ax(np.fromfile(f"{d}/out/g_it_{its}.bin") * math.sqrt(Nt)), rtol=2e-5, atol=1e-8)
+    # main_meth itself still refuses the probit-only run mode quietly (the reference's main does nothing for unknown modes)
+    res = subprocess.run([exe, "--meth-file", "x", "--N", "5"], stdout=subprocess.PIPE, text=True)
+    assert res.returncode == 1 and "FATAL" in res.stdout

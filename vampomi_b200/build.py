@@ -6,6 +6,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "lib", "libvampomi_cuda.so")
 MAIN_METH = os.path.join(PKG_DIR, "bin", "main_meth")
+MAIN_METH_PROBIT = os.path.join(PKG_DIR, "bin", "main_meth_probit")
 
 
 def build(verbose=False, jobs=None):

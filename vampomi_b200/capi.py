@@ -58,6 +58,7 @@ _SIGNATURES = {
     "vampomi_comm_get_unique_id": (C.c_int, [C.c_void_p]),
     "vampomi_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vampomi_comm_mode": (C.c_int, [C.c_void_p, c_int_p]),
+    "vampomi_barrier": (C.c_int, [C.c_void_p]),
     "vampomi_upload_columns": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     "vampomi_download_columns": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, c_double_p]),
     "vampomi_load_file": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -102,6 +103,7 @@ _SIGNATURES = {
     "vampomi_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     # host driver
     "vampomi_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "vampomi_main_probit": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "vampomi_solver_default_config": (None, [C.POINTER(SolverConfig)]),
     "vampomi_solver_create": (C.c_int, [C.c_void_p, C.POINTER(SolverConfig), c_double_p, c_double_p, c_double_p,
                                         C.POINTER(C.c_void_p)]),
@@ -223,6 +225,9 @@ class Shard:
 
     def __exit__(self, *a):
         self.close()
+
+    def barrier(self):
+        _check(self.lib.vampomi_barrier(self.h), "barrier")
 
     def comm_mode(self):
         """0 single shard, 1 NCCL all-reduce, 2 fused peer-memory all-reduce (include/vampomi.h)."""

@@ -61,6 +61,27 @@ int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n) {
     return VAMPOMI_OK;
 }
 
+int xchg_check(vampomi_ctx* c) {
+    if (c->xchg_err_host && *reinterpret_cast<volatile int*>(c->xchg_err_host) != 0) {
+        c->xchg.enabled = 0; c->xchg_ready = false;        // sequence numbers are out of step now: this context's exchange is over
+        set_error("cross-GPU exchange timed out on rank %d: a peer rank is gone or more than %.0f s behind (VAMPOMI_XCHG_TIMEOUT_S)",
+                  c->rank, (double)c->xchg.timeout_ns * 1e-9);
+        return VAMPOMI_ERR_STATE;
+    }
+    return VAMPOMI_OK;
+}
+
+int rank_barrier(vampomi_ctx* c) {
+    if (c->nranks == 1) return VAMPOMI_OK;
+    if (!c->comm) { set_error("nranks > 1 but vampomi_comm_init was not called"); return VAMPOMI_ERR_STATE; }
+    int* d = reinterpret_cast<int*>(c->sums + (MAX_SUMS - 2));      // scratch at the end of the packed-sums buffer (never used by the kernels)
+    VO_CUDA(cudaMemsetAsync(d, 0, sizeof(int), c->stream));
+    ncclResult_t r = c->nccl->AllReduce(d, d, 1, ncclInt, ncclSum, c->comm, c->stream);
+    if (r != ncclSuccess) { set_error("ncclAllReduce (barrier): %s", c->nccl->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    return VAMPOMI_OK;
+}
+
 // packed scalar sums over the GPUs: the peer-memory exchange when it is up (identically on all ranks), else NCCL
 static int sum_over_ranks(vampomi_ctx* c, double* dev, size_t n) {
     if (c->nranks == 1) return VAMPOMI_OK;
@@ -114,7 +135,8 @@ static void xchg_teardown(vampomi_ctx* c) {
         if (c->xchg_ipc_opened[g]) { cudaIpcCloseMemHandle(c->xchg_ipc_opened[g]); c->xchg_ipc_opened[g] = nullptr; }
     if (c->xchg_region) cudaFree(c->xchg_region);
     if (c->xchg_local) cudaFree(c->xchg_local);
-    c->xchg_region = nullptr; c->xchg_local = nullptr;
+    if (c->xchg_err_host) cudaFreeHost(c->xchg_err_host);
+    c->xchg_region = nullptr; c->xchg_local = nullptr; c->xchg_err_host = nullptr;
     c->xchg_ready = false; c->xchg.enabled = 0;
 }
 
@@ -138,24 +160,34 @@ static int xchg_setup(vampomi_ctx* c) {
     const size_t region_bytes = off;
     XchgInfo mine{};
     mine.pid = (long long)getpid(); mine.device = c->device;
+    int* err_dev = nullptr;
     if (ok && (cudaMalloc(&c->xchg_region, region_bytes) != cudaSuccess || cudaMemset(c->xchg_region, 0, region_bytes) != cudaSuccess ||
                cudaMalloc(&c->xchg_local, 4 * sizeof(unsigned int)) != cudaSuccess ||
                cudaMemset(c->xchg_local, 0, 4 * sizeof(unsigned int)) != cudaSuccess ||
+               cudaHostAlloc(&c->xchg_err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+               cudaHostGetDevicePointer(&err_dev, c->xchg_err_host, 0) != cudaSuccess ||
                cudaIpcGetMemHandle(&mine.handle, c->xchg_region) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess))
         ok = 0;
     cudaGetLastError();
+    if (c->xchg_err_host) *c->xchg_err_host = 0;
     mine.ok = ok; mine.ptr = (unsigned long long)(uintptr_t)c->xchg_region;
-    // all-gather the descriptors through NCCL itself (device staging), so no second bootstrap channel is needed
+    // all-gather the descriptors through NCCL itself (device staging), so no second bootstrap channel is needed. This function
+    // is collective: a LOCAL failure (allocation, copy) must not skip the collectives below — the other ranks would hang in
+    // them — so local failures only clear `ok`, both collectives are always reached, and only an NCCL failure returns early.
     std::vector<XchgInfo> all((size_t)c->nranks);
     XchgInfo *d_send = nullptr, *d_recv = nullptr;
-    VO_CUDA(cudaMalloc(&d_send, sizeof(XchgInfo)));
-    VO_CUDA(cudaMalloc(&d_recv, sizeof(XchgInfo) * c->nranks));
-    VO_CUDA(cudaMemcpyAsync(d_send, &mine, sizeof(XchgInfo), cudaMemcpyHostToDevice, c->stream));
-    ncclResult_t r = c->nccl->AllGather(d_send, d_recv, sizeof(XchgInfo), ncclChar, c->comm, c->stream);
-    if (r != ncclSuccess) { set_error("ncclAllGather: %s", c->nccl->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
-    VO_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(XchgInfo) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    for (int g = 0; g < c->nranks && ok; g++) {
+    int nccl_rc = VAMPOMI_OK;
+    bool staged = cudaMalloc(&d_send, sizeof(XchgInfo) > sizeof(int) * 2 ? sizeof(XchgInfo) : sizeof(int) * 2) == cudaSuccess &&
+                  cudaMalloc(&d_recv, sizeof(XchgInfo) * c->nranks) == cudaSuccess;
+    if (!staged) { ok = 0; mine.ok = 0; cudaGetLastError(); }
+    if (staged) {
+        if (cudaMemcpyAsync(d_send, &mine, sizeof(XchgInfo), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+        ncclResult_t r = c->nccl->AllGather(d_send, d_recv, sizeof(XchgInfo), ncclChar, c->comm, c->stream);
+        if (r != ncclSuccess) { set_error("ncclAllGather: %s", c->nccl->GetErrorString(r)); nccl_rc = VAMPOMI_ERR_NCCL; }
+        else if (cudaMemcpyAsync(all.data(), d_recv, sizeof(XchgInfo) * c->nranks, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                 cudaStreamSynchronize(c->stream) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    }
+    for (int g = 0; g < c->nranks && ok && nccl_rc == VAMPOMI_OK; g++) {
         if (!all[g].ok) { ok = 0; break; }
         if (g == c->rank) { x.peer[g] = c->xchg_region; continue; }
         if (all[g].pid == mine.pid) {                         // a rank thread of this process: direct peer access
@@ -170,16 +202,27 @@ static int xchg_setup(vampomi_ctx* c) {
         }
     }
     // enable only if EVERY rank succeeded (a mixed job would deadlock): min-reduce the flag; doubles as the barrier that
-    // guarantees every region is zeroed before the first push
-    int* d_ok = reinterpret_cast<int*>(d_send);
-    VO_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    r = c->nccl->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream);
-    if (r != ncclSuccess) { set_error("ncclAllReduce: %s", c->nccl->GetErrorString(r)); return VAMPOMI_ERR_NCCL; }
+    // guarantees every region is zeroed before the first push. A rank whose staging allocation failed cannot take part in a
+    // device collective at all: it falls back to a host-side int through the same all-reduce on its packed-sums buffer.
     int all_ok = 0;
-    VO_CUDA(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_send); cudaFree(d_recv);
+    if (nccl_rc == VAMPOMI_OK) {
+        int* d_ok = staged ? reinterpret_cast<int*>(d_send) : reinterpret_cast<int*>(c->sums + (MAX_SUMS - 2));
+        bool sent = cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+        ncclResult_t r = c->nccl->AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->stream);
+        if (r != ncclSuccess) { set_error("ncclAllReduce: %s", c->nccl->GetErrorString(r)); nccl_rc = VAMPOMI_ERR_NCCL; }
+        else if (!sent || cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                 cudaStreamSynchronize(c->stream) != cudaSuccess) { all_ok = 0; cudaGetLastError(); }
+    }
+    if (d_send) cudaFree(d_send);
+    if (d_recv) cudaFree(d_recv);
+    if (nccl_rc != VAMPOMI_OK) { xchg_teardown(c); return nccl_rc; }
     if (!all_ok) { xchg_teardown(c); return VAMPOMI_OK; }     // stay on the NCCL collectives
+    x.err = err_dev;
+    {
+        double tmo = 120.0;
+        if (const char* t = getenv("VAMPOMI_XCHG_TIMEOUT_S")) { const double v = atof(t); if (v > 0) tmo = v; }
+        x.timeout_ns = (unsigned long long)(tmo * 1e9);
+    }
     x.seq = c->xchg_local; x.ticket = c->xchg_local + 2;
     c->xchg_ready = true;
     x.enabled = c->tune.xchg ? 1 : 0;
@@ -201,6 +244,7 @@ static int fetch_sums(vampomi_ctx* c, int n, bool reduce, double* out) {
     if (reduce) VO_CHECK(sum_over_ranks(c, c->sums, (size_t)n));
     VO_CUDA(cudaMemcpyAsync(c->sums_host, c->sums, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
+    VO_CHECK(xchg_check(c));
     for (int i = 0; i < n; i++) out[i] = c->sums_host[i];
     return VAMPOMI_OK;
 }
@@ -236,6 +280,7 @@ static int d2h_vec(vampomi_ctx* c, double* host, const double* dev, long long n)
     VO_CHECK(ensure_stage(c, (size_t)n));
     VO_CUDA(cudaMemcpyAsync(c->stage, dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
+    VO_CHECK(xchg_check(c));
     memcpy(host, c->stage, (size_t)n * sizeof(double));
     return VAMPOMI_OK;
 }
@@ -363,6 +408,7 @@ int vampomi_destroy(vampomi_ctx* c) {
     if (c->sums_host) cudaFreeHost(c->sums_host);
     if (c->cg_poll_host) cudaFreeHost(c->cg_poll_host);
     if (c->stage) cudaFreeHost(c->stage);
+    for (auto e : c->cg_events) if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) {
         if (c->dump_dev[k]) cudaFree(c->dump_dev[k]);
         if (c->dump_host[k]) cudaFreeHost(c->dump_host[k]);
@@ -412,6 +458,12 @@ int vampomi_comm_init(vampomi_ctx* c, const void* id128) {
     ncclResult_t r = c->nccl->CommInitRank(&c->comm, c->nranks, id, c->rank);
     if (r != ncclSuccess) { set_error("ncclCommInitRank: %s", c->nccl->GetErrorString(r)); c->comm = nullptr; return VAMPOMI_ERR_NCCL; }
     return xchg_setup(c);
+}
+
+int vampomi_barrier(vampomi_ctx* c) {
+    VO_ARG(c, "barrier: NULL context");
+    VO_CUDA(cudaSetDevice(c->device));
+    return rank_barrier(c);
 }
 
 int vampomi_comm_mode(const vampomi_ctx* c, int* mode) {
@@ -567,7 +619,10 @@ int vampomi_compute_stats(vampomi_ctx* c, double alpha_scale) {
     VO_CHECK(launch_stats(c, alpha_scale));
     VO_CUDA(cudaStreamSynchronize(c->stream));
     c->stats_ready = true;
-    return VAMPOMI_OK;
+    // all ranks meet before the first operator call: the fused peer-memory exchange waits for its peers on the DEVICE with a
+    // wall-clock limit, so a rank that loaded its shard much faster than the slowest one (cold disk, uneven blocks) must not
+    // start that clock while the others are still reading
+    return rank_barrier(c);
 }
 
 int vampomi_get_stats(vampomi_ctx* c, double* mave, double* msig) {

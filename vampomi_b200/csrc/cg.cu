@@ -68,8 +68,10 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
     int depth = c->tune.cg_depth;
     if (depth < 1) depth = 1;
     if (depth > 32) depth = 32;
-    cudaEvent_t ev[32];
-    for (int k = 0; k < depth; k++) VO_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+    if (nccl_scalars && c->nranks > 1) depth = 1;        // library collectives on stale buffers are not free: no look-ahead launches there
+    cudaEvent_t* ev = c->cg_events;                      // created once per context, reused by every solve
+    for (int k = 0; k < depth; k++)
+        if (!ev[k]) VO_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
     int rc = VAMPOMI_OK;
     // bookkeeping of what was enqueued per CG iteration, so that look-ahead launches that turn out to be no-ops (the
     // done flags were already set when they ran) are not reported as matrix passes / streamed bytes / timed launches
@@ -168,7 +170,7 @@ static int cg_run(vampomi_ctx* c, CgBatch& b, const int* warm_ata_given, double 
     } else {
         cudaStreamSynchronize(c->stream);
     }
-    for (int k = 0; k < depth; k++) cudaEventDestroy(ev[k]);
+    if (rc == VAMPOMI_OK) rc = xchg_check(c);
     return rc;
 }
 

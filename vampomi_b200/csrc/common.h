@@ -171,6 +171,8 @@ struct vampomi_ctx {
     unsigned char* xchg_region = nullptr;
     unsigned int* xchg_local = nullptr;
     void* xchg_ipc_opened[vampomi::XCHG_MAX_RANKS] = {};
+    int* xchg_err_host = nullptr;    // pinned, device-mapped: raised by a peer wait that gave up (xchg.cuh XchgDeadline)
+    cudaEvent_t cg_events[32] = {};  // completion-poll ring of the CG loop, created once
     ncclComm_t comm = nullptr;
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;
@@ -264,6 +266,10 @@ int launch_cg_finish(vampomi_ctx* c, const CgBatch& b, int parity, double gam2, 
 int launch_xchg_sums(vampomi_ctx* c, double* sums_dev, int n);   // n <= XCHG_SCALARS packed sums over the GPUs via peer memory
 // all-reduce `n` doubles in place on the context stream (no-op for nranks == 1)
 int allreduce_inplace(vampomi_ctx* c, double* dev, size_t n);
+// VAMPOMI_ERR_STATE if a peer-memory wait on this context has given up (a rank is gone or too far behind); call after a stream sync
+int xchg_check(vampomi_ctx* c);
+// all ranks meet here (tiny NCCL all-reduce + stream sync); no-op for one rank
+int rank_barrier(vampomi_ctx* c);
 // profiling spans: begin returns an index (or -1 when profiling is off), end closes it
 int prof_begin(vampomi_ctx* c, int kind, double bytes);
 void prof_end(vampomi_ctx* c, int idx);

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -26,10 +27,30 @@ double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Host-side agreement of the rank threads of `main_meth --gpus G` BEFORE they enter a collective: where an MPI job would be
+// torn down by MPI_Abort (src/utilities.cpp:21-46), a rank thread that failed locally (unreadable file, allocation) tells the
+// others here, so that nobody is left waiting in ncclCommInitRank or in a device-side exchange for a peer that has returned.
+struct RankGate {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 1, arrived = 0, gen = 0;
+    bool failed = false;
+    bool agree(bool ok) {                       // true only if EVERY rank reported ok (now and at every earlier gate)
+        std::unique_lock<std::mutex> lk(m);
+        if (!ok) failed = true;
+        const int g = gen;
+        if (++arrived == n) { arrived = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+        return !failed;
+    }
+};
+
 struct Rank {
     const Options& opt;
     int rank, nranks;
     const void* nccl_id;
+    RankGate* gate = nullptr;
+    bool agree(bool ok) const { return gate ? gate->agree(ok) : ok; }
     vampomi_ctx* ctx = nullptr;
     long long M = 0, S = 0;
     bool root() const { return rank == 0; }
@@ -46,19 +67,36 @@ int fatal_abi(const Rank& r, const char* what) {
 
 // `class data` constructor (src/data.cpp:24-47): phenotype, marker block into HBM, marker statistics.
 int load_dataset(Rank& r, const std::string& phenfp, const std::string& methfp, int N, std::vector<double>* y) {
-    if (!read_phen(phenfp, r.opt.model != "bin_class", y)) return 1;                  // src/data.cpp:40-43
-    if ((int)y->size() != N) {
-        std::cout << "FATAL: phenotype file " << phenfp << " has " << y->size() << " rows but --N is " << N << std::endl;
-        return 1;                                                                      // assert(nas + nonas == N), :85
+    // stage 1, local: phenotype and context (host file I/O, cudaMalloc of the block) — then all rank threads agree
+    auto stage1 = [&]() -> int {
+        if (!read_phen(phenfp, r.opt.model != "bin_class", y)) return 1;                  // src/data.cpp:40-43
+        if ((int)y->size() != N) {
+            std::cout << "FATAL: phenotype file " << phenfp << " has " << y->size() << " rows but --N is " << N << std::endl;
+            return 1;                                                                      // assert(nas + nonas == N), :85
+        }
+        int ndev = 0;
+        if (vampomi_device_count(&ndev) != VAMPOMI_OK) return fatal_abi(r, "device query");
+        if (r.nranks > ndev) return fatal(r, "--gpus " + std::to_string(r.nranks) + " exceeds the " + std::to_string(ndev) + " visible CUDA devices");
+        const int storage = r.opt.storage == "f32" ? VAMPOMI_STORE_F32 : VAMPOMI_STORE_F64;
+        if (vampomi_create_ex(r.rank, N, (long long)r.opt.Mt, r.nranks, r.rank, storage, &r.ctx) != VAMPOMI_OK) return fatal_abi(r, "vampomi_create");
+        if (storage == VAMPOMI_STORE_F32 && r.root())
+            std::cout << "INFO  : --storage f32: the marker block is rounded to FP32 in GPU memory (all arithmetic stays FP64)" << std::endl;
+        return 0;
+    };
+    int rc = 1;
+    try {
+        rc = stage1();
+    } catch (const std::exception& e) {                                                    // e.g. an NA phenotype (src/data.cpp:74)
+        std::cout << "FATAL: " << e.what() << std::endl;
+    } catch (...) {
+        std::cout << "FATAL: unknown error while reading the inputs of rank " << r.rank << std::endl;
     }
-    int ndev = 0;
-    if (vampomi_device_count(&ndev) != VAMPOMI_OK) return fatal_abi(r, "device query");
-    if (r.nranks > ndev) return fatal(r, "--gpus " + std::to_string(r.nranks) + " exceeds the " + std::to_string(ndev) + " visible CUDA devices");
+    if (!r.agree(rc == 0)) return rc ? rc : 1;
+    // stage 2: communicator (collective), then the local read of the shard's block — and agreement again before the statistics,
+    // which end with the rank barrier
     const int storage = r.opt.storage == "f32" ? VAMPOMI_STORE_F32 : VAMPOMI_STORE_F64;
-    if (vampomi_create_ex(r.rank, N, (long long)r.opt.Mt, r.nranks, r.rank, storage, &r.ctx) != VAMPOMI_OK) return fatal_abi(r, "vampomi_create");
-    if (storage == VAMPOMI_STORE_F32 && r.root())
-        std::cout << "INFO  : --storage f32: the marker block is rounded to FP32 in GPU memory (all arithmetic stays FP64)" << std::endl;
-    if (r.nranks > 1 && vampomi_comm_init(r.ctx, r.nccl_id) != VAMPOMI_OK) return fatal_abi(r, "vampomi_comm_init");
+    rc = (r.nranks > 1 && vampomi_comm_init(r.ctx, r.nccl_id) != VAMPOMI_OK) ? fatal_abi(r, "vampomi_comm_init") : 0;
+    if (!r.agree(rc == 0)) return rc ? rc : 1;
     if (r.nranks > 1 && r.root()) {
         int mode = 0;
         vampomi_comm_mode(r.ctx, &mode);
@@ -69,7 +107,8 @@ int load_dataset(Rank& r, const std::string& phenfp, const std::string& methfp, 
     const size_t raw_bytes = (size_t)r.M * (size_t)N * (storage == VAMPOMI_STORE_F32 ? 4 : 8);
     printf("INFO  : rank %d has allocated %zu bytes (%.3f GB) for raw data.\n", r.rank, raw_bytes, double(raw_bytes) / 1.0E9);   // :131
     double ts = now_s();
-    if (vampomi_load_file(r.ctx, methfp.c_str()) != VAMPOMI_OK) return fatal_abi(r, "loading the methylation data");
+    rc = vampomi_load_file(r.ctx, methfp.c_str()) != VAMPOMI_OK ? fatal_abi(r, "loading the methylation data") : 0;
+    if (!r.agree(rc == 0)) return rc ? rc : 1;
     double te = now_s();
     if (r.root()) std::cout << "reading methylation data took " << te - ts << " seconds." << std::endl;   // :151
     if (vampomi_compute_stats(r.ctx, r.opt.alpha_scale) != VAMPOMI_OK) return fatal_abi(r, "marker statistics");
@@ -264,6 +303,71 @@ int run_test(Rank& r) {                                                         
     return 0;
 }
 
+// `test` as the reference's probit driver means it (src/main_meth_probit.cpp:104-200): per saved iteration the probit
+// prediction at threshold 0.5 on the test set, confusion matrix and accuracy -> _test.csv rows [TP, TN, FP, FN, ACC], no header.
+int run_test_probit(Rank& r) {
+    const Options& o = r.opt;
+    const int N_test = (int)o.N_test;
+    std::vector<double> y;
+    if (int rc = load_dataset(r, o.phen_file_test, o.meth_file_test, N_test, &y)) return rc;
+    CsvFile csv;
+    if (r.root() && !csv.open(o.out_dir + "/" + o.out_name + "_test.csv")) { fprintf(stderr, "*FATAL*: could not create _test.csv\n"); return 1; }
+    const std::string est = o.estimate_file;
+    const size_t pos_dot = est.find(".");                                                      // :130 (first dot, sic)
+    const std::string ext = pos_dot == std::string::npos ? est : est.substr(pos_dot + 1);
+    const size_t pos_it = est.rfind("it");
+    if (r.root()) std::cout << "est_file_name = " << est << std::endl
+                            << "iter range = [" << o.test_iter_range[0] << ", " << o.test_iter_range[1] << "]" << std::endl;
+    std::vector<double> z((size_t)N_test);
+    for (int it = o.test_iter_range[0]; it <= o.test_iter_range[1]; it++) {
+        const std::string f = est.substr(0, pos_it) + "it_" + std::to_string(it) + "." + ext;  // :146
+        std::vector<double> x = ext == "bin" ? read_vec(f, r.M, r.S) : read_text_vec(f, r.M, r.S);
+        for (double& v : x) v *= std::sqrt((double)N_test);                                    // :154-155
+        if (vampomi_vec_set(r.ctx, VAMPOMI_V_X1, x.data()) != VAMPOMI_OK || vampomi_ax_dev(r.ctx, VAMPOMI_V_X1, VAMPOMI_V_Z1) != VAMPOMI_OK ||
+            vampomi_vec_get(r.ctx, VAMPOMI_V_Z1, z.data()) != VAMPOMI_OK)
+            return fatal_abi(r, "Ax");                                                         // :158
+        int TP = 0, TN = 0, FP = 0, FN = 0;
+        for (int i = 0; i < N_test; i++) {
+            const double yhat = normal_cdf(z[i]) >= 0.5 ? 1.0 : 0.0;                           // :160-166
+            if (y[i] == 1 && yhat == 1) TP++;
+            else if (y[i] == 0 && yhat == 0) TN++;
+            else if (y[i] == 1 && yhat == 0) FN++;
+            else if (y[i] == 0 && yhat == 1) FP++;
+        }
+        const double ACC = (double)(TP + TN) / (double)(TP + TN + FP + FN);
+        if (r.root()) {
+            std::cout << "---- Iteration " << it << "----" << std::endl << "TP = " << TP << std::endl << "TN = " << TN << std::endl
+                      << "FP = " << FP << std::endl << "FN = " << FN << std::endl << "Accuracy = " << ACC << std::endl;
+            csv.row(it, {(double)TP, (double)TN, (double)FP, (double)FN, ACC});                // :198
+        }
+    }
+    return 0;
+}
+
+// `predict` (src/main_meth_probit.cpp:201-227): z_hat = A_test (x_est * sqrt(N_test)) -> text file "<estimate up to 'it'>.yhat"
+int run_predict(Rank& r) {
+    const Options& o = r.opt;
+    const int N_test = (int)o.N_test;
+    std::vector<double> y;
+    if (int rc = load_dataset(r, o.phen_file_test, o.meth_file_test, N_test, &y)) return rc;
+    const std::string est = o.estimate_file;
+    const size_t pos_it = est.rfind("it");
+    const std::string pred = est.substr(0, pos_it) + ".yhat";                                  // :208-209
+    std::vector<double> x = read_vec(est, r.M, r.S);
+    for (double& v : x) v *= std::sqrt((double)N_test);
+    std::vector<double> z((size_t)N_test);
+    if (vampomi_vec_set(r.ctx, VAMPOMI_V_X1, x.data()) != VAMPOMI_OK || vampomi_ax_dev(r.ctx, VAMPOMI_V_X1, VAMPOMI_V_Z1) != VAMPOMI_OK ||
+        vampomi_vec_get(r.ctx, VAMPOMI_V_Z1, z.data()) != VAMPOMI_OK)
+        return fatal_abi(r, "Ax");
+    if (r.root()) {                                                                            // store_vec_to_file, src/utilities.cpp:126-135
+        std::ofstream file(pred);
+        if (!file) return fatal(r, "could not write " + pred);
+        for (double v : z) file << v << std::endl;
+        std::cout << "Storing predictions to file " << pred << std::endl;
+    }
+    return 0;
+}
+
 int run_association(Rank& r) {                                                                 // src/main_meth.cpp:206-265
     const Options& o = r.opt;
     const int N = (int)o.N;
@@ -314,18 +418,27 @@ int run_association(Rank& r) {                                                  
     return 0;
 }
 
-int run_rank(const Options& opt, int rank, int nranks, const void* nccl_id) {
+int run_rank(const Options& opt, int rank, int nranks, const void* nccl_id, RankGate* gate) {
     Rank r{opt, rank, nranks, nccl_id};
+    r.gate = gate;
     if (vampomi_divide_work((long long)opt.Mt, nranks, rank, &r.M, &r.S) != VAMPOMI_OK) return fatal_abi(r, "divide_work");
     const long long Mm = opt.Mt % nranks != 0 ? opt.Mt / nranks + 1 : opt.Mt / nranks;
     printf("INFO   : rank %4d has %lld markers over tot Mt = %u, max Mm = %lld, starting at S = %lld\n", rank, r.M, opt.Mt, Mm, r.S);   // src/utilities.cpp:231
     int rc = 0;
     try {
         if (opt.run_mode == "infere") rc = run_infere(r);
+        else if (opt.run_mode == "test" && opt.probit_entry) rc = run_test_probit(r);
+        else if (opt.run_mode == "predict" && opt.probit_entry) rc = run_predict(r);
         else if (opt.run_mode == "test") rc = run_test(r);
         else if (opt.run_mode == "association_test") rc = run_association(r);
     } catch (const std::exception& e) {
         std::cout << "FATAL: " << e.what() << std::endl;     // the reference throws string literals and terminates
+        rc = 1;
+    } catch (const char* what) {
+        std::cout << "FATAL: " << what << std::endl;
+        rc = 1;
+    } catch (...) {
+        std::cout << "FATAL: unknown error on rank " << rank << std::endl;
         rc = 1;
     }
     if (r.ctx) vampomi_destroy(r.ctx);
@@ -335,18 +448,26 @@ int run_rank(const Options& opt, int rank, int nranks, const void* nccl_id) {
 }  // namespace
 }  // namespace vampomi_host
 
-extern "C" int vampomi_main(int argc, char** argv) {
+static int main_impl(int argc, char** argv, bool probit_entry) {
     using namespace vampomi_host;
     Options opt;
     std::string echo;
     if (!opt.parse(argc, argv, &echo)) return 1;
     std::cout << echo << std::endl;                                                            // rank 0 echo, src/options.cpp:288-289
-    if (opt.Mt == 0 || (opt.run_mode == "test" ? opt.N_test == 0 : opt.N == 0)) {
+    if (probit_entry) {
+        // main_meth_probit (src/main_meth_probit.cpp, BASELINE.json configuration 4): the reference's stale probit driver does not
+        // compile against its own vamp.hpp; what it means is main_meth with the probit model, plus its own
+        // `test` (confusion matrix) and `predict` run modes
+        opt.probit_entry = true;
+        opt.model = "bin_class";
+    }
+    const bool test_like = opt.run_mode == "test" || (probit_entry && opt.run_mode == "predict");
+    if (opt.Mt == 0 || (test_like ? opt.N_test == 0 : opt.N == 0)) {
         std::cout << "FATAL  : --Mt and --N (or --N-test in test mode) have to be given" << std::endl;
         return 1;
     }
     const int G = opt.gpus;
-    if (G == 1) return run_rank(opt, 0, 1, nullptr);
+    if (G == 1) return run_rank(opt, 0, 1, nullptr, nullptr);
     char id[128];
     if (vampomi_comm_get_unique_id(id) != VAMPOMI_OK) {
         std::cout << "FATAL: NCCL bootstrap failed: " << vampomi_last_error() << std::endl;
@@ -354,8 +475,13 @@ extern "C" int vampomi_main(int argc, char** argv) {
     }
     std::vector<int> rcs((size_t)G, 0);
     std::vector<std::thread> th;
-    for (int g = 0; g < G; g++) th.emplace_back([&, g]() { rcs[g] = run_rank(opt, g, G, id); });
+    RankGate gate;
+    gate.n = G;
+    for (int g = 0; g < G; g++) th.emplace_back([&, g]() { rcs[g] = run_rank(opt, g, G, id, &gate); });
     for (auto& t : th) t.join();
     for (int rc : rcs) if (rc) return rc;
     return 0;
 }
+
+extern "C" int vampomi_main(int argc, char** argv) { return main_impl(argc, argv, false); }
+extern "C" int vampomi_main_probit(int argc, char** argv) { return main_impl(argc, argv, true); }

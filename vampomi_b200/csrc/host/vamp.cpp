@@ -1,5 +1,6 @@
 #include "vamp.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <iostream>
@@ -9,6 +10,7 @@
 namespace vampomi_host {
 
 namespace {
+double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 constexpr double kGammaMin = 1e-11, kGammaMax = 1e11;      // src/vamp.hpp:33-34
 inline double clampg(double g) { return std::min(std::max(g, kGammaMin), kGammaMax); }
 }  // namespace
@@ -225,6 +227,7 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     res->params[0] = alpha1_; res->params[1] = gam1_;                           // :275-276
     if (!fuse) VH(measures1());
 
+    const double t_lmmse0 = wall_s();                                           // start_lmmse_step, :288
     VH(vampomi_draw_probe(ctx_, cfg_.seed, it));                                // :295-296
     if (cfg_.redundant_passes || !aty_ready_) {                                 // v = gamw * A^T y + gam2 * r2, :303-306
         VH(vampomi_atx_dev(ctx_, VAMPOMI_V_Y, VAMPOMI_V_ATY));
@@ -233,11 +236,18 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_V, gamw_, VAMPOMI_V_ATY, gam2_, VAMPOMI_V_R2, 1.0));
     int k1 = 0, k2 = 0;
     double rel = 0, vmu = 0;
+    // the reference's per-phase timing lines (src/vamp.cpp:316,333,399): host wall clock around the solves, which end with a
+    // synchronising read-back. In the lock-step schedules both solves run inside ONE call, reported as "CG took"; the Onsager
+    // solve then has no time of its own ("onsager took 0").
+    const double t_cg0 = wall_s();
+    double t_cg1 = t_cg0, t_ons1 = t_cg0;
     if (!fuse) {
         VH(vampomi_cg_solve(ctx_, VAMPOMI_V_V, VAMPOMI_V_X2, it > 1, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 0, &k1, &rel,
                             nullptr));                                          // :308-311
+        t_cg1 = wall_s();
         VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &k2,
                             &rel, &vmu));                                       // g2d_onsager, :494-501
+        t_ons1 = wall_s();
     } else {
         const int rhs[2] = {VAMPOMI_V_V, VAMPOMI_V_BERN}, sol[2] = {VAMPOMI_V_X2, VAMPOMI_V_QINV_BERN};
         const int warm[2] = {it > 1 ? 1 : 0, 0}, ata[2] = {ata_x2_ready_ ? VAMPOMI_V_ATA_X2 : -1, -1}, ons[2] = {0, 1};
@@ -250,8 +260,12 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
                                  VAMPOMI_V_Z1, track, its, rels, vmus));
         tau_solved = gamw_;
         k1 = its[0]; k2 = its[1]; vmu = vmus[1];
+        t_cg1 = t_ons1 = wall_s();
         VH(measures1());
     }
+    if (verbose)
+        std::cout << "CG took " << t_cg1 - t_cg0 << " seconds." << std::endl                                  // :316
+                  << "onsager took " << t_ons1 - t_cg1 << " seconds." << std::endl;                           // :333
     alpha2_ = gam2_ * vmu;
     res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
     eta2_ = gam2_ / alpha2_;                                                    // :341
@@ -309,7 +323,8 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     res->n_params = 5; res->n_metrics = 6;
     if (verbose)
         std::cout << "alpha2 = " << alpha2_ << std::endl << "gam2 = " << gam2_ << std::endl << "gam1 = " << gam1_ << std::endl
-                  << "true gam1 = " << res->true_gam1 << std::endl << "gamw = " << gamw_ << std::endl;
+                  << "true gam1 = " << res->true_gam1 << std::endl << "gamw = " << gamw_ << std::endl
+                  << "LMMSE step took " << wall_s() - t_lmmse0 << " seconds." << std::endl;                   // :399
     return VAMPOMI_OK;
 }
 

@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) k_ax_reduce_xchg(const double* __restrict
             if (i < N) {
                 for (int g = 0; g < x.G; g++) xchg_ll_store(xchg_recv_ll(x, g, slot, x.rank) + 2 * (size_t)i, t, seq);
                 double tot = 0.0;
-                for (int g = 0; g < x.G; g++) tot += xchg_ll_load(xchg_recv_ll(x, x.rank, slot, g) + 2 * (size_t)i, seq);
+                for (int g = 0; g < x.G; g++) tot += xchg_ll_load(x, xchg_recv_ll(x, x.rank, slot, g) + 2 * (size_t)i, seq);
                 out[i] = tot / divisor;
             }
         } else {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) k_ax_reduce_xchg(const double* __restrict
             __syncwarp();
             if (r < x.G) {
                 st_release_sys(xchg_flag_vec(x, r, x.rank, blockIdx.x), seq);
-                xchg_wait_flag(xchg_flag_vec(x, x.rank, r, blockIdx.x), seq);
+                xchg_wait_flag(x, xchg_flag_vec(x, x.rank, r, blockIdx.x), seq);
             }
             __syncwarp();
             if (i < N) {

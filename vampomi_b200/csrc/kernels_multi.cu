@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) k_ax_reduce_multi(const double* __restric
         if (i < N) {
             for (int g = 0; g < x.G; g++) xchg_ll_store(xchg_recv_ll(x, g, slot, x.rank) + 2 * (koff + i), t, seq);
             double tot = 0.0;
-            for (int g = 0; g < x.G; g++) tot += xchg_ll_load(xchg_recv_ll(x, x.rank, slot, g) + 2 * (koff + i), seq);
+            for (int g = 0; g < x.G; g++) tot += xchg_ll_load(x, xchg_recv_ll(x, x.rank, slot, g) + 2 * (koff + i), seq);
             out[i] = tot / divisor;
         }
         __syncwarp();
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_ax_reduce_multi(const double* __restric
         __syncwarp();
         if (r < x.G) {
             st_release_sys(xchg_flag_vec(x, r, x.rank, cta), seq);
-            xchg_wait_flag(xchg_flag_vec(x, x.rank, r, cta), seq);
+            xchg_wait_flag(x, xchg_flag_vec(x, x.rank, r, cta), seq);
         }
         __syncwarp();
         if (i < N) {

@@ -20,7 +20,8 @@
 // Slot reuse is safe with two slots: a rank can only start exchange s+2 after it has passed the wait of s+1, and a peer
 // raises its flag for s+1 only after it has finished reading slot (s & 1) of exchange s (stream order on that GPU).
 // `seq` lives in device memory and advances only when an exchange really ran, so launches that return early at the CG
-// done flag (identical on all ranks) do not desynchronise it. A peer that never arrives traps instead of hanging.
+// done flag (identical on all ranks) do not desynchronise it. A peer that never arrives makes the wait give up after a
+// wall-clock time-out and raise an error flag (XchgDeadline below) instead of hanging or trapping.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,6 +42,8 @@ struct Xchg {                           // passed by value to kernels; all offse
     unsigned char* peer[XCHG_MAX_RANKS];   // base of every rank's region as mapped into THIS rank's address space
     unsigned int* seq;                  // local: [0] vector exchanges done, [1] scalar exchanges done
     unsigned int* ticket;               // local: CTA completion counter of the vector exchange kernel
+    unsigned long long timeout_ns;      // how long a wait for a peer may last (by %globaltimer) before it gives up
+    int* err;                           // host-mapped flag: set to 1 by a wait that gave up (the host turns it into an error code)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -56,11 +59,33 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void xchg_wait_flag(const unsigned int* flag, unsigned int seq) {
-    unsigned long long spins = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// A peer that never arrives (a rank that died, or one that is more than the time-out behind) must not hang the GPU and must
+// not poison the context either: the wait is bounded in WALL time (%globaltimer, checked every 1024 polls; the limit is
+// Xchg::timeout_ns, 120 s unless VAMPOMI_XCHG_TIMEOUT_S says otherwise), and a wait that gives up raises the host-mapped
+// error flag and returns — the kernel finishes with meaningless values, and the next host synchronisation of the library
+// reports VAMPOMI_ERR_STATE instead of handing them out (capi.cu: xchg_check).
+struct XchgDeadline {
+    unsigned long long start = 0;
+    unsigned int polls = 0;
+    __device__ __forceinline__ bool expired(const Xchg& x) {
+        if ((++polls & 1023u) != 0) return false;
+        const unsigned long long now = globaltimer_ns();
+        if (start == 0) { start = now; return false; }
+        if (now - start < x.timeout_ns) return false;
+        *reinterpret_cast<volatile int*>(x.err) = 1;
+        return true;
+    }
+};
+__device__ __forceinline__ void xchg_wait_flag(const Xchg& x, const unsigned int* flag, unsigned int seq) {
+    XchgDeadline dl;
     // sequence numbers are monotonic; (int) difference tolerates 32-bit wrap
     while ((int)(ld_acquire_sys(flag) - seq) < 0)
-        if (++spins > (1ull << 26)) __trap();        // ~ tens of seconds: a rank is gone — fault instead of hanging
+        if (dl.expired(x)) return;
 }
 
 __device__ __forceinline__ double* xchg_recv_vec(const Xchg& x, int on_rank, unsigned slot, int from_rank) {
@@ -78,12 +103,13 @@ __device__ __forceinline__ void xchg_ll_store(unsigned long long* dst, double v,
     const unsigned long long lo = (bits & 0xffffffffull) | tag, hi = (bits >> 32) | tag;
     asm volatile("st.volatile.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(lo), "l"(hi) : "memory");
 }
-__device__ __forceinline__ double xchg_ll_load(const unsigned long long* src, unsigned int seq) {
-    unsigned long long lo, hi, spins = 0;
+__device__ __forceinline__ double xchg_ll_load(const Xchg& x, const unsigned long long* src, unsigned int seq) {
+    unsigned long long lo, hi;
+    XchgDeadline dl;
     for (;;) {
         asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(src) : "memory");
         if ((unsigned int)(lo >> 32) == seq && (unsigned int)(hi >> 32) == seq) break;
-        if (++spins > (1ull << 26)) __trap();        // a rank is gone — fault instead of hanging
+        if (dl.expired(x)) break;                    // a rank is gone: flag raised, value meaningless
     }
     return __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
 }
@@ -110,7 +136,7 @@ __device__ inline void xchg_allreduce_scalars(const Xchg& x, const double* vals,
             const double v = vals[tid];
             for (int g = 0; g < x.G; g++) xchg_ll_store(xchg_recv_sc_ll(x, g, slot, x.rank) + 2 * tid, v, seq);
             double t = 0.0;
-            for (int g = 0; g < x.G; g++) t += xchg_ll_load(xchg_recv_sc_ll(x, x.rank, slot, g) + 2 * tid, seq);
+            for (int g = 0; g < x.G; g++) t += xchg_ll_load(x, xchg_recv_sc_ll(x, x.rank, slot, g) + 2 * tid, seq);
             out[tid] = t;
         }
         __syncthreads();
@@ -125,7 +151,7 @@ __device__ inline void xchg_allreduce_scalars(const Xchg& x, const double* vals,
     __syncthreads();
     if (tid < x.G) {
         st_release_sys(xchg_flag_sc(x, tid, x.rank), seq);                  // tell rank `tid` that my K values have landed
-        xchg_wait_flag(xchg_flag_sc(x, x.rank, tid), seq);                  // and wait for rank `tid`'s values here
+        xchg_wait_flag(x, xchg_flag_sc(x, x.rank, tid), seq);                  // and wait for rank `tid`'s values here
     }
     __syncthreads();
     if (tid < K) {

@@ -68,7 +68,8 @@ enum {
     VAMPOMI_V_USER_N1 = 41,
     VAMPOMI_V_GRAM_W0 = 42, VAMPOMI_V_GRAM_W1 = 43,     /* work: w = A A^T q of the one-pass CG, one per system */
     VAMPOMI_V_GRAM_AR0 = 44, VAMPOMI_V_GRAM_AR1 = 45,   /* work: A r of the one-pass CG */
-    VAMPOMI_V_NUM_N = 14
+    VAMPOMI_V_MCOV = 46,       /* probit: covariate offset m_cov = Z cov_eff (src/vamp_probit.cpp:214-217); zero without covariates */
+    VAMPOMI_V_NUM_N = 15
 };
 
 /* Kinds for vampomi_dots(): out = sum_i f(a_i, b_i). */
@@ -227,7 +228,7 @@ int vampomi_cg_solve_pair(vampomi_ctx* ctx, const int rhs_vec[2], const int sol_
                           int iters[2], double rel_err[2], double rhs_dot_sol[2]);
 
 /* ---- probit z-channel: vamp::g1_bin_class / g1d_bin_class, src/vamp_probit.cpp:469-488 as used at :213-236 --- */
-/* Z1HAT <- g1_bin_class(P1, tau1, Y, 0); *sum_g1d = sum_i g1d_bin_class(P1_i, tau1, Y_i, 0). */
+/* Z1HAT <- g1_bin_class(P1, tau1, Y, m_cov); *sum_g1d = sum_i g1d_bin_class(P1_i, tau1, Y_i, m_cov_i), m_cov = VAMPOMI_V_MCOV (0 unless set). */
 int vampomi_probit_zdenoise(vampomi_ctx* ctx, double tau1, double* sum_g1d);
 
 /* ---- association tests -------------------------------------------------------------------------------------- */

@@ -91,6 +91,12 @@ int vampomi_solver_create(vampomi_ctx* ctx, const vampomi_solver_config* cfg, co
                           const double* true_signal_M, const double* x1hat_init_M, vampomi_solver** out);
 /* One VAMP iteration. If x1_scaled_M / r1_scaled_M are non-NULL they receive x1_hat/sqrt(N) and r1/sqrt(N) — the
  * content of _it_{k}.bin and _r1_it_{k}.bin (src/vamp.cpp:235-249) — for this shard. */
+/* Covariates (src/data.cpp:159-227, src/vamp_probit.cpp:490-617, call sites src/vamp.cpp:155-169 and src/vamp_probit.cpp:78-95,
+ * 213-232): Z = the standardised N x C matrix (row-major, e.g. from vampomi_host_read_covariates). Must be called before the first
+ * step; iteration 1 then fits the effects by the reference's Newton-Raphson and removes them (linear: from y; probit: as the offset
+ * m_cov of the z-channel denoiser, device vector VAMPOMI_V_MCOV). get_cov_eff returns the fitted effects. */
+int vampomi_solver_set_covariates(vampomi_solver* s, int C, const double* Z_NxC);
+int vampomi_solver_get_cov_eff(vampomi_solver* s, int C, double* out_C);
 int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M);
 int vampomi_solver_destroy(vampomi_solver* s);
 
@@ -102,6 +108,11 @@ int vampomi_host_csv_row(unsigned it, const double* values, int n, char* buf, in
  * `standardize`, never centred. Writes up to `cap` values, returns the number of rows, -1 if the file cannot be opened,
  * -2 on an NA value ("NAN in data!"). */
 long long vampomi_host_read_phen(const char* path, int standardize, double* out, long long cap);
+/* data::read_covariates (src/data.cpp:159-227): header line skipped, two ids skipped, C values per row, every covariate standardised
+ * with its population sd (constant -> 0). Writes N*C values row-major; returns that count, -1 on a malformed file / row count != N. */
+long long vampomi_host_read_covariates(const char* path, int C, int N, double* Z_NxC);
+/* vamp::Newton_method_cov (src/vamp_probit.cpp:525-617): eta_inout holds the start on entry and the fitted effects on return. */
+int vampomi_host_newton_cov(const double* y_N, const double* gg_N, const double* Z_NxC, int N, int C, double* eta_inout_C);
 /* linear_reg1d_pvals (src/utilities.cpp:269-282) with boost's Student-t complement restated by a continued fraction. */
 double vampomi_host_linear_reg1d_pvals(double sumx, double sumsqx, double sumxy, double sumy, double sumsqy, int n);
 /* The counter-hash stand-ins for std::random_device (oracle patches P2/P3): probe sign (+1/-1) and probit start p1. */

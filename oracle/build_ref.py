@@ -11,6 +11,8 @@ copy that never enters the repo; only the binary lands in oracle/_ref/ (git-igno
       std::random_device — sharding-invariant and reproducible (seed from env VAMPOMI_SEED)
   P3  vamp_probit.cpp:53  probit start p1 from a hashed Box-Muller of (seed, i)
   P4  data.cpp:297,351    size_t column offsets so one rank can hold N*M >= 2^31
+  P5  main_meth.cpp:48    the inference branch calls dataset.read_covariates(--cov-file, --C) after constructing the dataset: the
+      shipped main never loads covariates, so `--C > 0` would index an empty matrix; no effect when C = 0
 
 Flags follow README.md:28 minus -D_GLIBCXX_DEBUG -g, and -march=x86-64-v3 instead of native because the binary is
 built in this container but timed on the GPU box's host CPU.
@@ -29,6 +31,46 @@ OUT_BIN_STRICT = os.path.join(OUT_DIR, "main_meth_ref_O2")      # IEEE-strict bu
 OUT_BIN_V4 = os.path.join(OUT_DIR, "main_meth_ref_v4")         # README flags for an AVX-512 host (-march=x86-64-v4): the TIMING binary
 
 
+OUT_BIN_GPUDATA = os.path.join(OUT_DIR, "main_meth_ref_gpudata")   # the reference's main + vamp over OUR `class data` (ref_shims/data_gpu.cpp)
+
+
+def build_gpu_data(force=False, verbose=True):
+    """The reference's own main_meth.cpp / vamp.cpp / utilities.cpp / options.cpp (patches P1-P3) linked against the `class data`
+    adapter of INTEGRATION.md §2 (ref_shims/data_gpu.cpp) and libvampomi_cuda.so instead of src/data.cpp."""
+    if not available():
+        return os.path.isfile(OUT_BIN_GPUDATA)
+    root = os.path.dirname(HERE)
+    lib = os.path.join(root, "vampomi_b200", "lib", "libvampomi_cuda.so")
+    if not os.path.isfile(lib):
+        raise RuntimeError("libvampomi_cuda.so is not built yet")
+    deps = [os.path.abspath(__file__), os.path.join(HERE, "ref_shims", "data_gpu.cpp"), os.path.join(root, "include", "vampomi.h")]
+    if not force and os.path.isfile(OUT_BIN_GPUDATA) and all(os.path.getmtime(d) <= os.path.getmtime(OUT_BIN_GPUDATA) for d in deps):
+        return True
+    os.makedirs(OUT_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="vampomi_ref_")
+    try:
+        for f in os.listdir(REF_SRC):
+            if f.endswith((".cpp", ".hpp")):
+                with open(os.path.join(REF_SRC, f)) as fh:
+                    text = fh.read()
+                for old, new, count in PATCHES.get(f, []):
+                    text = text.replace(old, new)
+                with open(os.path.join(tmp, f), "w") as fh:
+                    fh.write(text)
+        shims = os.path.join(HERE, "ref_shims")
+        cmd = ["g++", "-std=c++17", "-O2", "-march=x86-64-v3", "-fopenmp", "-w", "-I", shims, "-I", tmp, "-I", os.path.join(root, "include"),
+               "-include", os.path.join(shims, "oracle_hooks.h")]
+        cmd += [os.path.join(tmp, u) for u in UNITS if u != "data.cpp"] + [os.path.join(shims, "data_gpu.cpp")]
+        cmd += ["-L", os.path.dirname(lib), "-lvampomi_cuda", "-Wl,-rpath,$ORIGIN/../../vampomi_b200/lib", "-o", OUT_BIN_GPUDATA + ".tmp"]
+        if verbose:
+            print("[oracle/_ref] " + " ".join(cmd))
+        subprocess.run(cmd, check=True)
+        os.replace(OUT_BIN_GPUDATA + ".tmp", OUT_BIN_GPUDATA)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return True
+
+
 def timing_binary():
     """The reference build to TIME on this host: the README asks for -march=native (README.md:28), but the binary is built in
     the build container and timed on the GPU box's CPU, so two ISA levels are built and the widest one this CPU runs is chosen
@@ -44,6 +86,9 @@ def timing_binary():
 
 
 PATCHES = {
+    "main_meth.cpp": [
+        ("        // Initialize model hyperparameters\n", "        dataset.read_covariates(opt.get_cov_file(), C);\n        // Initialize model hyperparameters\n", 1),
+    ],
     "vamp.cpp": [
         ("//x1_hat = std::vector<double> (M, 0.0);", "x1_hat = std::vector<double> (M, 0.0);", 1),
         ("//r1 = std::vector<double> (M, 0.0);", "r1 = std::vector<double> (M, 0.0);", 1),
@@ -120,5 +165,7 @@ if __name__ == "__main__":
     if "--strict" in sys.argv:
         ok = build(force="--force" in sys.argv, strict=True) and ok
     ok = build(force="--force" in sys.argv, v4=True) and ok
+    if "--gpu-data" in sys.argv:
+        ok = build_gpu_data(force="--force" in sys.argv) and ok
     print(OUT_BIN if ok else "unavailable")
     sys.exit(0 if ok else 1)

@@ -330,6 +330,102 @@ def g1d_bin_class(p, tau1, y, m_cov=0.0):
     return 1 - ratio / (1 + tau1 * PROBIT_VAR) * ((2 * y - 1) * c + ratio)
 
 
+def read_covariates(path, C, N):
+    """data::read_covariates, src/data.cpp:159-227: header line skipped, two ids skipped, C values per row; every covariate is
+    standardised with its population standard deviation (long double sums), a constant one becomes zeros. Returns (N, C)."""
+    if C == 0:
+        return np.zeros((N, 0))
+    rows = []
+    with open(path) as f:
+        for i, line in enumerate(f):
+            if i == 0:
+                continue
+            tok = line.rstrip("\n").split()
+            if line[:1].isspace():
+                tok = [""] + tok                     # the reference's regex split yields an empty first token then
+            vals = [float(t) for t in tok[2:]]
+            if len(vals) != C:
+                raise ValueError(f"FATAL: number of covariates = {len(vals)} does not match to the specified number of covariates = {C}")
+            rows.append(vals)
+    Z = np.array(rows, dtype=np.float64).reshape(len(rows), C)
+    assert Z.shape[0] == N
+    out = np.empty_like(Z)
+    for c in range(C):
+        col = Z[:, c].astype(np.longdouble)
+        cavg = col.sum() / np.longdouble(N)
+        csig = np.sqrt(((col - cavg) * (col - cavg)).sum() / np.longdouble(N))
+        out[:, c] = 0.0 if csig < 1e-8 else ((col - cavg) / csig).astype(np.float64)
+    return out
+
+
+def _lu_solve(Mx, b):
+    """Partial-pivot LU as uBLAS lu_factorize / lu_substitute are used at src/vamp_probit.cpp:551-558; zero RHS if singular."""
+    m, b = np.array(Mx, dtype=np.float64), np.array(b, dtype=np.float64)
+    n = len(b)
+    pm = list(range(n))
+    for k in range(n):
+        piv = k + int(np.argmax(np.abs(m[k:, k])))
+        pm[k] = piv
+        if m[piv, k] == 0.0:
+            return np.zeros(n)
+        if piv != k:
+            m[[k, piv], :] = m[[piv, k], :]
+        for i in range(k + 1, n):
+            m[i, k] /= m[k, k]
+            m[i, k + 1:] -= m[i, k] * m[k, k + 1:]
+    for k in range(n):
+        if pm[k] != k:
+            b[k], b[pm[k]] = b[pm[k]], b[k]
+    for i in range(n):
+        b[i] -= m[i, :i] @ b[:i]
+    for i in range(n - 1, -1, -1):
+        b[i] = (b[i] - m[i, i + 1:] @ b[i + 1:]) / m[i, i]
+    return b
+
+
+def mlogL_probit(y, gg, Z, eta):
+    """src/vamp_probit.cpp:490-502."""
+    arg = (2 * y - 1) / math.sqrt(PROBIT_VAR) * (gg + Z @ eta)
+    return float(-np.log(normal_cdf(arg)).sum()) / len(y)
+
+
+def grad_cov(y, gg, Z, eta):
+    """src/vamp_probit.cpp:504-523."""
+    arg = (2 * y - 1) / math.sqrt(PROBIT_VAR) * (gg + Z @ eta)
+    ratio = 2.0 / math.sqrt(2 * math.pi) / erfcx_ref(-arg / math.sqrt(2))
+    return ((-1) * ratio * (2 * y - 1) / math.sqrt(PROBIT_VAR)) @ Z / len(y)
+
+
+def newton_method_cov(y, gg, Z, eta):
+    """vamp::Newton_method_cov, src/vamp_probit.cpp:525-617."""
+    eta = np.array(eta, dtype=np.float64)
+    for it in range(501):
+        g = gg + Z @ eta
+        arg = (2 * y - 1) * g
+        ratio = 2.0 / math.sqrt(2 * math.pi) / erfcx_ref(-arg / math.sqrt(2))
+        lam = ratio * (2 * y - 1)
+        W = lam * (lam + g)
+        rhs = _lu_solve(Z.T @ (Z * W[:, None]), Z.T @ lam)
+        grad = grad_cov(y, gg, Z, eta)
+        scale, init_val = 1.0, mlogL_probit(y, gg, Z, eta)
+        eta_new = eta.copy()
+        for _ in range(1, 300):
+            displ = scale * rhs
+            eta_new = eta + displ
+            if mlogL_probit(y, gg, Z, eta_new) <= init_val + float(displ @ grad) / 2:
+                break
+            scale *= 0.9
+        norm_eta = math.sqrt(float(eta @ eta))
+        rel_err = 1.0 if norm_eta == 0 else math.sqrt(float((eta - eta_new) @ (eta - eta_new))) / norm_eta
+        if rel_err < 1e-4:
+            break
+        init_val = mlogL_probit(y, gg, Z, eta)
+        eta = eta_new
+        if mlogL_probit(y, gg, Z, eta) > init_val:
+            break
+    return eta
+
+
 def confusion_matrix(y, yhat):
     """src/vamp_probit.cpp:631-652 — [TP, TN, FP, FN]."""
     y, yhat = np.asarray(y), np.asarray(yhat)
@@ -352,8 +448,10 @@ class Vamp:
     def __init__(self, data, gam1=1e-6, gamw=2.0, max_iter=50, CG_max_iter=500, CG_err_tol=1e-5, EM_max_iter=1,
                  EM_err_thr=1e-2, rho=0.5, learn_vars=1, learn_prior_delay=1, stop_criteria_thr=0.01,
                  merge_vars_thr=5e-1, vars=None, probs=None, true_signal=None, x1hat_init=None,
-                 out_dir=None, out_name="out", model="linear", seed=0, verbosity=0):
+                 out_dir=None, out_name="out", model="linear", seed=0, verbosity=0, covs=None):
         d = self.data = data
+        self.covs = None if covs is None or np.asarray(covs).shape[1] == 0 else np.asarray(covs, dtype=np.float64)   # (N, C), standardised
+        self.cov_eff = None
         self.N, self.M, self.Mt, self.S, self.comm = d.N, d.M, d.Mt, d.S, d.comm
         self.gam1, self.gamw = float(gam1), float(gamw)
         self.max_iter, self.CG_max_iter, self.CG_err_tol = max_iter, CG_max_iter, CG_err_tol
@@ -591,6 +689,9 @@ class Vamp:
                                 + [f"var{i}" for i in range(len(self.vars))])
         for it in range(1, self.max_iter + 1):
             self._it = it
+            if it == 1 and self.covs is not None:                # src/vamp.cpp:155-169
+                self.cov_eff = newton_method_cov(y, np.zeros(N), self.covs, np.zeros(self.covs.shape[1]))
+                y = y - self.covs @ self.cov_eff
             if it > self.learn_prior_delay:
                 self.updatePrior()
             x1_hat_prev = self.x1_hat
@@ -647,8 +748,12 @@ class Vamp:
         self.r2 = np.zeros(M)
         self.alpha1 = 0.0
         z1_hat = np.zeros(N)
+        m_cov = 0.0
         for it in range(1, self.max_iter + 1):
             self._it = it
+            if it == 1 and self.covs is not None:                # src/vamp_probit.cpp:78-95
+                self.cov_eff = newton_method_cov(y, z1_hat, self.covs, np.zeros(self.covs.shape[1]))
+                m_cov = self.covs @ self.cov_eff                 # :214-217
             x1_hat_prev = self.x1_hat
             alpha1_prev = self.alpha1
             self.x1_hat = self.g1(self.r1, self.gam1)
@@ -666,8 +771,8 @@ class Vamp:
             self.gam2 = min(max(self.eta1 - self.gam1, GAMMA_MIN), GAMMA_MAX)
             self.r2 = (self.eta1 * self.x1_hat - self.gam1 * self.r1) / self.gam2
             # z channel
-            z1_hat = g1_bin_class(self.p1, tau1, y)
-            beta1 = float(g1d_bin_class(self.p1, tau1, y).sum())
+            z1_hat = g1_bin_class(self.p1, tau1, y, m_cov)
+            beta1 = float(g1d_bin_class(self.p1, tau1, y, m_cov).sum())
             if beta1 >= N:
                 beta1 = N - 1.0
             beta1 /= N

@@ -52,12 +52,29 @@ def golden_inputs(g, tmpdir=None):
     binary = g["model"] == "bin_class"
     X, y, beta = sim.simulate(int(g["N"]), int(g["M"]), float(g["lam"]), float(g["h2"]), int(g["data_seed"]), binary=binary)
     assert hashlib.sha256(X.tobytes()).hexdigest() == g["sha256_A"], "numpy generator drifted: regenerate tests/golden"
+    if "C" in g:                                              # covariate fixtures: phenotype carries the covariate effects
+        cov, y = sim.simulate_covariates(int(g["N"]), int(g["C"]), int(g["data_seed"]), y=y, binary=binary)
+        if tmpdir is not None:
+            sim.write_covariates(os.path.join(tmpdir, "ex.cov"), cov)
     y_txt = np.array([float("%0.10f" % v) for v in y])
     if tmpdir is not None:
         X.tofile(os.path.join(tmpdir, "ex.bin"))
         sim.write_phen(os.path.join(tmpdir, "ex.phen"), y)
         beta.tofile(os.path.join(tmpdir, "ex_ts.bin"))
     return X, y_txt, beta
+
+
+def golden_covariates(g):
+    """The standardised (N, C) covariate matrix of a covariate fixture, through the %0.10f text format the reference read."""
+    cov = sim.simulate_covariates(int(g["N"]), int(g["C"]), int(g["data_seed"]))
+    cov = np.array([[float("%0.10f" % v) for v in row] for row in cov])
+    out = np.empty_like(cov)
+    for c in range(cov.shape[1]):
+        col = cov[:, c].astype(np.longdouble)
+        avg = col.sum() / np.longdouble(len(col))
+        sig = np.sqrt(((col - avg) * (col - avg)).sum() / np.longdouble(len(col)))
+        out[:, c] = 0.0 if sig < 1e-8 else ((col - avg) / sig).astype(np.float64)
+    return out
 
 
 def standardize_phen(y):
@@ -124,6 +141,7 @@ def oracle_run(g, A, y_txt, beta, out_dir=None, comm=None, S=0, Mt=None, max_ite
     if init is not None:
         init = np.asarray(init)[S:S + A.shape[0]]
     v = vo.Vamp(d, gamw=1.0 / (1.0 - h2), max_iter=int(max_iter or g["iterations"]), true_signal=beta, out_dir=out_dir, out_name="o",
-                model=model, seed=int(g["probe_seed"]), stop_criteria_thr=float(g.get("stop_thr", 0.0)), x1hat_init=init, **kw)
+                model=model, seed=int(g["probe_seed"]), stop_criteria_thr=float(g.get("stop_thr", 0.0)), x1hat_init=init,
+                covs=golden_covariates(g) if "C" in g else None, **kw)
     v.infere()
     return v

@@ -11,12 +11,12 @@ import pytest
 from oracle import vamp_oracle as vo
 from vampomi_b200 import build, capi, sim
 from vampomi_b200.capi import V_QINV_BERN, V_USER_M0, V_USER_M1, V_USER_N0, V_USER_N1, V_V, V_X1, V_X2, V_Y
-from helpers import (assert_rows_close, csv_rows, extra_kwargs, golden_inputs, load_golden, oracle_run, rel_l2,
+from helpers import (assert_rows_close, csv_rows, extra_kwargs, golden_covariates, golden_inputs, load_golden, oracle_run, rel_l2,
                      standardize_phen, tolerances)
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+CASES = ["linear_cov", "probit_cov", "linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
          "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
          "linear_em_conv", "linear_h2"]
 
@@ -32,7 +32,10 @@ def solver_for(g, A, y_txt, beta, **over):
     sh = capi.Shard(int(g["N"]), int(g["M"]))
     sh.upload(A)
     sh.compute_stats(kw.pop("alpha_scale", 1.0))
-    return sh, capi.Solver(sh, y, model=model, true_signal=beta, x1hat_init=g.get("x1hat_init"), **kw)
+    sol = capi.Solver(sh, y, model=model, true_signal=beta, x1hat_init=g.get("x1hat_init"), **kw)
+    if "C" in g:                                              # --C / --cov-file: standardised covariates, effects fitted in iteration 1
+        sol.set_covariates(golden_covariates(g))
+    return sh, sol
 
 
 # schedules of the matrix passes: "onepass" (recycled + CG iterations that read the block once: fused A^T q / A A^T q pass), "recycled" (fused + A x2_hat, A Q^-1 u and A^T A of both kept by the solves themselves),
@@ -83,6 +86,8 @@ def test_solver_matches_reference_fixture(name, schedule):
     assert_rows_close(got_metrics, want_metrics, rel_csv, "metrics")
     if float(g.get("stop_thr", 0)) > 0:          # the reference stopped here on its own NMSE test (src/vamp.cpp:419-423)
         assert r["nmse"] < float(g["stop_thr"])
+    if "C" in g:                                 # the covariate effects the reference printed (6 significant digits)
+        assert np.allclose(sol.cov_eff(), g["cov_eff"], rtol=2e-5, atol=1e-9)
     sol.close()
     sh.close()
 
@@ -437,3 +442,27 @@ def test_main_meth_probit_entry_point(tmp_path):
     # main_meth itself still refuses the probit-only run mode quietly (the reference's main does nothing for unknown modes)
     res = subprocess.run([exe, "--meth-file", "x", "--N", "5"], stdout=subprocess.PIPE, text=True)
     assert res.returncode == 1 and "FATAL" in res.stdout
+
+
+@pytest.mark.parametrize("name", ["linear_cov", "probit_cov"])
+def test_main_meth_covariates_flags(name, tmp_path):
+    """--C / --cov-file through the command line (src/options.cpp:30-38,226; data::read_covariates; Newton_method_cov): the files of
+    the covariate fixtures, and the reference's FATAL for a covariate count that does not match."""
+    g = load_golden(name)
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    its = int(g["iterations"])
+    args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
+            "--iterations", its, "--true-signal-file", f"{d}/ex_ts.bin", "--model", g["model"], "--stop-criteria-thr", 0, "--seed", g["probe_seed"],
+            "--cov-file", f"{d}/ex.cov"] + list(g["extra"])
+    out = run_cli(args + ["--C", g["C"]])
+    effs = [float(v) for v in __import__("re").findall(r"cov_eff\[\d+\] = ([-+0-9.eE]+)", out)][:int(g["C"])]
+    assert np.allclose(effs, g["cov_eff"], rtol=2e-5, atol=1e-9)
+    for k in range(1, its + 1):
+        assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), g["x1"][k - 1]) < 1e-9
+        assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < 1e-9
+    for kind in ("params", "metrics"):
+        assert_rows_close(csv_rows(open(f"{d}/out/g_{kind}.csv", "rb").read()), csv_rows(g[f"csv_{kind}"]), 1e-8, kind)
+    res = subprocess.run([build.MAIN_METH] + [str(a) for a in args + ["--C", int(g["C"]) + 1]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 1 and "does not match to the specified number of covariates" in res.stdout

@@ -149,3 +149,32 @@ def test_recycled_products_are_identities_of_the_cg_recurrences():
         ata = (v - r - gam2 * mu) / tau
         want = d.ATx(d.Ax(mu))
         assert np.linalg.norm(ata - want) < 1e-12 * np.linalg.norm(want)
+
+
+def test_covariate_reader_and_newton_match_oracle(tmp_path):
+    """SURVEY.md §8 f3 on the host: data::read_covariates (src/data.cpp:159-227) and vamp::Newton_method_cov
+    (src/vamp_probit.cpp:525-617) of libvampomi_cuda's host layer against the numpy restatement — no GPU involved."""
+    import ctypes as C
+    from vampomi_b200 import capi, sim
+    lib = capi.load_library()
+    N, Cn = 150, 3
+    rng = np.random.default_rng(5)
+    cov = sim.simulate_covariates(N, Cn, 9)
+    cov[:, 1] = 4.25                                          # a constant covariate -> all zeros after standardisation
+    path = str(tmp_path / "c.cov")
+    sim.write_covariates(path, cov)
+    want = vo.read_covariates(path, Cn, N)
+    got = np.empty(N * Cn)
+    n = lib.vampomi_host_read_covariates(path.encode(), Cn, N, got.ctypes.data_as(capi.c_double_p))
+    assert n == N * Cn and np.array_equal(got.reshape(N, Cn), want) and np.all(want[:, 1] == 0)
+    assert abs(want[:, 0].mean()) < 1e-12 and abs(want[:, 0].std() - 1) < 1e-12
+    assert lib.vampomi_host_read_covariates(path.encode(), Cn + 1, N, got.ctypes.data_as(capi.c_double_p)) == -1      # wrong --C
+    assert lib.vampomi_host_read_covariates(path.encode(), Cn, N + 1, got.ctypes.data_as(capi.c_double_p)) == -1      # wrong --N
+    Z = vo.read_covariates(path, Cn, N)[:, [0, 2]].copy()
+    for y in ((Z @ np.array([0.8, -0.5]) + rng.standard_normal(N) > 0).astype(float), rng.standard_normal(N)):   # probit and linear use
+        gg = np.zeros(N)
+        eta_want = vo.newton_method_cov(y, gg, Z, np.zeros(2))
+        eta = np.zeros(2)
+        rc = lib.vampomi_host_newton_cov(y.ctypes.data_as(capi.c_double_p), gg.ctypes.data_as(capi.c_double_p),
+                                         np.ascontiguousarray(Z).ctypes.data_as(capi.c_double_p), N, 2, eta.ctypes.data_as(capi.c_double_p))
+        assert rc == 0 and np.allclose(eta, eta_want, rtol=1e-9, atol=1e-12), (eta, eta_want)

@@ -11,7 +11,7 @@ from helpers import (REL_CSV, REL_VEC, assert_rows_close, csv_rows, golden_input
                      standardize_phen, tolerances, REL_VEC_ILLCOND)
 
 
-ALL_CASES = ["linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+ALL_CASES = ["linear_cov", "probit_cov", "linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
              "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
          "linear_em_conv", "linear_h2"]
 
@@ -24,6 +24,8 @@ def test_oracle_matches_reference_run(name, tmp_path):
     # ask for more iterations than the reference ran when it stopped on its own NMSE criterion (src/vamp.cpp:419-423)
     v = oracle_run(g, A, y_txt, beta, out_dir=str(tmp_path), max_iter=40 if float(g.get("stop_thr", 0)) > 0 else None)
     assert len(v.history) == int(g["iterations"]), "number of VAMP iterations run"
+    if "C" in g:                                             # covariate effects as the reference printed them (6 significant digits)
+        assert np.allclose(v.cov_eff, g["cov_eff"], rtol=2e-5, atol=1e-9)
     for k in range(1, int(g["iterations"]) + 1):
         x1 = np.fromfile(tmp_path / f"o_it_{k}.bin")
         r1 = np.fromfile(tmp_path / f"o_r1_it_{k}.bin")

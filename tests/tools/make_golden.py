@@ -58,6 +58,11 @@ CASES = {
     # the headline's aspect ratio AND the CLI-default --gam1 1e-6 (the headline benchmark's own start): held to the measured
     # distance between the reference's two builds (x1_O2 / r1_O2), see tests/helpers.py
     "linear_wide_default": dict(N=100, M=4000, lam=0.01, h2=0.5, data_seed=41, probe_seed=15, iterations=6, model="linear", extra=[]),
+    # covariates (--C / --cov-file; oracle patch P5 makes the reference's main load them): effects fitted in iteration 1
+    "linear_cov": dict(N=240, M=400, lam=0.05, h2=0.6, data_seed=61, probe_seed=25, iterations=4, model="linear",
+                       extra=["--gam1", "1e-2"], C=3),
+    "probit_cov": dict(N=300, M=400, lam=0.05, h2=0.5, data_seed=62, probe_seed=26, iterations=4, model="bin_class",
+                       extra=["--gam1", "1e-2"], C=2),
     "probit_small": dict(N=400, M=600, lam=0.05, h2=0.5, data_seed=21, probe_seed=13, iterations=6, model="bin_class",
                          extra=["--gam1", "1e-2"]),
 }
@@ -109,9 +114,16 @@ def make_case(name, c):
     with tempfile.TemporaryDirectory() as d:
         X, y, beta = sim.write_dataset(d, "ex", c["N"], c["M"], c["lam"], c["h2"], c["data_seed"], binary=c["model"] == "bin_class")
         os.makedirs(os.path.join(d, "out"))
+        cov = None
+        if c.get("C"):
+            cov, y = sim.simulate_covariates(c["N"], c["C"], c["data_seed"], y=y, binary=c["model"] == "bin_class")
+            sim.write_phen(f"{d}/ex.phen", y)
+            sim.write_covariates(f"{d}/ex.cov", cov)
         args = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", str(c["N"]), "--Mt", str(c["M"]),
                 "--out-dir", f"{d}/out", "--out-name", "g", "--iterations", str(c["iterations"]), "--true-signal-file",
                 f"{d}/ex_ts.bin", "--model", c["model"], "--stop-criteria-thr", c.get("stop_thr", "0"), "--verbosity", "1"] + c["extra"]
+        if c.get("C"):
+            args += ["--C", str(c["C"]), "--cov-file", f"{d}/ex.cov"]
         init = None
         if c.get("warm_from"):
             # --estimate-file start (src/main_meth.cpp:75-80, src/vamp.cpp:71-79 with patch P1): first produce an estimate
@@ -131,6 +143,9 @@ def make_case(name, c):
                    iterations=c["iterations"], model=c["model"], extra=np.array(c["extra"], dtype="U32"),
                    sha256_A=hashlib.sha256(X.tobytes()).hexdigest(), sha256_phen=hashlib.sha256(open(f"{d}/ex.phen", "rb").read()).hexdigest())
         fix["stop_thr"] = float(c.get("stop_thr", "0"))
+        if cov is not None:
+            fix["C"] = c["C"]
+            fix["cov_eff"] = np.array([float(v) for v in re.findall(r"cov_eff\[\d+\] = ([-+0-9.eE]+|-?nan|-?inf)", log)][:c["C"]])
         if init is not None:
             fix["x1hat_init"] = init
         ex = dict(zip(c["extra"][::2], c["extra"][1::2]))

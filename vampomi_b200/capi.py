@@ -23,6 +23,7 @@ V_CG_R, V_CG_Z, V_CG_P, V_CG_D, V_USER_M0, V_USER_M1 = 12, 13, 14, 15, 16, 17
 V_CG2_R, V_CG2_Z, V_CG2_P, V_CG2_D, V_ATA_X2 = 18, 19, 20, 21, 22
 V_Y, V_Z1, V_Z2, V_P1, V_P2, V_Z1HAT, V_TMP_N0, V_TMP_N1, V_USER_N0, V_USER_N1 = range(32, 42)
 V_GRAM_W0, V_GRAM_W1, V_GRAM_AR0, V_GRAM_AR1 = range(42, 46)
+V_MCOV = 46
 DOT, DIFF2, SQDEV = 0, 1, 2
 
 
@@ -107,6 +108,10 @@ _SIGNATURES = {
     "vampomi_solver_default_config": (None, [C.POINTER(SolverConfig)]),
     "vampomi_solver_create": (C.c_int, [C.c_void_p, C.POINTER(SolverConfig), c_double_p, c_double_p, c_double_p,
                                         C.POINTER(C.c_void_p)]),
+    "vampomi_solver_set_covariates": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "vampomi_solver_get_cov_eff": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "vampomi_host_read_covariates": (C.c_longlong, [C.c_char_p, C.c_int, C.c_int, c_double_p]),
+    "vampomi_host_newton_cov": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]),
     "vampomi_solver_step": (C.c_int, [C.c_void_p, C.POINTER(IterResult), c_double_p, c_double_p]),
     "vampomi_solver_destroy": (C.c_int, [C.c_void_p]),
     "vampomi_host_csv_row": (C.c_int, [C.c_uint, c_double_p, C.c_int, C.c_char_p, C.c_int]),
@@ -461,6 +466,18 @@ class Solver:
         h = C.c_void_p()
         _check(self.lib.vampomi_solver_create(shard.h, C.byref(cfg), py, pts, px0, C.byref(h)), "solver_create")
         self.h = h
+
+    def set_covariates(self, Z):
+        """Z: standardised covariates, shape (N, C) (read_covariates). Before the first step."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        assert Z.ndim == 2 and Z.shape[0] == self.shard.N
+        self.C = Z.shape[1]
+        _check(self.lib.vampomi_solver_set_covariates(self.h, self.C, Z.ctypes.data_as(c_double_p)), "solver_set_covariates")
+
+    def cov_eff(self):
+        out, po = _out(self.C)
+        _check(self.lib.vampomi_solver_get_cov_eff(self.h, self.C, po), "solver_get_cov_eff")
+        return out
 
     def step(self, want_vectors=True, out_x1=None, out_r1=None):
         res = IterResult()

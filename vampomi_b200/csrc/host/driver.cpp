@@ -16,6 +16,7 @@
 #include <thread>
 #include <vector>
 #include "../../../include/vampomi_host.h"
+#include "cov.h"
 #include "io.h"
 #include "options.h"
 #include "vamp.h"
@@ -165,6 +166,18 @@ int run_infere(Rank& r) {
     vamp.verbose = r.root();
     vamp.verbosity = o.verbosity;
     if (vamp.init(y.data(), true_signal.data(), x1hat_init.data()) != VAMPOMI_OK) return fatal_abi(r, "solver initialisation");
+    if (o.C > 0) {
+        // data::read_covariates (src/data.cpp:159-227). The reference's compiling main never calls it, so `--C > 0` there reads
+        // an empty matrix out of bounds; here --C / --cov-file do what the loops' own covariate code expects.
+        std::vector<double> Z;
+        std::string err;
+        const double tc = now_s();
+        bool okc = false;
+        try { okc = read_covariates(o.cov_file, (int)o.C, N, &Z, &err); } catch (const std::exception&) { err = "covariate file " + o.cov_file + " holds a value that is not a number"; }
+        if (!okc) return fatal(r, err);
+        if (r.root()) std::cout << "rank = " << r.rank << ": reading covariates took " << now_s() - tc << " seconds to run." << std::endl;   // :200
+        if (vamp.set_covariates((int)o.C, Z.data()) != VAMPOMI_OK) return fatal_abi(r, "covariates");
+    }
 
     // setup_io (src/vamp.cpp:854-882): rank 0 owns the three CSVs
     const std::string base = o.out_dir + "/" + o.out_name;

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstring>
 #include <iostream>
+#include "cov.h"
 #include "io.h"
 #include "../rng.h"
 
@@ -80,6 +81,30 @@ int Vamp::init(const double* y, const double* true_signal, const double* x1hat_i
             VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, std::sqrt((double)N_), VAMPOMI_V_TRUE, 0.0, VAMPOMI_V_TRUE, 1.0));
             VH(vampomi_ax_dev(ctx_, VAMPOMI_V_USER_M0, VAMPOMI_V_USER_N0));
         }
+    }
+    return VAMPOMI_OK;
+}
+
+int Vamp::set_covariates(int C, const double* Z) {
+    if (C < 0 || (C > 0 && !Z) || it_ != 0) return VAMPOMI_ERR_ARG;
+    C_ = C;
+    Z_.assign(Z, Z + (size_t)C * (size_t)N_);
+    cov_eff_.assign((size_t)C, 0.0);
+    return VAMPOMI_OK;
+}
+
+// iteration 1 of both loops (src/vamp.cpp:155-169, src/vamp_probit.cpp:78-93): probit regression of y on the covariates with the
+// genetic predictor gg = z1_hat = 0, then the reference's print-out of the effects
+int Vamp::fit_covariates() {
+    const double t0 = wall_s();
+    cov_eff_ = newton_method_cov(y_host_, std::vector<double>((size_t)N_, 0.0), Z_, N_, C_, cov_eff_, verbose, verbosity);
+    if (verbose) {
+        for (int i0 = 0; i0 < C_; i0++) {
+            std::cout << "cov_eff[" << i0 << "] = " << cov_eff_[i0] << ", ";
+            if (i0 % 4 == 3) std::cout << std::endl;
+        }
+        std::cout << std::endl;
+        if (cfg_.model == 1) std::cout << "Computing covariate effects took " << wall_s() - t0 << " seconds." << std::endl;   // src/vamp_probit.cpp:94
     }
     return VAMPOMI_OK;
 }
@@ -171,6 +196,24 @@ int Vamp::step(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
 int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
     const int it = it_;
     const double sqrtN = std::sqrt((double)N_), rho = cfg_.rho;
+    {                                                                           // covariate effects, :153-173
+        const double t_cov0 = wall_s();
+        if (it == 1 && C_ > 0) {
+            VH(fit_covariates());
+            // y -= Z cov_eff (:166-168) changes the loop's LOCAL copy of the phenotype only: it feeds A^T y (:303), while
+            // updateNoisePrec (:506) and err_measures (:817) fetch the unadjusted phenotype from the dataset again. So the adjusted
+            // vector gets a device vector of its own (VAMPOMI_V_MCOV, unused by the linear model otherwise) and Y stays as it is.
+            std::vector<double> y_adj = y_host_;
+            for (int i = 0; i < N_; i++) {
+                double s = 0;
+                for (int j = 0; j < C_; j++) s += Z_[(size_t)i * C_ + j] * cov_eff_[j];
+                y_adj[i] -= s;
+            }
+            VH(vampomi_vec_set(ctx_, VAMPOMI_V_MCOV, y_adj.data()));
+            aty_ready_ = false;
+        }
+        if (verbose) std::cout << "time for covariates effects update = " << wall_s() - t_cov0 << " seconds." << std::endl;   // :173
+    }
     if (verbose) std::cout << "->DENOISING" << std::endl;
     if (it > cfg_.learn_prior_delay) VH(update_prior());                        // :186-187
     if (verbose) {
@@ -230,7 +273,7 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     const double t_lmmse0 = wall_s();                                           // start_lmmse_step, :288
     VH(vampomi_draw_probe(ctx_, cfg_.seed, it));                                // :295-296
     if (cfg_.redundant_passes || !aty_ready_) {                                 // v = gamw * A^T y + gam2 * r2, :303-306
-        VH(vampomi_atx_dev(ctx_, VAMPOMI_V_Y, VAMPOMI_V_ATY));
+        VH(vampomi_atx_dev(ctx_, C_ > 0 ? VAMPOMI_V_MCOV : VAMPOMI_V_Y, VAMPOMI_V_ATY));
         aty_ready_ = true;
     }
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_V, gamw_, VAMPOMI_V_ATY, gam2_, VAMPOMI_V_R2, 1.0));
@@ -332,7 +375,18 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
 int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled) {
     const int it = it_;
     const double sqrtN = std::sqrt((double)N_), rho = cfg_.rho;
-    if (verbose) std::cout << "...calculating covariate effects" << std::endl << "->DENOISING" << std::endl;
+    if (verbose) std::cout << "...calculating covariate effects" << std::endl;
+    if (it == 1 && C_ > 0) {                                                    // :78-95
+        VH(fit_covariates());
+        std::vector<double> mcov((size_t)N_);
+        for (int i = 0; i < N_; i++) {
+            double s = 0;
+            for (int j = 0; j < C_; j++) s += Z_[(size_t)i * C_ + j] * cov_eff_[j];
+            mcov[i] = s;                                                        // m_cov of g1_bin_class / g1d_bin_class, :214-232
+        }
+        VH(vampomi_vec_set(ctx_, VAMPOMI_V_MCOV, mcov.data()));
+    }
+    if (verbose) std::cout << "->DENOISING" << std::endl;
     const double alpha1_prev = alpha1_;
     double sum_d = 0;
     // g1 / g1d with the CURRENT prior, no damping yet (:112-130)
@@ -486,6 +540,39 @@ int vampomi_solver_create(vampomi_ctx* ctx, const vampomi_solver_config* cfg, co
     if (rc != VAMPOMI_OK) { delete v; return rc; }
     *out = new vampomi_solver{v};
     return VAMPOMI_OK;
+}
+
+int vampomi_solver_set_covariates(vampomi_solver* s, int C, const double* Z_NxC) {
+    if (!s || !s->impl) return VAMPOMI_ERR_ARG;
+    return s->impl->set_covariates(C, Z_NxC);
+}
+
+int vampomi_solver_get_cov_eff(vampomi_solver* s, int C, double* out) {
+    if (!s || !s->impl || !out || (int)s->impl->cov_eff().size() != C) return VAMPOMI_ERR_ARG;
+    for (int j = 0; j < C; j++) out[j] = s->impl->cov_eff()[j];
+    return VAMPOMI_OK;
+}
+
+long long vampomi_host_read_covariates(const char* path, int C, int N, double* Z_NxC) {
+    std::vector<double> Z;
+    std::string err;
+    if (!path || !Z_NxC) return -1;
+    try {
+        if (!vampomi_host::read_covariates(path, C, N, &Z, &err)) return -1;
+    } catch (const std::exception&) {
+        return -2;
+    }
+    for (size_t i = 0; i < Z.size(); i++) Z_NxC[i] = Z[i];
+    return (long long)Z.size();
+}
+
+int vampomi_host_newton_cov(const double* y, const double* gg, const double* Z_NxC, int N, int C, double* eta_inout) {
+    if (!y || !gg || !Z_NxC || !eta_inout || N < 1 || C < 1) return -1;
+    std::vector<double> eta = vampomi_host::newton_method_cov(std::vector<double>(y, y + N), std::vector<double>(gg, gg + N),
+                                                               std::vector<double>(Z_NxC, Z_NxC + (size_t)N * C), N, C,
+                                                               std::vector<double>(eta_inout, eta_inout + C), false, 0);
+    for (int j = 0; j < C; j++) eta_inout[j] = eta[j];
+    return 0;
 }
 
 int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M) {

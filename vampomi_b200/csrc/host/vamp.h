@@ -17,6 +17,11 @@ public:
     // y: phenotype (length N). true_signal / x1hat_init: this shard's M values or nullptr.
     int init(const double* y, const double* true_signal, const double* x1hat_init);
     int step(vampomi_iter_result* res, double* x1_scaled, double* r1_scaled);
+    // Covariates: Z is the standardised N x C matrix of read_covariates, row-major. Call before the first step:
+    // iteration 1 then fits the covariate effects (Newton_method_cov) and removes them (linear: y -= Z cov_eff, src/vamp.cpp:155-169;
+    // probit: offset m_cov = Z cov_eff inside the z-channel denoiser, src/vamp_probit.cpp:213-232).
+    int set_covariates(int C, const double* Z);
+    const std::vector<double>& cov_eff() const { return cov_eff_; }
     int iteration() const { return it_; }
     const std::vector<double>& probs() const { return probs_; }
     const std::vector<double>& vars() const { return vars_; }
@@ -39,6 +44,9 @@ private:
     double gam1_, gamw_, gam2_ = 0, eta1_ = 0, eta2_ = 0, alpha1_ = 0, alpha2_ = 0, tau1_ = 0;
     std::vector<double> probs_, vars_;     // vars_ are the internal ones (x N, src/vamp.cpp:87-88)
     std::vector<double> y_host_, zbuf_;
+    int C_ = 0;
+    std::vector<double> Z_, cov_eff_;
+    int fit_covariates();
     double* pending_x1_ = nullptr;   // host buffers of read-outs begun by dump() and not yet collected
     double* pending_r1_ = nullptr;
     bool aty_ready_ = false;

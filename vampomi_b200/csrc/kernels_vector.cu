@@ -279,7 +279,7 @@ __device__ __forceinline__ double erfcx_ref(double x) {
     return erfcx(x);
 }
 
-__global__ void __launch_bounds__(RED_THREADS) k_probit_z(const double* __restrict__ p1, const double* __restrict__ y,
+__global__ void __launch_bounds__(RED_THREADS) k_probit_z(const double* __restrict__ p1, const double* __restrict__ y, const double* __restrict__ mcov,
                                                           double* __restrict__ z1hat, long long N, double tau1,
                                                           double* __restrict__ partials, unsigned int* ticket,
                                                           double* __restrict__ out) {
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_probit_z(const double* __restri
     double sum_d = 0.0;
     GRID_STRIDE(i, N) {
         const double p = p1[i], s = 2.0 * y[i] - 1.0;
-        const double cc = (p + 0.0) / sroot;
+        const double cc = (p + mcov[i]) / sroot;                               // m_cov = Z cov_eff, 0 without covariates (:471,:482)
         const double ratio = 2.0 / sqrt(2.0 * 3.14159265358979323846) / erfcx_ref(-s * cc / sqrt(2.0));
         z1hat[i] = p + s * ratio / tau1 / sroot;
         sum_d += 1.0 - ratio / (1.0 + tau1 * probit_var) * (s * cc + ratio);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_probit_z(const double* __restri
 }
 
 int launch_probit_z(vampomi_ctx* c, double tau1, double* sums_dev) {
-    k_probit_z<<<vec_blocks(c->N), RED_THREADS, 0, c->stream>>>(c->nvec[VAMPOMI_V_P1 - 32], c->nvec[VAMPOMI_V_Y - 32],
+    k_probit_z<<<vec_blocks(c->N), RED_THREADS, 0, c->stream>>>(c->nvec[VAMPOMI_V_P1 - 32], c->nvec[VAMPOMI_V_Y - 32], c->nvec[VAMPOMI_V_MCOV - 32],
                                                                c->nvec[VAMPOMI_V_Z1HAT - 32], c->N, tau1, c->red_partials,
                                                                c->red_tickets, sums_dev);
     c->counters[0]++;

@@ -25,6 +25,30 @@ def simulate(N, M, lam=0.1, h2=0.8, seed=1234, binary=False, dtype=np.float64):
     return X, y, beta
 
 
+def simulate_covariates(N, C, seed, y=None, effects=None, binary=False):
+    """C raw covariates per individual (seeded, with a mean and a scale of their own so that standardisation matters) and,
+    when y is given, a phenotype that carries their effects: continuous y gets +cov @ effects; a binary outcome is re-drawn
+    from the shifted liability's sign (the original 0/1 flipped where the covariate shift dominates)."""
+    rng = np.random.default_rng(seed + 7919)
+    cov = rng.standard_normal((N, C)) * rng.uniform(0.5, 3.0, C) + rng.uniform(-2.0, 2.0, C)
+    if y is None:
+        return cov
+    eff = np.asarray(effects if effects is not None else np.linspace(0.4, -0.3, C))
+    shift = (cov - cov.mean(0)) / cov.std(0) @ eff
+    if binary:
+        liab = (2 * y - 1) * np.abs(rng.standard_normal(N)) + shift
+        return cov, (liab > 0).astype(np.float64)
+    return cov, y + shift
+
+
+def write_covariates(path, cov):
+    """The covariate file format of data::read_covariates (src/data.cpp:159-227): a header line, then `IID FID c1 .. cC`."""
+    with open(path, "w") as f:
+        f.write("IID FID " + " ".join(f"cov{j}" for j in range(cov.shape[1])) + "\n")
+        for i, row in enumerate(cov):
+            f.write("%d %d " % (i, i) + " ".join("%0.10f" % v for v in row) + "\n")
+
+
 def write_phen(path, y):
     with open(path, "w") as f:
         for i, v in enumerate(y):

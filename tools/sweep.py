@@ -50,12 +50,11 @@ if a.gram:
     t(4, "read_probe", a.gram)
     t(5, "ax_multi_K2_default", a.gram)
     t(6, "atx_multi_K2_default", a.gram)
-    for shape in range(8):
+    for shape in range(11):
         t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0)
         t(10, "gram_K1", a.gram, gram_shape=shape, gram_clusters=0)
-    for shape in (0, 2):
-        for pfd in (0, 2, 4):
-            t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0, gram_prefetch=pfd)
+    for shape in (9, 10, 6, 9, 10, 6):
+        t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0)
     if not a.quick:
         for shape in (0, 1):
             for ncl in (14, 15, 30, 45, 60):

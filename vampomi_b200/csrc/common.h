@@ -177,7 +177,7 @@ struct vampomi_ctx {
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;
     long long counters[4] = {0, 0, 0, 0};
-    int gram_clusters[8][4][2] = {};    // co-resident clusters of k_gram per (shape, cluster size 1/2/4/8, systems), 0 = not queried yet
+    int gram_clusters[12][5][2] = {};    // co-resident clusters of k_gram per (shape, cluster size 1/2/4/8/16, systems), 0 = not queried yet
     bool bulk_attr_ax = false, bulk_attr_atx = false;   // opt-in shared-memory size set for the bulk kernels on this device
     // optional per-launch device timing (vampomi_profile_*)
     bool profile = false;

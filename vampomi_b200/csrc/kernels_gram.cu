@@ -78,9 +78,17 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 // 32/NV - 1 lanes after it) ends up with the warp total of value v.
 template <int NV>
 __device__ __forceinline__ double warp_sum_multi(const double (&v)[NV], int lane) {
-    static_assert(NV == 1 || NV == 2 || NV == 4, "1, 2 or 4 values");
+    static_assert(NV == 1 || NV == 2 || NV == 4 || NV == 8, "1, 2, 4 or 8 values");
     double t;
-    if constexpr (NV == 4) {
+    if constexpr (NV == 8) {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+        double a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = (up16 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, up16 ? v[i] : v[i + 4], 16);
+        const double b0 = (up8 ? a[2] : a[0]) + __shfl_xor_sync(0xffffffffu, up8 ? a[0] : a[2], 8);
+        const double b1 = (up8 ? a[3] : a[1]) + __shfl_xor_sync(0xffffffffu, up8 ? a[1] : a[3], 8);
+        t = (up4 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, up4 ? b0 : b1, 4);
+    } else if constexpr (NV == 4) {
         const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
         const double a0 = (up16 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[2], 16);
         const double a1 = (up16 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, up16 ? v[1] : v[3], 16);
@@ -554,20 +562,28 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
 }
 
 // DIRECT = 1: every compute warp sends its own partial sums to all CTAs (one st.async per lane, no block-level stage in between)
-template <int K, int NCW, int RP, int C, int R, int CS, int DIRECT>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+// DEF: how many steps the axpy of a step is deferred (DEF + 1 register buffers of one step each): 1 hides one step time of the
+// cluster round trip, 2 hides two — affordable where a CTA holds few rows (RP = 2)
+// NCOMM: 1 = one communication warp sends and receives in turn; 2 = a sender warp and a receiver warp, so that the partial sums of
+// step s+1 leave while those of step s are still on their way (needed for DEF = 2 to pay)
+template <int K, int NCW, int RP, int C, int R, int CS, int DIRECT, int DEF = 1, int NCOMM = 1>
+__global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                               const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
                                                               long long M, double scale, double* __restrict__ partial, int nchunks) {
     constexpr int CK = C * K, CT = NCW * 32, PIECE = CT * RP * 2;      // compute threads; doubles per column piece slot in the ring
-    static_assert(CS * CK <= 32, "one warp sends the partial sums of a step");
+    // the communication warp handles the CS*CK (destination or rank, value) items of a step in ROUNDS rounds of 32; with CK a
+    // power of two <= 8 a lane keeps the same value index ck = lane % CK in every round and walks the ranks lane/CK + j*32/CK
+    static_assert(CK == 1 || CK == 2 || CK == 4 || CK == 8, "values per step");
+    constexpr int ROUNDS = (CS * CK + 31) / 32, RSTEP = 32 / CK;
     extern __shared__ __align__(128) double ring[];              // [R][C][PIECE]
     constexpr int NSRC = DIRECT ? NCW : 1;                       // partial sums per (rank, value) that arrive per step
     static_assert(!DIRECT || CS <= 32 / CK, "the lanes that hold value ck after the butterfly send it to the CS ranks");
-    __shared__ double red[2][NCW][CK];
+    __shared__ double red[4][NCW][CK];
     __shared__ __align__(16) double xbuf[4][CS][NSRC][CK];
     __shared__ __align__(8) uint64_t empty[R];
     __shared__ __align__(16) double wbuf[4][CK];
-    __shared__ __align__(8) uint64_t full[4], wready[4], redbar[2], ringbar[R];
+    __shared__ __align__(8) uint64_t full[4], wready[4], redbar[4], ringbar[R];
+    static_assert(DEF == 1 || DEF == 2, "deferral of the axpy: one or two steps");
     bool active[K];
     bool any = false;
 #pragma unroll
@@ -587,7 +603,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __r
 #pragma unroll
         for (int i = 0; i < 4; i++) { mbar_init(&full[i], 1); mbar_init(&wready[i], 1); }
 #pragma unroll
-        for (int i = 0; i < 2; i++) mbar_init(&redbar[i], NCW);
+        for (int i = 0; i < 4; i++) mbar_init(&redbar[i], NCW);
 #pragma unroll
         for (int i = 0; i < R; i++) { mbar_init(&ringbar[i], 1); mbar_init(&empty[i], NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -597,8 +613,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __r
     __syncthreads();
     cluster_sync_all();                                          // every CTA's mbarriers are armed before anybody sends
 
-    if (wid == NCW) {
-        // ------------------------------------------- communication warp -------------------------------------------
+    if (wid >= NCW) {
+        // ------------------------------------------- communication warp(s) -------------------------------------------
+        const bool do_send = NCOMM == 1 || wid == NCW, do_recv = NCOMM == 1 || wid == NCW + 1;
         auto issue_step = [&](long long s) {                     // lane 0: the C column pieces of step s into stage s % R
             const int st = (int)(s % R);
             mbar_expect_tx(&ringbar[st], C * piece_bytes);
@@ -608,41 +625,48 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __r
                     bulk_g2s(ring + ((size_t)st * C + cc) * PIECE, A + rbase + (size_t)col_of(s, cc) * ld, piece_bytes, &ringbar[st]);
             }
         };
-        if (lane == 0)
+        if (lane == 0 && do_send)
             for (long long s = 0; s < R && s < nsteps; s++) issue_step(s);
-        const int ck = lane % CK, r = lane / CK, cc_l = ck / K, k_l = ck % K;
+        const int ck = lane % CK, r0 = lane / CK, cc_l = ck / K, k_l = ck % K;
         bool act = active[0];
 #pragma unroll
         for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
         double* tout = K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0];
         double sg_next = nsteps > 0 ? __ldg(msig + col_of(0, cc_l)) : 0.0;
         for (long long s = 0; s < nsteps; s++) {
-            const int rb = (int)(s & 1), slot = (int)(s & 3);
+            const int rb = (int)(s & 3), slot = (int)(s & 3);
             const double sgl = sg_next;
             sg_next = __ldg(msig + col_of(s + 1 < nsteps ? s + 1 : s, cc_l));
+            if (do_send) {
             if (DIRECT) {
                 if (lane == 0 && s + R < nsteps) {               // refill stage s % R once every compute warp has copied it into registers
                     mbar_wait_cta(&empty[s % R], (uint32_t)((s / R) & 1));
                     issue_step(s + R);
                 }
             } else {
-                mbar_wait_cta(&redbar[rb], (uint32_t)((s >> 1) & 1));
+                mbar_wait_cta(&redbar[rb], (uint32_t)((s >> 2) & 1));
                 if (lane == 0 && s + R < nsteps) issue_step(s + R);  // every compute warp has copied stage s % R into registers
-                if (lane < CS * CK) {                            // lane = (dest r, value ck)
-                    double ts = red[rb][0][ck];
+                double ts = red[rb][0][ck];                      // every lane: the CTA's sum of value ck, warps in order
 #pragma unroll
-                    for (int w = 1; w < NCW; w++) ts += red[rb][w][ck];
-                    st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][0][ck]), (uint32_t)r), ts, mapa_u32(smem_u32(&full[slot]), (uint32_t)r));
+                for (int w = 1; w < NCW; w++) ts += red[rb][w][ck];
+#pragma unroll
+                for (int j = 0; j < ROUNDS; j++) {               // lane = (destination r0 + j*RSTEP, value ck)
+                    const int dest = r0 + j * RSTEP;
+                    if (dest < CS)
+                        st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][0][ck]), (uint32_t)dest), ts, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
                 }
             }
+            }
+            if (!do_recv) continue;
             mbar_wait_cluster(&full[slot], (uint32_t)((s >> 2) & 1));
             double tot = 0.0;
-            if (r < CS) {
-                double part[NSRC];
 #pragma unroll
-                for (int w = 0; w < NSRC; w++) part[w] = xbuf[slot][r][w][ck];
+            for (int j = 0; j < ROUNDS; j++) {                   // this lane's ranks in rising order, then the butterfly over the lanes
+                const int r = r0 + j * RSTEP;
+                if (r < CS) {
 #pragma unroll
-                for (int w = 0; w < NSRC; w++) tot += part[w];   // warp order: fixed
+                    for (int w = 0; w < NSRC; w++) tot += xbuf[slot][r][w][ck];
+                }
             }
 #pragma unroll
             for (int o = CK; o < CK * CS && o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // the same tree in every CTA
@@ -675,7 +699,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __r
                 qr[k][i][0] = qv.x; qr[k][i][1] = qv.y;
             }
         }
-        double a[2][C][RP][2];                                   // the step being dotted and the step whose axpy is pending
+        double a[DEF + 1][C][RP][2];                             // the step being dotted and the DEF steps whose axpy is pending
         double m_n[C];
 #pragma unroll
         for (int cc = 0; cc < C; cc++) m_n[cc] = __ldg(mave + (nsteps > 0 ? col_of(0, cc) : 0));
@@ -721,9 +745,9 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __r
                 if (dest < CS)
                     st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][wid][ck]), (uint32_t)dest), sw, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
             } else {
-                if ((lane & (32 / CK - 1)) == 0) red[s & 1][wid][lane / (32 / CK)] = sw;
+                if ((lane & (32 / CK - 1)) == 0) red[s & 3][wid][lane / (32 / CK)] = sw;
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cta(&redbar[s & 1]);
+                if (lane == 0) mbar_arrive_cta(&redbar[s & 3]);
             }
         };
         auto axpy_step = [&](const int b, long long sp) {
@@ -742,12 +766,12 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) k_gram_ws(const double* __r
                         acc[k][i][1] = fma(a[b][cc][i][1], wgt[cc * K + k], acc[k][i][1]);
                     }
         };
-        for (long long s0 = 0; s0 <= nsteps; s0 += 2) {
+        for (long long s0 = 0; s0 < nsteps + DEF; s0 += DEF + 1) {
 #pragma unroll
-            for (int b = 0; b < 2; b++) {
+            for (int b = 0; b <= DEF; b++) {
                 const long long s = s0 + b;
                 if (s < nsteps) dot_step(b, s);
-                if (s >= 1 && s <= nsteps) axpy_step(b ^ 1, s - 1);
+                if (s >= DEF && s < nsteps + DEF) axpy_step((b + 1) % (DEF + 1), s - DEF);
             }
         }
 #pragma unroll
@@ -773,10 +797,11 @@ int gram_launch_any(vampomi_ctx* c, Kern kern, int TPB, int ROWS, size_t smem, i
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream; cfg.attrs = attr; cfg.numAttrs = 1;
     // co-resident clusters of this (shape, cluster size, systems) on this device: queried once per context
-    constexpr int csi = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : 3;
+    constexpr int csi = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : CS == 8 ? 3 : 4;
     int& ncl = c->gram_clusters[shape][csi][K - 1];
     if (ncl <= 0) {
         if (smem > 40 * 1024) VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (CS > 8) VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16 CTAs: one cluster per GPC
         cfg.gridDim = dim3(CS, c->num_sms);
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = c->num_sms / CS; }
@@ -807,10 +832,10 @@ int gram_launch(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape
     return gram_launch_any<K, C, CS>(c, k_gram<K, TPB, RV, C, D, CS, QS>, TPB, ROWS, QS ? (size_t)K * ROWS * sizeof(double) : 0, shape, gv, mw,
                                      c->tune.gram_prefetch);
 }
-template <int K, int NCW, int RP, int C, int R, int CS, int DIRECT>
+template <int K, int NCW, int RP, int C, int R, int CS, int DIRECT, int DEF = 1, int NCOMM = 1>
 int gram_launch_ws(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
     constexpr int ROWS = NCW * 32 * RP * 2;
-    return gram_launch_any<K, C, CS>(c, k_gram_ws<K, NCW, RP, C, R, CS, DIRECT>, (NCW + 1) * 32, ROWS, (size_t)R * C * ROWS * sizeof(double), shape, gv, mw);
+    return gram_launch_any<K, C, CS>(c, k_gram_ws<K, NCW, RP, C, R, CS, DIRECT, DEF, NCOMM>, (NCW + NCOMM) * 32, ROWS, (size_t)R * C * ROWS * sizeof(double), shape, gv, mw);
 }
 template <int K, int TPB, int RP, int C, int R, int CS>
 int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
@@ -825,7 +850,11 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //     3  256, 5, 2, 4          4  256, 5, 2, 3          5  256, 5, 1, 6
 //   warp-specialised bulk-copy ring (k_gram_ws): compute warps, row pairs per thread, columns per step, ring stages
 //     6  10, 4, 2, 4           7  the same, every compute warp sending its own partial sums (no block-level stage)
-constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : 2560; }
+//     8  10, 2, 4, 4: half the rows per CTA (16 CTAs per cluster at N = 20 000, one cluster per GPC) and FOUR columns per step, so the
+//        cluster round trip of a step (~0.6 us) is shorter than the step's own HBM time (80 kB per SM pair ... 40 kB per SM: 0.7 us)
+//     9  as 8 with the axpy deferred by TWO steps (three register buffers)     10  as 9 with separate sender and receiver warps
+constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape >= 8 ? 1280 : 2560; }
+constexpr int gram_max_cluster_of_shape(int shape) { return shape >= 8 ? 16 : 8; }
 
 template <int K, int CS>
 int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
@@ -838,6 +867,9 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 5: return gram_launch_bulk<K, 256, 5, 1, 6, CS>(c, gv, mw, shape);
         case 6: return gram_launch_ws<K, 10, 4, 2, 4, CS, 0>(c, gv, mw, shape);
         case 7: return gram_launch_ws<K, 10, 4, 2, 4, CS, 1>(c, gv, mw, shape);
+        case 8: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0>(c, gv, mw, shape);
+        case 9: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0, 2>(c, gv, mw, shape);
+        case 10: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0, 2, 2>(c, gv, mw, shape);
         default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
     }
 }
@@ -846,7 +878,14 @@ template <int K>
 int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
     const int shape = c->tune.gram_shape;
     int cs = c->tune.gram_cluster;
-    if (cs == 0) { cs = 1; while (cs < 8 && (c->ld + cs - 1) / cs > (size_t)gram_rows_of_shape(shape)) cs *= 2; }
+    if (cs == 0) { cs = 1; while (cs < gram_max_cluster_of_shape(shape) && (c->ld + cs - 1) / cs > (size_t)gram_rows_of_shape(shape)) cs *= 2; }
+    if (cs == 16) {
+        if (shape == 8) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0>(c, gv, mw, shape);
+        if (shape == 9) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0, 2>(c, gv, mw, shape);
+        if (shape == 10) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0, 2, 2>(c, gv, mw, shape);
+        set_error("gram: 16 CTAs per cluster only with shapes 8-10");
+        return VAMPOMI_ERR_ARG;
+    }
     switch (cs) {
         case 1: return gram_shape<K, 1>(c, gv, mw, shape);
         case 2: return gram_shape<K, 2>(c, gv, mw, shape);
@@ -858,13 +897,15 @@ int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
 
 }  // namespace
 
-bool gram_supported(const vampomi_ctx* c) { return c->storage == 0 && c->ld <= (size_t)8 * gram_rows_of_shape(c->tune.gram_shape); }
+bool gram_supported(const vampomi_ctx* c) {
+    return c->storage == 0 && c->ld <= (size_t)gram_max_cluster_of_shape(c->tune.gram_shape) * gram_rows_of_shape(c->tune.gram_shape);
+}
 
 // t_k = A^T q_k (M-vectors), w_k = A t_k (N-vectors, summed over the GPUs, / sqrt(N)) for K <= 2 systems in ONE pass.
 // mq: in = q_k (N-vectors), out = t_k (M-vectors); w_out: the N-vectors that receive w_k. done flags from mq.
 int launch_gram(vampomi_ctx* c, const MultiVec& mq, double* const* w_out) {
     if (mq.K < 1 || mq.K > 2) { set_error("gram: 1 or 2 systems"); return VAMPOMI_ERR_ARG; }
-    if (!gram_supported(c)) { set_error("gram: needs FP64 storage and N <= %d", 8 * gram_rows_of_shape(c->tune.gram_shape)); return VAMPOMI_ERR_ARG; }
+    if (!gram_supported(c)) { set_error("gram: needs FP64 storage and N <= 20480"); return VAMPOMI_ERR_ARG; }
     GramVec gv{};
     MultiVec mw{};
     mw.K = mq.K;

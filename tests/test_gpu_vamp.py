@@ -16,7 +16,7 @@ from helpers import (assert_rows_close, csv_rows, extra_kwargs, golden_covariate
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["linear_cov", "probit_cov", "linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+CASES = ["linear_large_gam2", "linear_cov", "probit_cov", "linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
          "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
          "linear_em_conv", "linear_h2"]
 
@@ -54,6 +54,7 @@ def test_solver_matches_reference_fixture(name, schedule):
     sh, sol = solver_for(g, A, y_txt, beta, **SCHEDULES[schedule])
     want_params, want_metrics = csv_rows(g["csv_params"]), csv_rows(g["csv_metrics"])
     got_params, got_metrics = {}, {}
+    gamw_used = sol.cfg.gamw                     # tau of this iteration's solves = gamw after the previous iteration (src/vamp.cpp:308)
     for k in range(1, int(g["iterations"]) + 1):
         r = sol.step()
         assert r["it"] == k
@@ -69,10 +70,14 @@ def test_solver_matches_reference_fixture(name, schedule):
                 assert r["matrix_passes"] == base + (5 if k == 1 else 6)
             elif schedule == "fused":     # A^T y once; both solves in lock-step; A [x2, Q^-1 u] and A^T [.., A x2] one pass each
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (3 if k == 1 else 2)
-            elif schedule == "onepass":   # A [p0 p1 x1] once, then ONE fused pass per lock-step CG iteration (and A^T y once)
-                assert r["matrix_passes"] == max(r["k1"], r["k2"]) + 1 + (1 if k == 1 else 0)
-            else:                         # nothing but the lock-step solves (and A^T y once)
-                assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + (1 if k == 1 else 0)
+            elif schedule in ("onepass", "recycled"):
+                # recycled: nothing but the lock-step solves (and A^T y once); onepass: A [p0 p1 x1] once, then ONE fused pass per
+                # lock-step CG iteration. Both recompute the recycled products by two explicit passes every 16th iteration and
+                # whenever gam2/tau > 1e5 (cancellation in (rhs - r - gam2 sol)/tau, host/vamp.cpp)
+                refresh = 2 if (k % 16 == 0 or r["params"][3] / gamw_used > 1e5) else 0
+                solves = max(r["k1"], r["k2"]) + 1 if schedule == "onepass" else 2 * max(r["k1"], r["k2"])
+                assert r["matrix_passes"] == solves + (1 if k == 1 else 0) + refresh
+            gamw_used = r["params"][4]
         else:
             if schedule == "fused":       # A^T p2, lock-step solves, A [x2, x2/sqrt(N)]
                 assert r["matrix_passes"] == 2 * max(r["k1"], r["k2"]) + 2

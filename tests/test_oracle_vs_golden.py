@@ -11,7 +11,7 @@ from helpers import (REL_CSV, REL_VEC, assert_rows_close, csv_rows, golden_input
                      standardize_phen, tolerances, REL_VEC_ILLCOND)
 
 
-ALL_CASES = ["linear_cov", "probit_cov", "linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
+ALL_CASES = ["linear_large_gam2", "linear_cov", "probit_cov", "linear_wide_default", "linear_small", "linear_readme", "linear_ragged", "linear_wellcond", "linear_two_comp", "linear_alpha_scale",
              "linear_stops_early", "linear_warm_start", "probit_small", "probit_ragged", "linear_wide", "probit_wide", "linear_cg_cap", "linear_tight_cg",
          "linear_em_conv", "linear_h2"]
 

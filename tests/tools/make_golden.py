@@ -58,6 +58,10 @@ CASES = {
     # the headline's aspect ratio AND the CLI-default --gam1 1e-6 (the headline benchmark's own start): held to the measured
     # distance between the reference's two builds (x1_O2 / r1_O2), see tests/helpers.py
     "linear_wide_default": dict(N=100, M=4000, lam=0.01, h2=0.5, data_seed=41, probe_seed=15, iterations=6, model="linear", extra=[]),
+    # gam2 / gamw ~ 4e6: the regime in which products recycled from the solves' residuals would cancel catastrophically
+    # (the recycled / onepass schedules recompute them by explicit passes there), with a tight CG tolerance
+    "linear_large_gam2": dict(N=220, M=450, lam=0.05, h2=0.7, data_seed=55, probe_seed=27, iterations=5, model="linear",
+                              extra=["--gam1", "1e4", "--CG-err-tol", "1e-10"]),
     # covariates (--C / --cov-file; oracle patch P5 makes the reference's main load them): effects fitted in iteration 1
     "linear_cov": dict(N=240, M=400, lam=0.05, h2=0.6, data_seed=61, probe_seed=25, iterations=4, model="linear",
                        extra=["--gam1", "1e-2"], C=3),

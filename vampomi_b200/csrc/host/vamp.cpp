@@ -13,6 +13,8 @@ namespace vampomi_host {
 namespace {
 double wall_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 constexpr double kGammaMin = 1e-11, kGammaMax = 1e11;      // src/vamp.hpp:33-34
+constexpr double kRecycleMaxRatio = 1e5;                   // gam2/tau above which recycled products are recomputed (eps * 1e5 = 2e-11)
+constexpr int kRecycleRefresh = 16;                        // ... and every this many VAMP iterations regardless
 inline double clampg(double g) { return std::min(std::max(g, kGammaMin), kGammaMax); }
 }  // namespace
 
@@ -318,12 +320,17 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_R1, eta2_, VAMPOMI_V_X2, -gam2_, VAMPOMI_V_R2, gam1_));   // :348-350
 
     // updateNoisePrec (:504-529) + err_measures(2) share A x2_hat; the reference computes it twice (:508, :826)
+    // The recycled products are differences of the solves' own vectors: A^T A sol = (rhs - r - gam2 sol)/tau loses
+    // ~eps*gam2/(tau*lambda) to cancellation, and Z2 = A x2_hat is advanced by recurrence from one VAMP iteration to the next.
+    // So they are recomputed by explicit passes (the `fused` schedule's two passes) whenever gam2/tau is large enough for the
+    // cancellation to matter at the 1e-9 contract, and every kRecycleRefresh iterations to cut the accumulated recurrence.
+    const bool refresh_products = recycle && (gam2_ / tau_solved > kRecycleMaxRatio || it % kRecycleRefresh == 0);
     if (!fuse) {
         VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
         VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));       // :518
         VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));        // :519
         if (cfg_.redundant_passes) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
-    } else if (!recycle) {
+    } else if (!recycle || refresh_products) {
         const int xin[2] = {VAMPOMI_V_X2, VAMPOMI_V_QINV_BERN}, xout[2] = {VAMPOMI_V_Z2, VAMPOMI_V_USER_N0};
         VH(vampomi_ax_multi_dev(ctx_, 2, xin, xout));
         const int pin[2] = {VAMPOMI_V_USER_N0, VAMPOMI_V_Z2}, pout[2] = {VAMPOMI_V_USER_M0, VAMPOMI_V_ATA_X2};

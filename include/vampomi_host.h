@@ -63,6 +63,10 @@ typedef struct vampomi_solver_config {
                                   (vampomi_aat_multi_dev) — max(k1,k2) + 1 passes per iteration; contexts that cannot run the
                                   fused pass (FP32 storage, N > 20480) silently keep the two-pass iterations.
                                   Ignored (0) when redundant_passes = 1. */
+    int probes;                /* Hutchinson probes per iteration: 1 = the reference's single +-1/sqrt(Mt) probe
+                                  (src/vamp.cpp:295-296); P > 1 averages u^T Q^-1 u (alpha2) and u^T A^T A Q^-1 u (noise precision) over P
+                                  independent probes — P-1 more Onsager solves per iteration, off the reference's parity (its runs
+                                  differ from each other by ~10 % because of this one-probe estimate). 0 reads as 1. */
 } vampomi_solver_config;
 
 typedef struct vampomi_iter_result {
@@ -97,6 +101,13 @@ int vampomi_solver_create(vampomi_ctx* ctx, const vampomi_solver_config* cfg, co
  * m_cov of the z-channel denoiser, device vector VAMPOMI_V_MCOV). get_cov_eff returns the fitted effects. */
 int vampomi_solver_set_covariates(vampomi_solver* s, int C, const double* Z_NxC);
 int vampomi_solver_get_cov_eff(vampomi_solver* s, int C, double* out_C);
+/* Checkpoint / resume (the reference's --estimate-file restart is dead code, src/vamp.cpp:71-79): save_state
+ * writes everything the next iteration depends on — iteration number, gam1, gamw, the prior, the covariate effects and the vectors
+ * r1, x1_hat, x2_hat (and the probit p1, tau1, alpha1) — into ONE file that all ranks share (every rank writes its marker slice at
+ * its offset; rank 0 the header); load_state on a freshly created solver of the same problem restores it, so that the following
+ * iterations equal those of an uninterrupted run (to rounding of two products that are recomputed instead of recycled). */
+int vampomi_solver_save_state(vampomi_solver* s, const char* path);
+int vampomi_solver_load_state(vampomi_solver* s, const char* path);
 int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M);
 int vampomi_solver_destroy(vampomi_solver* s);
 

@@ -123,6 +123,20 @@ def test_load_file_reads_the_shard_block(tmp_path):
         sh.load_file(str(tmp_path / "a.bin"))
         assert np.array_equal(sh.download(), A)
     sh.close()
+    # several 32 MB column groups per reader (the ring wraps around), buffered and O_DIRECT reads (4 KB-aligned spans around
+    # columns that are not 4 KB-aligned themselves; falls back to buffered reads where the file system has no O_DIRECT), a
+    # shard that starts in the middle of the file, padded (N = 4099) and unpadded (N = 4096) column strides
+    for N2, Mt2 in ((4099, 5000), (4096, 3000)):
+        B = np.random.default_rng(2).standard_normal((Mt2, N2))
+        B.tofile(tmp_path / "b.bin")
+        for rank, nranks in ((0, 1), (1, 3)):
+            sh = capi.Shard(N2, Mt2, nranks=nranks, rank=rank, nccl_id=False)
+            for direct, threads, depth in ((0, 2, 2), (1, 2, 3), (1, 1, 8), (0, 5, 3)):
+                sh.set_tuning("load_direct", direct); sh.set_tuning("load_threads", threads); sh.set_tuning("load_depth", depth)
+                sh.fill(0, 0.0)
+                sh.load_file(str(tmp_path / "b.bin"))
+                assert np.array_equal(sh.download(), B[sh.S:sh.S + sh.M]), (N2, rank, direct, threads, depth)
+            sh.close()
     sh = capi.Shard(N, Mt + 1)
     with pytest.raises(capi.VampomiError, match="too short"):
         sh.load_file(str(tmp_path / "a.bin"))

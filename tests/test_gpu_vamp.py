@@ -471,3 +471,96 @@ def test_main_meth_covariates_flags(name, tmp_path):
         assert_rows_close(csv_rows(open(f"{d}/out/g_{kind}.csv", "rb").read()), csv_rows(g[f"csv_{kind}"]), 1e-8, kind)
     res = subprocess.run([build.MAIN_METH] + [str(a) for a in args + ["--C", int(g["C"]) + 1]], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert res.returncode == 1 and "does not match to the specified number of covariates" in res.stdout
+
+
+@pytest.mark.parametrize("name,schedule", [("linear_wellcond", "onepass"), ("linear_wellcond", "plain"), ("probit_small", "onepass"),
+                                           ("linear_cov", "recycled"), ("probit_cov", "fused")])
+def test_checkpoint_and_resume_continue_the_same_run(name, schedule, tmp_path):
+    """vampomi_solver_save_state / _load_state: a run stopped after iteration 3 and resumed in a NEW context
+    continues with the iterates, CSV values and CG counts of the uninterrupted run."""
+    g = load_golden(name)
+    A, y_txt, beta = golden_inputs(g)
+    its = int(g["iterations"])
+    sh, sol = solver_for(g, A, y_txt, beta, **SCHEDULES[schedule])
+    full = [sol.step() for _ in range(its)]
+    sol.close(); sh.close()
+    stop = 2 if its <= 4 else 3
+    sh, sol = solver_for(g, A, y_txt, beta, **SCHEDULES[schedule])
+    for _ in range(stop):
+        sol.step()
+    ck = str(tmp_path / "ck.bin")
+    sol.save_state(ck)
+    sol.close(); sh.close()
+    sh, sol = solver_for(g, A, y_txt, beta, **SCHEDULES[schedule])
+    sol.load_state(ck)
+    for k in range(stop, its):
+        r = sol.step()
+        assert r["it"] == k + 1 and (r["k1"], r["k2"]) == (full[k]["k1"], full[k]["k2"])
+        assert rel_l2(r["x1"], full[k]["x1"]) < 1e-11 and rel_l2(r["r1"], full[k]["r1"]) < 1e-11, k
+        assert np.allclose(r["params"], full[k]["params"], rtol=1e-10, atol=1e-300) and np.allclose(r["metrics"], full[k]["metrics"], rtol=1e-10, equal_nan=True)
+        assert rel_l2(r["x1"], g["x1"][k]) < 1e-9                                 # and, with that, the reference's
+    with pytest.raises(capi.VampomiError):
+        sol.load_state(ck)                                                        # only a freshly created solver can be restored
+    sol.close(); sh.close()
+    sh2 = capi.Shard(int(g["N"]), int(g["M"]) - 1)
+    sh2.upload(A[:-1]); sh2.compute_stats()
+    other = capi.Solver(sh2, standardize_phen(y_txt) if g["model"] == "linear" else y_txt, model=g["model"])
+    with pytest.raises(capi.VampomiError):
+        other.load_state(ck)                                                      # written for another problem
+    other.close(); sh2.close()
+
+
+def test_main_meth_checkpoint_every_and_resume_from(tmp_path):
+    g = load_golden("linear_wellcond")
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    its = int(g["iterations"])
+    base = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
+            "--true-signal-file", f"{d}/ex_ts.bin", "--stop-criteria-thr", 0, "--seed", g["probe_seed"]] + list(g["extra"])
+    out = run_cli(base + ["--iterations", 4, "--checkpoint-every", 2])
+    assert os.path.isfile(f"{d}/out/g_checkpoint_it_2.bin") and os.path.isfile(f"{d}/out/g_checkpoint_it_4.bin") and "--checkpoint-every 2" in out
+    size4 = os.path.getsize(f"{d}/out/g_params.csv")
+    out = run_cli(base + ["--iterations", its, "--resume-from", f"{d}/out/g_checkpoint_it_4.bin"])
+    assert "resuming after iteration 4" in out and "iteration = 5" in out and "iteration = 4\n" not in out
+    assert os.path.getsize(f"{d}/out/g_params.csv") > size4
+    for k in range(1, its + 1):
+        assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), g["x1"][k - 1]) < 1e-9
+        assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < 1e-9
+    for kind in ("params", "metrics"):
+        got = open(f"{d}/out/g_{kind}.csv", "rb").read()
+        assert len(got) == len(bytes(g[f"csv_{kind}"]))
+        assert_rows_close(csv_rows(got), csv_rows(g[f"csv_{kind}"]), 1e-8, kind)
+    res = subprocess.run([build.MAIN_METH] + [str(a) for a in base + ["--iterations", its, "--resume-from", f"{d}/out/nothing.bin"]],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert res.returncode == 1 and "could not resume" in res.stdout
+
+
+def test_several_hutchinson_probes_average_the_single_probe_estimates():
+    """cfg.probes = P (not in the reference): alpha2 = gam2 * mean over P probes of u^T Q^-1 u, with the probes of
+    the counter hash under seeds seed + p * golden ratio; P = 1 is the reference-parity run."""
+    g = load_golden("linear_wellcond")
+    A, y_txt, beta = golden_inputs(g)
+    seed = int(g["probe_seed"])
+    sh, sol = solver_for(g, A, y_txt, beta, probes=3)
+    r = sol.step()
+    alpha2, gam2 = r["params"][2], r["params"][3]
+    vm = []
+    for p in range(3):
+        sh.draw_probe((seed + 0x9E3779B97F4A7C15 * p) % 2 ** 64, 1)
+        _, _, vmu = sh.cg_solve(capi.V_BERN, V_QINV_BERN, sol.cfg.gamw, gam2, tol=1e-5, onsager_mode=True)
+        vm.append(vmu)
+    assert abs(alpha2 - gam2 * np.mean(vm)) < 1e-12 * alpha2 and len(set(vm)) == 3
+    r2 = sol.step()
+    assert 0 < r2["params"][2] < 1 and np.isfinite(r2["x1"]).all()
+    sol.close(); sh.close()
+    sh, sol = solver_for(g, A, y_txt, beta, probes=3)
+    rr = sol.step()
+    assert rr["params"] == r["params"]                                            # reproducible
+    sol.close(); sh.close()
+    gp = load_golden("probit_small")
+    Ap, yp, bp = golden_inputs(gp)
+    sh, sol = solver_for(gp, Ap, yp, bp, probes=2)
+    r = sol.step(); r = sol.step()
+    assert 0 < r["params"][4] < 1 and np.isfinite(r["r1"]).all()
+    sol.close(); sh.close()

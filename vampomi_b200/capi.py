@@ -33,7 +33,7 @@ class SolverConfig(C.Structure):
                 ("EM_err_thr", C.c_double), ("learn_vars", C.c_int), ("learn_prior_delay", C.c_int),
                 ("merge_vars_thr", C.c_double), ("L", C.c_int), ("probs", C.c_double * MAX_MIX),
                 ("vars", C.c_double * MAX_MIX), ("seed", C.c_ulonglong), ("redundant_passes", C.c_int),
-                ("fuse_passes", C.c_int)]
+                ("fuse_passes", C.c_int), ("probes", C.c_int)]
 
 
 class IterResult(C.Structure):
@@ -112,6 +112,8 @@ _SIGNATURES = {
     "vampomi_solver_get_cov_eff": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "vampomi_host_read_covariates": (C.c_longlong, [C.c_char_p, C.c_int, C.c_int, c_double_p]),
     "vampomi_host_newton_cov": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int, C.c_int, c_double_p]),
+    "vampomi_solver_save_state": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vampomi_solver_load_state": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vampomi_solver_step": (C.c_int, [C.c_void_p, C.POINTER(IterResult), c_double_p, c_double_p]),
     "vampomi_solver_destroy": (C.c_int, [C.c_void_p]),
     "vampomi_host_csv_row": (C.c_int, [C.c_uint, c_double_p, C.c_int, C.c_char_p, C.c_int]),
@@ -478,6 +480,12 @@ class Solver:
         out, po = _out(self.C)
         _check(self.lib.vampomi_solver_get_cov_eff(self.h, self.C, po), "solver_get_cov_eff")
         return out
+
+    def save_state(self, path):
+        _check(self.lib.vampomi_solver_save_state(self.h, str(path).encode()), "solver_save_state")
+
+    def load_state(self, path):
+        _check(self.lib.vampomi_solver_load_state(self.h, str(path).encode()), "solver_load_state")
 
     def step(self, want_vectors=True, out_x1=None, out_r1=None):
         res = IterResult()

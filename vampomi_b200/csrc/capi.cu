@@ -291,6 +291,8 @@ using namespace vampomi;
 
 extern "C" {
 
+static void load_ring_free(vampomi_ctx* c);
+
 const char* vampomi_last_error(void) { return g_err; }
 int vampomi_abi_version(void) { return VAMPOMI_ABI_VERSION; }
 
@@ -409,6 +411,7 @@ int vampomi_destroy(vampomi_ctx* c) {
     if (c->cg_poll_host) cudaFreeHost(c->cg_poll_host);
     if (c->stage) cudaFreeHost(c->stage);
     for (auto e : c->cg_events) if (e) cudaEventDestroy(e);
+    load_ring_free(c);
     for (int k = 0; k < 2; k++) {
         if (c->dump_dev[k]) cudaFree(c->dump_dev[k]);
         if (c->dump_host[k]) cudaFreeHost(c->dump_host[k]);
@@ -528,10 +531,63 @@ int vampomi_download_columns(vampomi_ctx* c, long long j0, long long ncols, doub
     return VAMPOMI_OK;
 }
 
+// The ingest path (data::read_methylation_data, src/data.cpp:116-153): T reader threads, each with a ring of `load_depth` pinned
+// slots of 32 MB and its own copy stream — a slot is read from the file while the earlier ones are still on their way to HBM —
+// column groups dealt round-robin. The pinned ring belongs to the CONTEXT and is allocated once (pinning 64 MB takes tens of
+// milliseconds; a ring allocated inside the call, per thread, made the thread scaling erratic). Page-cache reads are a kernel
+// memcpy per byte: several threads are needed to feed PCIe gen5 (~50 GB/s). With knob load_direct = 1 the file is opened with
+// O_DIRECT and read in 4 KB-aligned spans straight into the pinned slots (no page-cache copy; the span's head and tail
+// padding is skipped by the device copy), which is the path for files larger than host memory.
+namespace {
+constexpr size_t kLoadSlotBytes = 32ull << 20;
+constexpr size_t kLoadAlign = 4096;
+struct LoadRing {
+    int threads = 0, depth = 0;
+    std::vector<unsigned char*> slot;          // [threads][depth], each kLoadSlotBytes + 2 * kLoadAlign
+    std::vector<double*> dslot;                // FP32 storage: dense FP64 staging on the device, rounded into place
+    std::vector<cudaEvent_t> ev;
+    std::vector<cudaStream_t> st;
+};
+}  // namespace
+
+static void load_ring_free(vampomi_ctx* c) {
+    LoadRing* r = static_cast<LoadRing*>(c->load_ring);
+    if (!r) return;
+    for (auto p : r->slot) if (p) cudaFreeHost(p);
+    for (auto p : r->dslot) if (p) cudaFree(p);
+    for (auto e : r->ev) if (e) cudaEventDestroy(e);
+    for (auto s : r->st) if (s) cudaStreamDestroy(s);
+    delete r;
+    c->load_ring = nullptr;
+}
+
+static int load_ring_ensure(vampomi_ctx* c, int T, int depth) {
+    LoadRing* r = static_cast<LoadRing*>(c->load_ring);
+    if (r && r->threads >= T && r->depth >= depth) return VAMPOMI_OK;
+    load_ring_free(c);
+    r = new (std::nothrow) LoadRing();
+    VO_ARG(r != nullptr, "load_file: out of host memory");
+    c->load_ring = r;
+    r->threads = T; r->depth = depth;
+    r->slot.assign((size_t)T * depth, nullptr);
+    r->dslot.assign((size_t)T * depth, nullptr);
+    r->ev.assign((size_t)T * depth, nullptr);
+    r->st.assign((size_t)T, nullptr);
+    for (int t = 0; t < T; t++) VO_CUDA(cudaStreamCreateWithFlags(&r->st[t], cudaStreamNonBlocking));
+    for (size_t i = 0; i < r->slot.size(); i++) {
+        VO_CUDA(cudaMallocHost(&r->slot[i], kLoadSlotBytes + 2 * kLoadAlign));
+        VO_CUDA(cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming));
+        if (c->storage == VAMPOMI_STORE_F32) VO_CUDA(cudaMalloc(&r->dslot[i], kLoadSlotBytes));
+    }
+    return VAMPOMI_OK;
+}
+
 int vampomi_load_file(vampomi_ctx* c, const char* path) {
     VO_ARG(c && path, "load_file: NULL argument");
     VO_CUDA(cudaSetDevice(c->device));
-    int fd = open(path, O_RDONLY);
+    const bool direct = c->tune.load_direct != 0;
+    int fd = open(path, direct ? (O_RDONLY | O_DIRECT) : O_RDONLY);
+    if (fd < 0 && direct) fd = open(path, O_RDONLY);           // file systems without O_DIRECT (tmpfs): the buffered path
     if (fd < 0) { set_error("could not open methylation file %s", path); return VAMPOMI_ERR_IO; }
     const size_t col_bytes = (size_t)c->N * sizeof(double);
     struct stat sb;
@@ -540,58 +596,62 @@ int vampomi_load_file(vampomi_ctx* c, const char* path) {
         set_error("%s is too short for N=%d and markers [%lld,%lld)", path, c->N, c->S, c->S + c->M);
         return VAMPOMI_ERR_IO;
     }
-    // T reader threads, each with two pinned staging buffers and its own copy stream: pread of one 32 MB column group
-    // overlaps the host-to-device copy of the previous one, and T of these pipelines run side by side (a single pread
-    // stream tops out at a few GB/s; PCIe gen5 takes ~50 GB/s). Column groups are dealt round-robin.
-    long long cols_per_slot = (long long)((32ull << 20) / col_bytes);
-    if (cols_per_slot < 1) cols_per_slot = 1;
+    const size_t file_size = (size_t)sb.st_size;
+    long long cols_per_slot = (long long)(kLoadSlotBytes / col_bytes);
+    if (cols_per_slot < 1) { close(fd); set_error("load_file: one column (%zu bytes) does not fit a staging slot", col_bytes); return VAMPOMI_ERR_ARG; }
     if (cols_per_slot > c->M) cols_per_slot = c->M;
     const long long nitems = (c->M + cols_per_slot - 1) / cols_per_slot;
     int T = c->tune.load_threads;
     if (T < 1) T = 1;
     if (T > 16) T = 16;
     if ((long long)T > nitems) T = (int)nitems;
+    int depth = c->tune.load_depth;
+    if (depth < 2) depth = 2;
+    if (depth > 8) depth = 8;
+    int rc_ring = load_ring_ensure(c, T, depth);
+    if (rc_ring != VAMPOMI_OK) { close(fd); return rc_ring; }
+    LoadRing* ring = static_cast<LoadRing*>(c->load_ring);
+    depth = ring->depth;
     std::vector<int> rcs((size_t)T, VAMPOMI_OK);
     std::vector<std::string> errs((size_t)T);
     auto worker = [&](int t) {
         auto fail = [&](int code, const std::string& msg) { rcs[t] = code; errs[t] = msg; };
         if (cudaSetDevice(c->device) != cudaSuccess) return fail(VAMPOMI_ERR_CUDA, "cudaSetDevice failed in a loader thread");
-        double* slot[2] = {nullptr, nullptr};
-        double* dslot[2] = {nullptr, nullptr};              // FP32 storage: dense FP64 staging on the device, rounded into place
-        cudaEvent_t ev[2] = {nullptr, nullptr};
-        cudaStream_t st = nullptr;
-        bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
-        for (int k = 0; k < 2 && ok; k++) {
-            ok = cudaMallocHost(&slot[k], (size_t)cols_per_slot * col_bytes) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) == cudaSuccess;
-            if (ok && c->storage == VAMPOMI_STORE_F32) ok = cudaMalloc(&dslot[k], (size_t)cols_per_slot * col_bytes) == cudaSuccess;
-        }
-        if (!ok) fail(VAMPOMI_ERR_CUDA, "could not allocate pinned staging buffers");
+        cudaStream_t st = ring->st[t];
         int k = 0;
-        for (long long item = t; item < nitems && ok; item += T, k ^= 1) {
+        for (long long item = t; item < nitems; item += T, k = (k + 1) % depth) {
+            const size_t si = (size_t)t * ring->depth + k;
             const long long j = item * cols_per_slot;
             const long long nc = c->M - j < cols_per_slot ? c->M - j : cols_per_slot;
-            if (cudaEventSynchronize(ev[k]) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "event sync failed"); break; }   // slot free again?
-            size_t want = (size_t)nc * col_bytes, got = 0;
-            const off_t off = (off_t)((size_t)(c->S + j) * col_bytes);     // byte offset S*N*8, src/data.cpp:134
-            while (got < want) {
-                ssize_t r = pread(fd, (char*)slot[k] + got, want - got, off + (off_t)got);
-                if (r <= 0) { fail(VAMPOMI_ERR_IO, std::string("short read from ") + path); ok = false; break; }
+            if (cudaEventSynchronize(ring->ev[si]) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "event sync failed"); break; }   // slot free again?
+            const size_t want = (size_t)nc * col_bytes;
+            const size_t off = (size_t)(c->S + j) * col_bytes;                 // byte offset S*N*8, src/data.cpp:134
+            // O_DIRECT wants offset, length and buffer aligned: read the enclosing 4 KB-aligned span, copy from inside it
+            const size_t a0 = direct ? off / kLoadAlign * kLoadAlign : off;
+            size_t a1 = direct ? (off + want + kLoadAlign - 1) / kLoadAlign * kLoadAlign : off + want;
+            unsigned char* base = (unsigned char*)(((uintptr_t)ring->slot[si] + kLoadAlign - 1) / kLoadAlign * kLoadAlign);
+            size_t got = 0, span = a1 - a0;
+            bool ok = true;
+            while (got < span) {
+                ssize_t r = pread(fd, base + got, span - got, (off_t)(a0 + got));
+                if (r < 0) { ok = false; break; }
+                if (r == 0) break;                                             // end of file inside the padded tail of the last span
                 got += (size_t)r;
             }
-            if (!ok) break;
+            if (!ok || a0 + got < off + want || (got < span && a0 + got < file_size)) { fail(VAMPOMI_ERR_IO, std::string("short read from ") + path); break; }
+            const unsigned char* src = base + (off - a0);
             bool copied;
             if (c->storage == VAMPOMI_STORE_F32)
-                copied = cudaMemcpyAsync(dslot[k], slot[k], want, cudaMemcpyHostToDevice, st) == cudaSuccess &&
-                         launch_f64_to_f32(c, c->A32 + (size_t)j * c->ld, dslot[k], nc, st) == VAMPOMI_OK;
+                copied = cudaMemcpyAsync(ring->dslot[si], src, want, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                         launch_f64_to_f32(c, c->A32 + (size_t)j * c->ld, ring->dslot[si], nc, st) == VAMPOMI_OK;
+            else if (c->ld == (size_t)c->N)                                    // no pad rows: one linear copy
+                copied = cudaMemcpyAsync(c->A + (size_t)j * c->ld, src, want, cudaMemcpyHostToDevice, st) == cudaSuccess;
             else
-                copied = cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), slot[k], col_bytes, col_bytes, (size_t)nc,
+                copied = cudaMemcpy2DAsync(c->A + (size_t)j * c->ld, c->ld * sizeof(double), src, col_bytes, col_bytes, (size_t)nc,
                                            cudaMemcpyHostToDevice, st) == cudaSuccess;
-            if (!copied || cudaEventRecord(ev[k], st) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "host-to-device copy failed"); break; }
+            if (!copied || cudaEventRecord(ring->ev[si], st) != cudaSuccess) { fail(VAMPOMI_ERR_CUDA, "host-to-device copy failed"); break; }
         }
-        if (st) cudaStreamSynchronize(st);
-        for (int q = 0; q < 2; q++) { if (slot[q]) cudaFreeHost(slot[q]); if (dslot[q]) cudaFree(dslot[q]); if (ev[q]) cudaEventDestroy(ev[q]); }
-        if (st) cudaStreamDestroy(st);
+        cudaStreamSynchronize(st);
     };
     std::vector<std::thread> th;
     for (int t = 1; t < T; t++) th.emplace_back(worker, t);
@@ -992,7 +1052,7 @@ int vampomi_set_tuning(vampomi_ctx* c, const char* name, int value) {
         {"atx_unroll", &c->tune.atx_unroll, 0, 8}, {"atx_ctas_per_sm", &c->tune.atx_ctas_per_sm, 0, 32},
         {"cg_depth", &c->tune.cg_depth, 1, 32},     {"ax_impl", &c->tune.ax_impl, 0, 1},
         {"atx_impl", &c->tune.atx_impl, 0, 3},       {"xchg", &c->tune.xchg, 0, 1},
-        {"load_threads", &c->tune.load_threads, 1, 16}, {"ld_hint", &c->tune.ld_hint, 0, 3},
+        {"load_threads", &c->tune.load_threads, 1, 16}, {"load_depth", &c->tune.load_depth, 2, 8}, {"load_direct", &c->tune.load_direct, 0, 1}, {"ld_hint", &c->tune.ld_hint, 0, 3},
         {"interleave", &c->tune.interleave, 0, 1},       {"center_split", &c->tune.center_split, 0, 1},
         {"grid_balance", &c->tune.grid_balance, 0, 1},   {"dump_stream", &c->tune.dump_stream, 0, 1},
         {"xchg_ll", &c->tune.xchg_ll, 0, 1},             {"multi_ax_occ", &c->tune.multi_ax_occ, 0, 3},

@@ -109,7 +109,9 @@ struct Tuning {
     int atx_impl = 3;                // 0 = warp per column group, 1 = bulk-copy pipeline, 2 = CTA per column group, 3 = auto (2 when N >= 4096, else 0)
     int xchg = 1;                    // 1 = fused peer-memory all-reduce (xchg.cuh) when it could be set up, 0 = NCCL collectives
     int xchg_ll = 1;                 // vector exchange: 1 = tagged words (no fence, no flags), 0 = payload + system fence + per-CTA flags
-    int load_threads = 4;            // parallel pread -> pinned -> HBM pipelines of vampomi_load_file
+    int load_threads = 8;            // parallel pread -> pinned -> HBM pipelines of vampomi_load_file
+    int load_depth = 3;              // pinned 32 MB slots per reader thread (reads in flight behind the one being filled)
+    int load_direct = 0;             // 1 = O_DIRECT reads in 4 KB-aligned spans straight into the pinned slots (no page-cache copy)
     int ld_hint = 0;                 // L2 hint on the streaming loads of the default kernel shapes: 0 none, 1 L2::256B, 2 L2::evict_first, 3 both
     int interleave = 0;              // experiment: deal column groups round-robin over the grid instead of one contiguous range per CTA
     int multi_ax_rv = 0;             // multi-vector A x: 32-byte vectors per thread per column (0 = 1)
@@ -171,6 +173,7 @@ struct vampomi_ctx {
     unsigned char* xchg_region = nullptr;
     unsigned int* xchg_local = nullptr;
     void* xchg_ipc_opened[vampomi::XCHG_MAX_RANKS] = {};
+    void* load_ring = nullptr;       // pinned staging ring of vampomi_load_file (capi.cu LoadRing), allocated once
     int* xchg_err_host = nullptr;    // pinned, device-mapped: raised by a peer wait that gave up (xchg.cuh XchgDeadline)
     cudaEvent_t cg_events[32] = {};  // completion-poll ring of the CG loop, created once
     ncclComm_t comm = nullptr;

@@ -159,6 +159,7 @@ int run_infere(Rank& r) {
     cfg.L = (int)o.probs.size();
     for (int i = 0; i < cfg.L; i++) { cfg.probs[i] = o.probs[i]; cfg.vars[i] = o.vars[i]; }
     cfg.seed = o.seed;
+    cfg.probes = o.probes;
     cfg.redundant_passes = o.schedule == "reference" ? 1 : 0;
     cfg.fuse_passes = o.schedule == "onepass" ? 3 : o.schedule == "recycled" ? 2 : o.schedule == "fused" ? 1 : 0;
 
@@ -179,15 +180,25 @@ int run_infere(Rank& r) {
         if (vamp.set_covariates((int)o.C, Z.data()) != VAMPOMI_OK) return fatal_abi(r, "covariates");
     }
 
+    // --resume-from: continue from a checkpoint of this very problem (vampomi_solver_load_state); the CSV files are kept and the
+    // remaining rows land at their usual offsets
+    int first_it = 1;
+    const bool resuming = !o.resume_from.empty();
+    if (resuming) {
+        const int rc_load = vamp.load_state(o.resume_from.c_str());
+        if (!r.agree(rc_load == VAMPOMI_OK)) return fatal(r, "could not resume from " + o.resume_from + " (missing, damaged or written for another problem)");
+        first_it = vamp.iteration() + 1;
+        if (r.root()) std::cout << "INFO  : resuming after iteration " << vamp.iteration() << " from " << o.resume_from << std::endl;
+    }
     // setup_io (src/vamp.cpp:854-882): rank 0 owns the three CSVs
     const std::string base = o.out_dir + "/" + o.out_name;
     CsvFile csv_metrics, csv_params, csv_prior;
     if (r.root()) {
-        if (!csv_metrics.open(base + "_metrics.csv") || !csv_params.open(base + "_params.csv") || !csv_prior.open(base + "_prior.csv")) {
+        if (!csv_metrics.open(base + "_metrics.csv", resuming) || !csv_params.open(base + "_params.csv", resuming) || !csv_prior.open(base + "_prior.csv", resuming)) {
             fprintf(stderr, "*FATAL*: could not create the CSV files under %s\n", o.out_dir.c_str());   // check_mpi abort
             return 1;
         }
-        if (cfg.model == 0) {                                                                  // headers only in infere_linear, src/vamp.cpp:115-123
+        if (cfg.model == 0 && !resuming) {                                                     // headers only in infere_linear, src/vamp.cpp:115-123
             csv_metrics.header({"iteration", "R2 denoising", "x1 correlation denoising", "R2 LMMSE", "x2 correlation LMMSE",
                                 "z1 correlation denoising", "z2 correlation LMMSE"});
             csv_params.header({"iteration", "alpha1", "gam1", "alpha2", "gam2", "gamw"});
@@ -208,7 +219,7 @@ int run_infere(Rank& r) {
     auto join_writer = [&]() -> bool { return !writer.valid() || writer.get(); };
     double total_time = 0;
     const int max_iter = (int)o.iterations;
-    for (int it = 1; it <= max_iter; it++) {
+    for (int it = first_it; it <= max_iter; it++) {
         std::vector<double>&x1s = x1buf[it & 1], &r1s = r1buf[it & 1];
         if (r.root())
             std::cout << std::endl << "********************" << std::endl << "iteration = " << it << std::endl
@@ -243,6 +254,11 @@ int run_infere(Rank& r) {
             std::cout << "...stopping criteria assessment" << std::endl;
             std::cout << "x1_hat NMSE = " << res.nmse << std::endl;                            // :415-417
             std::cout << "stop_criteria_thr = " << o.stop_criteria_thr << std::endl;
+        }
+        if (o.checkpoint_every > 0 && it % o.checkpoint_every == 0) {
+            const std::string ck = base + "_checkpoint_it_" + std::to_string(it) + ".bin";
+            if (!r.agree(vamp.save_state(ck.c_str()) == VAMPOMI_OK)) return fatal(r, "could not write " + ck);
+            if (r.root()) std::cout << "checkpoint filepath_out is " << ck << std::endl;
         }
         if (it > 1 && res.nmse < o.stop_criteria_thr) {                                        // :419-423
             if (r.root()) std::cout << "...stopping criteria fulfilled" << std::endl;

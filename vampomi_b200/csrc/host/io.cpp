@@ -83,8 +83,12 @@ bool store_vec(const std::string& path, const double* v, long long M, long long 
     return done == want;
 }
 
-bool CsvFile::open(const std::string& path) {
+bool CsvFile::open(const std::string& path, bool keep_existing) {
     close();
+    if (keep_existing) {
+        fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT, 0644);
+        return fd_ >= 0;
+    }
     unlink(path.c_str());
     fd_ = ::open(path.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0644);
     return fd_ >= 0;

@@ -22,7 +22,7 @@ class CsvFile {
 public:
     CsvFile() = default;
     ~CsvFile() { close(); }
-    bool open(const std::string& path);
+    bool open(const std::string& path, bool keep_existing = false);   // keep_existing: resume — rows land at their usual offsets
     void header(const std::vector<std::string>& names);
     void row(unsigned it, const std::vector<double>& values);
     void close();

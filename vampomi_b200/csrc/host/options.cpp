@@ -122,6 +122,19 @@ bool Options::parse(int argc, char** argv, std::string* echo) {
                 return false;
             }
             ss << "--schedule " << schedule << "\n";
+        } else if (!strcmp(a, "--probes") || !strcmp(a, "--checkpoint-every")) {
+            if (!need_value()) return false;
+            const int v = atoi(argv[++i]);
+            if (v < (a[2] == 'p' ? 1 : 0)) {
+                std::cout << "FATAL  : option " << a << " has to be a " << (a[2] == 'p' ? "strictly positive" : "non-negative") << " integer! (" << argv[i] << " was passed)" << std::endl;
+                return false;
+            }
+            (a[2] == 'p' ? probes : checkpoint_every) = v;
+            ss << a << " " << v << "\n";
+        } else if (!strcmp(a, "--resume-from")) {
+            if (!need_value()) return false;
+            resume_from = argv[++i];
+            ss << "--resume-from " << resume_from << "\n";
         } else if (!strcmp(a, "--gpus")) {
             if (!need_value()) return false;
             gpus = atoi(argv[++i]);

@@ -29,6 +29,9 @@ struct Options {
     // additions
     unsigned long long seed = 0;
     int gpus = 1;
+    int probes = 1;                     // --probes P: Hutchinson probes per iteration (1 = the reference)
+    int checkpoint_every = 0;           // --checkpoint-every n: write {out}_checkpoint_it_{k}.bin after every n-th iteration
+    std::string resume_from;            // --resume-from file: continue a run from such a checkpoint
     bool probit_entry = false;          // entered through main_meth_probit: model forced to bin_class, probit `test` / `predict` run modes
     std::string schedule = "onepass";   // onepass | recycled | fused | plain | reference (vampomi_solver_config::fuse_passes / redundant_passes)
     std::string storage = "f64";     // "f32": hold the marker block rounded to FP32 in HBM (arithmetic stays FP64)

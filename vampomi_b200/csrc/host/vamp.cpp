@@ -3,6 +3,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <iostream>
 #include "cov.h"
 #include "io.h"
@@ -45,7 +47,7 @@ Vamp::Vamp(vampomi_ctx* ctx, const vampomi_solver_config& cfg) : ctx_(ctx), cfg_
 }
 
 int Vamp::init(const double* y, const double* true_signal, const double* x1hat_init) {
-    VH(vampomi_dims(ctx_, &N_, &Mt_, nullptr, nullptr));
+    VH(vampomi_dims(ctx_, &N_, &Mt_, nullptr, &rank_));
     VH(vampomi_shard(ctx_, &M_, &S_));
     if (cfg_.L < 1 || cfg_.L > VAMPOMI_MAX_MIX) return VAMPOMI_ERR_ARG;
     probs_.assign(cfg_.probs, cfg_.probs + cfg_.L);
@@ -108,6 +110,114 @@ int Vamp::fit_covariates() {
         std::cout << std::endl;
         if (cfg_.model == 1) std::cout << "Computing covariate effects took " << wall_s() - t0 << " seconds." << std::endl;   // src/vamp_probit.cpp:94
     }
+    return VAMPOMI_OK;
+}
+
+int Vamp::apply_covariates() {
+    std::vector<double> v((size_t)N_);
+    for (int i = 0; i < N_; i++) {
+        double s = 0;
+        for (int j = 0; j < C_; j++) s += Z_[(size_t)i * C_ + j] * cov_eff_[j];
+        // linear: y -= Z cov_eff (src/vamp.cpp:166-168) changes the loop's LOCAL copy of the phenotype only: it feeds A^T y (:303),
+        // while updateNoisePrec (:506) and err_measures (:817) fetch the unadjusted phenotype from the dataset again — so the
+        // adjusted vector gets a device vector of its own (VAMPOMI_V_MCOV, otherwise unused by the linear model) and Y stays.
+        // probit: m_cov of g1_bin_class / g1d_bin_class (src/vamp_probit.cpp:214-232)
+        v[i] = cfg_.model == 0 ? y_host_[i] - s : s;
+    }
+    VH(vampomi_vec_set(ctx_, VAMPOMI_V_MCOV, v.data()));
+    aty_ready_ = false;
+    return VAMPOMI_OK;
+}
+
+// ---- checkpoint file: 4096-byte header, then r1[Mt], x1_hat[Mt], x2_hat[Mt], p1[N] as FP64 -----------------------------------
+namespace {
+struct CkptHeader {
+    char magic[8];
+    int model, it, N, L, C, reserved;
+    long long Mt;
+    double gam1, gamw, alpha1, tau1, gam2, eta1, eta2, alpha2;
+    double probs[VAMPOMI_MAX_MIX], vars[VAMPOMI_MAX_MIX];
+    double cov_eff[64];
+};
+static_assert(sizeof(CkptHeader) <= 4096, "checkpoint header");
+constexpr long long kCkptData = 4096;
+bool pwrite_all(int fd, const void* buf, size_t n, long long off) {
+    size_t done = 0;
+    while (done < n) {
+        ssize_t r = pwrite(fd, (const char*)buf + done, n - done, (off_t)(off + (long long)done));
+        if (r <= 0) return false;
+        done += (size_t)r;
+    }
+    return true;
+}
+bool pread_all(int fd, void* buf, size_t n, long long off) {
+    size_t done = 0;
+    while (done < n) {
+        ssize_t r = pread(fd, (char*)buf + done, n - done, (off_t)(off + (long long)done));
+        if (r <= 0) return false;
+        done += (size_t)r;
+    }
+    return true;
+}
+}  // namespace
+
+int Vamp::save_state(const char* path) {
+    if (!path || it_ < 1 || C_ > 64) return VAMPOMI_ERR_ARG;
+    int fd = ::open(path, O_WRONLY | O_CREAT, 0644);
+    if (fd < 0) return VAMPOMI_ERR_IO;
+    bool ok = true;
+    std::vector<double> buf((size_t)std::max<long long>(M_, N_));
+    const int vecs[3] = {VAMPOMI_V_R1, VAMPOMI_V_X1, VAMPOMI_V_X2};
+    for (int k = 0; k < 3 && ok; k++) {
+        ok = vampomi_vec_get(ctx_, vecs[k], buf.data()) == VAMPOMI_OK &&
+             pwrite_all(fd, buf.data(), (size_t)M_ * sizeof(double), kCkptData + ((long long)k * Mt_ + S_) * 8);
+    }
+    if (ok && rank_ == 0) {
+        CkptHeader h;
+        std::memset(&h, 0, sizeof(h));
+        std::memcpy(h.magic, "VAMPCKP1", 8);
+        h.model = cfg_.model; h.it = it_; h.N = N_; h.L = (int)probs_.size(); h.C = C_; h.Mt = Mt_;
+        h.gam1 = gam1_; h.gamw = gamw_; h.alpha1 = alpha1_; h.tau1 = tau1_; h.gam2 = gam2_; h.eta1 = eta1_; h.eta2 = eta2_; h.alpha2 = alpha2_;
+        for (int i = 0; i < h.L; i++) { h.probs[i] = probs_[i]; h.vars[i] = vars_[i]; }
+        for (int j = 0; j < C_; j++) h.cov_eff[j] = cov_eff_[j];
+        ok = pwrite_all(fd, &h, sizeof(h), 0);
+        if (ok && cfg_.model == 1)
+            ok = vampomi_vec_get(ctx_, VAMPOMI_V_P1, buf.data()) == VAMPOMI_OK &&
+                 pwrite_all(fd, buf.data(), (size_t)N_ * sizeof(double), kCkptData + 3LL * Mt_ * 8);
+    }
+    ::close(fd);
+    return ok ? VAMPOMI_OK : VAMPOMI_ERR_IO;
+}
+
+int Vamp::load_state(const char* path) {
+    if (!path || it_ != 0) return VAMPOMI_ERR_ARG;            // on a freshly initialised solver only
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return VAMPOMI_ERR_IO;
+    CkptHeader h;
+    bool ok = pread_all(fd, &h, sizeof(h), 0) && !std::memcmp(h.magic, "VAMPCKP1", 8);
+    if (ok && (h.model != cfg_.model || h.N != N_ || h.Mt != Mt_ || h.L < 1 || h.L > VAMPOMI_MAX_MIX || h.C != C_)) { ::close(fd); return VAMPOMI_ERR_ARG; }
+    std::vector<double> buf((size_t)std::max<long long>(M_, N_));
+    const int vecs[3] = {VAMPOMI_V_R1, VAMPOMI_V_X1, VAMPOMI_V_X2};
+    for (int k = 0; k < 3 && ok; k++)
+        ok = pread_all(fd, buf.data(), (size_t)M_ * sizeof(double), kCkptData + ((long long)k * Mt_ + S_) * 8) &&
+             vampomi_vec_set(ctx_, vecs[k], buf.data()) == VAMPOMI_OK;
+    if (ok && cfg_.model == 1)
+        ok = pread_all(fd, buf.data(), (size_t)N_ * sizeof(double), kCkptData + 3LL * Mt_ * 8) && vampomi_vec_set(ctx_, VAMPOMI_V_P1, buf.data()) == VAMPOMI_OK;
+    ::close(fd);
+    if (!ok) return VAMPOMI_ERR_IO;
+    it_ = h.it;
+    gam1_ = h.gam1; gamw_ = h.gamw; alpha1_ = h.alpha1; tau1_ = h.tau1; gam2_ = h.gam2; eta1_ = h.eta1; eta2_ = h.eta2; alpha2_ = h.alpha2;
+    probs_.assign(h.probs, h.probs + h.L);
+    vars_.assign(h.vars, h.vars + h.L);
+    if (C_ > 0) {
+        cov_eff_.assign(h.cov_eff, h.cov_eff + C_);
+        VH(apply_covariates());
+    }
+    // what an uninterrupted run would carry over by recycling is recomputed: A^T y at its next use, A^T A x2_hat inside the next
+    // solve, and Z2 = A x2_hat (the tracked product of the warm system must hold A * start on entry)
+    aty_ready_ = false;
+    ata_x2_ready_ = false;
+    if (cfg_.model == 0) VH(vampomi_ax_dev(ctx_, VAMPOMI_V_X2, VAMPOMI_V_Z2));
     return VAMPOMI_OK;
 }
 
@@ -202,17 +312,7 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         const double t_cov0 = wall_s();
         if (it == 1 && C_ > 0) {
             VH(fit_covariates());
-            // y -= Z cov_eff (:166-168) changes the loop's LOCAL copy of the phenotype only: it feeds A^T y (:303), while
-            // updateNoisePrec (:506) and err_measures (:817) fetch the unadjusted phenotype from the dataset again. So the adjusted
-            // vector gets a device vector of its own (VAMPOMI_V_MCOV, unused by the linear model otherwise) and Y stays as it is.
-            std::vector<double> y_adj = y_host_;
-            for (int i = 0; i < N_; i++) {
-                double s = 0;
-                for (int j = 0; j < C_; j++) s += Z_[(size_t)i * C_ + j] * cov_eff_[j];
-                y_adj[i] -= s;
-            }
-            VH(vampomi_vec_set(ctx_, VAMPOMI_V_MCOV, y_adj.data()));
-            aty_ready_ = false;
+            VH(apply_covariates());
         }
         if (verbose) std::cout << "time for covariates effects update = " << wall_s() - t_cov0 << " seconds." << std::endl;   // :173
     }
@@ -308,9 +408,44 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         t_cg1 = t_ons1 = wall_s();
         VH(measures1());
     }
+    // further Hutchinson probes (cfg.probes > 1; not in the reference): one more Onsager solve each, from the same counter hash
+    // with the probe index folded into the seed; u^T Q^-1 u and u^T A^T A Q^-1 u are averaged over the probes
+    const int P = cfg_.probes > 1 ? cfg_.probes : 1;
+    double trace_extra = 0;                                     // sum over the extra probes of <u, A^T A Q^-1 u>
+    double trace_first = 0;
+    bool ata_x2_recycled = false;
+    if (P > 1) {
+        // <u_1, A^T A Q^-1 u_1> of the first probe must be taken now: BERN / QINV_BERN and the CG work vectors are about to be
+        // reused by the extra solves — and so must the recycled A^T A x2_hat, which lives in the LMMSE solve's residual
+        if (recycle) {
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_V, -1.0, VAMPOMI_V_CG_R, 1.0));
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_ATA_X2, -gam2_, VAMPOMI_V_X2, tau_solved));
+            ata_x2_recycled = true;
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_BERN, -1.0, VAMPOMI_V_CG2_R, 1.0));
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_USER_M0, -gam2_, VAMPOMI_V_QINV_BERN, tau_solved));
+        } else {
+            VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));
+            VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));
+        }
+        const int kd[1] = {VAMPOMI_DOT}, ad[1] = {VAMPOMI_V_BERN}, bd[1] = {VAMPOMI_V_USER_M0};
+        VH(vampomi_dots(ctx_, 1, kd, ad, bd, nullptr, &trace_first));
+        for (int p = 1; p < P; p++) {
+            VH(vampomi_draw_probe(ctx_, cfg_.seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)p, it));
+            int kp = 0;
+            double relp = 0, vmup = 0;
+            VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, gamw_, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &kp, &relp, &vmup));
+            vmu += vmup;
+            VH(vampomi_ax_dev(ctx_, VAMPOMI_V_QINV_BERN, VAMPOMI_V_USER_N0));
+            VH(vampomi_atx_dev(ctx_, VAMPOMI_V_USER_N0, VAMPOMI_V_USER_M0));
+            double tp = 0;
+            VH(vampomi_dots(ctx_, 1, kd, ad, bd, nullptr, &tp));
+            trace_extra += tp;
+        }
+        vmu /= P;
+    }
     if (verbose)
         std::cout << "CG took " << t_cg1 - t_cg0 << " seconds." << std::endl                                  // :316
-                  << "onsager took " << t_ons1 - t_cg1 << " seconds." << std::endl;                           // :333
+                  << "onsager took " << (P > 1 ? wall_s() - t_cg1 : t_ons1 - t_cg1) << " seconds." << std::endl;   // :333
     alpha2_ = gam2_ * vmu;
     res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
     eta2_ = gam2_ / alpha2_;                                                    // :341
@@ -339,10 +474,12 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     } else {
         // no pass at all: Z2 = A x2_hat and A Q^-1 u were kept by the solves; A^T A of both solutions follows from the solves'
         // own residuals, r = rhs - (tau A^T A + gam2 I) sol  =>  A^T A sol = (rhs - r - gam2 sol) / tau
-        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_V, -1.0, VAMPOMI_V_CG_R, 1.0));
-        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_ATA_X2, -gam2_, VAMPOMI_V_X2, tau_solved));
-        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_BERN, -1.0, VAMPOMI_V_CG2_R, 1.0));
-        VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_USER_M0, -gam2_, VAMPOMI_V_QINV_BERN, tau_solved));
+        if (!ata_x2_recycled) {
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_V, -1.0, VAMPOMI_V_CG_R, 1.0));
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_ATA_X2, 1.0, VAMPOMI_V_ATA_X2, -gam2_, VAMPOMI_V_X2, tau_solved));
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_BERN, -1.0, VAMPOMI_V_CG2_R, 1.0));
+            VH(vampomi_vec_lincomb(ctx_, VAMPOMI_V_USER_M0, 1.0, VAMPOMI_V_USER_M0, -gam2_, VAMPOMI_V_QINV_BERN, tau_solved));
+        }
         ata_x2_ready_ = true;
     }
     {
@@ -355,7 +492,7 @@ int Vamp::step_linear(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         double scale[9] = {1, 1, sqrtN, 1, 1, 1, 1, 1, 1}, d[9];
         VH(vampomi_dots(ctx_, 9, kind, a, b, scale, d));
         const double temp_norm2 = d[0];
-        const double trace_corr = d[1] * (double)Mt_;                           // :521
+        const double trace_corr = (P > 1 ? (trace_first + trace_extra) / P : d[1]) * (double)Mt_;   // :521
         if (verbose)
             std::cout << "l2_norm2(temp) / N = " << temp_norm2 / N_ << std::endl << "trace_correction / N = " << trace_corr / N_ << std::endl;
         gamw_ = (double)N_ / (temp_norm2 + trace_corr);                         // :528
@@ -385,13 +522,7 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
     if (verbose) std::cout << "...calculating covariate effects" << std::endl;
     if (it == 1 && C_ > 0) {                                                    // :78-95
         VH(fit_covariates());
-        std::vector<double> mcov((size_t)N_);
-        for (int i = 0; i < N_; i++) {
-            double s = 0;
-            for (int j = 0; j < C_; j++) s += Z_[(size_t)i * C_ + j] * cov_eff_[j];
-            mcov[i] = s;                                                        // m_cov of g1_bin_class / g1d_bin_class, :214-232
-        }
-        VH(vampomi_vec_set(ctx_, VAMPOMI_V_MCOV, mcov.data()));
+        VH(apply_covariates());
     }
     if (verbose) std::cout << "->DENOISING" << std::endl;
     const double alpha1_prev = alpha1_;
@@ -490,6 +621,14 @@ int Vamp::step_probit(vampomi_iter_result* res, double* x1_scaled, double* r1_sc
         VH(confusion_eval(VAMPOMI_V_USER_N0, res->metrics, x1_corr));
         report1();
     }
+    for (int p = 1; p < cfg_.probes; p++) {                                     // further Hutchinson probes (not in the reference), averaged
+        VH(vampomi_draw_probe(ctx_, cfg_.seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)p, it));
+        int kp = 0;
+        double relp = 0, vmup = 0;
+        VH(vampomi_cg_solve(ctx_, VAMPOMI_V_BERN, VAMPOMI_V_QINV_BERN, 0, tau2, gam2_, cfg_.CG_err_tol, cfg_.CG_max_iter, 1, &kp, &relp, &vmup));
+        vmu += vmup;
+    }
+    if (cfg_.probes > 1) vmu /= cfg_.probes;
     const double alpha2 = gam2_ * vmu;                                          // :311
     res->cg_iters_lmmse = k1; res->cg_iters_onsager = k2;
     double x2_corr;
@@ -582,6 +721,15 @@ int vampomi_host_newton_cov(const double* y, const double* gg, const double* Z_N
     return 0;
 }
 
+int vampomi_solver_save_state(vampomi_solver* s, const char* path) {
+    if (!s || !s->impl) return VAMPOMI_ERR_ARG;
+    return s->impl->save_state(path);
+}
+int vampomi_solver_load_state(vampomi_solver* s, const char* path) {
+    if (!s || !s->impl) return VAMPOMI_ERR_ARG;
+    return s->impl->load_state(path);
+}
+
 int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M) {
     if (!s || !s->impl) return VAMPOMI_ERR_ARG;
     return s->impl->step(res, x1_scaled_M, r1_scaled_M);
@@ -647,6 +795,7 @@ void vampomi_solver_default_config(vampomi_solver_config* cfg) {
     cfg->seed = 0;
     cfg->redundant_passes = 0;
     cfg->fuse_passes = 3;
+    cfg->probes = 1;
 }
 
 }  // extern "C"

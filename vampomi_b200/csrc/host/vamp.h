@@ -22,6 +22,9 @@ public:
     // probit: offset m_cov = Z cov_eff inside the z-channel denoiser, src/vamp_probit.cpp:213-232).
     int set_covariates(int C, const double* Z);
     const std::vector<double>& cov_eff() const { return cov_eff_; }
+    // checkpoint / resume (include/vampomi_host.h: vampomi_solver_save_state / _load_state)
+    int save_state(const char* path);
+    int load_state(const char* path);
     int iteration() const { return it_; }
     const std::vector<double>& probs() const { return probs_; }
     const std::vector<double>& vars() const { return vars_; }
@@ -47,6 +50,8 @@ private:
     int C_ = 0;
     std::vector<double> Z_, cov_eff_;
     int fit_covariates();
+    int apply_covariates();          // device vectors that follow from cov_eff_ (linear: adjusted y; probit: m_cov)
+    int rank_ = 0;
     double* pending_x1_ = nullptr;   // host buffers of read-outs begun by dump() and not yet collected
     double* pending_r1_ = nullptr;
     bool aty_ready_ = false;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One single-GPU visit that produces everything profiles/ cites for the current default (recycled schedule): smoke, GPU parity
+# One single-GPU visit that produces everything profiles/ cites for the current default (onepass schedule): smoke, GPU parity
 # tests, parity reports against the reference fixtures per schedule, headline bench (both arms), ncu launch list of the
 # bench command and one full capture of the two dominant kernels on one 8-GPU shard of the headline configuration.
 set -u
@@ -14,12 +14,12 @@ nvidia-smi > $OUT/nvidia-smi.txt 2>&1
 step smoke timeout 600 python -c "import __graft_entry__ as g; g.smoke()"
 step pytest_gpu timeout 1500 python -m pytest tests -m gpu -q --timeout 600
 tail -3 $OUT/pytest_gpu.log
-for s in recycled fused plain; do
+for s in onepass recycled fused plain; do
   timeout 600 python tests/tools/parity_report.py $s > $OUT/parity_report_$s.json 2> $OUT/parity_report_$s.err; echo "parity_report_$s rc=$?" | tee -a $STATUS
 done
 BENCH="python bench.py --steps ${BENCH_STEPS:-5} --warmup ${BENCH_WARMUP:-3}"
 step bench timeout 1200 $BENCH
-step bench_ref timeout 900 python bench.py --impl reference --steps 2 --warmup 1
+step bench_ref timeout 900 python bench.py --impl reference --steps ${BENCH_STEPS:-5} --warmup ${BENCH_WARMUP:-3}
 if [ "${SKIP_C2:-0}" != "1" ]; then
   timeout 1500 python tests/tools/parity_c2.py > $OUT/parity_c2.json 2> $OUT/parity_c2.err; echo "parity_c2 rc=$?" | tee -a $STATUS
 fi
@@ -32,6 +32,6 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   step ncu_launches timeout 2400 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_bench_default.csv $NB
   SMALL="python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab"
   step ncu_small_plain timeout 600 $SMALL && \
-  step ncu_full timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_ax_multi|k_atx_smem' -s 12 -c 4 -f -o $OUT/prof_multi $SMALL
+  step ncu_full timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_ax_multi' -s 6 -c 4 -f -o $OUT/prof_multi $SMALL
 fi
 cat $STATUS

@@ -13,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 
 
 def last_json(path):
@@ -65,16 +65,16 @@ if os.path.isfile(rep):
                                        r"lts__t_sector_hit_rate.pct|smsp__average_warps_issue_stalled_.*_per_issue_active|sm__throughput.avg.pct|sm__cycles_active.avg$|sm__cycles_elapsed.max$)", h)]
     traffic = {}
     with open(os.path.join(PROF, f"{tag}_ncu_full_matrix_kernels.txt"), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:'k_ax_multi|k_atx_smem' -s 12 -c 4,\n"
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_ax_multi' -s 6 -c 4,\n"
                 "# `python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab`\n"
-                "# (one 8-GPU shard of the headline configuration: 17.000 GB of A per pass). Default (recycled) schedule: every pass of an\n"
-                "# iteration is one of these two kernels. Per-launch values.\n")
+                "# (one 8-GPU shard of the headline configuration: 17.000 GB of A per pass). Default (onepass) schedule: every pass of an\n"
+                "# iteration is one of these two kernels (k_gram_ws: A^T q and A A^T q of both systems; k_ax_multi: the first A p of the solves). Per-launch values.\n")
         for r in rows[2:]:
             name = r[idx["Kernel Name"]]
             f.write("\nKernel Name".ljust(77) + name[:160] + "\n")
             for h in keep:
                 f.write(f"{h:76s}{r[idx[h]]} {units[idx[h]]}\n")
-            short = "k_ax_multi" if "k_ax_multi" in name else "k_atx_smem"
+            short = "k_ax_multi" if "k_ax_multi" in name else "k_gram" if "k_gram" in name else "k_atx_smem"
             def gb(h):
                 v, u = float(r[idx[h]].replace(",", "")), units[idx[h]]
                 return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}[u]
@@ -95,7 +95,7 @@ for src, dst in (("bench.log", f"{tag}_bench_1gpu.json"), ("bench_ref.log", f"{t
         if d:
             json.dump(d, open(os.path.join(PROF, dst), "w"), indent=1)
 rep = {}
-for s in ("recycled", "fused", "plain"):
+for s in ("onepass", "recycled", "fused", "plain"):
     p = os.path.join(OUT, f"parity_report_{s}.json")
     if os.path.isfile(p):
         try:

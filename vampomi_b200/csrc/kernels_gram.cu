@@ -73,6 +73,21 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// Pairwise (tree) sum of N values held in registers: depth log2(N) instead of N - 1 dependent additions — what the
+// communication warp's latency chain wants; the order is fixed, so every CTA adds the same values the same way.
+template <int N>
+__device__ __forceinline__ double tree_sum(const double (&v)[N]) {
+    if constexpr (N == 1) {
+        return v[0];
+    } else {
+        double h[(N + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < N / 2; i++) h[i] = v[2 * i] + v[2 * i + 1];
+        if constexpr ((N & 1) != 0) h[N / 2] = v[N - 1];
+        return tree_sum<(N + 1) / 2>(h);
+    }
+}
+
 // Sums NV (1, 2, 4 or 8) values over the 32 lanes of a warp with 5 exchange levels in total: at each of the first log2(NV)
 // levels a lane hands half of its values to its partner and keeps the sums of the other half, so lane v * (32/NV) (and the
 // 32/NV - 1 lanes after it) ends up with the warp total of value v.
@@ -646,9 +661,10 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
             } else {
                 mbar_wait_cta(&redbar[rb], (uint32_t)((s >> 2) & 1));
                 if (lane == 0 && s + R < nsteps) issue_step(s + R);  // every compute warp has copied stage s % R into registers
-                double ts = red[rb][0][ck];                      // every lane: the CTA's sum of value ck, warps in order
+                double pw[NCW];                                  // every lane: the CTA's sum of value ck over the warps (fixed tree)
 #pragma unroll
-                for (int w = 1; w < NCW; w++) ts += red[rb][w][ck];
+                for (int w = 0; w < NCW; w++) pw[w] = red[rb][w][ck];
+                const double ts = tree_sum<NCW>(pw);
 #pragma unroll
                 for (int j = 0; j < ROUNDS; j++) {               // lane = (destination r0 + j*RSTEP, value ck)
                     const int dest = r0 + j * RSTEP;
@@ -659,17 +675,16 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
             }
             if (!do_recv) continue;
             mbar_wait_cluster(&full[slot], (uint32_t)((s >> 2) & 1));
-            double tot = 0.0;
+            // every lane reads the CS partial sums of its value ck itself and adds them by the same fixed tree: bitwise the same
+            // t_j in every CTA of the cluster, and no shuffle on the latency chain
+            double pr[CS];
 #pragma unroll
-            for (int j = 0; j < ROUNDS; j++) {                   // this lane's ranks in rising order, then the butterfly over the lanes
-                const int r = r0 + j * RSTEP;
-                if (r < CS) {
+            for (int r = 0; r < CS; r++) {
+                pr[r] = xbuf[slot][r][0][ck];
 #pragma unroll
-                    for (int w = 0; w < NSRC; w++) tot += xbuf[slot][r][w][ck];
-                }
+                for (int w = 1; w < NSRC; w++) pr[r] += xbuf[slot][r][w][ck];
             }
-#pragma unroll
-            for (int o = CK; o < CK * CS && o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // the same tree in every CTA
+            const double tot = tree_sum<CS>(pr);
             const long long j = c0 + s * C + cc_l;
             const double tj = (sgl * tot) * scale;                              // sigma_inv * dpa (:306), then * scale (:330)
             const bool live = j < c1 && act;

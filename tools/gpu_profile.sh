@@ -26,11 +26,12 @@ fi
 if [ "${SKIP_CONFIGS:-0}" != "1" ]; then
   timeout 900 python tools/run_configs.py > $OUT/configs.json 2> $OUT/configs.err; echo "configs rc=$?" | tee -a $STATUS
 fi
+if [ "${ONLY_NCU:-0}" == "1" ]; then :; fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-  NB="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-ab"
+  NB="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-ab --no-parity"
   step ncu_plain timeout 900 $NB && \
   step ncu_launches timeout 2400 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_bench_default.csv $NB
-  SMALL="python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab"
+  SMALL="python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab --no-parity"
   step ncu_small_plain timeout 600 $SMALL && \
   step ncu_full timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_ax_multi' -s 6 -c 4 -f -o $OUT/prof_multi $SMALL
 fi

@@ -43,7 +43,7 @@ for k in range(5):
     r = sol.step()
     its.append(dict(it=r["it"], s=round(time.time() - t, 4), k1=r["k1"], k2=r["k2"], passes=r["matrix_passes"],
                     acc1=r["metrics"][4], acc2=r["metrics"][10], corr_x2=r["metrics"][11]))
-out["schedule"] = "recycled (default)"
+out["schedule"] = "onepass (default)"
 out["C4_probit_N20000_M400000"] = dict(iterations=its, gbs=[round(i["passes"] * N * Mt * 8 / i["s"] / 1e9) for i in its],
                                        finite=bool(np.all(np.isfinite(r["x1"]))))
 sol.close()

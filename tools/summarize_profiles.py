@@ -42,7 +42,7 @@ if os.path.isfile(src):
     tot_it = sum(a[1] for a in it.values())
     with open(os.path.join(PROF, f"{tag}_launch_shares.txt"), "w") as f:
         f.write(f"# aggregated from profiles/{tag}_launches_bench_default_cmd.csv:\n"
-                "#   ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-ab\n"
+                "#   ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-ab --no-parity\n"
                 "# (the bench command minus the CPU-baseline and A/B legs; per-launch times are cold-cache and serialised: compare shares).\n"
                 "# k_generate_iid / k_stats / k_read_probe run before the timed region. n counts every launch, including the look-ahead\n"
                 "# launches of a finished solve that return at their first instruction (n_busy = launches longer than 100 us).\n"
@@ -66,7 +66,7 @@ if os.path.isfile(rep):
     traffic = {}
     with open(os.path.join(PROF, f"{tag}_ncu_full_matrix_kernels.txt"), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_ax_multi' -s 6 -c 4,\n"
-                "# `python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab`\n"
+                "# `python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab --no-parity`\n"
                 "# (one 8-GPU shard of the headline configuration: 17.000 GB of A per pass). Default (onepass) schedule: every pass of an\n"
                 "# iteration is one of these two kernels (k_gram_ws: A^T q and A A^T q of both systems; k_ax_multi: the first A p of the solves). Per-launch values.\n")
         for r in rows[2:]:

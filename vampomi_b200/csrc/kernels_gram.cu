@@ -598,7 +598,8 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
     __shared__ __align__(8) uint64_t empty[R];
     __shared__ __align__(16) double wbuf[4][CK];
     __shared__ __align__(8) uint64_t full[4], wready[4], redbar[4], ringbar[R];
-    static_assert(DEF == 1 || DEF == 2, "deferral of the axpy: one or two steps");
+    static_assert(DEF == 1, "four exchange slots are only proven safe for a deferral of one step with one communication warp");
+    static_assert(NCOMM == 1, "see DEF");
     bool active[K];
     bool any = false;
 #pragma unroll
@@ -867,7 +868,9 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //     6  10, 4, 2, 4           7  the same, every compute warp sending its own partial sums (no block-level stage)
 //     8  10, 2, 4, 4: half the rows per CTA (16 CTAs per cluster at N = 20 000, one cluster per GPC) and FOUR columns per step, so the
 //        cluster round trip of a step (~0.6 us) is shorter than the step's own HBM time (80 kB per SM pair ... 40 kB per SM: 0.7 us)
-//     9  as 8 with the axpy deferred by TWO steps (three register buffers)     10  as 9 with separate sender and receiver warps
+//        (measured, profiles/r02_sweep_gram_kernel_shapes.jsonl: 3.9 ms against 3.1 ms of shape 6; deferring the axpy by two steps
+//        (DEF = 2) and separate sender / receiver warps (NCOMM = 2) changed nothing there — 3.9 / 3.8 ms — so those variants are
+//        not instantiated: with DEF = 2 the four exchange slots would also have to become eight)
 constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape >= 8 ? 1280 : 2560; }
 constexpr int gram_max_cluster_of_shape(int shape) { return shape >= 8 ? 16 : 8; }
 
@@ -883,8 +886,6 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 6: return gram_launch_ws<K, 10, 4, 2, 4, CS, 0>(c, gv, mw, shape);
         case 7: return gram_launch_ws<K, 10, 4, 2, 4, CS, 1>(c, gv, mw, shape);
         case 8: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0>(c, gv, mw, shape);
-        case 9: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0, 2>(c, gv, mw, shape);
-        case 10: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0, 2, 2>(c, gv, mw, shape);
         default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
     }
 }
@@ -896,9 +897,7 @@ int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
     if (cs == 0) { cs = 1; while (cs < gram_max_cluster_of_shape(shape) && (c->ld + cs - 1) / cs > (size_t)gram_rows_of_shape(shape)) cs *= 2; }
     if (cs == 16) {
         if (shape == 8) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0>(c, gv, mw, shape);
-        if (shape == 9) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0, 2>(c, gv, mw, shape);
-        if (shape == 10) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0, 2, 2>(c, gv, mw, shape);
-        set_error("gram: 16 CTAs per cluster only with shapes 8-10");
+        set_error("gram: 16 CTAs per cluster only with shape 8");
         return VAMPOMI_ERR_ARG;
     }
     switch (cs) {

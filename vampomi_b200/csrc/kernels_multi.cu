@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256, (OCC > 0 ? OCC : (K * RV >= 4 ? 1 : 2))) 
 // out_k[i] = (sum_c partial[k][c][i]) / divisor; blockIdx.y = k. With x.enabled the cross-GPU sum happens here (xchg.cuh).
 template <int SL>
 __global__ void __launch_bounds__(256) k_ax_reduce_multi(const double* __restrict__ partial, size_t ld, int nchunks, int N,
-                                                         double divisor, MultiVec mv, Xchg x, int use_xchg) {
+                                                         double divisor, const __grid_constant__ MultiVec mv, const __grid_constant__ Xchg x,
+                                                         int use_xchg) {      // __grid_constant__: indexed straight from the constant bank, no stack copy
     __shared__ double sm[SL][256 / SL];
     __shared__ unsigned int s_seq;
     constexpr int ROWS = 256 / SL;

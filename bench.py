@@ -593,6 +593,17 @@ def main_ours(args):
                                     "note": "passes = reads of the whole marker block actually made in the timed steps (bytes = passes x N x Mt x 8); "
                                             "matrix_vector_products = products those steps computed — the one-product-per-pass schedule "
                                             "reads the block once for each"}}
+    if dom == "gram":
+        # one k_gram_ws launch delivers BOTH products of a CG iteration (A^T q and A A^T q, for both systems): by BASELINE.json's
+        # own unit — a CG iteration = 2*N*M*8 bytes — it does the work of two reads while reading the block once
+        roofline["cg_iteration_equivalent_gbs"] = 2.0 * achieved
+        roofline["achieved_note"] = ("achieved counts ONE read of the block per launch (the bytes the launch needs); the reference's "
+                                     "unit for the same work is 2*N*M*8 per CG iteration")
+    equiv = products * float(N) * float(Mt) * 8.0 / (ms_dev * 1e-3) / 1e9 / world
+    roofline["whole_iteration"]["equivalent_gbs_per_gpu"] = equiv
+    roofline["whole_iteration"]["equivalent_frac_of_8TBs_spec"] = equiv / 8000.0
+    roofline["whole_iteration"]["equivalent_note"] = ("SURVEY.md §8d / north_star unit: P = 2(k1+k2)+6 necessary passes per iteration, each N*Mt*8 bytes, "
+                                                      "over the measured time — what the products delivered would cost read one by one")
     if per_rank:
         roofline["per_rank"] = per_rank
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

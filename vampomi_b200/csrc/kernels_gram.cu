@@ -871,8 +871,10 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //        (measured, profiles/r02_sweep_gram_kernel_shapes.jsonl: 3.9 ms against 3.1 ms of shape 6; deferring the axpy by two steps
 //        (DEF = 2) and separate sender / receiver warps (NCOMM = 2) changed nothing there — 3.9 / 3.8 ms — so those variants are
 //        not instantiated: with DEF = 2 the four exchange slots would also have to become eight)
-constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape >= 8 ? 1280 : 2560; }
-constexpr int gram_max_cluster_of_shape(int shape) { return shape >= 8 ? 16 : 8; }
+//     (14 compute warps x 3 row pairs — 15 warps per SM under a 128-register cap — measured 3.35-3.45 ms against 3.08-3.30 of shape 6
+//     on the same box: more warps do not pay for the smaller register budget; not instantiated)
+constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape == 8 ? 1280 : 2560; }
+constexpr int gram_max_cluster_of_shape(int shape) { return shape == 8 ? 16 : 8; }
 
 template <int K, int CS>
 int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {

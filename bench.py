@@ -85,6 +85,8 @@ def ncu_traffic(kernel, N, M_local, bytes_per_launch):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             rec = json.load(f)[kernel]
+        if isinstance(rec, list):        # several captured launch shapes: the matching one, else the first for scaling
+            rec = next((r for r in rec if r["N"] == N and r["M_local"] == M_local), rec[0])
     except Exception:
         return None, None
     if rec["N"] == N and rec["M_local"] == M_local:

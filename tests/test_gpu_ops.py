@@ -634,3 +634,25 @@ def test_instrumentation_and_error_paths():
         fresh.Ax(x)
     fresh.close()
     sh.close()
+
+
+def test_onepass_falls_back_where_the_fused_pass_cannot_run():
+    """N > 20 480 rows (more than 8 CTAs x 2 560 rows hold) and FP32 storage: vampomi_aat_supported says no, the fused entry point
+    refuses, and a solve with cg_onepass set runs the two-pass iterations with the same answer."""
+    N, M = 20496, 40
+    sh, A, y, rng = make(N, M, seed=5)
+    assert not sh.aat_supported()
+    with pytest.raises(capi.VampomiError):
+        sh.aat_multi_dev([V_USER_N0], [V_R1], [V_Z1])
+    d = vo.Data(A, y)
+    o = vo.Vamp(d, CG_err_tol=1e-7)
+    o.gam2 = 1.9
+    v = rng.standard_normal(M)
+    want = o.precondCG_solver(v, None, 2.3, 1)
+    sh.set(V_V, v)
+    sh.set_tuning("cg_onepass", 1)
+    sh.counters(reset=True)
+    it, _, _ = sh.cg_solve(V_V, V_X2, 2.3, 1.9, tol=1e-7)
+    assert it == o.cg_iters[-1][2] and rel_l2(sh.get(V_X2), want) < 1e-11
+    assert sh.counters()["matrix_passes"] == 2 * it
+    sh.close()

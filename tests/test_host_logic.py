@@ -178,3 +178,54 @@ def test_covariate_reader_and_newton_match_oracle(tmp_path):
         rc = lib.vampomi_host_newton_cov(y.ctypes.data_as(capi.c_double_p), gg.ctypes.data_as(capi.c_double_p),
                                          np.ascontiguousarray(Z).ctypes.data_as(capi.c_double_p), N, 2, eta.ctypes.data_as(capi.c_double_p))
         assert rc == 0 and np.allclose(eta, eta_want, rtol=1e-9, atol=1e-12), (eta, eta_want)
+
+
+def test_onepass_cg_recurrences_reproduce_the_two_pass_iterates():
+    """The `onepass` schedule in numpy, with the oracle's operators: carrying q = A p as a vector of its own — one
+    fused product pair t = A^T q, w = A t per iteration, then A r -= alpha (tau w + gam2 q) and q = (A r)/diag + beta q — gives the
+    iterates, residuals and step lengths of precondCG_solver's own recurrences (src/vamp.cpp:671-757), which apply A and A^T to p in
+    every iteration; q stays equal to A p to rounding, with and without the periodic recomputation."""
+    rng = np.random.default_rng(12)
+    N, M = 250, 900
+    A = rng.standard_normal((M, N)) * 0.1 + 0.5
+    d = vo.Data(A, rng.standard_normal(N))
+    tau, gam2 = 2.3, 0.7
+    diag = tau * (N - 1) / N + gam2
+    v = rng.standard_normal(M)
+    for refresh in (0, 5):
+        # two passes per iteration: the reference's recurrences
+        mu2, r2 = np.zeros(M), v.copy()
+        z2 = r2 / diag
+        p2 = z2.copy()
+        # one pass per iteration
+        mu, r = np.zeros(M), v.copy()
+        z = r / diag
+        p = z.copy()
+        q = d.Ax(p)                                   # the solve's only A* pass
+        Ar = diag * q
+        for it in range(14):
+            d2 = tau * d.ATx(d.Ax(p2)) + gam2 * p2
+            a2 = (r2 @ z2) / (d2 @ p2)
+            mu2 = mu2 + a2 * p2
+            rz2 = r2 @ z2
+            r2 = r2 - d2 * a2
+            z2 = r2 / diag
+            p2 = z2 + (r2 @ z2) / rz2 * p2
+
+            if refresh and it > 0 and it % refresh == 0:            # q and A r afresh from p and z (cg.cu, gram_refresh)
+                q, Ar = d.Ax(p), diag * d.Ax(z)
+            t = d.ATx(q)                                            # the fused pass: A^T q ...
+            w = d.Ax(t)                                             # ... and A A^T q
+            dvec = tau * t + gam2 * p
+            alpha = (r @ z) / (dvec @ p)
+            mu = mu + alpha * p
+            rz = r @ z
+            r = r - dvec * alpha
+            z = r / diag
+            beta = (r @ z) / rz
+            p = z + beta * p
+            Ar = Ar - alpha * (tau * w + gam2 * q)
+            q = Ar / diag + beta * q
+            assert abs(alpha - a2) < 1e-11 * abs(a2)
+            assert np.linalg.norm(mu - mu2) < 1e-11 * np.linalg.norm(mu2) and np.linalg.norm(r - r2) < 1e-9 * np.linalg.norm(v)
+            assert np.linalg.norm(q - d.Ax(p)) < 1e-10 * np.linalg.norm(q)

@@ -57,13 +57,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    unsigned long long spins = 0;
+    uint32_t ok = 0, spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!ok && ++spins > (1ull << 28)) __trap();            // a protocol bug must fault, not hang the GPU
+        if (!ok && ++spins > (1u << 28)) __trap();              // a protocol bug must fault, not hang the GPU
     } while (!ok);
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -368,13 +367,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cta(uint64_t* bar, uint32_t parity) {
-    uint32_t ok = 0;
-    unsigned long long spins = 0;
+    uint32_t ok = 0, spins = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!ok && ++spins > (1ull << 28)) __trap();
+        if (!ok && ++spins > (1u << 28)) __trap();
     } while (!ok);
 }
 
@@ -572,6 +570,45 @@ __global__ void __launch_bounds__(TPB, 1) k_gram_bulk(const double* __restrict__
 // Compute warps never wait for the cluster round trip of the step they just dotted — only for the one before it, which the
 // communication warp has been carrying meanwhile.
 // ---------------------------------------------------------------------------------------------------------------
+// The same operations on PRECOMPUTED 32-bit shared-window addresses: inside a cluster launch the compiler re-derives the window
+// base of every __shared__ object from SR_CgaCtaId at each use (S2R + LEA per access), which the hot loop can do without.
+__device__ __forceinline__ void mbar_wait_cta_u(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 28)) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_cta_u(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster_u(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 28)) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -612,9 +649,19 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
     const long long c0 = (long long)blockIdx.y * cols_per_chunk;
     long long c1 = c0 + cols_per_chunk;
     if (c1 > M) c1 = M;
-    const long long nsteps = c1 > c0 ? (c1 - c0 + C - 1) / C : 0;
+    // steps, stage indices and column offsets are 32-bit (a chunk has far fewer than 2^31 columns): the loop bookkeeping of the
+    // first version — 64-bit products and divisions, register moves feeding predicated loads — was 45 % of the instructions issued
+    const int ncols = c1 > c0 ? (int)(c1 - c0) : 0;
+    const int nsteps = (ncols + C - 1) / C;
     const uint32_t piece_bytes = rbase < ld ? (uint32_t)((ld - rbase < (size_t)tile_rows ? ld - rbase : (size_t)tile_rows) * sizeof(double)) : 0u;
-    auto col_of = [&](long long s, int cc) { const long long j = c0 + s * C + cc; return j < c1 ? j : c1 - 1; };
+    const double* const mave_c = mave + c0;                      // this chunk's statistics and columns
+    const double* const msig_c = msig + c0;
+    auto col_of = [&](int s, int cc) { const int j = s * C + cc; return j < ncols ? j : ncols - 1; };   // offset inside the chunk; ragged last step clamped
+    // rows of the ring slots that no bulk copy ever writes (the tile's tail, or all of it for a CTA without rows) are zeroed once:
+    // every compute thread can then load its row pairs unconditionally — a zero row has q = 0 and its w is never stored
+    for (int i = (int)(piece_bytes / 8) + tid; i < PIECE; i += blockDim.x)
+#pragma unroll
+        for (int sc = 0; sc < R * C; sc++) ring[(size_t)sc * PIECE + i] = 0.0;
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < 4; i++) { mbar_init(&full[i], 1); mbar_init(&wready[i], 1); }
@@ -632,27 +679,40 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
     if (wid >= NCW) {
         // ------------------------------------------- communication warp(s) -------------------------------------------
         const bool do_send = NCOMM == 1 || wid == NCW, do_recv = NCOMM == 1 || wid == NCW + 1;
-        auto issue_step = [&](long long s) {                     // lane 0: the C column pieces of step s into stage s % R
-            const int st = (int)(s % R);
+        const double* const a_c = A + rbase + (size_t)c0 * ld;
+        auto issue_step = [&](int s) {                           // lane 0: the C column pieces of step s into stage s % R
+            const int st = s % R;
             mbar_expect_tx(&ringbar[st], C * piece_bytes);
             if (piece_bytes != 0) {
 #pragma unroll
                 for (int cc = 0; cc < C; cc++)
-                    bulk_g2s(ring + ((size_t)st * C + cc) * PIECE, A + rbase + (size_t)col_of(s, cc) * ld, piece_bytes, &ringbar[st]);
+                    bulk_g2s(ring + (st * C + cc) * PIECE, a_c + (size_t)col_of(s, cc) * ld, piece_bytes, &ringbar[st]);
             }
         };
         if (lane == 0 && do_send)
-            for (long long s = 0; s < R && s < nsteps; s++) issue_step(s);
+            for (int s = 0; s < R && s < nsteps; s++) issue_step(s);
         const int ck = lane % CK, r0 = lane / CK, cc_l = ck / K, k_l = ck % K;
         bool act = active[0];
 #pragma unroll
         for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
         double* tout = K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0];
-        double sg_next = nsteps > 0 ? __ldg(msig + col_of(0, cc_l)) : 0.0;
-        for (long long s = 0; s < nsteps; s++) {
-            const int rb = (int)(s & 3), slot = (int)(s & 3);
+        double sg_next = nsteps > 0 ? __ldg(msig_c + col_of(0, cc_l)) : 0.0;
+        // everything the per-step chain addresses, as 32-bit shared-window addresses computed once: the local barriers and buffers,
+        // and — through mapa — this lane's slot in every destination CTA's receive buffer and that CTA's arrival barrier
+        const uint32_t redbar_u = smem_u32(&redbar[0]), full_u = smem_u32(&full[0]), wready_u = smem_u32(&wready[0]);
+        const uint32_t red_u = smem_u32(&red[0][0][ck]), xbuf_u = smem_u32(&xbuf[0][0][0][ck]), wbuf_u = smem_u32(&wbuf[0][ck]);
+        uint32_t rx[ROUNDS], rf[ROUNDS];                         // slot 0 of destination r0 + j*RSTEP; other slots at fixed strides
+#pragma unroll
+        for (int j = 0; j < ROUNDS; j++) {
+            const uint32_t dest = (uint32_t)(r0 + j * RSTEP < CS ? r0 + j * RSTEP : 0);
+            rx[j] = mapa_u32(smem_u32(&xbuf[0][crank][0][ck]), dest);
+            rf[j] = mapa_u32(full_u, dest);
+        }
+        constexpr uint32_t XSLOT = CS * NSRC * CK * 8, XRANK = NSRC * CK * 8;
+        for (int s = 0; s < nsteps; s++) {
+            const int rb = s & 3, slot = s & 3;
             const double sgl = sg_next;
-            sg_next = __ldg(msig + col_of(s + 1 < nsteps ? s + 1 : s, cc_l));
+            sg_next = __ldg(msig_c + col_of(s + 1 < nsteps ? s + 1 : s, cc_l));
             if (do_send) {
             if (DIRECT) {
                 if (lane == 0 && s + R < nsteps) {               // refill stage s % R once every compute warp has copied it into registers
@@ -660,43 +720,40 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
                     issue_step(s + R);
                 }
             } else {
-                mbar_wait_cta(&redbar[rb], (uint32_t)((s >> 2) & 1));
+                mbar_wait_cta_u(redbar_u + 8u * rb, (uint32_t)((s >> 2) & 1));
                 if (lane == 0 && s + R < nsteps) issue_step(s + R);  // every compute warp has copied stage s % R into registers
                 double pw[NCW];                                  // every lane: the CTA's sum of value ck over the warps (fixed tree)
 #pragma unroll
-                for (int w = 0; w < NCW; w++) pw[w] = red[rb][w][ck];
+                for (int w = 0; w < NCW; w++) pw[w] = lds_f64(red_u + (uint32_t)((rb * NCW + w) * CK * 8));
                 const double ts = tree_sum<NCW>(pw);
 #pragma unroll
-                for (int j = 0; j < ROUNDS; j++) {               // lane = (destination r0 + j*RSTEP, value ck)
-                    const int dest = r0 + j * RSTEP;
-                    if (dest < CS)
-                        st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][0][ck]), (uint32_t)dest), ts, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
-                }
+                for (int j = 0; j < ROUNDS; j++)                 // lane = (destination r0 + j*RSTEP, value ck)
+                    if (r0 + j * RSTEP < CS) st_async_f64(rx[j] + slot * XSLOT, ts, rf[j] + 8u * slot);
             }
             }
             if (!do_recv) continue;
-            mbar_wait_cluster(&full[slot], (uint32_t)((s >> 2) & 1));
+            mbar_wait_cluster_u(full_u + 8u * slot, (uint32_t)((s >> 2) & 1));
             // every lane reads the CS partial sums of its value ck itself and adds them by the same fixed tree: bitwise the same
             // t_j in every CTA of the cluster, and no shuffle on the latency chain
             double pr[CS];
 #pragma unroll
             for (int r = 0; r < CS; r++) {
-                pr[r] = xbuf[slot][r][0][ck];
+                pr[r] = lds_f64(xbuf_u + slot * XSLOT + r * XRANK);
 #pragma unroll
-                for (int w = 1; w < NSRC; w++) pr[r] += xbuf[slot][r][w][ck];
+                for (int w = 1; w < NSRC; w++) pr[r] += lds_f64(xbuf_u + slot * XSLOT + r * XRANK + w * CK * 8);
             }
             const double tot = tree_sum<CS>(pr);
-            const long long j = c0 + s * C + cc_l;
+            const int j = s * C + cc_l;
             const double tj = (sgl * tot) * scale;                              // sigma_inv * dpa (:306), then * scale (:330)
-            const bool live = j < c1 && act;
+            const bool live = j < ncols && act;
             if (lane < CK) {
-                if (live && crank == 0) tout[j] = tj;
-                wbuf[slot][ck] = live ? sgl * tj : 0.0;                         // sig_phen_i = msig * x, src/data.cpp:354
+                if (live && crank == 0) tout[c0 + j] = tj;
+                sts_f64(wbuf_u + (uint32_t)(slot * CK * 8), live ? sgl * tj : 0.0);   // sig_phen_i = msig * x, src/data.cpp:354
             }
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_cta(&wready[slot]);
-                mbar_expect_tx(&full[slot], CS * NSRC * CK * 8);                // re-arm the slot for step s + 4
+                mbar_arrive_cta_u(wready_u + 8u * slot);
+                mbar_expect_tx_u(full_u + 8u * slot, CS * NSRC * CK * 8);       // re-arm the slot for step s + 4
             }
         }
     } else {
@@ -718,26 +775,29 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
         double a[DEF + 1][C][RP][2];                             // the step being dotted and the DEF steps whose axpy is pending
         double m_n[C];
 #pragma unroll
-        for (int cc = 0; cc < C; cc++) m_n[cc] = __ldg(mave + (nsteps > 0 ? col_of(0, cc) : 0));
+        for (int cc = 0; cc < C; cc++) m_n[cc] = nsteps > 0 ? __ldg(mave_c + col_of(0, cc)) : 0.0;
+        // shared-window addresses of everything the loop touches, computed once
+        const uint32_t rows_u = smem_u32(ring) + (uint32_t)tid * 16u;            // this thread's first row pair inside a ring slot
+        const uint32_t ringbar_u = smem_u32(&ringbar[0]), redbar_u = smem_u32(&redbar[0]), wready_u = smem_u32(&wready[0]);
+        const uint32_t red_u = smem_u32(&red[0][wid][0]), wbuf_u = smem_u32(&wbuf[0][0]);
 
-        auto dot_step = [&](const int b, long long s) {
+        auto dot_step = [&](const int b, int s) {
             double m[C], pd[C][K][2];
 #pragma unroll
             for (int cc = 0; cc < C; cc++) {
                 m[cc] = m_n[cc];
-                m_n[cc] = __ldg(mave + col_of(s + 1 < nsteps ? s + 1 : s, cc));
+                m_n[cc] = __ldg(mave_c + col_of(s + 1 < nsteps ? s + 1 : s, cc));
 #pragma unroll
                 for (int k = 0; k < K; k++) pd[cc][k][0] = pd[cc][k][1] = 0.0;
             }
-            const int st = (int)(s % R);
-            mbar_wait_cta(&ringbar[st], (uint32_t)((s / R) & 1));
-            const double* stage = ring + (size_t)st * C * PIECE;
+            const int st = s % R;
+            mbar_wait_cta_u(ringbar_u + 8u * st, (uint32_t)((s / R) & 1));
+            const uint32_t stage = rows_u + (uint32_t)(st * C * PIECE * 8);
 #pragma unroll
             for (int cc = 0; cc < C; cc++)
 #pragma unroll
                 for (int i = 0; i < RP; i++) {
-                    double2 v = make_double2(m[cc], m[cc]);      // rows this thread does not own: centred value 0
-                    if (valid[i]) v = *reinterpret_cast<const double2*>(stage + (size_t)cc * PIECE + (i * CT + tid) * 2);
+                    const double2 v = lds_f64x2(stage + (uint32_t)((cc * PIECE + i * CT * 2) * 8));         // rows beyond the tile read zeros
                     const double d0 = v.x - m[cc], d1 = v.y - m[cc];            // meth[i] - mu, src/data.cpp:304 and :360
                     a[b][cc][i][0] = d0; a[b][cc][i][1] = d1;                   // kept centred for the deferred axpy
 #pragma unroll
@@ -757,21 +817,28 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
                 for (int k = 0; k < K; k++) v[cc * K + k] = pd[cc][k][0] + pd[cc][k][1];
             const double sw = warp_sum_multi<CK>(v, lane);      // lanes [ck*32/CK, (ck+1)*32/CK) hold the warp total of value ck
             if (DIRECT) {
-                const int dest = lane & (32 / CK - 1), ck = lane / (32 / CK), slot = (int)(s & 3);
+                const int dest = lane & (32 / CK - 1), ck = lane / (32 / CK), slot = s & 3;
                 if (dest < CS)
                     st_async_f64(mapa_u32(smem_u32(&xbuf[slot][crank][wid][ck]), (uint32_t)dest), sw, mapa_u32(smem_u32(&full[slot]), (uint32_t)dest));
             } else {
-                if ((lane & (32 / CK - 1)) == 0) red[s & 3][wid][lane / (32 / CK)] = sw;
+                if ((lane & (32 / CK - 1)) == 0) sts_f64(red_u + (uint32_t)(((s & 3) * NCW * CK + lane / (32 / CK)) * 8), sw);
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cta(&redbar[s & 3]);
+                if (lane == 0) mbar_arrive_cta_u(redbar_u + 8u * (s & 3));
             }
         };
-        auto axpy_step = [&](const int b, long long sp) {
-            const int slot = (int)(sp & 3);
-            mbar_wait_cta(&wready[slot], (uint32_t)((sp >> 2) & 1));
+        auto axpy_step = [&](const int b, int sp) {
+            const int slot = sp & 3;
+            mbar_wait_cta_u(wready_u + 8u * slot, (uint32_t)((sp >> 2) & 1));
             double wgt[CK];
+            if constexpr (CK >= 2) {
 #pragma unroll
-            for (int i = 0; i < CK; i++) wgt[i] = wbuf[slot][i];
+                for (int i = 0; i < CK; i += 2) {
+                    const double2 w2 = lds_f64x2(wbuf_u + (uint32_t)((slot * CK + i) * 8));
+                    wgt[i] = w2.x; wgt[i + 1] = w2.y;
+                }
+            } else {
+                wgt[0] = wbuf[slot][0];
+            }
 #pragma unroll
             for (int cc = 0; cc < C; cc++)
 #pragma unroll
@@ -782,10 +849,10 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
                         acc[k][i][1] = fma(a[b][cc][i][1], wgt[cc * K + k], acc[k][i][1]);
                     }
         };
-        for (long long s0 = 0; s0 < nsteps + DEF; s0 += DEF + 1) {
+        for (int s0 = 0; s0 < nsteps + DEF; s0 += DEF + 1) {
 #pragma unroll
             for (int b = 0; b <= DEF; b++) {
-                const long long s = s0 + b;
+                const int s = s0 + b;
                 if (s < nsteps) dot_step(b, s);
                 if (s >= DEF && s < nsteps + DEF) axpy_step((b + 1) % (DEF + 1), s - DEF);
             }

@@ -869,6 +869,306 @@ __global__ void __launch_bounds__((NCW + NCOMM) * 32, 1) k_gram_ws(const double*
     cluster_sync_all();                                          // nobody leaves while a peer may still write into its shared memory
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k_gram_wsx: the warp-specialised ring of k_gram_ws with the compute warps' instruction stream cut down to what the arithmetic
+// needs. The ncu capture of k_gram_ws (profiles/r02_ncu_full_k_gram_ws.txt) shows a kernel bound by issue slots and dependent
+// latencies, not by HBM: 225 instructions per compute warp and step, of which only 64 DFMA + 16 DADD are the products. The rest,
+// and where it goes here:
+//   * the 5-level shuffle butterfly over the lanes (12 SHFL + 12 FSEL + 10 MOV + 7 DADD, ~150 cycles of dependent latency per
+//     warp and step): the lanes store their CK partial sums as they are (one 16-byte store per value pair, conflict-free) and
+//     the COMMUNICATION warp adds the NCW x 32 partial sums of a value — once per CTA and step instead of once per warp;
+//   * slot, stage and parity arithmetic of the four-deep exchange: the step loop is unrolled by four, so ring stage, exchange
+//     slot and barrier are compile-time offsets from ONE shared-window base register and the parity is one bit flipped per trip;
+//   * column means: address arithmetic + LDG per column and step in every thread: the communication warp's lane 0 bulk-copies
+//     the C means of a step next to its column pieces (same mbarrier), a compute thread reads them with one broadcast LDS.128;
+//   * barrier waits: one try_wait + one branch on the fast path (the spin counter only exists on the slow path).
+// Same protocol, same summation trees across warps and ranks (so the same t_j in every CTA of a cluster); the lanes of a warp are
+// now added by the communication warp's butterfly instead of each warp's own.
+// 132 instead of 225 instructions per compute warp and step — and, measured, NOT ONE microsecond faster (2.827 ms per 17 GB shard for
+// both, to four digits; time exactly proportional to 1 / clusters; one system as slow as two): what paced k_gram_ws was not the
+// arithmetic but the refill of the ring, which sat in the communication warp's loop BEHIND the cluster round trip of the previous
+// step — a stage was re-issued one exchange latency after it had been consumed, and 3 x 40 kB in flight per SM then cover only
+// ~50 GB/s per SM (tools/tma_ingest.cu: the copy engine itself sustains 62 GB/s per SM = 7.5 TB/s on 120 SMs with the same ring).
+// PROD = 1 gives the ring its own PRODUCER warp: its lane 0 waits for the compute warps' arrival on a stage and re-issues it at
+// once, whatever the exchange is doing. 2.46 ms cold (6.9 TB/s, ncu) / 2.58-2.74 ms in bursts for two systems, 2.37 ms (7.16 TB/s,
+// the read probe's speed) for one; with the lean compute loop the issue slots are 27 % busy. An extra cp.async.bulk.prefetch.L2 ahead
+// of the ring only costs (2.76-2.93 ms): removed.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {       // keeps the compiler from re-deriving a shared-window address (S2R + LEA) at every use
+    asm volatile("" : "+r"(x));
+    return x;
+}
+__device__ __forceinline__ bool mbar_try_cta_u(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_cluster_u(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin_cta_u(uint32_t bar, uint32_t parity) {
+    if (mbar_try_cta_u(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_cta_u(bar, parity))
+        if (++spins > (1u << 28)) __trap();                      // a protocol bug must fault, not hang the GPU
+}
+__device__ __forceinline__ void mbar_spin_cluster_u(uint32_t bar, uint32_t parity) {
+    if (mbar_try_cluster_u(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_cluster_u(bar, parity))
+        if (++spins > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void mbar_init_u(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int K, int NCW, int RP, int C, int CS, int PROD>
+__global__ void __launch_bounds__((NCW + 1 + PROD) * 32, 1) k_gram_wsx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+                                                               const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
+                                                               long long M, double scale, double* __restrict__ partial, int nchunks) {
+    constexpr int R = 4, CK = C * K, NPAIR = CK / 2, LPV = 32 / CK, CT = NCW * 32, PIECE = CT * RP * 2;
+    static_assert(C == 2 && (K == 1 || K == 2), "two columns per step: their means are one 16-byte bulk copy, their sums one or two value pairs");
+    static_assert(CS <= LPV, "after the butterfly the LPV lanes that hold value ck send it to the CS ranks");
+    // one control block, addressed as base register + compile-time offset (bytes)
+    constexpr uint32_t XSLOT = CS * CK * 8;                      // xbuf[4][CS][CK]: partial sums of the ranks, per exchange slot
+    constexpr uint32_t XBUF_O = 0, WBUF_O = XBUF_O + 4 * XSLOT;  // wbuf[4][CK]: axpy weights of a step
+    constexpr uint32_t MST_O = WBUF_O + 4 * CK * 8;              // mst[R][C]: column means of a ring stage
+    constexpr uint32_t FULL_O = MST_O + R * C * 8, WREADY_O = FULL_O + 32, REDBAR_O = WREADY_O + 32, RINGBAR_O = REDBAR_O + 32;
+    constexpr uint32_t RED_O = RINGBAR_O + R * 8;                // red[2][NCW][NPAIR][32 lanes] value pairs
+    constexpr uint32_t REDSLOT = NCW * NPAIR * 512, CTL_BYTES = RED_O + 2 * REDSLOT;
+    static_assert(RED_O % 16 == 0, "16-byte stores");
+    extern __shared__ __align__(128) double ring[];              // [R][C][PIECE]
+    __shared__ __align__(16) unsigned char ctl[CTL_BYTES];
+    bool active[K];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < K; k++) { active[k] = gv.done[k] == nullptr || *gv.done[k] == 0; any |= active[k]; }
+    if (!any) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const size_t rbase = (size_t)crank * tile_rows;
+    const long long c0 = (long long)blockIdx.y * cols_per_chunk;
+    long long c1 = c0 + cols_per_chunk;
+    if (c1 > M) c1 = M;
+    const int ncols = c1 > c0 ? (int)(c1 - c0) : 0;
+    const int nsteps = (ncols + C - 1) / C;
+    const uint32_t piece_bytes = rbase < ld ? (uint32_t)((ld - rbase < (size_t)tile_rows ? ld - rbase : (size_t)tile_rows) * sizeof(double)) : 0u;
+    const double* const mave_c = mave + c0;
+    const double* const msig_c = msig + c0;
+    auto col_of = [&](int s, int cc) { const int j = s * C + cc; return j < ncols ? j : ncols - 1; };
+    // rows of the ring slots that no bulk copy ever writes are zeroed once (see k_gram_ws)
+    for (int i = (int)(piece_bytes / 8) + tid; i < PIECE; i += blockDim.x)
+#pragma unroll
+        for (int sc = 0; sc < R * C; sc++) ring[(size_t)sc * PIECE + i] = 0.0;
+    const uint32_t cb = opaque_u32(smem_u32(ctl)), ring_u = opaque_u32(smem_u32(ring));
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            mbar_init_u(cb + FULL_O + 8 * i, 1); mbar_init_u(cb + WREADY_O + 8 * i, 1);
+            mbar_init_u(cb + REDBAR_O + 8 * i, NCW); mbar_init_u(cb + RINGBAR_O + 8 * i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_expect_tx_u(cb + FULL_O + 8 * i, XSLOT);
+    }
+    __syncthreads();
+    cluster_sync_all();                                          // every CTA's mbarriers are armed before anybody sends
+
+    if (wid >= NCW) {
+        // ------------------------- communication warp (and, with PROD, the ring's producer warp) -------------------------
+        const double* const a_c = A + rbase + (size_t)c0 * ld;
+        const bool m_aligned = (reinterpret_cast<uintptr_t>(mave_c) & 15) == 0;
+        auto issue_step = [&](int s, int st) {                   // lane 0: the C column pieces and means of step s into stage st = s % 4
+            const uint32_t bar = cb + RINGBAR_O + 8 * st;
+            const bool mb = m_aligned && s * C + C <= ncols;     // a ragged last step repeats its last column: means written by hand
+            if (!mb) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++) sts_f64(cb + MST_O + (uint32_t)((st * C + cc) * 8), __ldg(mave_c + col_of(s, cc)));
+            }
+            mbar_expect_tx_u(bar, C * piece_bytes + (mb ? C * 8u : 0u));
+            if (mb) bulk_g2s_u(cb + MST_O + (uint32_t)(st * C * 8), mave_c + s * C, C * 8, bar);
+            if (piece_bytes != 0) {
+#pragma unroll
+                for (int cc = 0; cc < C; cc++)
+                    bulk_g2s_u(ring_u + (uint32_t)((st * C + cc) * PIECE * 8), a_c + (size_t)col_of(s, cc) * ld, piece_bytes, bar);
+            }
+        };
+        if (lane == 0 && wid == NCW + PROD) {
+            for (int s = 0; s < R && s < nsteps; s++) issue_step(s, s);
+        }
+        if (PROD && wid == NCW + 1) {
+            // producer warp: refills a ring stage the moment every compute warp has consumed it, however far the communication warp's
+            // exchange of that step has got (as part of the communication warp's loop the refill waited for the previous step's
+            // cluster round trip)
+            if (lane == 0) {
+                uint32_t php = 0;
+                for (int s0 = 0; s0 + R < nsteps; s0 += 4, php ^= 1u) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int s = s0 + u;
+                        if (s + R >= nsteps) break;
+                        mbar_spin_cta_u(cb + REDBAR_O + 8 * u, php);
+                        issue_step(s + R, u);
+                    }
+                }
+            }
+        } else {
+        const int ck = lane / LPV, dst = lane % LPV, cc_l = ck / K, k_l = ck % K;   // after the butterfly lanes [ck*LPV, (ck+1)*LPV) hold value ck
+        bool act = active[0];
+#pragma unroll
+        for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
+        double* tout = K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0];
+        double sg_next = nsteps > 0 ? __ldg(msig_c + col_of(0, cc_l)) : 0.0;
+        const uint32_t peer = (uint32_t)(dst < CS ? dst : 0);
+        const uint32_t rx = mapa_u32(cb + XBUF_O + (crank * CK + ck) * 8, peer), rf = mapa_u32(cb + FULL_O, peer);
+        const uint32_t red_l = cb + RED_O + (uint32_t)lane * 16u, xb_l = cb + XBUF_O + (uint32_t)ck * 8u, wb_l = cb + WBUF_O + (uint32_t)ck * 8u;
+        uint32_t ph = 0;                                         // (s / 4) & 1: phase parity of every four-deep barrier ring
+        for (int s0 = 0; s0 < nsteps; s0 += 4, ph ^= 1u) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int s = s0 + u;
+                if (s >= nsteps) break;
+                const double sgl = sg_next;
+                sg_next = __ldg(msig_c + col_of(s + 1 < nsteps ? s + 1 : s, cc_l));
+                mbar_spin_cta_u(cb + REDBAR_O + 8 * u, ph);       // every compute warp has read stage u and stored its partial sums
+                if (!PROD && lane == 0 && s + R < nsteps) issue_step(s + R, u);
+                double vs[CK];                                   // this lane's sum over the warps (fixed tree) of its slice of every value
+#pragma unroll
+                for (int pr = 0; pr < NPAIR; pr++) {
+                    double px[NCW], py[NCW];
+#pragma unroll
+                    for (int w = 0; w < NCW; w++) {
+                        const double2 x = lds_f64x2(red_l + (uint32_t)((u & 1) * REDSLOT + (w * NPAIR + pr) * 512));
+                        px[w] = x.x; py[w] = x.y;
+                    }
+                    vs[2 * pr] = tree_sum<NCW>(px); vs[2 * pr + 1] = tree_sum<NCW>(py);
+                }
+                const double sw = warp_sum_multi<CK>(vs, lane);  // the CTA's partial sum of value ck
+                if (dst < CS) st_async_f64(rx + u * XSLOT, sw, rf + 8 * u);
+                mbar_spin_cluster_u(cb + FULL_O + 8 * u, ph);
+                // every lane adds the CS partial sums of its value by the same fixed tree: bitwise the same t_j in every CTA
+                double pr[CS];
+#pragma unroll
+                for (int r = 0; r < CS; r++) pr[r] = lds_f64(xb_l + (uint32_t)(u * XSLOT + r * CK * 8));
+                const double tot = tree_sum<CS>(pr);
+                const int j = s * C + cc_l;
+                const double tj = (sgl * tot) * scale;                          // sigma_inv * dpa (:306), then * scale (:330)
+                const bool live = j < ncols && act;
+                if (dst == 0) {
+                    if (live && crank == 0) tout[c0 + j] = tj;
+                    sts_f64(wb_l + (uint32_t)(u * CK * 8), live ? sgl * tj : 0.0);   // sig_phen_i = msig * x, src/data.cpp:354
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_cta_u(cb + WREADY_O + 8 * u);
+                    mbar_expect_tx_u(cb + FULL_O + 8 * u, XSLOT);               // re-arm the slot for step s + 4
+                }
+            }
+        }
+        }
+    } else {
+        // ---------------------------------------------- compute warps ----------------------------------------------
+        bool valid[RP];
+        double qr[K][RP][2], acc[K][RP][2];
+#pragma unroll
+        for (int i = 0; i < RP; i++) {
+            const int off = (i * CT + tid) * 2;
+            valid[i] = off < tile_rows && rbase + off < ld;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                acc[k][i][0] = acc[k][i][1] = 0.0;
+                double2 qv = make_double2(0.0, 0.0);
+                if (valid[i] && active[k]) qv = *reinterpret_cast<const double2*>(gv.q[k] + rbase + off);   // pad rows of q are zero
+                qr[k][i][0] = qv.x; qr[k][i][1] = qv.y;
+            }
+        }
+        double a[2][C][RP][2];                                   // the step being dotted and the step whose axpy is pending
+        const uint32_t rows_u = opaque_u32(ring_u + (uint32_t)tid * 16u);             // this thread's first row pair inside a ring slot
+        const uint32_t red_w = opaque_u32(cb + RED_O + (uint32_t)(wid * NPAIR) * 512u + (uint32_t)lane * 16u);
+
+        auto dot_step = [&](const int u, const uint32_t par) {   // u = s % 4: ring stage, barrier; u & 1: register buffer, red slot
+            double pd[C][K][2];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) pd[cc][k][0] = pd[cc][k][1] = 0.0;
+            mbar_spin_cta_u(cb + RINGBAR_O + 8 * u, par);
+            const double2 mm = lds_f64x2(cb + MST_O + (uint32_t)(u * C * 8));
+            const double m[2] = {mm.x, mm.y};
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int i = 0; i < RP; i++) {
+                    const double2 v = lds_f64x2(rows_u + (uint32_t)(((u * C + cc) * PIECE + i * CT * 2) * 8));   // rows beyond the tile read zeros
+                    const double d0 = v.x - m[cc], d1 = v.y - m[cc];            // meth[i] - mu, src/data.cpp:304 and :360
+                    a[u & 1][cc][i][0] = d0; a[u & 1][cc][i][1] = d1;           // kept centred for the deferred axpy
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        pd[cc][k][0] = fma(d0, qr[k][i][0], pd[cc][k][0]);
+                        pd[cc][k][1] = fma(d1, qr[k][i][1], pd[cc][k][1]);
+                    }
+                }
+            double v[CK];
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int k = 0; k < K; k++) v[cc * K + k] = pd[cc][k][0] + pd[cc][k][1];
+#pragma unroll
+            for (int pr = 0; pr < NPAIR; pr++) sts_f64x2(red_w + (uint32_t)((u & 1) * REDSLOT + pr * 512), v[2 * pr], v[2 * pr + 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cta_u(cb + REDBAR_O + 8 * u);
+        };
+        auto axpy_step = [&](const int slot, const uint32_t par, const int b) {
+            mbar_spin_cta_u(cb + WREADY_O + 8 * slot, par);
+            double wgt[CK];
+#pragma unroll
+            for (int i = 0; i < CK; i += 2) {
+                const double2 w2 = lds_f64x2(cb + WBUF_O + (uint32_t)((slot * CK + i) * 8));
+                wgt[i] = w2.x; wgt[i + 1] = w2.y;
+            }
+#pragma unroll
+            for (int cc = 0; cc < C; cc++)
+#pragma unroll
+                for (int i = 0; i < RP; i++)
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        acc[k][i][0] = fma(a[b][cc][i][0], wgt[cc * K + k], acc[k][i][0]);
+                        acc[k][i][1] = fma(a[b][cc][i][1], wgt[cc * K + k], acc[k][i][1]);
+                    }
+        };
+        uint32_t ph = 0;
+        for (int s0 = 0; s0 <= nsteps; s0 += 4, ph ^= 1u) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int s = s0 + u;
+                if (s < nsteps) dot_step(u, ph);
+                if (s >= 1 && s <= nsteps) axpy_step((u + 3) & 3, u == 0 ? ph ^ 1u : ph, (u + 1) & 1);   // step s - 1
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (!active[k]) continue;
+            double* prow = partial + ((size_t)k * nchunks + blockIdx.y) * ld + rbase;
+#pragma unroll
+            for (int i = 0; i < RP; i++)
+                if (valid[i]) *reinterpret_cast<double2*>(prow + (i * CT + tid) * 2) = make_double2(acc[k][i][0], acc[k][i][1]);
+        }
+    }
+    cluster_sync_all();                                          // nobody leaves while a peer may still write into its shared memory
+}
+
 template <int K, int C, int CS, typename Kern, typename... Extra>
 int gram_launch_any(vampomi_ctx* c, Kern kern, int TPB, int ROWS, size_t smem, int shape, const GramVec& gv, const MultiVec& mw, Extra... extra) {
     const size_t tr = (c->ld + CS - 1) / CS;
@@ -920,6 +1220,16 @@ int gram_launch_ws(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int sh
     constexpr int ROWS = NCW * 32 * RP * 2;
     return gram_launch_any<K, C, CS>(c, k_gram_ws<K, NCW, RP, C, R, CS, DIRECT, DEF, NCOMM>, (NCW + NCOMM) * 32, ROWS, (size_t)R * C * ROWS * sizeof(double), shape, gv, mw);
 }
+template <int K, int NCW, int RP, int C, int CS, int PROD>
+int gram_launch_wsx(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
+    constexpr int ROWS = NCW * 32 * RP * 2;
+    if constexpr (CS <= 32 / (C * K)) {
+        return gram_launch_any<K, C, CS>(c, k_gram_wsx<K, NCW, RP, C, CS, PROD>, (NCW + 1 + PROD) * 32, ROWS, (size_t)4 * C * ROWS * sizeof(double), shape, gv, mw);
+    } else {
+        set_error("gram: shape %d holds at most %d CTAs per cluster", shape, 32 / (C * K));
+        return VAMPOMI_ERR_ARG;
+    }
+}
 template <int K, int TPB, int RP, int C, int R, int CS>
 int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
     constexpr int ROWS = TPB * RP * 2;
@@ -938,6 +1248,8 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //        (measured, profiles/r02_sweep_gram_kernel_shapes.jsonl: 3.9 ms against 3.1 ms of shape 6; deferring the axpy by two steps
 //        (DEF = 2) and separate sender / receiver warps (NCOMM = 2) changed nothing there — 3.9 / 3.8 ms — so those variants are
 //        not instantiated: with DEF = 2 the four exchange slots would also have to become eight)
+//     9  k_gram_wsx: shape 6 with the lean compute loop (lane sums in the communication warp, 4x unrolled step loop, column means by
+//        bulk copy)   10  the same with a producer warp for the ring (default)
 //     (14 compute warps x 3 row pairs — 15 warps per SM under a 128-register cap — measured 3.35-3.45 ms against 3.08-3.30 of shape 6
 //     on the same box: more warps do not pay for the smaller register budget; not instantiated)
 constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape == 8 ? 1280 : 2560; }
@@ -955,6 +1267,8 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 6: return gram_launch_ws<K, 10, 4, 2, 4, CS, 0>(c, gv, mw, shape);
         case 7: return gram_launch_ws<K, 10, 4, 2, 4, CS, 1>(c, gv, mw, shape);
         case 8: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0>(c, gv, mw, shape);
+        case 9: return gram_launch_wsx<K, 10, 4, 2, CS, 0>(c, gv, mw, shape);
+        case 10: return gram_launch_wsx<K, 10, 4, 2, CS, 1>(c, gv, mw, shape);
         default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
     }
 }

@@ -20,6 +20,8 @@
 // Output: t (M-vector, written by cluster rank 0) and the per-chunk partials of w, which go through the same
 // k_ax_reduce_multi (fixed-order reduction + fused peer-memory all-reduce + 1/sqrt(N)) as the A x passes.
 // Algorithmic bytes per launch: N*M_local*8, for t AND w, for up to two systems.
+#include <cuda.h>                                               // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.h"
 #include "vec32.cuh"
 
@@ -934,9 +936,11 @@ __device__ __forceinline__ void bulk_g2s_u(uint32_t dst, const void* src, uint32
 }
 
 template <int K, int NCW, int RP, int C, int CS, int PROD>
-__global__ void __launch_bounds__((NCW + 1 + PROD) * 32, 1) k_gram_wsx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+__global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                                const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
-                                                               long long M, double scale, double* __restrict__ partial, int nchunks) {
+                                                               long long M, double scale, double* __restrict__ partial, int nchunks,
+                                                               const __grid_constant__ CUtensorMap tmap) {
+    constexpr bool TENSOR = PROD == 2;                           // one tensor copy per step (all C column pieces) instead of C + 1 bulk copies
     constexpr int R = 4, CK = C * K, NPAIR = CK / 2, LPV = 32 / CK, CT = NCW * 32, PIECE = CT * RP * 2;
     static_assert(C == 2 && (K == 1 || K == 2), "two columns per step: their means are one 16-byte bulk copy, their sums one or two value pairs");
     static_assert(CS <= LPV, "after the butterfly the LPV lanes that hold value ck send it to the CS ranks");
@@ -969,9 +973,17 @@ __global__ void __launch_bounds__((NCW + 1 + PROD) * 32, 1) k_gram_wsx(const dou
     const double* const msig_c = msig + c0;
     auto col_of = [&](int s, int cc) { const int j = s * C + cc; return j < ncols ? j : ncols - 1; };
     // rows of the ring slots that no bulk copy ever writes are zeroed once (see k_gram_ws)
-    for (int i = (int)(piece_bytes / 8) + tid; i < PIECE; i += blockDim.x)
+    if (TENSOR) {
+        // a stage holds the C column pieces back to back, tile_rows rows each (rows past the end of the column arrive as zeros: the
+        // copy engine fills what lies outside the tensor); the stage's tail behind them is never written
+        for (int i = C * tile_rows + tid; i < C * PIECE; i += blockDim.x)
 #pragma unroll
-        for (int sc = 0; sc < R * C; sc++) ring[(size_t)sc * PIECE + i] = 0.0;
+            for (int st = 0; st < R; st++) ring[(size_t)st * C * PIECE + i] = 0.0;
+    } else {
+        for (int i = (int)(piece_bytes / 8) + tid; i < PIECE; i += blockDim.x)
+#pragma unroll
+            for (int sc = 0; sc < R * C; sc++) ring[(size_t)sc * PIECE + i] = 0.0;
+    }
     const uint32_t cb = opaque_u32(smem_u32(ctl)), ring_u = opaque_u32(smem_u32(ring));
     if (tid == 0) {
 #pragma unroll
@@ -1005,10 +1017,42 @@ __global__ void __launch_bounds__((NCW + 1 + PROD) * 32, 1) k_gram_wsx(const dou
                     bulk_g2s_u(ring_u + (uint32_t)((st * C + cc) * PIECE * 8), a_c + (size_t)col_of(s, cc) * ld, piece_bytes, bar);
             }
         };
-        if (lane == 0 && wid == NCW + PROD) {
+        if (TENSOR && wid == NCW + 1) {
+            // producer warp, tensor form: ONE cp.async.bulk.tensor per step brings all C column pieces (box 16 x tile_rows/16 x C of the
+            // {16, ld/16, M} view of the marker block). A warp gets one bulk copy of any size under way every ~500-650 cycles
+            // (tools/tma_ingest2.cu: the rate scales with the number of ISSUING WARPS, not with bytes or copies in flight), so the
+            // C + 1 copies per step of the PROD = 1 form cost the producer ~1300 cycles per step — exactly what that form measures
+            // per step at any clock and any number of clusters (profiles/r02_gram_sustained_clock.jsonl). The column means travel
+            // beside the copy: lanes < C fetch them before waiting for the stage and store them before lane 0 arrives on its barrier.
+            const int row16 = (int)(rbase >> 4), box_bytes = C * tile_rows * 8;
+            auto issue_tensor = [&](int s, int st, double mv) {
+                if (lane < C) sts_f64(cb + MST_O + (uint32_t)((st * C + lane) * 8), mv);
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t bar = cb + RINGBAR_O + 8 * st;
+                    mbar_expect_tx_u(bar, (uint32_t)box_bytes);
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 ::"r"(ring_u + (uint32_t)(st * C * PIECE * 8)), "l"(&tmap), "r"(0), "r"(row16), "r"((int)(c0 + (long long)s * C)), "r"(bar) : "memory");
+                }
+            };
+            auto mean_of = [&](int s) { return lane < C ? __ldg(mave_c + col_of(s, lane)) : 0.0; };
+            for (int s = 0; s < R && s < nsteps; s++) issue_tensor(s, s, mean_of(s));
+            uint32_t php = 0;
+            for (int s0 = 0; s0 + R < nsteps; s0 += 4, php ^= 1u) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int s = s0 + u;
+                    if (s + R >= nsteps) break;
+                    const double mv = mean_of(s + R);
+                    mbar_spin_cta_u(cb + REDBAR_O + 8 * u, php);
+                    issue_tensor(s + R, u, mv);
+                }
+            }
+        } else if (lane == 0 && wid == NCW + (PROD ? 1 : 0)) {
             for (int s = 0; s < R && s < nsteps; s++) issue_step(s, s);
         }
-        if (PROD && wid == NCW + 1) {
+        if (TENSOR && wid == NCW + 1) {
+        } else if (PROD && wid == NCW + 1) {
             // producer warp: refills a ring stage the moment every compute warp has consumed it, however far the communication warp's
             // exchange of that step has got (as part of the communication warp's loop the refill waited for the previous step's
             // cluster round trip)
@@ -1096,6 +1140,7 @@ __global__ void __launch_bounds__((NCW + 1 + PROD) * 32, 1) k_gram_wsx(const dou
         }
         double a[2][C][RP][2];                                   // the step being dotted and the step whose axpy is pending
         const uint32_t rows_u = opaque_u32(ring_u + (uint32_t)tid * 16u);             // this thread's first row pair inside a ring slot
+        const uint32_t col_stride = TENSOR ? (uint32_t)tile_rows * 8u : (uint32_t)PIECE * 8u;   // bytes between the column pieces of a stage
         const uint32_t red_w = opaque_u32(cb + RED_O + (uint32_t)(wid * NPAIR) * 512u + (uint32_t)lane * 16u);
 
         auto dot_step = [&](const int u, const uint32_t par) {   // u = s % 4: ring stage, barrier; u & 1: register buffer, red slot
@@ -1111,7 +1156,8 @@ __global__ void __launch_bounds__((NCW + 1 + PROD) * 32, 1) k_gram_wsx(const dou
             for (int cc = 0; cc < C; cc++)
 #pragma unroll
                 for (int i = 0; i < RP; i++) {
-                    const double2 v = lds_f64x2(rows_u + (uint32_t)(((u * C + cc) * PIECE + i * CT * 2) * 8));   // rows beyond the tile read zeros
+                    // rows beyond the tile read zeros (tensor form: or the next column's first rows — they only meet q = 0 and unsaved sums)
+                    const double2 v = lds_f64x2(rows_u + (uint32_t)((u * C * PIECE + i * CT * 2) * 8) + (uint32_t)cc * col_stride);
                     const double d0 = v.x - m[cc], d1 = v.y - m[cc];            // meth[i] - mu, src/data.cpp:304 and :360
                     a[u & 1][cc][i][0] = d0; a[u & 1][cc][i][1] = d1;           // kept centred for the deferred axpy
 #pragma unroll
@@ -1220,11 +1266,51 @@ int gram_launch_ws(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int sh
     constexpr int ROWS = NCW * 32 * RP * 2;
     return gram_launch_any<K, C, CS>(c, k_gram_ws<K, NCW, RP, C, R, CS, DIRECT, DEF, NCOMM>, (NCW + NCOMM) * 32, ROWS, (size_t)R * C * ROWS * sizeof(double), shape, gv, mw);
 }
+// {16, ld/16, M} view of the column-major marker block (a column = ld/16 groups of 16 rows) with a box of one CTA's row tile of C
+// columns: 16 x tile_rows/16 x C doubles land in shared memory as C contiguous column pieces. Cached in the context.
+int gram_tensor_map(vampomi_ctx* c, int tile_rows, int C, CUtensorMap* out) {
+    if (c->gram_tmap_A != (const void*)c->A || c->gram_tmap_ld != c->ld || c->gram_tmap_M != c->M || c->gram_tmap_rows != tile_rows || c->gram_tmap_C != C) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+                cudaGetLastError();
+                set_error("gram: cuTensorMapEncodeTiled is not available from this driver");
+                return VAMPOMI_ERR_CUDA;
+            }
+            encode = (EncodeFn)fn;
+        }
+        if (c->ld % 16 != 0 || tile_rows % 16 != 0 || tile_rows / 16 > 256) { set_error("gram: tensor map needs ld and the row tile in multiples of 16 rows, at most 4096 rows per tile"); return VAMPOMI_ERR_ARG; }
+        const cuuint64_t dims[3] = {16, (cuuint64_t)(c->ld / 16), (cuuint64_t)c->M};
+        const cuuint64_t strides[2] = {16 * sizeof(double), (cuuint64_t)c->ld * sizeof(double)};
+        const cuuint32_t box[3] = {16, (cuuint32_t)(tile_rows / 16), (cuuint32_t)C};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUtensorMap tm;
+        const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)c->A, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("gram: cuTensorMapEncodeTiled failed (%d) for ld=%zu M=%lld tile_rows=%d", (int)r, c->ld, c->M, tile_rows); return VAMPOMI_ERR_CUDA; }
+        static_assert(sizeof(CUtensorMap) == sizeof(c->gram_tmap), "CUtensorMap is 128 bytes");
+        memcpy(c->gram_tmap, &tm, sizeof(tm));
+        c->gram_tmap_A = (const void*)c->A; c->gram_tmap_ld = c->ld; c->gram_tmap_M = c->M; c->gram_tmap_rows = tile_rows; c->gram_tmap_C = C;
+    }
+    memcpy(out, c->gram_tmap, sizeof(*out));
+    return VAMPOMI_OK;
+}
+
 template <int K, int NCW, int RP, int C, int CS, int PROD>
 int gram_launch_wsx(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
     constexpr int ROWS = NCW * 32 * RP * 2;
     if constexpr (CS <= 32 / (C * K)) {
-        return gram_launch_any<K, C, CS>(c, k_gram_wsx<K, NCW, RP, C, CS, PROD>, (NCW + 1 + PROD) * 32, ROWS, (size_t)4 * C * ROWS * sizeof(double), shape, gv, mw);
+        CUtensorMap tm;
+        memset(&tm, 0, sizeof(tm));
+        if (PROD == 2) {
+            const size_t tr = (c->ld + CS - 1) / CS;
+            VO_CHECK(gram_tensor_map(c, (int)((tr + 15) / 16 * 16), C, &tm));
+        }
+        return gram_launch_any<K, C, CS>(c, k_gram_wsx<K, NCW, RP, C, CS, PROD>, (NCW + 1 + (PROD ? 1 : 0)) * 32, ROWS, (size_t)4 * C * ROWS * sizeof(double), shape, gv, mw, tm);
     } else {
         set_error("gram: shape %d holds at most %d CTAs per cluster", shape, 32 / (C * K));
         return VAMPOMI_ERR_ARG;
@@ -1249,7 +1335,8 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //        (DEF = 2) and separate sender / receiver warps (NCOMM = 2) changed nothing there — 3.9 / 3.8 ms — so those variants are
 //        not instantiated: with DEF = 2 the four exchange slots would also have to become eight)
 //     9  k_gram_wsx: shape 6 with the lean compute loop (lane sums in the communication warp, 4x unrolled step loop, column means by
-//        bulk copy)   10  the same with a producer warp for the ring (default)
+//        bulk copy)   10  the same with a producer warp for the ring
+//    11  shape 10 with ONE tensor copy per step (cp.async.bulk.tensor.3d: both column pieces) instead of three bulk copies (default)
 //     (14 compute warps x 3 row pairs — 15 warps per SM under a 128-register cap — measured 3.35-3.45 ms against 3.08-3.30 of shape 6
 //     on the same box: more warps do not pay for the smaller register budget; not instantiated)
 constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape == 8 ? 1280 : 2560; }
@@ -1269,6 +1356,7 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 8: return gram_launch_ws<K, 10, 2, 4, 4, CS, 0>(c, gv, mw, shape);
         case 9: return gram_launch_wsx<K, 10, 4, 2, CS, 0>(c, gv, mw, shape);
         case 10: return gram_launch_wsx<K, 10, 4, 2, CS, 1>(c, gv, mw, shape);
+        case 11: return gram_launch_wsx<K, 10, 4, 2, CS, 2>(c, gv, mw, shape);
         default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
     }
 }

@@ -180,7 +180,7 @@ int vampomi_atx_multi_dev(vampomi_ctx* ctx, int K, const int* p_vecs, const int*
  * K <= 2 vectors in ONE pass over the marker block: each column is kept on chip between its dot product and its axpy
  * (csrc/kernels_gram.cu). This is lmmse_mult's ATx(Ax(.)) (src/vamp.cpp:653-654) re-associated around the N-side vector, and
  * what lets a CG iteration read the block once instead of twice (tuning knob cg_onepass / schedule "onepass"). Every
- * product keeps the per-element arithmetic of vampomi_atx_dev / vampomi_ax_dev. Needs FP64 storage and N <= 20480
+ * product keeps the per-element arithmetic of vampomi_atx_dev / vampomi_ax_dev. Needs FP64 storage and N <= 40960 (clusters of 8 CTAs up to 20480 rows, of 16 beyond)
  * (vampomi_aat_supported); q_vecs / w_out_vecs name N-vectors, t_out_vecs M-vectors, all distinct. */
 int vampomi_aat_multi_dev(vampomi_ctx* ctx, int K, const int* q_vecs, const int* t_out_vecs, const int* w_out_vecs);
 int vampomi_aat_supported(const vampomi_ctx* ctx, int* yes);

@@ -61,7 +61,7 @@ typedef struct vampomi_solver_config {
                                   keep q = A p as a vector of its own and one fused pass delivers A^T q (= A^T A p) and A A^T q
                                   (what the recurrence of q needs), each column staying on chip between its two uses
                                   (vampomi_aat_multi_dev) — max(k1,k2) + 1 passes per iteration; contexts that cannot run the
-                                  fused pass (FP32 storage, N > 20480) silently keep the two-pass iterations.
+                                  fused pass (FP32 storage, N > 40960) silently keep the two-pass iterations.
                                   Ignored (0) when redundant_passes = 1. */
     int probes;                /* Hutchinson probes per iteration: 1 = the reference's single +-1/sqrt(Mt) probe
                                   (src/vamp.cpp:295-296); P > 1 averages u^T Q^-1 u (alpha2) and u^T A^T A Q^-1 u (noise precision) over P

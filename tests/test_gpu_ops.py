@@ -380,7 +380,7 @@ def test_multi_vector_passes_match_oracle(N, M, storage):
     sh.close()
 
 
-@pytest.mark.parametrize("N,M", SHAPES + [(9000, 77), (20000, 300), (20480, 40)])
+@pytest.mark.parametrize("N,M", SHAPES + [(9000, 77), (20000, 300), (20480, 40), (20496, 40), (33000, 31), (40960, 10)])
 def test_fused_gram_pass_matches_the_two_products(N, M):
     """vampomi_aat_multi_dev: t = A^T q and w = A t from ONE read of the marker block (kernels_gram.cu). Both must equal what
     the two separate products (and the oracle) give, for every kernel shape and every cluster size that holds N, for one and
@@ -397,12 +397,14 @@ def test_fused_gram_pass_matches_the_two_products(N, M):
     want_t = [d.ATx(q) for q in qs]
     want_w = [d.Ax(t) for t in want_t]
     qin, tout, wout = [V_USER_N0, V_USER_N1], [V_R1, V_R2], [V_Z1, V_Z2]
-    rows = {0: 2560, 1: 3072, 2: 2560, 3: 2560, 4: 2560, 5: 2560, 6: 2560, 7: 2560, 8: 1280, 9: 2560, 10: 2560, 11: 2560}
+    rows = {0: 2560, 1: 3072, 2: 2560, 3: 2560, 4: 2560, 5: 2560, 6: 2560, 7: 2560, 8: 1280, 9: 2560, 10: 2560, 11: 2560, 12: 2560, 16: 2560}
     ran = 0
-    for shape in range(12):
+    for shape in list(range(13)) + [16]:
         sh.set_tuning("gram_shape", shape)
         for cs in (0, 1, 2, 4, 8, 16):
-            if (cs and -(-((N + 15) // 16 * 16) // cs) > rows[shape]) or (cs == 16 and shape != 8):
+            ld = (N + 15) // 16 * 16
+            maxcs = 16 if shape in (8, 11, 12, 16) else 8
+            if (cs and -(-ld // cs) > rows[shape]) or cs > maxcs or (cs == 0 and -(-ld // maxcs) > rows[shape]):
                 continue                                             # this cluster size cannot hold a column of N rows
             sh.set_tuning("gram_cluster", cs)
             for K in (1, 2):
@@ -417,8 +419,8 @@ def test_fused_gram_pass_matches_the_two_products(N, M):
                 for i in range(K, 2):
                     assert np.all(sh.get(tout[i]) == -7.0) and np.all(sh.get(wout[i]) == -7.0)
                 ran += 1
-    assert ran >= 12
-    sh.set_tuning("gram_shape", 11)
+    assert ran >= (12 if N <= 20480 else 4)                          # beyond 20 480 rows only the 16-CTA clusters of shape 11 hold a column
+    sh.set_tuning("gram_shape", 16)
     sh.set_tuning("gram_cluster", 0)
     for clusters in (1, 3, 1000):                                    # any number of column chunks, more than there are columns included
         sh.set_tuning("gram_clusters", clusters)
@@ -637,9 +639,9 @@ def test_instrumentation_and_error_paths():
 
 
 def test_onepass_falls_back_where_the_fused_pass_cannot_run():
-    """N > 20 480 rows (more than 8 CTAs x 2 560 rows hold) and FP32 storage: vampomi_aat_supported says no, the fused entry point
+    """N > 40 960 rows (more than 16 CTAs x 2 560 rows hold) and FP32 storage: vampomi_aat_supported says no, the fused entry point
     refuses, and a solve with cg_onepass set runs the two-pass iterations with the same answer."""
-    N, M = 20496, 40
+    N, M = 40976, 24
     sh, A, y, rng = make(N, M, seed=5)
     assert not sh.aat_supported()
     with pytest.raises(capi.VampomiError):

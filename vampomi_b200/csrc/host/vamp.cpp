@@ -68,7 +68,7 @@ int Vamp::init(const double* y, const double* true_signal, const double* x1hat_i
     VH(vampomi_vec_fill(ctx_, VAMPOMI_V_X2, 0.0));
     VH(vampomi_vec_fill(ctx_, VAMPOMI_V_R2, 0.0));
     // schedule "onepass" (fuse_passes >= 3): the recycled schedule with CG iterations that read the marker block once
-    // (fused A^T q / A A^T q pass); contexts that cannot run it (FP32 storage, N > 20480) keep the two-pass iterations
+    // (fused A^T q / A A^T q pass); contexts that cannot run it (FP32 storage, N > 40960) keep the two-pass iterations
     if (cfg_.fuse_passes >= 3 && cfg_.redundant_passes == 0) VH(vampomi_set_tuning(ctx_, "cg_onepass", 1));
     else if (cfg_.fuse_passes >= 0) VH(vampomi_set_tuning(ctx_, "cg_onepass", 0));
     it_ = 0;

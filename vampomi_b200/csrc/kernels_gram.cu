@@ -935,22 +935,59 @@ __device__ __forceinline__ void bulk_g2s_u(uint32_t dst, const void* src, uint32
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int K, int NCW, int RP, int C, int CS, int PROD>
-__global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
+// Sums of NV (2 or 4) values over the lane quadruples {l, l^8, l^16, l^24}: the first two levels of warp_sum_multi. Lane l is left with the
+// quadruple's sum of value l / (32 / NV); the levels 4, 2, 1 that remain are the same for every NV.
+template <int NV>
+__device__ __forceinline__ double quad_sum_multi(const double (&v)[NV], int lane) {
+    static_assert(NV == 2 || NV == 4, "2 or 4 values");
+    const bool up16 = (lane & 16) != 0;
+    if constexpr (NV == 4) {
+        const bool up8 = (lane & 8) != 0;
+        const double a0 = (up16 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[2], 16);
+        const double a1 = (up16 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, up16 ? v[1] : v[3], 16);
+        return (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+    } else {
+        const double t = (up16 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[1], 16);
+        return t + __shfl_xor_sync(0xffffffffu, t, 8);
+    }
+}
+
+template <int K, int NCW, int RP, int C, int CS, int PROD, int DBG = 0, int RED = 0>
+__global__ void __launch_bounds__((NCW + (PROD == 3 ? 4 : 1 + (PROD ? 1 : 0))) * 32, 1) k_gram_wsx(const double* __restrict__ A, size_t ld, const double* __restrict__ mave,
                                                                const double* __restrict__ msig, GramVec gv, int tile_rows, int cols_per_chunk,
                                                                long long M, double scale, double* __restrict__ partial, int nchunks,
                                                                const __grid_constant__ CUtensorMap tmap) {
-    constexpr bool TENSOR = PROD == 2;                           // one tensor copy per step (all C column pieces) instead of C + 1 bulk copies
+    constexpr bool TENSOR = PROD >= 2;                           // one tensor copy per step (all C column pieces) instead of C + 1 bulk copies
+    // PROD = 3: the service warps form a warpgroup of their own (communication warp, producer warp, two idle warps) that hands its
+    // registers to the compute warpgroups (setmaxnreg): 8 compute warps x 5 row pairs need ~200 registers, and a CTA of 10 warps is
+    // allotted registers as if it had 12 (168 per thread) — with two compute warps on every scheduler instead of 3 / 3 / 2 / 2
+    constexpr bool REALLOC = PROD == 3;
+    // DBG 3: cluster 0's rank 0 writes clock64() stamps of every hand-over of its first 3000 steps into t[0] (32 slots per step) instead of the
+    // products (tools/gram_trace.py reads them back); wrong results, timing experiments only
+    long long* const trace = DBG == 3 && blockIdx.y == 0 ? reinterpret_cast<long long*>(gv.t[0]) : nullptr;
+    auto stamp = [&](int s, int slot) {
+        if (DBG == 3) {
+            uint32_t cr;
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cr));
+            if (trace != nullptr && cr == 0 && s < 3000 && (threadIdx.x & 31) == 0) trace[s * 32 + slot] = clock64();
+        }
+    };
+    static_assert(!REALLOC || NCW % 4 == 0, "whole warpgroups of compute warps");
     constexpr int R = 4, CK = C * K, NPAIR = CK / 2, LPV = 32 / CK, CT = NCW * 32, PIECE = CT * RP * 2;
     static_assert(C == 2 && (K == 1 || K == 2), "two columns per step: their means are one 16-byte bulk copy, their sums one or two value pairs");
-    static_assert(CS <= LPV, "after the butterfly the LPV lanes that hold value ck send it to the CS ranks");
+    static_assert(CS <= 2 * LPV, "after the butterfly the LPV lanes that hold value ck send it to the CS ranks, at most two each");
     // one control block, addressed as base register + compile-time offset (bytes)
     constexpr uint32_t XSLOT = CS * CK * 8;                      // xbuf[4][CS][CK]: partial sums of the ranks, per exchange slot
     constexpr uint32_t XBUF_O = 0, WBUF_O = XBUF_O + 4 * XSLOT;  // wbuf[4][CK]: axpy weights of a step
     constexpr uint32_t MST_O = WBUF_O + 4 * CK * 8;              // mst[R][C]: column means of a ring stage
     constexpr uint32_t FULL_O = MST_O + R * C * 8, WREADY_O = FULL_O + 32, REDBAR_O = WREADY_O + 32, RINGBAR_O = REDBAR_O + 32;
-    constexpr uint32_t RED_O = RINGBAR_O + R * 8;                // red[2][NCW][NPAIR][32 lanes] value pairs
-    constexpr uint32_t REDSLOT = NCW * NPAIR * 512, CTL_BYTES = RED_O + 2 * REDSLOT;
+    // RED = 0: red[2][NCW][NPAIR][32 lanes] value pairs — the lanes' sums as they are, the communication warp adds warps and lanes;
+    // RED = 1: red[2][NCW][32 lanes] — every compute warp first adds its lane quadruples (two shuffle levels, hidden in the time the
+    //          warp waits for the previous step's weights anyway), the communication warp adds the warps and the three levels left.
+    //          The time stamps of shape 15 (tools/gram_trace.py) show the communication warp to be the step's critical path:
+    //          ~670 of its ~1180 cycles per step went into reading and adding the 10 x 32 x 4 lane sums
+    constexpr uint32_t RED_O = RINGBAR_O + R * 8;
+    constexpr uint32_t REDSLOT = RED ? NCW * 256 : NCW * NPAIR * 512, CTL_BYTES = RED_O + 2 * REDSLOT;
     static_assert(RED_O % 16 == 0, "16-byte stores");
     extern __shared__ __align__(128) double ring[];              // [R][C][PIECE]
     __shared__ __align__(16) unsigned char ctl[CTL_BYTES];
@@ -1000,6 +1037,7 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
 
     if (wid >= NCW) {
         // ------------------------- communication warp (and, with PROD, the ring's producer warp) -------------------------
+        if (REALLOC) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         const double* const a_c = A + rbase + (size_t)c0 * ld;
         const bool m_aligned = (reinterpret_cast<uintptr_t>(mave_c) & 15) == 0;
         auto issue_step = [&](int s, int st) {                   // lane 0: the C column pieces and means of step s into stage st = s % 4
@@ -1051,7 +1089,7 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
         } else if (lane == 0 && wid == NCW + (PROD ? 1 : 0)) {
             for (int s = 0; s < R && s < nsteps; s++) issue_step(s, s);
         }
-        if (TENSOR && wid == NCW + 1) {
+        if ((TENSOR && wid == NCW + 1) || (REALLOC && wid > NCW + 1)) {
         } else if (PROD && wid == NCW + 1) {
             // producer warp: refills a ring stage the moment every compute warp has consumed it, however far the communication warp's
             // exchange of that step has got (as part of the communication warp's loop the refill waited for the previous step's
@@ -1075,8 +1113,9 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
         for (int k = 1; k < K; k++) act = k_l == k ? active[k] : act;
         double* tout = K > 1 && k_l == 1 ? gv.t[K - 1] : gv.t[0];
         double sg_next = nsteps > 0 ? __ldg(msig_c + col_of(0, cc_l)) : 0.0;
-        const uint32_t peer = (uint32_t)(dst < CS ? dst : 0);
+        const uint32_t peer = (uint32_t)(dst < CS ? dst : 0), peer2 = (uint32_t)(dst + LPV < CS ? dst + LPV : 0);   // 16-CTA clusters: two ranks per lane
         const uint32_t rx = mapa_u32(cb + XBUF_O + (crank * CK + ck) * 8, peer), rf = mapa_u32(cb + FULL_O, peer);
+        const uint32_t rx2 = mapa_u32(cb + XBUF_O + (crank * CK + ck) * 8, peer2), rf2 = mapa_u32(cb + FULL_O, peer2);
         const uint32_t red_l = cb + RED_O + (uint32_t)lane * 16u, xb_l = cb + XBUF_O + (uint32_t)ck * 8u, wb_l = cb + WBUF_O + (uint32_t)ck * 8u;
         uint32_t ph = 0;                                         // (s / 4) & 1: phase parity of every four-deep barrier ring
         for (int s0 = 0; s0 < nsteps; s0 += 4, ph ^= 1u) {
@@ -1087,21 +1126,39 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
                 const double sgl = sg_next;
                 sg_next = __ldg(msig_c + col_of(s + 1 < nsteps ? s + 1 : s, cc_l));
                 mbar_spin_cta_u(cb + REDBAR_O + 8 * u, ph);       // every compute warp has read stage u and stored its partial sums
+                stamp(s, 24);
                 if (!PROD && lane == 0 && s + R < nsteps) issue_step(s + R, u);
+                double sw;                                       // the CTA's partial sum of value ck
+                if constexpr (RED == 1) {
+                    double pw[NCW];
+#pragma unroll
+                    for (int w = 0; w < NCW; w++) pw[w] = lds_f64(cb + RED_O + (uint32_t)((u & 1) * REDSLOT + w * 256) + (uint32_t)lane * 8u);
+                    sw = tree_sum<NCW>(pw);
+                    sw += __shfl_xor_sync(0xffffffffu, sw, 4);
+                    sw += __shfl_xor_sync(0xffffffffu, sw, 2);
+                    sw += __shfl_xor_sync(0xffffffffu, sw, 1);
+                } else {
                 double vs[CK];                                   // this lane's sum over the warps (fixed tree) of its slice of every value
 #pragma unroll
                 for (int pr = 0; pr < NPAIR; pr++) {
                     double px[NCW], py[NCW];
 #pragma unroll
                     for (int w = 0; w < NCW; w++) {
-                        const double2 x = lds_f64x2(red_l + (uint32_t)((u & 1) * REDSLOT + (w * NPAIR + pr) * 512));
+                        const double2 x = DBG == 2 && w > 0 ? make_double2(px[0] + 1.0, py[0] + 1.0) : lds_f64x2(red_l + (uint32_t)((u & 1) * REDSLOT + (w * NPAIR + pr) * 512));
                         px[w] = x.x; py[w] = x.y;
                     }
                     vs[2 * pr] = tree_sum<NCW>(px); vs[2 * pr + 1] = tree_sum<NCW>(py);
                 }
-                const double sw = warp_sum_multi<CK>(vs, lane);  // the CTA's partial sum of value ck
+                sw = warp_sum_multi<CK>(vs, lane);
+                }
                 if (dst < CS) st_async_f64(rx + u * XSLOT, sw, rf + 8 * u);
-                mbar_spin_cluster_u(cb + FULL_O + 8 * u, ph);
+                if (CS > LPV && dst + LPV < CS) st_async_f64(rx2 + u * XSLOT, sw, rf2 + 8 * u);
+                stamp(s, 25);
+                // the ranks' values arrive as st.async transactions ON this barrier (data and count are one message), so the CTA-scope wait
+                // orders them; the cluster-scope acquire form costs a CCTL.IVALL (L1 invalidation) per step — 14 % of this warp's time in
+                // the ncu samples of shape 10 — that shared memory does not need
+                if (TENSOR) mbar_spin_cta_u(cb + FULL_O + 8 * u, ph); else mbar_spin_cluster_u(cb + FULL_O + 8 * u, ph);
+                stamp(s, 26);
                 // every lane adds the CS partial sums of its value by the same fixed tree: bitwise the same t_j in every CTA
                 double pr[CS];
 #pragma unroll
@@ -1111,7 +1168,7 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
                 const double tj = (sgl * tot) * scale;                          // sigma_inv * dpa (:306), then * scale (:330)
                 const bool live = j < ncols && act;
                 if (dst == 0) {
-                    if (live && crank == 0) tout[c0 + j] = tj;
+                    if (live && crank == 0 && DBG != 3) tout[c0 + j] = tj;
                     sts_f64(wb_l + (uint32_t)(u * CK * 8), live ? sgl * tj : 0.0);   // sig_phen_i = msig * x, src/data.cpp:354
                 }
                 __syncwarp();
@@ -1119,11 +1176,13 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
                     mbar_arrive_cta_u(cb + WREADY_O + 8 * u);
                     mbar_expect_tx_u(cb + FULL_O + 8 * u, XSLOT);               // re-arm the slot for step s + 4
                 }
+                stamp(s, 27);
             }
         }
         }
     } else {
         // ---------------------------------------------- compute warps ----------------------------------------------
+        if (REALLOC) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
         bool valid[RP];
         double qr[K][RP][2], acc[K][RP][2];
 #pragma unroll
@@ -1143,13 +1202,15 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
         const uint32_t col_stride = TENSOR ? (uint32_t)tile_rows * 8u : (uint32_t)PIECE * 8u;   // bytes between the column pieces of a stage
         const uint32_t red_w = opaque_u32(cb + RED_O + (uint32_t)(wid * NPAIR) * 512u + (uint32_t)lane * 16u);
 
-        auto dot_step = [&](const int u, const uint32_t par) {   // u = s % 4: ring stage, barrier; u & 1: register buffer, red slot
+        auto dot_step = [&](const int u, const uint32_t par, const int s) {   // u = s % 4: ring stage, barrier; u & 1: register buffer, red slot
             double pd[C][K][2];
 #pragma unroll
             for (int cc = 0; cc < C; cc++)
 #pragma unroll
                 for (int k = 0; k < K; k++) pd[cc][k][0] = pd[cc][k][1] = 0.0;
+            if (wid == 0) stamp(s, 20);
             mbar_spin_cta_u(cb + RINGBAR_O + 8 * u, par);
+            if (wid == 0) stamp(s, 21);
             const double2 mm = lds_f64x2(cb + MST_O + (uint32_t)(u * C * 8));
             const double m[2] = {mm.x, mm.y};
 #pragma unroll
@@ -1157,7 +1218,9 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
 #pragma unroll
                 for (int i = 0; i < RP; i++) {
                     // rows beyond the tile read zeros (tensor form: or the next column's first rows — they only meet q = 0 and unsaved sums)
-                    const double2 v = lds_f64x2(rows_u + (uint32_t)((u * C * PIECE + i * CT * 2) * 8) + (uint32_t)cc * col_stride);
+                    // DBG (timing experiments only, wrong results): 1 = the second column of a step is not read from shared memory
+                    const double2 v = DBG == 1 && cc > 0 ? make_double2(a[u & 1][0][i][0] + m[0], a[u & 1][0][i][1] + m[0])
+                                                         : lds_f64x2(rows_u + (uint32_t)((u * C * PIECE + i * CT * 2) * 8) + (uint32_t)cc * col_stride);
                     const double d0 = v.x - m[cc], d1 = v.y - m[cc];            // meth[i] - mu, src/data.cpp:304 and :360
                     a[u & 1][cc][i][0] = d0; a[u & 1][cc][i][1] = d1;           // kept centred for the deferred axpy
 #pragma unroll
@@ -1171,13 +1234,20 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
             for (int cc = 0; cc < C; cc++)
 #pragma unroll
                 for (int k = 0; k < K; k++) v[cc * K + k] = pd[cc][k][0] + pd[cc][k][1];
+            if constexpr (RED == 1) {
+                sts_f64(cb + RED_O + (uint32_t)((u & 1) * REDSLOT + wid * 256) + (uint32_t)lane * 8u, quad_sum_multi<CK>(v, lane));
+            } else {
 #pragma unroll
-            for (int pr = 0; pr < NPAIR; pr++) sts_f64x2(red_w + (uint32_t)((u & 1) * REDSLOT + pr * 512), v[2 * pr], v[2 * pr + 1]);
+            for (int pr = 0; pr < NPAIR; pr++)
+                if (DBG != 2 || v[2 * pr] == 123.456) sts_f64x2(red_w + (uint32_t)((u & 1) * REDSLOT + pr * 512), v[2 * pr], v[2 * pr + 1]);   // DBG 2: partial sums never stored
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive_cta_u(cb + REDBAR_O + 8 * u);
+            stamp(s, wid);
         };
-        auto axpy_step = [&](const int slot, const uint32_t par, const int b) {
+        auto axpy_step = [&](const int slot, const uint32_t par, const int b, const int s) {
             mbar_spin_cta_u(cb + WREADY_O + 8 * slot, par);
+            stamp(s, 10 + wid);
             double wgt[CK];
 #pragma unroll
             for (int i = 0; i < CK; i += 2) {
@@ -1199,8 +1269,8 @@ __global__ void __launch_bounds__((NCW + 1 + (PROD ? 1 : 0)) * 32, 1) k_gram_wsx
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int s = s0 + u;
-                if (s < nsteps) dot_step(u, ph);
-                if (s >= 1 && s <= nsteps) axpy_step((u + 3) & 3, u == 0 ? ph ^ 1u : ph, (u + 1) & 1);   // step s - 1
+                if (s < nsteps) dot_step(u, ph, s);
+                if (s >= 1 && s <= nsteps) axpy_step((u + 3) & 3, u == 0 ? ph ^ 1u : ph, (u + 1) & 1, s - 1);   // step s - 1
             }
         }
 #pragma unroll
@@ -1300,19 +1370,19 @@ int gram_tensor_map(vampomi_ctx* c, int tile_rows, int C, CUtensorMap* out) {
     return VAMPOMI_OK;
 }
 
-template <int K, int NCW, int RP, int C, int CS, int PROD>
+template <int K, int NCW, int RP, int C, int CS, int PROD, int DBG = 0, int RED = 0>
 int gram_launch_wsx(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
     constexpr int ROWS = NCW * 32 * RP * 2;
-    if constexpr (CS <= 32 / (C * K)) {
+    if constexpr (CS <= 2 * (32 / (C * K))) {
         CUtensorMap tm;
         memset(&tm, 0, sizeof(tm));
-        if (PROD == 2) {
+        if (PROD >= 2) {
             const size_t tr = (c->ld + CS - 1) / CS;
             VO_CHECK(gram_tensor_map(c, (int)((tr + 15) / 16 * 16), C, &tm));
         }
-        return gram_launch_any<K, C, CS>(c, k_gram_wsx<K, NCW, RP, C, CS, PROD>, (NCW + 1 + (PROD ? 1 : 0)) * 32, ROWS, (size_t)4 * C * ROWS * sizeof(double), shape, gv, mw, tm);
+        return gram_launch_any<K, C, CS>(c, k_gram_wsx<K, NCW, RP, C, CS, PROD, DBG, RED>, (NCW + (PROD == 3 ? 4 : 1 + (PROD ? 1 : 0))) * 32, ROWS, (size_t)4 * C * ROWS * sizeof(double), shape, gv, mw, tm);
     } else {
-        set_error("gram: shape %d holds at most %d CTAs per cluster", shape, 32 / (C * K));
+        set_error("gram: shape %d holds at most %d CTAs per cluster", shape, 2 * (32 / (C * K)));
         return VAMPOMI_ERR_ARG;
     }
 }
@@ -1337,10 +1407,12 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //     9  k_gram_wsx: shape 6 with the lean compute loop (lane sums in the communication warp, 4x unrolled step loop, column means by
 //        bulk copy)   10  the same with a producer warp for the ring
 //    11  shape 10 with ONE tensor copy per step (cp.async.bulk.tensor.3d: both column pieces) instead of three bulk copies (default)
+//    12  shape 11 with 8 compute warps x 5 row pairs — two compute warps on every scheduler (10 leave two schedulers with three) — and a
+//        service warpgroup that hands its registers to the compute warpgroups (setmaxnreg 96 / 200: the pool is the 384 x 168 registers the CTA was launched with)
 //     (14 compute warps x 3 row pairs — 15 warps per SM under a 128-register cap — measured 3.35-3.45 ms against 3.08-3.30 of shape 6
 //     on the same box: more warps do not pay for the smaller register budget; not instantiated)
 constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape == 8 ? 1280 : 2560; }
-constexpr int gram_max_cluster_of_shape(int shape) { return shape == 8 ? 16 : 8; }
+constexpr int gram_max_cluster_of_shape(int shape) { return shape == 8 || shape == 11 || shape == 12 || shape == 16 ? 16 : 8; }   // 16: non-portable cluster size, one cluster per GPC
 
 template <int K, int CS>
 int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
@@ -1357,8 +1429,16 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 9: return gram_launch_wsx<K, 10, 4, 2, CS, 0>(c, gv, mw, shape);
         case 10: return gram_launch_wsx<K, 10, 4, 2, CS, 1>(c, gv, mw, shape);
         case 11: return gram_launch_wsx<K, 10, 4, 2, CS, 2>(c, gv, mw, shape);
-        default: set_error("gram: unknown shape %d", shape); return VAMPOMI_ERR_ARG;
+        case 12: return gram_launch_wsx<K, 8, 5, 2, CS, 3>(c, gv, mw, shape);
+        case 13: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 1>(c, gv, mw, shape); else break;   // timing experiments (wrong results)
+        case 14: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 2>(c, gv, mw, shape); else break;
+        case 16: return gram_launch_wsx<K, 10, 4, 2, CS, 2, 0, 1>(c, gv, mw, shape);
+        case 17: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3, 1>(c, gv, mw, shape); else break;   // shape 16 with time stamps
+        case 15: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3>(c, gv, mw, shape); else break;   // hand-over time stamps (tools/gram_trace.py)
+        default: break;
     }
+    set_error("gram: unknown shape %d", shape);
+    return VAMPOMI_ERR_ARG;
 }
 
 template <int K>
@@ -1368,7 +1448,10 @@ int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
     if (cs == 0) { cs = 1; while (cs < gram_max_cluster_of_shape(shape) && (c->ld + cs - 1) / cs > (size_t)gram_rows_of_shape(shape)) cs *= 2; }
     if (cs == 16) {
         if (shape == 8) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0>(c, gv, mw, shape);
-        set_error("gram: 16 CTAs per cluster only with shape 8");
+        if (shape == 11) return gram_launch_wsx<K, 10, 4, 2, 16, 2>(c, gv, mw, shape);     // 20 480 < N <= 40 960
+        if (shape == 12) return gram_launch_wsx<K, 8, 5, 2, 16, 3>(c, gv, mw, shape);
+        if (shape == 16) return gram_launch_wsx<K, 10, 4, 2, 16, 2, 0, 1>(c, gv, mw, shape);
+        set_error("gram: 16 CTAs per cluster only with shapes 8 and 11");
         return VAMPOMI_ERR_ARG;
     }
     switch (cs) {
@@ -1390,7 +1473,7 @@ bool gram_supported(const vampomi_ctx* c) {
 // mq: in = q_k (N-vectors), out = t_k (M-vectors); w_out: the N-vectors that receive w_k. done flags from mq.
 int launch_gram(vampomi_ctx* c, const MultiVec& mq, double* const* w_out) {
     if (mq.K < 1 || mq.K > 2) { set_error("gram: 1 or 2 systems"); return VAMPOMI_ERR_ARG; }
-    if (!gram_supported(c)) { set_error("gram: needs FP64 storage and N <= 20480"); return VAMPOMI_ERR_ARG; }
+    if (!gram_supported(c)) { set_error("gram: needs FP64 storage and N <= 40960"); return VAMPOMI_ERR_ARG; }
     GramVec gv{};
     MultiVec mw{};
     mw.K = mq.K;

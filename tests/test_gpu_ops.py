@@ -397,13 +397,13 @@ def test_fused_gram_pass_matches_the_two_products(N, M):
     want_t = [d.ATx(q) for q in qs]
     want_w = [d.Ax(t) for t in want_t]
     qin, tout, wout = [V_USER_N0, V_USER_N1], [V_R1, V_R2], [V_Z1, V_Z2]
-    rows = {0: 2560, 1: 3072, 2: 2560, 3: 2560, 4: 2560, 5: 2560, 6: 2560, 7: 2560, 8: 1280, 9: 2560, 10: 2560, 11: 2560, 12: 2560, 16: 2560}
+    rows = {0: 2560, 1: 3072, 2: 2560, 3: 2560, 4: 2560, 5: 2560, 6: 2560, 7: 2560, 8: 1280, 9: 2560, 10: 2560, 11: 2560, 12: 2560, 16: 2560, 18: 2560}
     ran = 0
-    for shape in list(range(13)) + [16]:
+    for shape in list(range(13)) + [16, 18]:
         sh.set_tuning("gram_shape", shape)
         for cs in (0, 1, 2, 4, 8, 16):
             ld = (N + 15) // 16 * 16
-            maxcs = 16 if shape in (8, 11, 12, 16) else 8
+            maxcs = 16 if shape in (8, 11, 12, 16, 18) else 8
             if (cs and -(-ld // cs) > rows[shape]) or cs > maxcs or (cs == 0 and -(-ld // maxcs) > rows[shape]):
                 continue                                             # this cluster size cannot hold a column of N rows
             sh.set_tuning("gram_cluster", cs)
@@ -420,7 +420,7 @@ def test_fused_gram_pass_matches_the_two_products(N, M):
                     assert np.all(sh.get(tout[i]) == -7.0) and np.all(sh.get(wout[i]) == -7.0)
                 ran += 1
     assert ran >= (12 if N <= 20480 else 4)                          # beyond 20 480 rows only the 16-CTA clusters of shape 11 hold a column
-    sh.set_tuning("gram_shape", 16)
+    sh.set_tuning("gram_shape", 18)
     sh.set_tuning("gram_cluster", 0)
     for clusters in (1, 3, 1000):                                    # any number of column chunks, more than there are columns included
         sh.set_tuning("gram_clusters", clusters)

@@ -256,12 +256,12 @@ def test_full_size_properties():
     sh.atx_multi_dev([V_USER_N0, V_USER_N1], [V_R1, V_R2])
     assert rel_l2(sh.get(V_R1), ATp) < 1e-13 and rel_l2(sh.get(V_R2), ATp2) < 1e-13
     assert abs(sh.get(V_Z2) @ p2 - x2 @ sh.get(V_R2)) <= 1e-11 * math.sqrt((Ax2 @ Ax2) * (p2 @ p2))
-    for shape in (16, 11, 10, 6, 3, 0):
+    for shape in (18, 16, 11, 10, 6, 3, 0):
         sh.set_tuning("gram_shape", shape)
         sh.aat_multi_dev([V_USER_N0, V_USER_N1], [V_R1, V_R2], [V_Z1, V_Z2])
         assert rel_l2(sh.get(V_R1), ATp) < 1e-13 and rel_l2(sh.get(V_R2), ATp2) < 1e-13, shape
         assert rel_l2(sh.get(V_Z1), sh.Ax(ATp)) < 1e-13 and rel_l2(sh.get(V_Z2), sh.Ax(ATp2)) < 1e-13, shape
-    sh.set_tuning("gram_shape", 16)
+    sh.set_tuning("gram_shape", 18)
     w1 = sh.get(V_Z1)
     assert abs(w1 @ p2 - ATp @ ATp2) <= 1e-11 * math.sqrt((w1 @ w1) * (p2 @ p2))       # <A A^T p, p2> = <A^T p, A^T p2>
     # CG: ||(tau A^T A + gam2) mu - v|| / ||v|| below the tolerance, evaluated with separate operator calls

@@ -50,10 +50,10 @@ if a.gram:
     t(4, "read_probe", a.gram)
     t(5, "ax_multi_K2_default", a.gram)
     t(6, "atx_multi_K2_default", a.gram)
-    for shape in list(range(13)) + [16]:
+    for shape in list(range(13)) + [16, 18]:
         t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0)
         t(10, "gram_K1", a.gram, gram_shape=shape, gram_clusters=0)
-    for shape in (16, 11, 10, 6, 16, 11, 10, 6):
+    for shape in (18, 16, 11, 6, 18, 16, 11, 6):
         t(9, "gram_K2", a.gram, gram_shape=shape, gram_clusters=0)
     if not a.quick:
         for shape in (0, 1):

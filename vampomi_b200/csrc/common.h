@@ -125,7 +125,7 @@ struct Tuning {
     int dump_stream = 0;             // asynchronous read-outs copy on 0 = the context's stream (stream-ordered), 1 = the copy stream
     int center_split = 0;            // 1 = subtract the column mean once per sum instead of once per element (LDG variants)
     int cg_onepass = 0;              // 1 = CG iterations read the marker block ONCE (fused A^T q / A A^T q pass, kernels_gram.cu) where supported
-    int gram_shape = 16;             // fused pass: kernel shape (threads, rows per thread, columns per step, steps in flight; kernels_gram.cu)
+    int gram_shape = 18;             // fused pass: kernel shape (threads, rows per thread, columns per step, steps in flight; kernels_gram.cu)
     int gram_prefetch = 4;           // fused pass: steps ahead that one lane per CTA pulls into L2 (cp.async.bulk.prefetch), 0 = off
     int gram_cluster = 0;            // fused pass: CTAs per cluster = row tiles of a column (0 = smallest of 1, 2, 4, 8 that holds N)
     int gram_clusters = 0;           // fused pass: clusters in the grid (0 = as many as are co-resident, occupancy query)

@@ -1412,7 +1412,7 @@ int gram_launch_bulk(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int 
 //     (14 compute warps x 3 row pairs — 15 warps per SM under a 128-register cap — measured 3.35-3.45 ms against 3.08-3.30 of shape 6
 //     on the same box: more warps do not pay for the smaller register budget; not instantiated)
 constexpr int gram_rows_of_shape(int shape) { return shape == 1 ? 3072 : shape == 8 ? 1280 : 2560; }
-constexpr int gram_max_cluster_of_shape(int shape) { return shape == 8 || shape == 11 || shape == 12 || shape == 16 ? 16 : 8; }   // 16: non-portable cluster size, one cluster per GPC
+constexpr int gram_max_cluster_of_shape(int shape) { return shape == 8 || shape == 11 || shape == 12 || shape == 16 || shape == 18 ? 16 : 8; }   // 16: non-portable cluster size, one cluster per GPC
 
 template <int K, int CS>
 int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape) {
@@ -1433,6 +1433,7 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 13: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 1>(c, gv, mw, shape); else break;   // timing experiments (wrong results)
         case 14: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 2>(c, gv, mw, shape); else break;
         case 16: return gram_launch_wsx<K, 10, 4, 2, CS, 2, 0, 1>(c, gv, mw, shape);
+        case 18: return gram_launch_wsx<K, 8, 5, 2, CS, 3, 0, 1>(c, gv, mw, shape);       // shape 12's warp layout with shape 16's sums
         case 17: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3, 1>(c, gv, mw, shape); else break;   // shape 16 with time stamps
         case 15: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3>(c, gv, mw, shape); else break;   // hand-over time stamps (tools/gram_trace.py)
         default: break;
@@ -1451,6 +1452,7 @@ int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
         if (shape == 11) return gram_launch_wsx<K, 10, 4, 2, 16, 2>(c, gv, mw, shape);     // 20 480 < N <= 40 960
         if (shape == 12) return gram_launch_wsx<K, 8, 5, 2, 16, 3>(c, gv, mw, shape);
         if (shape == 16) return gram_launch_wsx<K, 10, 4, 2, 16, 2, 0, 1>(c, gv, mw, shape);
+        if (shape == 18) return gram_launch_wsx<K, 8, 5, 2, 16, 3, 0, 1>(c, gv, mw, shape);
         set_error("gram: 16 CTAs per cluster only with shapes 8 and 11");
         return VAMPOMI_ERR_ARG;
     }

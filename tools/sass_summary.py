@@ -9,9 +9,9 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WANT = [("kernels_gram.o", r"k_gram_wsxILi2ELi8ELi5ELi2ELi8ELi3ELi0ELi1E"), ("kernels_gram.o", r"k_gram_wsxILi1ELi8ELi5ELi2ELi8ELi3ELi0ELi1E"),
         ("kernels_multi.o", r"k_ax_multiIdLi3ELi1ELi4ELi0E"), ("kernels_multi.o", r"k_ax_reduce_multiILi8E")]
-KEEP = re.compile(r"^(DFMA|DADD|DMUL|LDG|STG|LDS|STS|LDL|STL|SHFL|UBLKCP|SYNCS|BAR|UCGABAR|CCTL|MEMBAR|ATOM|RED|ST\.|STAS|MAPA|UMOV|ERRBAR|FENCE)")
+KEEP = re.compile(r"^(DFMA|DADD|DMUL|LDG|STG|LDS|STS|LDL|STL|SHFL|UBLKCP|UTMALDG|USETMAXREG|SYNCS|BAR|UCGABAR|CCTL|MEMBAR|ATOM|RED|ST\.|STAS|MAPA|UMOV|ERRBAR|FENCE)")
 print("# SASS mnemonic counts of the default kernels of an iteration (cuobjdump -sass of vampomi_b200/build/*.o, sm_100a).\n"
-      "# k_gram_ws: UBLKCP = cp.async.bulk (bulk-copy ring), SYNCS.* = mbarrier arrive / expect_tx / try_wait, STAS = st.async into a peer\n"
+      "# k_gram_wsx: UTMALDG.3D = cp.async.bulk.tensor.3d (one per ring stage), USETMAXREG = setmaxnreg, SYNCS.* = mbarrier arrive / expect_tx / try_wait,\n# STAS = st.async into a peer\n"
       "# CTA's shared memory (distributed shared memory), no LDL/STL (no local-memory traffic), LDS.128 conflict-free row pairs.\n")
 for obj, pat in WANT:
     out = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "vampomi_b200", "build", obj)], stdout=subprocess.PIPE, text=True).stdout

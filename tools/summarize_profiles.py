@@ -68,7 +68,7 @@ if os.path.isfile(rep):
         f.write("# ncu --set full --clock-control none --import-source on -k regex:'k_gram|k_ax_multi' -s 6 -c 4,\n"
                 "# `python bench.py --N 20000 --Mt 106250 --steps 1 --warmup 1 --no-cpu-baseline --no-ab --no-parity`\n"
                 "# (one 8-GPU shard of the headline configuration: 17.000 GB of A per pass). Default (onepass) schedule: every pass of an\n"
-                "# iteration is one of these two kernels (k_gram_ws: A^T q and A A^T q of both systems; k_ax_multi: the first A p of the solves). Per-launch values.\n")
+                "# iteration is one of these two kernels (k_gram_wsx: A^T q and A A^T q of both systems; k_ax_multi: the first A p of the solves). Per-launch values.\n")
         for r in rows[2:]:
             name = r[idx["Kernel Name"]]
             f.write("\nKernel Name".ljust(77) + name[:160] + "\n")
@@ -82,10 +82,52 @@ if os.path.isfile(rep):
     tj_path = os.path.join(PROF, "ncu_traffic.json")
     tj = json.load(open(tj_path))
     for k, v in traffic.items():
-        tj[k] = {"N": 20000, "M_local": 106250, "algorithmic_bytes": 17000000000, "dram_bytes": sum(v) / len(v),
-                 "source": f"profiles/{tag}_ncu_full_matrix_kernels.txt ({k}, mean of {len(v)} launches)"}
+        rec = {"N": 20000, "M_local": 106250, "algorithmic_bytes": 17000000000, "dram_bytes": sum(v) / len(v),
+               "source": f"profiles/{tag}_ncu_full_matrix_kernels.txt ({k}, mean of {len(v)} launches)"}
+        old = tj.get(k)
+        others = [r for r in old if r.get("M_local") != 106250] if isinstance(old, list) else []    # captures of other launch shapes stay
+        tj[k] = others + [rec] if others else rec
     json.dump(tj, open(tj_path, "w"), indent=1)
     print("ncu summary written", {k: sum(v) / len(v) for k, v in traffic.items()})
+
+# ---- the fused pass at the 1-GPU bench's own launch shape (136 GB), one launch --------------------------------------
+rep = os.path.join(OUT, "prof_gram136.ncu-rep")
+if os.path.isfile(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    r = rows[2]
+
+    def val(h):
+        v, u = float(r[idx[h]].replace(",", "")), units[idx[h]]
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}.get(u, 1.0)
+    dst = f"{tag}_ncu_full_k_gram_wsx_136GB.txt"
+    with open(os.path.join(PROF, dst), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:k_gram -s 8 -c 1,\n"
+                "# `python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ab --no-parity` (N = 20000, Mt = 850000: the 1-GPU bench's launch shape, 136.000 GB per pass)\n\n")
+        f.write("Kernel Name".ljust(76) + r[idx["Kernel Name"]][:160] + "\n")
+        for h in hdr:
+            if re.match(r"(gpu__time_duration.sum|dram__bytes_(read|write).sum($|\.per_second)|launch__(registers_per_thread$|grid_size|block_size)|"
+                        r"sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active|lts__t_sector_hit_rate.pct|sm__throughput.avg.pct)", h):
+                f.write(f"{h:76s}{r[idx[h]]} {units[idx[h]]}\n")
+    tj_path = os.path.join(PROF, "ncu_traffic.json")
+    tj = json.load(open(tj_path))
+    big = {"N": 20000, "M_local": 850000, "algorithmic_bytes": 136000000000, "dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+           "source": f"profiles/{dst} (ncu --set full capture of one k_gram_wsx launch of the 1-GPU bench command)"}
+    old = tj.get("k_gram")
+    small = [x for x in (old if isinstance(old, list) else [old]) if x and x.get("M_local") != 850000]
+    tj["k_gram"] = [big] + small
+    json.dump(tj, open(tj_path, "w"), indent=1)
+    print("136 GB capture written", big["dram_bytes"])
+
+# ---- multi-GPU bench lines (tools/gpu_scale.sh) ------------------------------------------------------------------------
+for f_ in sorted(os.listdir(OUT)) if os.path.isdir(OUT) else []:
+    m = re.fullmatch(r"bench_g(\d+)_of(\d+)\.log", f_)
+    if m and int(m.group(1)) > 1:
+        d = last_json(os.path.join(OUT, f_))
+        if d:
+            json.dump(d, open(os.path.join(PROF, f"{tag}_bench_{m.group(1)}gpu.json"), "w"), indent=1)
 
 # ---- bench lines, parity reports ---------------------------------------------------------------------------------
 for src, dst in (("bench.log", f"{tag}_bench_1gpu.json"), ("bench_ref.log", f"{tag}_bench_reference_arm.json")):

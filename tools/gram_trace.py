@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Hand-over time stamps of the fused pass (gram_shape 15 = shape 11 with clock64() stamps written by cluster 0's rank 0 instead of the
+"""Needs a library built with the experiment shapes: make -C vampomi_b200/csrc clean all EXTRA_NVFLAGS=-DVAMPOMI_GRAM_EXPERIMENTS
+Hand-over time stamps of the fused pass (gram_shape 15 = shape 11 with clock64() stamps written by cluster 0's rank 0 instead of the
 products): where a step's ~1300 SM cycles go. Prints, over the traced steps, the mean and quartiles of every leg.
 slots per step: 0-9 compute warp w finished its dot (arrives on REDBAR); 10-19 warp w saw WREADY of the step; 20 / 21 warp 0 before / after the
 ring barrier; 24 communication warp saw REDBAR; 25 sent; 26 saw FULL; 27 set WREADY."""

@@ -1086,11 +1086,11 @@ __global__ void __launch_bounds__((NCW + (PROD == 3 ? 4 : 1 + (PROD ? 1 : 0))) *
                     issue_tensor(s + R, u, mv);
                 }
             }
-        } else if (lane == 0 && wid == NCW + (PROD ? 1 : 0)) {
+        } else if (!TENSOR && lane == 0 && wid == NCW + (PROD ? 1 : 0)) {
             for (int s = 0; s < R && s < nsteps; s++) issue_step(s, s);
         }
         if ((TENSOR && wid == NCW + 1) || (REALLOC && wid > NCW + 1)) {
-        } else if (PROD && wid == NCW + 1) {
+        } else if (!TENSOR && PROD && wid == NCW + 1) {
             // producer warp: refills a ring stage the moment every compute warp has consumed it, however far the communication warp's
             // exchange of that step has got (as part of the communication warp's loop the refill waited for the previous step's
             // cluster round trip)
@@ -1430,12 +1430,15 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 10: return gram_launch_wsx<K, 10, 4, 2, CS, 1>(c, gv, mw, shape);
         case 11: return gram_launch_wsx<K, 10, 4, 2, CS, 2>(c, gv, mw, shape);
         case 12: return gram_launch_wsx<K, 8, 5, 2, CS, 3>(c, gv, mw, shape);
-        case 13: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 1>(c, gv, mw, shape); else break;   // timing experiments (wrong results)
+#ifdef VAMPOMI_GRAM_EXPERIMENTS
+        // timing experiments with deliberately WRONG results — not in the product library: make EXTRA_NVFLAGS=-DVAMPOMI_GRAM_EXPERIMENTS
+        case 13: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 1>(c, gv, mw, shape); else break;
         case 14: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 2>(c, gv, mw, shape); else break;
         case 16: return gram_launch_wsx<K, 10, 4, 2, CS, 2, 0, 1>(c, gv, mw, shape);
         case 18: return gram_launch_wsx<K, 8, 5, 2, CS, 3, 0, 1>(c, gv, mw, shape);       // shape 12's warp layout with shape 16's sums
-        case 17: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3, 1>(c, gv, mw, shape); else break;   // shape 16 with time stamps
         case 15: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3>(c, gv, mw, shape); else break;   // hand-over time stamps (tools/gram_trace.py)
+        case 17: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3, 1>(c, gv, mw, shape); else break;   // shape 16 with time stamps
+#endif
         default: break;
     }
     set_error("gram: unknown shape %d", shape);

@@ -229,3 +229,29 @@ def test_onepass_cg_recurrences_reproduce_the_two_pass_iterates():
             assert abs(alpha - a2) < 1e-11 * abs(a2)
             assert np.linalg.norm(mu - mu2) < 1e-11 * np.linalg.norm(mu2) and np.linalg.norm(r - r2) < 1e-9 * np.linalg.norm(v)
             assert np.linalg.norm(q - d.Ax(p)) < 1e-10 * np.linalg.norm(q)
+
+
+def test_default_fused_pass_shape_is_built_into_the_product_library():
+    """The default `gram_shape` (csrc/common.h) must be a case of the shape switch OUTSIDE the experiment-only block
+    (`#ifdef VAMPOMI_GRAM_EXPERIMENTS`: timing variants with wrong results), and the library must hold its kernel."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    default = int(re.search(r"int gram_shape = (\d+);", open(os.path.join(root, "vampomi_b200", "csrc", "common.h")).read()).group(1))
+    product_cases, depth = {}, 0
+    for line in open(os.path.join(root, "vampomi_b200", "csrc", "kernels_gram.cu")):
+        if line.startswith("#ifdef VAMPOMI_GRAM_EXPERIMENTS"):
+            depth += 1
+        elif line.startswith("#endif") and depth:
+            depth -= 1
+        m = re.match(r"\s+case (\d+): return gram_launch_wsx<K, (\d+), (\d+), (\d+), CS, (\d+)(?:, (\d+), (\d+))?>", line)
+        if m and depth == 0:
+            product_cases[int(m.group(1))] = [int(x) if x else 0 for x in m.groups()[1:]]
+    assert default in product_cases, (default, sorted(product_cases))
+    ncw, rp, c, prod, dbg, red = product_cases[default]
+    assert dbg == 0                                                  # DBG variants leave work out or write time stamps instead of results
+    lib = os.path.join(root, "vampomi_b200", "lib", "libvampomi_cuda.so")
+    out = subprocess.run(["cuobjdump", "-res-usage", lib], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    for k in (1, 2):
+        assert f"k_gram_wsxILi{k}ELi{ncw}ELi{rp}ELi{c}ELi8ELi{prod}ELi{dbg}ELi{red}E" in out, (k, default)

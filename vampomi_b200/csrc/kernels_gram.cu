@@ -1430,12 +1430,12 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 10: return gram_launch_wsx<K, 10, 4, 2, CS, 1>(c, gv, mw, shape);
         case 11: return gram_launch_wsx<K, 10, 4, 2, CS, 2>(c, gv, mw, shape);
         case 12: return gram_launch_wsx<K, 8, 5, 2, CS, 3>(c, gv, mw, shape);
+        case 16: return gram_launch_wsx<K, 10, 4, 2, CS, 2, 0, 1>(c, gv, mw, shape);
+        case 18: return gram_launch_wsx<K, 8, 5, 2, CS, 3, 0, 1>(c, gv, mw, shape);       // shape 12's warp layout with shape 16's sums
 #ifdef VAMPOMI_GRAM_EXPERIMENTS
         // timing experiments with deliberately WRONG results — not in the product library: make EXTRA_NVFLAGS=-DVAMPOMI_GRAM_EXPERIMENTS
         case 13: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 1>(c, gv, mw, shape); else break;
         case 14: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 2>(c, gv, mw, shape); else break;
-        case 16: return gram_launch_wsx<K, 10, 4, 2, CS, 2, 0, 1>(c, gv, mw, shape);
-        case 18: return gram_launch_wsx<K, 8, 5, 2, CS, 3, 0, 1>(c, gv, mw, shape);       // shape 12's warp layout with shape 16's sums
         case 15: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3>(c, gv, mw, shape); else break;   // hand-over time stamps (tools/gram_trace.py)
         case 17: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 3, 1>(c, gv, mw, shape); else break;   // shape 16 with time stamps
 #endif

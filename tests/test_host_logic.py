@@ -248,6 +248,12 @@ def test_default_fused_pass_shape_is_built_into_the_product_library():
         m = re.match(r"\s+case (\d+): return gram_launch_wsx<K, (\d+), (\d+), (\d+), CS, (\d+)(?:, (\d+), (\d+))?>", line)
         if m and depth == 0:
             product_cases[int(m.group(1))] = [int(x) if x else 0 for x in m.groups()[1:]]
+        m = re.match(r"\s+if \(shape == (\d+)\) \{", line)
+        if m:
+            any_cluster_shape = int(m.group(1))                     # gram_cluster(): a shape instantiated for every cluster size 1 ... 16
+        m = re.match(r"#define VAMPOMI_GRAM_CS\(n\) case n: return gram_launch_wsx<K, (\d+), (\d+), (\d+), n, (\d+), (\d+), (\d+)>", line)
+        if m and depth == 0:
+            product_cases[any_cluster_shape] = [int(x) for x in m.groups()]
     assert default in product_cases, (default, sorted(product_cases))
     ncw, rp, c, prod, dbg, red = product_cases[default]
     assert dbg == 0                                                  # DBG variants leave work out or write time stamps instead of results

@@ -180,7 +180,7 @@ struct vampomi_ctx {
     vampomi::NcclApi* nccl = nullptr;
     vampomi::Tuning tune;
     long long counters[4] = {0, 0, 0, 0};
-    int gram_clusters[20][5][2] = {};    // co-resident clusters of k_gram per (shape, cluster size 1/2/4/8/16, systems), 0 = not queried yet
+    int gram_clusters[20][17][2] = {};   // co-resident clusters of k_gram per (shape, cluster size 1 ... 16, systems), 0 = not queried yet
     // tensor map of the marker block for the fused pass's one-copy-per-step producer (a CUtensorMap; kernels_gram.cu), with its key
     alignas(64) unsigned char gram_tmap[128] = {};
     const void* gram_tmap_A = nullptr;

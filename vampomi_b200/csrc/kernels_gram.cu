@@ -1296,8 +1296,8 @@ int gram_launch_any(vampomi_ctx* c, Kern kern, int TPB, int ROWS, size_t smem, i
     attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(TPB); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream; cfg.attrs = attr; cfg.numAttrs = 1;
     // co-resident clusters of this (shape, cluster size, systems) on this device: queried once per context
-    constexpr int csi = CS == 1 ? 0 : CS == 2 ? 1 : CS == 4 ? 2 : CS == 8 ? 3 : 4;
-    int& ncl = c->gram_clusters[shape][csi][K - 1];
+    static_assert(CS >= 1 && CS <= 16, "cluster size");
+    int& ncl = c->gram_clusters[shape][CS][K - 1];
     if (ncl <= 0) {
         if (smem > 40 * 1024) VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (CS > 8) VO_CUDA(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));   // 16 CTAs: one cluster per GPC
@@ -1342,17 +1342,13 @@ int gram_tensor_map(vampomi_ctx* c, int tile_rows, int C, CUtensorMap* out) {
     if (c->gram_tmap_A != (const void*)c->A || c->gram_tmap_ld != c->ld || c->gram_tmap_M != c->M || c->gram_tmap_rows != tile_rows || c->gram_tmap_C != C) {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-        static EncodeFn encode = nullptr;
-        if (!encode) {
+        static const EncodeFn encode = [] {                      // resolved once (thread-safe: the rank threads of main_meth --gpus share it)
             void* fn = nullptr;
             cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
-                cudaGetLastError();
-                set_error("gram: cuTensorMapEncodeTiled is not available from this driver");
-                return VAMPOMI_ERR_CUDA;
-            }
-            encode = (EncodeFn)fn;
-        }
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess) { cudaGetLastError(); fn = nullptr; }
+            return (EncodeFn)fn;
+        }();
+        if (encode == nullptr) { set_error("gram: cuTensorMapEncodeTiled is not available from this driver"); return VAMPOMI_ERR_CUDA; }
         if (c->ld % 16 != 0 || tile_rows % 16 != 0 || tile_rows / 16 > 256) { set_error("gram: tensor map needs ld and the row tile in multiples of 16 rows, at most 4096 rows per tile"); return VAMPOMI_ERR_ARG; }
         const cuuint64_t dims[3] = {16, (cuuint64_t)(c->ld / 16), (cuuint64_t)c->M};
         const cuuint64_t strides[2] = {16 * sizeof(double), (cuuint64_t)c->ld * sizeof(double)};
@@ -1431,7 +1427,7 @@ int gram_shape(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw, int shape)
         case 11: return gram_launch_wsx<K, 10, 4, 2, CS, 2>(c, gv, mw, shape);
         case 12: return gram_launch_wsx<K, 8, 5, 2, CS, 3>(c, gv, mw, shape);
         case 16: return gram_launch_wsx<K, 10, 4, 2, CS, 2, 0, 1>(c, gv, mw, shape);
-        case 18: return gram_launch_wsx<K, 8, 5, 2, CS, 3, 0, 1>(c, gv, mw, shape);       // shape 12's warp layout with shape 16's sums
+        case 18: break;                                          // shape 12's warp layout with shape 16's sums: gram_cluster() (any cluster size)
 #ifdef VAMPOMI_GRAM_EXPERIMENTS
         // timing experiments with deliberately WRONG results — not in the product library: make EXTRA_NVFLAGS=-DVAMPOMI_GRAM_EXPERIMENTS
         case 13: if constexpr (CS == 8) return gram_launch_wsx<K, 10, 4, 2, CS, 2, 1>(c, gv, mw, shape); else break;
@@ -1449,14 +1445,26 @@ template <int K>
 int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
     const int shape = c->tune.gram_shape;
     int cs = c->tune.gram_cluster;
+    if (shape == 18) {
+        // the default shape runs on ANY cluster size up to 16 — the smallest that holds a column, so that a CTA's row tile (and with it
+        // the bytes a step moves per exchange) is as full as it can be: N = 12 000 on 5 CTAs x 2 400 rows instead of 8 x 1 500
+        // (tools/gram_large_n.py: a step costs ~1100 cycles whatever it carries)
+        if (cs == 0) cs = (int)((c->ld + gram_rows_of_shape(shape) - 1) / gram_rows_of_shape(shape));
+        switch (cs) {
+#define VAMPOMI_GRAM_CS(n) case n: return gram_launch_wsx<K, 8, 5, 2, n, 3, 0, 1>(c, gv, mw, shape);
+            VAMPOMI_GRAM_CS(1) VAMPOMI_GRAM_CS(2) VAMPOMI_GRAM_CS(3) VAMPOMI_GRAM_CS(4) VAMPOMI_GRAM_CS(5) VAMPOMI_GRAM_CS(6) VAMPOMI_GRAM_CS(7) VAMPOMI_GRAM_CS(8)
+            VAMPOMI_GRAM_CS(9) VAMPOMI_GRAM_CS(10) VAMPOMI_GRAM_CS(11) VAMPOMI_GRAM_CS(12) VAMPOMI_GRAM_CS(13) VAMPOMI_GRAM_CS(14) VAMPOMI_GRAM_CS(15) VAMPOMI_GRAM_CS(16)
+#undef VAMPOMI_GRAM_CS
+            default: set_error("gram: cluster size must be 1 ... 16"); return VAMPOMI_ERR_ARG;
+        }
+    }
     if (cs == 0) { cs = 1; while (cs < gram_max_cluster_of_shape(shape) && (c->ld + cs - 1) / cs > (size_t)gram_rows_of_shape(shape)) cs *= 2; }
     if (cs == 16) {
         if (shape == 8) return gram_launch_ws<K, 10, 2, 4, 4, 16, 0>(c, gv, mw, shape);
         if (shape == 11) return gram_launch_wsx<K, 10, 4, 2, 16, 2>(c, gv, mw, shape);     // 20 480 < N <= 40 960
         if (shape == 12) return gram_launch_wsx<K, 8, 5, 2, 16, 3>(c, gv, mw, shape);
         if (shape == 16) return gram_launch_wsx<K, 10, 4, 2, 16, 2, 0, 1>(c, gv, mw, shape);
-        if (shape == 18) return gram_launch_wsx<K, 8, 5, 2, 16, 3, 0, 1>(c, gv, mw, shape);
-        set_error("gram: 16 CTAs per cluster only with shapes 8 and 11");
+        set_error("gram: 16 CTAs per cluster only with shapes 8, 11, 12, 16 and 18");
         return VAMPOMI_ERR_ARG;
     }
     switch (cs) {
@@ -1464,7 +1472,7 @@ int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
         case 2: return gram_shape<K, 2>(c, gv, mw, shape);
         case 4: return gram_shape<K, 4>(c, gv, mw, shape);
         case 8: return gram_shape<K, 8>(c, gv, mw, shape);
-        default: set_error("gram: cluster size must be 1, 2, 4 or 8"); return VAMPOMI_ERR_ARG;
+        default: set_error("gram: cluster size must be 1, 2, 4 or 8 for this shape"); return VAMPOMI_ERR_ARG;
     }
 }
 

@@ -126,6 +126,9 @@ long long vampomi_host_read_covariates(const char* path, int C, int N, double* Z
 int vampomi_host_newton_cov(const double* y_N, const double* gg_N, const double* Z_NxC, int N, int C, double* eta_inout_C);
 /* linear_reg1d_pvals (src/utilities.cpp:269-282) with boost's Student-t complement restated by a continued fraction. */
 double vampomi_host_linear_reg1d_pvals(double sumx, double sumsqx, double sumxy, double sumy, double sumsqy, int n);
+/* The per-marker tail of data::pvals_loo (src/data.cpp:400-414) for M markers at once, on `threads` host threads (0 = all, at most
+ * 32): x1_M = x1_hat * sqrt(N), sums_3M = what vampomi_loo_sums returns, sum_w / sumsq_w = sum and sum of squares of y_mod. */
+void vampomi_host_loo_pvals(const double* x1_M, const double* sums_3M, double sum_w, double sumsq_w, int N, long long M, double* pvals_M, int threads);
 /* The counter-hash stand-ins for std::random_device (oracle patches P2/P3): probe sign (+1/-1) and probit start p1. */
 double vampomi_host_probe_sign(unsigned long long seed, int it, unsigned long long global_marker);
 void vampomi_host_probit_p1(unsigned long long seed, int N, double* out);

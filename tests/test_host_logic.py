@@ -72,6 +72,30 @@ def test_students_t_pvalues_match_scipy(lib):
             assert got == pytest.approx(spstats.linregress(x, yv).pvalue, rel=1e-7, abs=1e-300)
 
 
+def test_loo_pvalues_of_a_marker_block_are_the_same_on_any_number_of_threads(lib):
+    """vampomi_host_loo_pvals: the per-marker tail of data::pvals_loo (src/data.cpp:400-414) for a block of markers — equal to the
+    per-marker function (and so to scipy) marker by marker, bit for bit on 1, 3 and all host threads."""
+    rng = np.random.default_rng(5)
+    n, M = 400, 20000
+    A = rng.standard_normal((M, n)) * 0.3 + 0.5                     # raw, unstandardised columns
+    w = rng.standard_normal(n)                                      # y_mod
+    x1 = rng.standard_normal(M) * (rng.random(M) < 0.1)
+    sums = np.ascontiguousarray(np.stack([A.sum(1), (A * A).sum(1), A @ w], axis=1))
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    outs = []
+    for threads in (1, 3, 0):
+        out = np.full(M, -1.0)
+        lib.vampomi_host_loo_pvals(dp(x1), dp(sums), w.sum(), (w * w).sum(), n, M, dp(out), threads)
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    for j in list(range(0, M, 997)) + [M - 1]:
+        c = x1[j] / np.sqrt(n)
+        ym = w + A[j] * c
+        one = lib.vampomi_host_linear_reg1d_pvals(A[j].sum(), (A[j] * A[j]).sum(), (A[j] * ym).sum(), ym.sum(), (ym * ym).sum(), n)
+        assert outs[0][j] == pytest.approx(one, rel=1e-9, abs=1e-300)
+        assert outs[0][j] == pytest.approx(spstats.linregress(A[j], ym).pvalue, rel=1e-6, abs=1e-300)
+
+
 def test_counter_hash_matches_oracle_and_reference_hooks(lib):
     for seed in (0, 7, 2 ** 63 + 5):
         for it in (1, 2, 50):

@@ -119,6 +119,7 @@ _SIGNATURES = {
     "vampomi_host_csv_row": (C.c_int, [C.c_uint, c_double_p, C.c_int, C.c_char_p, C.c_int]),
     "vampomi_host_read_phen": (C.c_longlong, [C.c_char_p, C.c_int, c_double_p, C.c_longlong]),
     "vampomi_host_linear_reg1d_pvals": (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
+    "vampomi_host_loo_pvals": (None, [c_double_p, c_double_p, C.c_double, C.c_double, C.c_int, C.c_longlong, c_double_p, C.c_int]),
     "vampomi_host_probe_sign": (C.c_double, [C.c_ulonglong, C.c_int, C.c_ulonglong]),
     "vampomi_host_probit_p1": (None, [C.c_ulonglong, C.c_int, c_double_p]),
     "vampomi_host_merge_components": (C.c_int, [c_double_p, c_double_p, C.c_int, C.c_double]),

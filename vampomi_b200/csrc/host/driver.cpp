@@ -432,12 +432,7 @@ int run_association(Rank& r) {                                                  
             return fatal_abi(r, "loo sums");
         double sw = 0, sww = 0;
         for (double v : w) { sw += v; sww += v * v; }
-        for (long long j = 0; j < r.M; j++) {
-            // y_mark = y_mod + x * c, c = x1_hat[j]/sqrt(N) (src/data.cpp:404-405): its sums follow from those of x and y_mod
-            const double c = x1[j] / sqrtN, sx = sums[3 * j], sxx = sums[3 * j + 1], sxw = sums[3 * j + 2];
-            const double sumy = sw + c * sx, sumxy = sxw + c * sxx, sumsqy = sww + 2 * c * sxw + c * c * sxx;
-            pvals[j] = linear_reg1d_pvals(sx, sxx, sumxy, sumy, sumsqy, N);                    // :414
-        }
+        loo_pvals(x1.data(), sums.data(), sw, sww, N, r.M, pvals.data());                      // Student-t per marker, on the host's threads
         out = o.out_dir + "/" + o.out_name + "_it_" + tag + "_pval_loo.bin";
     } else {
         return 0;                                                                              // the reference silently does nothing

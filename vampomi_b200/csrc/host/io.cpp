@@ -10,6 +10,9 @@
 #include <iostream>
 #include <numeric>
 #include <stdexcept>
+#include <algorithm>
+#include <thread>
+#include <vector>
 #include "../rng.h"
 
 namespace vampomi_host {
@@ -148,10 +151,21 @@ double betacf(double a, double b, double x) {
     }
     return h;
 }
+// ln(Gamma(a+b) / (Gamma(a) Gamma(b))): one (a, b) serves every marker of a run (a = (N-2)/2, b = 1/2), so the last pair is kept
+// per thread; lgamma_r because std::lgamma writes the global signgam and the markers are spread over threads (loo_pvals)
+double ln_inv_beta(double a, double b) {
+    thread_local double ka = -1.0, kb = -1.0, kv = 0.0;
+    if (a != ka || b != kb) {
+        int sg;
+        kv = lgamma_r(a + b, &sg) - lgamma_r(a, &sg) - lgamma_r(b, &sg);
+        ka = a; kb = b;
+    }
+    return kv;
+}
 double ibeta(double a, double b, double x) {
     if (x <= 0.0) return 0.0;
     if (x >= 1.0) return 1.0;
-    const double lnbt = std::lgamma(a + b) - std::lgamma(a) - std::lgamma(b) + a * std::log(x) + b * std::log1p(-x);
+    const double lnbt = ln_inv_beta(a, b) + a * std::log(x) + b * std::log1p(-x);
     const double bt = std::exp(lnbt);
     if (x < (a + 1.0) / (a + b + 2.0)) return bt * betacf(a, b, x) / a;
     return 1.0 - bt * betacf(b, a, 1.0 - x) / b;
@@ -171,6 +185,29 @@ double linear_reg1d_pvals(double sumx, double sumsqx, double sumxy, double sumy,
     const double rxy = sxy / std::sqrt(s2x * s2y);
     const double t = rxy * std::sqrt((n - 2) / (1 - rxy * rxy));
     return students_t_two_sided(t > 0 ? t : (0 - t), (double)(n - 2));
+}
+
+void loo_pvals(const double* x1, const double* sums, double sw, double sww, int N, long long M, double* pvals, int threads) {
+    const double sqrtN = std::sqrt((double)N);
+    auto work = [&](long long j0, long long j1) {
+        for (long long j = j0; j < j1; j++) {
+            // y_mark = y_mod + x * c, c = x1_hat[j]/sqrt(N) (src/data.cpp:404-405): its sums follow from those of x and y_mod
+            const double c = x1[j] / sqrtN, sx = sums[3 * j], sxx = sums[3 * j + 1], sxw = sums[3 * j + 2];
+            const double sumy = sw + c * sx, sumxy = sxw + c * sxx, sumsqy = sww + 2 * c * sxw + c * c * sxx;
+            pvals[j] = linear_reg1d_pvals(sx, sxx, sumxy, sumy, sumsqy, N);                    // src/data.cpp:414
+        }
+    };
+    if (threads <= 0) threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    const long long per = 4096;                              // markers are independent: any split gives the same bits
+    threads = (int)std::min<long long>(threads, (M + per - 1) / per);
+    if (threads <= 1) { work(0, M); return; }
+    std::vector<std::thread> pool;
+    const long long chunk = (M + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const long long j0 = t * chunk, j1 = std::min(M, j0 + chunk);
+        if (j0 < j1) pool.emplace_back(work, j0, j1);
+    }
+    for (auto& th : pool) th.join();
 }
 
 double calc_stdev(const std::vector<double>& v) {

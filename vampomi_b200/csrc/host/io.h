@@ -35,6 +35,10 @@ private:
 double students_t_two_sided(double t, double dof);
 // src/utilities.cpp:269-282
 double linear_reg1d_pvals(double sumx, double sumsqx, double sumxy, double sumy, double sumsqy, int n);
+// data::pvals_loo's per-marker tail (src/data.cpp:400-414) for M markers from the three streamed sums per raw column (sum x, sum x^2,
+// sum x*y_mod; vampomi_loo_sums), the scaled estimate x1 (x1_hat * sqrt(N)) and sum / sum of squares of y_mod, spread over host
+// threads (0 = all hardware threads, at most 32).
+void loo_pvals(const double* x1, const double* sums, double sw, double sww, int N, long long M, double* pvals, int threads = 0);
 // src/utilities.cpp:183-205 with sync = 0
 double calc_stdev(const std::vector<double>& v);
 // src/utilities.cpp:284-287

@@ -763,6 +763,10 @@ double vampomi_host_linear_reg1d_pvals(double sumx, double sumsqx, double sumxy,
     return vampomi_host::linear_reg1d_pvals(sumx, sumsqx, sumxy, sumy, sumsqy, n);
 }
 
+void vampomi_host_loo_pvals(const double* x1_M, const double* sums_3M, double sum_w, double sumsq_w, int N, long long M, double* pvals_M, int threads) {
+    vampomi_host::loo_pvals(x1_M, sums_3M, sum_w, sumsq_w, N, M, pvals_M, threads);
+}
+
 double vampomi_host_probe_sign(unsigned long long seed, int it, unsigned long long global_marker) {
     return vampomi::probe_sign(seed, it, global_marker);
 }

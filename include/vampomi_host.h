@@ -104,8 +104,11 @@ int vampomi_solver_get_cov_eff(vampomi_solver* s, int C, double* out_C);
 /* Checkpoint / resume (the reference's --estimate-file restart is dead code, src/vamp.cpp:71-79): save_state
  * writes everything the next iteration depends on — iteration number, gam1, gamw, the prior, the covariate effects and the vectors
  * r1, x1_hat, x2_hat (and the probit p1, tau1, alpha1) — into ONE file that all ranks share (every rank writes its marker slice at
- * its offset; rank 0 the header); load_state on a freshly created solver of the same problem restores it, so that the following
- * iterations equal those of an uninterrupted run (to rounding of two products that are recomputed instead of recycled). */
+ * its offset; rank 0 the header; every rank ends, after its data are on disk, with a completion record of the marker block it wrote);
+ * load_state on a freshly created solver of the same problem — on any number of GPUs — restores it, so that the following
+ * iterations equal those of an uninterrupted run (to rounding of two products that are recomputed instead of recycled). A file
+ * whose completion records do not tile all Mt markers at the header's iteration (a writer died) is refused with VAMPOMI_ERR_IO
+ * and leaves the solver as it was. */
 int vampomi_solver_save_state(vampomi_solver* s, const char* path);
 int vampomi_solver_load_state(vampomi_solver* s, const char* path);
 int vampomi_solver_step(vampomi_solver* s, vampomi_iter_result* res, double* x1_scaled_M, double* r1_scaled_M);

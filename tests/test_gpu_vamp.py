@@ -492,7 +492,12 @@ def test_checkpoint_and_resume_continue_the_same_run(name, schedule, tmp_path):
     sol.save_state(ck)
     sol.close(); sh.close()
     sh, sol = solver_for(g, A, y_txt, beta, **SCHEDULES[schedule])
-    sol.load_state(ck)
+    torn = bytearray(open(ck, "rb").read())                                       # a writer that died before its completion record
+    torn[2048:2048 + 24] = bytes(24)
+    open(tmp_path / "torn.bin", "wb").write(torn)
+    with pytest.raises(capi.VampomiError):
+        sol.load_state(str(tmp_path / "torn.bin"))
+    sol.load_state(ck)                                                            # a refused checkpoint leaves the solver untouched
     for k in range(stop, its):
         r = sol.step()
         assert r["it"] == k + 1 and (r["k1"], r["k2"]) == (full[k]["k1"], full[k]["k2"])

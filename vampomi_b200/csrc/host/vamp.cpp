@@ -47,7 +47,7 @@ Vamp::Vamp(vampomi_ctx* ctx, const vampomi_solver_config& cfg) : ctx_(ctx), cfg_
 }
 
 int Vamp::init(const double* y, const double* true_signal, const double* x1hat_init) {
-    VH(vampomi_dims(ctx_, &N_, &Mt_, nullptr, &rank_));
+    VH(vampomi_dims(ctx_, &N_, &Mt_, &nranks_, &rank_));
     VH(vampomi_shard(ctx_, &M_, &S_));
     if (cfg_.L < 1 || cfg_.L > VAMPOMI_MAX_MIX) return VAMPOMI_ERR_ARG;
     probs_.assign(cfg_.probs, cfg_.probs + cfg_.L);
@@ -133,13 +133,20 @@ int Vamp::apply_covariates() {
 namespace {
 struct CkptHeader {
     char magic[8];
-    int model, it, N, L, C, reserved;
+    int model, it, N, L, C, nranks;
     long long Mt;
     double gam1, gamw, alpha1, tau1, gam2, eta1, eta2, alpha2;
     double probs[VAMPOMI_MAX_MIX], vars[VAMPOMI_MAX_MIX];
     double cov_eff[64];
 };
-static_assert(sizeof(CkptHeader) <= 4096, "checkpoint header");
+// A checkpoint is written by all ranks into one file with no ordering between them, so a run that dies while writing leaves a file
+// that can look whole (holes read as zeros). Every rank therefore ends with a record of the marker block it wrote, after its data are
+// on disk; a checkpoint is complete when the records of all h.nranks writers carry the header's iteration and tile [0, Mt).
+struct CkptShard {
+    long long it, S, M;
+};
+constexpr long long kCkptShards = 2048, kCkptMaxRanks = 64;
+static_assert(sizeof(CkptHeader) <= kCkptShards && kCkptShards + kCkptMaxRanks * sizeof(CkptShard) <= 4096, "checkpoint header");
 constexpr long long kCkptData = 4096;
 bool pwrite_all(int fd, const void* buf, size_t n, long long off) {
     size_t done = 0;
@@ -162,10 +169,11 @@ bool pread_all(int fd, void* buf, size_t n, long long off) {
 }  // namespace
 
 int Vamp::save_state(const char* path) {
-    if (!path || it_ < 1 || C_ > 64) return VAMPOMI_ERR_ARG;
+    if (!path || it_ < 1 || C_ > 64 || nranks_ > kCkptMaxRanks) return VAMPOMI_ERR_ARG;
     int fd = ::open(path, O_WRONLY | O_CREAT, 0644);
     if (fd < 0) return VAMPOMI_ERR_IO;
-    bool ok = true;
+    CkptShard rec = {0, 0, 0};
+    bool ok = pwrite_all(fd, &rec, sizeof(rec), kCkptShards + rank_ * (long long)sizeof(rec));   // a file of this name may be there already
     std::vector<double> buf((size_t)std::max<long long>(M_, N_));
     const int vecs[3] = {VAMPOMI_V_R1, VAMPOMI_V_X1, VAMPOMI_V_X2};
     for (int k = 0; k < 3 && ok; k++) {
@@ -175,8 +183,8 @@ int Vamp::save_state(const char* path) {
     if (ok && rank_ == 0) {
         CkptHeader h;
         std::memset(&h, 0, sizeof(h));
-        std::memcpy(h.magic, "VAMPCKP1", 8);
-        h.model = cfg_.model; h.it = it_; h.N = N_; h.L = (int)probs_.size(); h.C = C_; h.Mt = Mt_;
+        std::memcpy(h.magic, "VAMPCKP2", 8);
+        h.model = cfg_.model; h.it = it_; h.N = N_; h.nranks = nranks_; h.L = (int)probs_.size(); h.C = C_; h.Mt = Mt_;
         h.gam1 = gam1_; h.gamw = gamw_; h.alpha1 = alpha1_; h.tau1 = tau1_; h.gam2 = gam2_; h.eta1 = eta1_; h.eta2 = eta2_; h.alpha2 = alpha2_;
         for (int i = 0; i < h.L; i++) { h.probs[i] = probs_[i]; h.vars[i] = vars_[i]; }
         for (int j = 0; j < C_; j++) h.cov_eff[j] = cov_eff_[j];
@@ -184,6 +192,10 @@ int Vamp::save_state(const char* path) {
         if (ok && cfg_.model == 1)
             ok = vampomi_vec_get(ctx_, VAMPOMI_V_P1, buf.data()) == VAMPOMI_OK &&
                  pwrite_all(fd, buf.data(), (size_t)N_ * sizeof(double), kCkptData + 3LL * Mt_ * 8);
+    }
+    if (ok) {
+        rec = {it_, S_, M_};
+        ok = ::fdatasync(fd) == 0 && pwrite_all(fd, &rec, sizeof(rec), kCkptShards + rank_ * (long long)sizeof(rec)) && ::fdatasync(fd) == 0;
     }
     ::close(fd);
     return ok ? VAMPOMI_OK : VAMPOMI_ERR_IO;
@@ -194,8 +206,19 @@ int Vamp::load_state(const char* path) {
     int fd = ::open(path, O_RDONLY);
     if (fd < 0) return VAMPOMI_ERR_IO;
     CkptHeader h;
-    bool ok = pread_all(fd, &h, sizeof(h), 0) && !std::memcmp(h.magic, "VAMPCKP1", 8);
+    bool ok = pread_all(fd, &h, sizeof(h), 0) && !std::memcmp(h.magic, "VAMPCKP2", 8);
     if (ok && (h.model != cfg_.model || h.N != N_ || h.Mt != Mt_ || h.L < 1 || h.L > VAMPOMI_MAX_MIX || h.C != C_)) { ::close(fd); return VAMPOMI_ERR_ARG; }
+    if (ok) {                                                 // every writer finished: their marker blocks tile [0, Mt) (any order of ranks)
+        CkptShard recs[kCkptMaxRanks];
+        ok = h.nranks >= 1 && h.nranks <= kCkptMaxRanks && pread_all(fd, recs, (size_t)h.nranks * sizeof(CkptShard), kCkptShards);
+        long long next = 0;
+        for (int found = 1; ok && found && next < Mt_;) {
+            found = 0;
+            for (int k = 0; k < h.nranks; k++)
+                if (recs[k].it == h.it && recs[k].S == next && recs[k].M > 0) { next += recs[k].M; found = 1; break; }
+        }
+        ok = ok && next == Mt_;
+    }
     std::vector<double> buf((size_t)std::max<long long>(M_, N_));
     const int vecs[3] = {VAMPOMI_V_R1, VAMPOMI_V_X1, VAMPOMI_V_X2};
     for (int k = 0; k < 3 && ok; k++)

@@ -51,7 +51,7 @@ private:
     std::vector<double> Z_, cov_eff_;
     int fit_covariates();
     int apply_covariates();          // device vectors that follow from cov_eff_ (linear: adjusted y; probit: m_cov)
-    int rank_ = 0;
+    int rank_ = 0, nranks_ = 1;
     double* pending_x1_ = nullptr;   // host buffers of read-outs begun by dump() and not yet collected
     double* pending_r1_ = nullptr;
     bool aty_ready_ = false;

@@ -95,3 +95,35 @@ def test_association_and_test_modes_on_two_gpus(tmp_path):
     run(["--meth-file-test", f"{d}/tst.bin", "--phen-file-test", f"{d}/tst.phen", "--N-test", Nt, "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
          "--run-mode", "test", "--estimate-file", f"{d}/out/g_it_1.bin", "--test-iter-range", f"1,{last}", "--gpus", 2])
     assert_rows_close(csv_rows(open(f"{d}/out/g_test.csv", "rb").read()), csv_rows(g["csv_test"]), 1e-8, "test.csv")
+
+
+@pytest.mark.parametrize("write_gpus,resume_gpus", [(2, 1), (1, 2)])
+def test_checkpoint_written_on_one_sharding_resumes_on_another(write_gpus, resume_gpus, tmp_path):
+    """--checkpoint-every / --resume-from across GPU counts: the checkpoint holds the marker vectors at their GLOBAL offsets and one
+    completion record per writing rank, so a run checkpointed on 2 GPUs continues on 1 (and the reverse) with the reference's iterates."""
+    if capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = load_golden("linear_wellcond")
+    d = str(tmp_path)
+    golden_inputs(g, d)
+    os.makedirs(tmp_path / "out")
+    its = int(g["iterations"])
+    base = ["--meth-file", f"{d}/ex.bin", "--phen-file", f"{d}/ex.phen", "--N", g["N"], "--Mt", g["M"], "--out-dir", f"{d}/out", "--out-name", "g",
+            "--true-signal-file", f"{d}/ex_ts.bin", "--stop-criteria-thr", 0, "--seed", g["probe_seed"]] + list(g["extra"])
+
+    def run(args):
+        res = subprocess.run([build.MAIN_METH] + [str(a) for a in base + args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert res.returncode == 0, res.stdout[-3000:]
+        return res.stdout
+
+    run(["--iterations", 3, "--checkpoint-every", 3, "--gpus", write_gpus])
+    ck = f"{d}/out/g_checkpoint_it_3.bin"
+    recs = np.frombuffer(open(ck, "rb").read()[2048:2048 + 24 * write_gpus], dtype=np.int64).reshape(write_gpus, 3)
+    assert np.all(recs[:, 0] == 3) and recs[:, 2].sum() == int(g["M"]) and recs[0, 1] == 0        # (iteration, first marker, markers) per writer
+    out = run(["--iterations", its, "--resume-from", ck, "--gpus", resume_gpus])
+    assert "resuming after iteration 3" in out
+    for k in range(1, its + 1):
+        assert rel_l2(np.fromfile(f"{d}/out/g_it_{k}.bin"), g["x1"][k - 1]) < 1e-9
+        assert rel_l2(np.fromfile(f"{d}/out/g_r1_it_{k}.bin"), g["r1"][k - 1]) < 1e-9
+    for kind in ("params", "metrics"):
+        assert_rows_close(csv_rows(open(f"{d}/out/g_{kind}.csv", "rb").read()), csv_rows(g[f"csv_{kind}"]), 1e-8, kind)

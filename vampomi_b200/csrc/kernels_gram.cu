@@ -1478,6 +1478,33 @@ int gram_cluster(vampomi_ctx* c, const GramVec& gv, const MultiVec& mw) {
 
 }  // namespace
 
+// The instantiations for one system (K = 1) and for two (K = 2) compile independently: the Makefile builds this file twice, with
+// -DVAMPOMI_GRAM_K=1 (gram_run_k1 only) and -DVAMPOMI_GRAM_K=2 (everything else), to halve the build's longest step; without the
+// macro one translation unit holds both.
+#ifndef VAMPOMI_GRAM_K
+#define VAMPOMI_GRAM_K 0
+#endif
+
+namespace {
+template <int K>
+int gram_run(vampomi_ctx* c, const MultiVec& mq, double* const* w_out) {
+    GramVec gv{};
+    MultiVec mw{};
+    mw.K = K;
+    for (int k = 0; k < K; k++) {
+        gv.q[k] = mq.in[k]; gv.t[k] = mq.out[k]; gv.done[k] = mq.done[k];
+        mw.in[k] = nullptr; mw.out[k] = w_out[k]; mw.done[k] = mq.done[k];
+    }
+    return gram_cluster<K>(c, gv, mw);
+}
+}  // namespace
+
+int gram_run_k1(vampomi_ctx* c, const MultiVec& mq, double* const* w_out);
+#if VAMPOMI_GRAM_K != 2
+int gram_run_k1(vampomi_ctx* c, const MultiVec& mq, double* const* w_out) { return gram_run<1>(c, mq, w_out); }
+#endif
+
+#if VAMPOMI_GRAM_K != 1
 bool gram_supported(const vampomi_ctx* c) {
     return c->storage == 0 && c->ld <= (size_t)gram_max_cluster_of_shape(c->tune.gram_shape) * gram_rows_of_shape(c->tune.gram_shape);
 }
@@ -1487,14 +1514,8 @@ bool gram_supported(const vampomi_ctx* c) {
 int launch_gram(vampomi_ctx* c, const MultiVec& mq, double* const* w_out) {
     if (mq.K < 1 || mq.K > 2) { set_error("gram: 1 or 2 systems"); return VAMPOMI_ERR_ARG; }
     if (!gram_supported(c)) { set_error("gram: needs FP64 storage and N <= 40960"); return VAMPOMI_ERR_ARG; }
-    GramVec gv{};
-    MultiVec mw{};
-    mw.K = mq.K;
-    for (int k = 0; k < mq.K; k++) {
-        gv.q[k] = mq.in[k]; gv.t[k] = mq.out[k]; gv.done[k] = mq.done[k];
-        mw.in[k] = nullptr; mw.out[k] = w_out[k]; mw.done[k] = mq.done[k];
-    }
-    return mq.K == 1 ? gram_cluster<1>(c, gv, mw) : gram_cluster<2>(c, gv, mw);
+    return mq.K == 1 ? gram_run_k1(c, mq, w_out) : gram_run<2>(c, mq, w_out);
 }
+#endif
 
 }  // namespace vampomi

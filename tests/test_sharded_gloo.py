@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, name):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -21,7 +21,7 @@ def _worker(rank, world, port, out_dir):
     from helpers import golden_inputs, load_golden, oracle_run
     from oracle import vamp_oracle as vo
     from vampomi_b200 import capi
-    g = load_golden("linear_wellcond")
+    g = load_golden(name)
     g["iterations"] = 4
     A, y_txt, beta = golden_inputs(g)
     M, S = capi.divide_work(int(g["M"]), world, rank)            # the product's own work split (host-side C ABI)
@@ -31,11 +31,12 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(300)
-def test_two_shards_match_one_shard(tmp_path, lib):
+@pytest.mark.parametrize("name", ["linear_wellcond", "probit_small"])
+def test_two_shards_match_one_shard(name, tmp_path, lib):
     from helpers import REL_CSV, REL_VEC, assert_rows_close, csv_rows, load_golden, rel_l2
     port = 29500 + os.getpid() % 2000
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    g = load_golden("linear_wellcond")
+    mp.spawn(_worker, args=(2, port, str(tmp_path), name), nprocs=2, join=True)
+    g = load_golden(name)
     for k in range(1, 5):
         x1 = np.fromfile(tmp_path / f"o_it_{k}.bin")
         r1 = np.fromfile(tmp_path / f"o_r1_it_{k}.bin")

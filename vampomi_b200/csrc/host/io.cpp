@@ -11,6 +11,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <algorithm>
+#include <system_error>
 #include <thread>
 #include <vector>
 #include "../rng.h"
@@ -205,7 +206,9 @@ void loo_pvals(const double* x1, const double* sums, double sw, double sww, int 
     const long long chunk = (M + threads - 1) / threads;
     for (int t = 0; t < threads; t++) {
         const long long j0 = t * chunk, j1 = std::min(M, j0 + chunk);
-        if (j0 < j1) pool.emplace_back(work, j0, j1);
+        if (j0 >= j1) continue;
+        try { pool.emplace_back(work, j0, j1); }
+        catch (const std::system_error&) { work(j0, j1); }   // no more threads to be had: this block on the calling thread
     }
     for (auto& th : pool) th.join();
 }
